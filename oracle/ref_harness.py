@@ -1,0 +1,201 @@
+"""TEST INFRASTRUCTURE ONLY -- live-reference harness (runs only where /root/reference exists).
+
+Imports the *unmodified* reference (WaimenMak/PedNStream) from a writable temp copy of
+/root/reference with runtime shims only (matplotlib / pettingzoo / gymnasium stubs, a
+`verbose` kwarg for create_network -- SURVEY.md Appendix C).  Used by
+`oracle/gen_golden.py` to produce the committed fixtures under `tests/golden/` and by
+CPU-side tests (skipped when /root/reference is absent) to pin the oracle restatement.
+
+Nothing in the product package, the `-m gpu` tests, `bench.py` or `smoke()` imports this
+file: /root/reference does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = "/root/reference"
+
+LINK_FIELDS_F64 = ("inflow", "outflow", "cumulative_inflow", "cumulative_outflow",
+                   "sending_flow", "receiving_flow", "back_gate_width_data")
+LINK_FIELDS_F32 = ("num_pedestrians", "density", "speed", "travel_time",
+                   "avg_travel_time", "link_flow")
+LINK_FIELDS = LINK_FIELDS_F64 + LINK_FIELDS_F32
+
+_REF_COPY = None
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM"))
+
+
+def _install_stubs():
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl.use = lambda *a, **k: None
+        plt = types.ModuleType("matplotlib.pyplot")
+        anim = types.ModuleType("matplotlib.animation")
+        anim.PillowWriter = type("PillowWriter", (), {})
+        anim.FuncAnimation = type("FuncAnimation", (), {})
+        for name in ("cm", "colors", "patches", "lines", "collections", "gridspec", "ticker"):
+            sub = types.ModuleType(f"matplotlib.{name}")
+            setattr(mpl, name, sub)
+            sys.modules[f"matplotlib.{name}"] = sub
+        mpl.pyplot, mpl.animation = plt, anim
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt,
+                            "matplotlib.animation": anim})
+    if "pettingzoo" not in sys.modules:
+        pz = types.ModuleType("pettingzoo")
+        pz.ParallelEnv = type("ParallelEnv", (), {"__init__": lambda self, *a, **k: None})
+        sys.modules["pettingzoo"] = pz
+    if "gymnasium" not in sys.modules:
+        gym = types.ModuleType("gymnasium")
+        spaces = types.ModuleType("gymnasium.spaces")
+
+        class Space:  # minimal duck type
+            pass
+
+        class Box(Space):
+            def __init__(self, low, high, shape=None, dtype=np.float32):
+                self.dtype = dtype
+                self.shape = tuple(shape) if shape is not None else np.shape(low)
+                self.low = np.broadcast_to(np.asarray(low, dtype=dtype), self.shape).copy()
+                self.high = np.broadcast_to(np.asarray(high, dtype=dtype), self.shape).copy()
+
+            def sample(self):
+                return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+        spaces.Space, spaces.Box = Space, Box
+        gym.spaces = spaces
+        sys.modules.update({"gymnasium": gym, "gymnasium.spaces": spaces})
+
+
+def reference_copy() -> str:
+    """Writable copy of the reference tree (the reference mkdirs outputs/logs and data/)."""
+    global _REF_COPY
+    if _REF_COPY is None:
+        dst = tempfile.mkdtemp(prefix="pns_ref_")
+        for sub in ("src", "data", "handlers", "rl"):
+            shutil.copytree(os.path.join(REFERENCE_ROOT, sub), os.path.join(dst, sub),
+                            ignore=shutil.ignore_patterns("*.pt", "outputs", "*_agents_*", "*.gif"))
+        _REF_COPY = dst
+    return _REF_COPY
+
+
+def import_reference():
+    """Returns (Network class, NetworkEnvGenerator class) of the live reference."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    _install_stubs()
+    root = reference_copy()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import logging
+    from src.LTM.network import Network  # noqa
+    from src.utils.env_loader import NetworkEnvGenerator  # noqa
+    logging.getLogger("src.LTM.network").setLevel(logging.ERROR)
+    return Network, NetworkEnvGenerator
+
+
+def create_network(name: str, steps_override: int | None = None, verbose: bool = True, **kw):
+    """reference NetworkEnvGenerator.create_network(name) (env_loader.py:81), optional
+    simulation_steps override."""
+    import logging
+    Network, Gen = import_reference()
+    g = Gen()
+    if steps_override is not None:
+        g.network_data = g.load_network_data(name)
+        g.config["params"]["simulation_steps"] = steps_override
+    net = g.create_network(name, **kw)
+    if net.logger is not None:
+        net.logger.setLevel(logging.ERROR)
+    return net, g
+
+
+class DrawRecorder:
+    """Records every in-step RNG draw of the reference keyed (site, link_id, time index).
+
+    Sites: 'R1' release binomial (link.py:337,343), 'R2' activity binomial (:356),
+    'R3' reverse-pedestrian binomial (:382), 'R4' speed noise normal (functions.py:133).
+    Pure observation: the global MT19937 stream is not perturbed.
+    """
+
+    def __init__(self):
+        self.draws = {}      # (site, link_id, t) -> value
+        self.requests = {}   # (site, link_id, t) -> (n, p) / (loc, scale)
+        self._ctx = None
+        self._k = 0
+
+    def install(self):
+        import src.LTM.link as rl
+        self._orig = (np.random.binomial, np.random.normal,
+                      rl.Link.cal_sending_flow, rl.Link.cal_receiving_flow, rl.Link.update_speeds,
+                      rl.Separator.cal_receiving_flow, rl.Separator.update_speeds)
+        rec = self
+        ob, on = np.random.binomial, np.random.normal
+
+        def binomial(n, p, size=None):
+            v = ob(n, p, size)
+            if rec._ctx is not None:
+                kind, link, t = rec._ctx
+                lid = link.link_id
+                if kind == "recv":
+                    site = "R3"
+                else:  # first binomial in cal_sending_flow is R2 when the diffusion branch skipped R1
+                    ap = link.activity_probability
+                    site = "R2" if (ap > 0 and float(p) == float(ap)) else "R1"
+                rec.draws[(site, lid, t)] = int(v)
+                rec.requests[(site, lid, t)] = (int(n), float(p))
+                rec._k += 1
+            return v
+
+        def normal(loc=0.0, scale=1.0, size=None):
+            v = on(loc, scale, size)
+            if rec._ctx is not None and rec._ctx[0] == "speed":
+                _, link, t = rec._ctx
+                rec.draws[("R4", link.link_id, t)] = float(v)
+            return v
+
+        def wrap(fn, kind):
+            def inner(self_, time_step, *a, **k):
+                prev, prevk = rec._ctx, rec._k
+                rec._ctx, rec._k = (kind, self_, time_step), 0
+                try:
+                    return fn(self_, time_step, *a, **k)
+                finally:
+                    rec._ctx, rec._k = prev, prevk
+            return inner
+
+        np.random.binomial, np.random.normal = binomial, normal
+        rl.Link.cal_sending_flow = wrap(self._orig[2], "send")
+        rl.Link.cal_receiving_flow = wrap(self._orig[3], "recv")
+        rl.Link.update_speeds = wrap(self._orig[4], "speed")
+        rl.Separator.cal_receiving_flow = wrap(self._orig[5], "recv")
+        rl.Separator.update_speeds = wrap(self._orig[6], "speed")
+        return self
+
+    def uninstall(self):
+        import src.LTM.link as rl
+        (np.random.binomial, np.random.normal, rl.Link.cal_sending_flow, rl.Link.cal_receiving_flow,
+         rl.Link.update_speeds, rl.Separator.cal_receiving_flow, rl.Separator.update_speeds) = self._orig
+
+
+def collect_link_arrays(net) -> dict:
+    """Stack every per-link history array into [S+1, L] matrices in network.links order."""
+    out = {}
+    links = list(net.links.values())
+    for f in LINK_FIELDS:
+        out[f] = np.stack([np.asarray(getattr(l, f)) for l in links], axis=1)
+    out["link_keys"] = np.array(list(net.links.keys()), dtype=np.int64)
+    return out
+
+
+def array_digest(a: np.ndarray) -> str:
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()
