@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Benchmark of the LTM timestep (BASELINE.json metric: link-timesteps/sec, fp64 state).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload grid512|env45]
+
+Workload at N=1 (`config.workload`): BASELINE config 4, the synthetic 512x512-node lattice of
+data/create_grid.py's rule (1 046 528 directed links, default_link of data/45_intersections, 35
+origins = 4 corners + every 64th boundary node, gaussian-peak Poisson demand pre-drawn on the host,
+uniform turning fractions), single replica, on-device Philox draws.  configs[1] (nine_intersections,
+24 links) is a parity-test case: at 24 links a step is pure launch latency and says nothing about the
+HBM roofline the metric is quoted against; the 512x512 grid is the largest single-GPU configuration.
+A "step" is one `network_loading(t)` over the whole network.  With N>1 every rank runs an
+independent replica of the grid (replicas only, no data-path collective; weak scaling).
+
+One JSON line on stdout (rank 0).  See the tier contract in the task brief for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_ALG = 176.0            # algorithmic bytes per link-timestep, SURVEY.md section 8(d)
+# split of B_ALG by pass (DESIGN.md "kernels"; sums to 176): link_flows = 92 B lagged/previous-row reads
+# + 16 B sending/receiving writes; node_flows = 32 B flow/cumulative-count writes; link_update = 4 B
+# lagged read + 32 B state writes.  Intermediate re-reads between passes are not algorithmic bytes.
+B_ALG_PASS = {"link_flows": 108.0, "route_probs": 0.0, "node_flows": 32.0, "link_update": 36.0}
+GRID_SIZE = 512
+REF_SAMPLE_SIZE = 32
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------- reference arm
+def oracle_sample(steps, warmup):
+    """The reference's algorithm on the host: the Python oracle (kind 'port'; the reference itself is
+    Python and does not travel to the GPU box) on a 32x32 lattice with the workload's link
+    parameters, origin rule and demand pattern.  Per-link-step cost of this code is size-independent
+    (12.2k vs 12.7k link-steps/s at 16x16 / 32x32)."""
+    import numpy as np
+    from oracle.ltm_oracle import LtmOracle
+    from pednstream_b200 import Network
+    from pednstream_b200.grid import DEFAULT_LINK, default_origins, grid_adjacency
+    size = REF_SAMPLE_SIZE
+    origins = default_origins(size, stride=64)
+    S = max(1000, warmup + steps + 1)
+    params = {"unit_time": 10, "simulation_steps": S, "default_link": dict(DEFAULT_LINK),
+              "demand": {f"origin_{o}": {"peak_lambda": 50, "base_lambda": 30} for o in origins}}
+    np.random.seed(0)
+    net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
+    o = LtmOracle(net)
+    for t in range(1, warmup + 1):
+        o.network_loading(t)
+    t0 = time.perf_counter()
+    for t in range(warmup + 1, warmup + steps + 1):
+        o.network_loading(t)
+    dt = time.perf_counter() - t0
+    L = len(net.links)
+    return L * steps / dt, dt, L
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 60)
+    value, dt, L = oracle_sample(steps, min(args.warmup, 3))
+    cores = 1
+    sample = (f"{REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({L} links), {steps} steps, same link parameters / "
+              f"origin rule / demand pattern as the workload; single Python process")
+    line = {"impl": "reference", "metric": "link-timesteps/sec", "value": value, "unit": "link-timesteps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"grid{GRID_SIZE} (config 4: synthetic {GRID_SIZE}x{GRID_SIZE}-node lattice)",
+                       "reference_sample": sample},
+            "cpu_baseline": {"value": value, "unit": "link-timesteps/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "link-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pednstream_b200 import _native
+    from pednstream_b200.engine import Engine
+    from pednstream_b200.grid import build_grid_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    size = args.grid
+    S = 2 * (W + K) + 2                                  # two timed regions (value, e2e) + headroom
+    plan, widths, tf, demand = build_grid_plan(size, S, demand_seed=rank)
+    L = plan["n_links"]
+    eng = Engine(plan, replicas=1, rng="philox", seed=rank, device=dev)
+    eng.initialise(widths, None, tf, demand, None)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed region: inputs resident in HBM, K steps in one native call ----
+    eng.run(1, W)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run(W + 1, K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t_next = W + K + 1
+
+    # ---- per-kernel durations (CUDA events on the launching stream, inside the library) --------
+    Kp = min(K, 50)
+    k_ms, k_cnt = eng.run_profiled(t_next, Kp)
+    t_next += Kp
+    names = ("link_flows", "route_probs", "node_flows", "link_update")
+    per_kernel = {n: (k_ms[i] / k_cnt[i] if k_cnt[i] else None) for i, n in enumerate(names)}
+
+    # ---- end to end through the public call, host buffers: every step copies its demand row from
+    # pinned host memory, launches the step, and reads the network-wide pedestrian count back ----
+    Ke = min(K, S - t_next - 1)
+    pinned = torch.from_numpy(np.ascontiguousarray(demand)).pin_memory()
+    result_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    num_hist = eng.history("num_pedestrians")
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for t in range(t_next, t_next + Ke):
+        eng.demand[t - 1, : pinned.shape[1]].copy_(pinned[t - 1], non_blocking=True)
+        eng.run(t, 1)
+        result_host.copy_(num_hist[t].sum().reshape(1), non_blocking=False)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    eng.check_errors()
+    total_peds = float(result_host[0])
+
+    t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = world * L * K / (ms * 1e-3)
+        e2e = world * L * Ke / (ms_e2e * 1e-3)
+        dom = max((n for n in names if per_kernel[n]), key=lambda n: per_kernel[n])
+        step_gbs = B_ALG * L / (ms / K * 1e-3) / 1e9
+        dom_gbs = B_ALG_PASS[dom] * L / (per_kernel[dom] * 1e-3) / 1e9
+        cpu_v, cpu_dt, cpu_L = (None, None, None)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_steps = 40
+            cpu_v, cpu_dt, cpu_L = oracle_sample(cpu_steps, 2)
+        line = {
+            "metric": "link-timesteps/sec", "value": value, "unit": "link-timesteps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"grid{size} (config 4: synthetic {size}x{size}-node lattice, {L} directed links, "
+                                   f"1 replica per GPU, philox draws, uniform turning fractions)",
+                       "links": L, "nodes": plan["n_nodes"], "origins": plan["n_demand_rows"],
+                       "l2_policy": "inputs larger than L2: one step touches >= 176 B x links = "
+                                    f"{B_ALG * L / 1e6:.0f} MB of history",
+                       "multi_gpu": "replicas only: one independent grid per rank, no data-path collective"},
+            "e2e": {"value": e2e, "unit": "link-timesteps/s", "steps": Ke,
+                    "h2d_bytes_per_step": int(pinned.shape[1] * 8), "d2h_bytes_per_step": 4,
+                    "note": "per step: H2D of the demand row from pinned memory, one native step call, "
+                            "D2H of the network-wide pedestrian count (host sync every step)"},
+            "gpu_launches": int(3 * K + (K if plan["rt_grp_node"].size else 0)),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_link_step": B_ALG_PASS[dom],
+                         "kernel_ms": {k: v for k, v in per_kernel.items() if v},
+                         "step": {"achieved": step_gbs, "frac": step_gbs / peak, "alg_bytes_per_link_step": B_ALG}},
+            "check": {"pedestrians_on_links_last_step": total_peds},
+        }
+        if cpu_v is not None:
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "link-timesteps/s", "cores": 1, "kind": "port",
+                                    "sample": f"Python oracle, {REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({cpu_L} links), "
+                                              f"40 steps, {cpu_dt:.1f} s; host has {os.cpu_count()} cores, the "
+                                              f"reference algorithm is single-threaded"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=GRID_SIZE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

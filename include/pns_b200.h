@@ -1,0 +1,179 @@
+/*
+ * pns_b200.h -- C-ABI of the B200-native PedNStream Link-Transmission-Model timestep.
+ *
+ * The reference (WaimenMak/PedNStream) has no FFI layer: its hot path is the Python method
+ * `Network.network_loading(t)` (src/LTM/network.py:266-287) and the per-object methods it calls.
+ * Each entry point below replaces one slice of that call tree; the reference line ranges are
+ * cited per function.  Conventions:
+ *
+ *   - plain C: POD structs of raw *device* pointers and sizes, no torch / C++ types;
+ *   - the library owns no memory: every buffer is allocated by the caller (the Python host uses
+ *     torch tensors) and must stay alive while a launch that uses it is in flight;
+ *   - every launch is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value 0 = launched, non-zero = error, message via pns_last_error() (thread local);
+ *     physics-level faults that the reference raises as Python exceptions (negative flows,
+ *     out-of-range history index) set bits in `pns_state.err[replica]` instead.
+ *
+ * Memory layout ("time-major structure of arrays", replica index fastest):
+ *   hist64[f][t][c*R + r]   f < n_f64, t <= sim_steps, c < n_cols64      (double)
+ *   hist32[f][t][l*R + r]   f < 6,                      l < n_links       (float)
+ * Column c < n_links is physical link c (network.links order; the reverse direction of link l
+ * is l^1); columns >= n_links are the virtual origin/destination links.
+ */
+#ifndef PNS_B200_H
+#define PNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNS_ABI_VERSION 1
+#define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
+
+/* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
+enum {
+    PNS_F64_INFLOW = 0,
+    PNS_F64_OUTFLOW = 1,
+    PNS_F64_CUM_INFLOW = 2,
+    PNS_F64_CUM_OUTFLOW = 3,
+    PNS_F64_SENDING = 4,
+    PNS_F64_RECEIVING = 5,
+    PNS_F64_BACK_GATE = 6,
+    PNS_F64_SEP_WIDTH = 7 /* present only when n_f64 == 8 */
+};
+/* fp32 history fields (reference src/LTM/link.py:82-97) */
+enum {
+    PNS_F32_NUM_PED = 0,
+    PNS_F32_DENSITY = 1,
+    PNS_F32_SPEED = 2,
+    PNS_F32_TRAVEL_TIME = 3,
+    PNS_F32_AVG_TRAVEL_TIME = 4,
+    PNS_F32_LINK_FLOW = 5
+};
+
+/* where the in-step random draws come from (SURVEY.md "RNG ledger", sites R1..R4) */
+enum {
+    PNS_RNG_TABLE = 0,   /* outcomes supplied by the caller (replay / numpy-compatible stepping) */
+    PNS_RNG_PHILOX = 1,  /* Philox4x32-10 keyed (seed, replica; t, link, site) on the device */
+    PNS_RNG_REQUEST = 2  /* write the draw requests of this step, change no state (pass 1 of
+                            numpy-compatible stepping) */
+};
+
+/* bits of pns_state.err[replica] */
+enum {
+    PNS_ERR_NEG_SENDING = 1,     /* link.py:346,366 ValueError */
+    PNS_ERR_NEG_NODE_FLOW = 2,   /* node.py:194,219,238 Warning */
+    PNS_ERR_HISTORY_INDEX = 4,   /* numpy IndexError in link.py:210-212 */
+    PNS_ERR_ZERO_LAG = 8         /* tau == 0: the reference result depends on node visiting order */
+};
+
+/* Immutable network description.  All pointers are device pointers. */
+typedef struct pns_net {
+    int32_t abi_version;
+    int32_t n_links, n_nodes, n_cols64, sim_steps, replicas, window, n_edges, n_od, n_demand_rows;
+    int32_t n_routed, n_groups, n_opts, n_rows, n_terms;
+    double unit_time;
+    /* link table [n_links] -- parameters of src/LTM/link.py:52-100 */
+    const double *lk_length, *lk_width, *lk_vf, *lk_kc, *lk_kj, *lk_gamma, *lk_act, *lk_bi, *lk_sigma;
+    const float *lk_tt0;                 /* travel_time[0], fp32 (link.py:83) */
+    const int32_t *lk_fftau, *lk_swtau;  /* free-flow lag (link.py:86), shock-wave lag (link.py:380) */
+    const int32_t *lk_flags;             /* bit0 separator, bits1-2 fd type (0 yperman 1 greenshields 2 smulders) */
+    /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id) */
+    const int32_t *nd_ptr;      /* [n_nodes+1] */
+    const int32_t *nd_in_col;   /* [slots] history column of the incoming link of each slot */
+    const int32_t *nd_out_col;  /* [slots] history column of the outgoing link of each slot */
+    const int32_t *nd_kind;     /* 0 one-to-one (node.py:230), 1 regular/classic (node.py:272) */
+    const int32_t *nd_dem_row;  /* row of the demand table, -1 if the node has no virtual links */
+    const int32_t *nd_tf_ptr;   /* [n_nodes+1] offset of the node's m(m-1) turning fractions */
+    const int32_t *nd_routed;   /* index into the routed-node arrays, -1 = static fractions */
+    /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
+    const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
+    const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
+    const int32_t *rt_opt_link, *rt_opt_slot;
+    const double *rt_opt_dist;
+    const int32_t *rt_row_ptr, *rt_row_od, *rt_term_ptr, *rt_term_opt, *rt_term_row_entry;
+    double rt_temp, rt_alpha, rt_beta, rt_omega, rt_eps; /* path_finder.py:158-163 */
+} pns_net;
+
+/* Mutable simulation state; all device pointers, caller-owned. */
+typedef struct pns_state {
+    double *hist64;      /* [n_f64][sim_steps+1][n_cols64*R] */
+    float *hist32;       /* [6][sim_steps+1][n_links*R] */
+    double *widths;      /* [3][n_links*R]: front gate, back gate, separator width (link.py:54-55, 422) */
+    int32_t *sep_np64;   /* [n_links*R] separator width was set from a numpy float64 (dtype ledger) */
+    float *runsum;       /* [n_links*R] fp32 running sum of travel times (link.py:84,183-186) */
+    double *tf_static;   /* [n_edges] host-owned turning fractions (uniform default / user supplied) */
+    double *tf_routed;   /* [n_edges*R] fractions computed this step for routed nodes */
+    double *probs;       /* [n_opts*R] scratch: P(down | up, od) of this step */
+    int32_t *err;        /* [R] error bits */
+    int32_t n_f64;       /* 7, or 8 when the network has separators */
+} pns_state;
+
+/* Per-call inputs of one or more consecutive steps. */
+typedef struct pns_step_io {
+    const double *demand;   /* [>= t][n_demand_rows*R]: row t-1 is node.demand[t-1] (node.py:176) */
+    const double *od_w;     /* [sim_steps+1][n_od]: od_flows[(o,d)][t] (od_manager.py:52-54) */
+    const int32_t *draw_b;  /* TABLE: [rows][3][n_links*R] outcomes of sites R1, R2, R3 */
+    const double *draw_n;   /* TABLE: [rows][n_links*R] speed noise (site R4) */
+    int64_t draw_row_stride;/* rows advance by one per step when != 0 (0: one row reused) */
+    /* REQUEST outputs, [n_links*R] each */
+    int32_t *req_kind;      /* 0 no R1 draw and flow fixed, 1 diffusion branch (flow in req_sval), 2 binomial */
+    int32_t *req_n1;        /* trials of R1 */
+    float *req_rf;          /* releasing factor: p = 0.7 + 0.15*rf**0.8 is evaluated by the host in numpy */
+    double *req_sval;       /* sending flow after the release stage when kind != 2 */
+    int32_t *req_n3;        /* trials of R3 (-1: separator, no draw) */
+    uint64_t seed;          /* PHILOX */
+} pns_step_io;
+
+int pns_abi_version(void);
+const char *pns_last_error(void);
+
+/* Initial state of every history field, width table and running sum
+ * (reference Link.__init__/Separator.__init__, link.py:12-17, 32-100, 420-425).
+ * `widths` must already hold the initial widths. */
+int pns_state_init(const pns_net *net, const pns_state *st, void *stream);
+
+/* Link demand/supply pass for step t (time index tau = t-1), one thread per link pair and replica:
+ * Link.cal_sending_flow (link.py:216-370) incl. get_outflow (:199-214) and
+ * Link/Separator.cal_receiving_flow_with_reverse (:372-416, :480-512).
+ * Writes sending_flow[tau], receiving_flow[tau] (or the draw requests in REQUEST mode). */
+int pns_link_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
+                   void *stream);
+
+/* Logit route choice for step t, one thread per (od, upstream) group and replica:
+ * PathFinder.update_node_turn_probs (path_finder.py:561-589). Writes st->probs. */
+int pns_route_probs(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, void *stream);
+
+/* Node pass for step t, one thread per node and replica: turning fractions
+ * (path_finder.py:591-715), Node.assign_flows / solve / update_links (node.py:146-300).
+ * Writes inflow/outflow/cumulative counts at row t. */
+int pns_node_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, void *stream);
+
+/* Link state update for step t, one thread per link pair and replica:
+ * Link.update_link_density_flow + update_speeds (link.py:133-188, 430-452) and
+ * BiDirectionalFd.__call__ (src/utils/functions.py:112-134). */
+int pns_link_update(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
+                    void *stream);
+
+/* Network.network_loading(t) for t = t0 .. t0+n_steps-1 (network.py:266-287): the four passes
+ * above per step, back to back on `stream` (TABLE or PHILOX mode). */
+int pns_step(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
+             int rng_mode, void *stream);
+
+/* pns_step with CUDA-event timing of every launch on `stream` (bench/roofline instrumentation):
+ * adds the elapsed milliseconds of each pass to ms[0..3] (link_flows, route_probs, node_flows,
+ * link_update) and the launch counts to launches[0..3].  Synchronises the stream before returning. */
+int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
+                      int rng_mode, void *stream, double *ms, int64_t *launches);
+
+/* Draw `n` samples with the on-device Philox samplers (test hook for oracle/philox.py):
+ * kind 0: binomial(n_trials[i], p[i]) -> out_i; kind 1: standard normal -> out_d. */
+int pns_rng_selftest(int kind, int n, const int32_t *n_trials, const double *p, uint64_t seed, int t,
+                     int site, int32_t *out_i, double *out_d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNS_B200_H */

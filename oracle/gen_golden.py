@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the *live, unmodified* reference.
+
+Run in the build container (needs /root/reference):  python -m oracle.gen_golden [case ...]
+
+The reference has no golden vectors of its own, so parity is pinned on
+trajectories produced here by importing the reference (oracle/ref_harness.py) with
+`np.random.seed(seed)` before network construction.  Per case the fixture stores, for each of the
+13 per-link history fields, one 64-bit digest per time row (sha256 of the row bytes over the
+physical links, reference `network.links` order) plus the full series of a few links and the
+origin demand, which is enough to localise a divergence to (field, first bad row).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+if __package__ in (None, ""):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> (dataset | None for inline params, steps simulated, steps override, seed)
+CASES = {
+    "long_corridor_example": dict(inline="long_corridor_example", run=499, seed=0),
+    "long_corridor": dict(dataset="long_corridor", run=599, seed=0),
+    "nine_intersections": dict(dataset="nine_intersections", run=499, seed=0),
+    "45_intersections": dict(dataset="45_intersections", run=699, seed=0),
+    "butterfly_scA": dict(dataset="butterfly_scA", run=599, seed=0),
+    "small_network": dict(dataset="small_network", run=499, seed=0),
+    "one_intersection_v0": dict(dataset="one_intersection_v0", run=599, seed=0),
+    "od_flow_example": dict(dataset="od_flow_example", run=499, seed=0),
+    "delft": dict(dataset="delft", run=120, seed=0),
+    "melbourne_2000": dict(dataset="melbourne", run=1999, steps_override=2000, seed=0),
+}
+
+# parameters of reference examples/long_corridor.py:25-63 (scenario 1), restated as data
+LONG_CORRIDOR_EXAMPLE = dict(
+    adjacency=[[0, 1, 0, 0, 0, 0], [1, 0, 1, 0, 0, 0], [0, 1, 0, 1, 0, 0],
+               [0, 0, 1, 0, 1, 0], [0, 0, 0, 1, 0, 1], [0, 0, 0, 0, 1, 0]],
+    params={"unit_time": 10, "simulation_steps": 600,
+            "default_link": {"length": 100, "width": 2, "free_flow_speed": 1.1, "k_critical": 2,
+                             "k_jam": 6, "fd_type": "yperman", "bi_factor": 1, "controller_type": "gate"},
+            "demand": {"origin_0": {"peak_lambda": 25, "base_lambda": 5},
+                       "origin_5": {"peak_lambda": 25, "base_lambda": 5}}},
+    origin_nodes=[5, 0])
+
+
+def row_digests(a: np.ndarray) -> np.ndarray:
+    out = np.empty(a.shape[0], dtype=np.uint64)
+    for t in range(a.shape[0]):
+        out[t] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a[t]).tobytes()).digest()[:8], dtype=np.uint64)[0]
+    return out
+
+
+def build_reference_network(case):
+    import copy
+    np.random.seed(case["seed"])
+    if "inline" in case:
+        Network, _ = rh.import_reference()
+        spec = copy.deepcopy(LONG_CORRIDOR_EXAMPLE)
+        net = Network(np.array(spec["adjacency"]), spec["params"], origin_nodes=spec["origin_nodes"])
+        import logging
+        net.logger.setLevel(logging.ERROR)
+        return net
+    net, _ = rh.create_network(case["dataset"], steps_override=case.get("steps_override"))
+    return net
+
+
+def generate(name):
+    case = CASES[name]
+    net = build_reference_network(case)
+    t0 = time.time()
+    for t in range(1, case["run"] + 1):
+        net.network_loading(t)
+    wall = time.time() - t0
+    arrays = rh.collect_link_arrays(net)
+    L = arrays["inflow"].shape[1]
+    keep = sorted(set([0, 1, L // 2, L - 1]))
+    out = {"steps_run": np.int64(case["run"]), "seed": np.int64(case["seed"]),
+           "sim_steps": np.int64(net.simulation_steps), "n_links": np.int64(L),
+           "link_keys": arrays["link_keys"], "sample_links": np.asarray(keep, dtype=np.int64),
+           "reference_seconds": np.float64(wall)}
+    for f in rh.LINK_FIELDS:
+        out["rows_" + f] = row_digests(arrays[f])
+        out["sample_" + f] = arrays[f][:, keep]
+    dem_nodes = [n for n in net.nodes.values() if n.demand is not None]
+    out["demand_nodes"] = np.asarray([n.node_id for n in dem_nodes], dtype=np.int64)
+    for n in dem_nodes:
+        out[f"demand_{n.node_id}"] = np.asarray(n.demand)
+    out["total_in"] = arrays["cumulative_inflow"][case["run"]].sum()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {L} links, {case['run']} steps, reference {wall:.1f}s -> {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or list(CASES)):
+        generate(nm)

@@ -32,8 +32,15 @@ F32_FIELDS = ("num_pedestrians", "density", "speed", "travel_time", "avg_travel_
 
 
 # ----------------------------------------------------------------------------- draw providers
+def numpy_release_prob(rel):
+    """link.py:317 evaluated with numpy scalar semantics (float32 powf with a demoted exponent)."""
+    return 0.7 + (0.85 - 0.7) * rel ** 0.8
+
+
 class NumpyDraws:
     """The reference's own sampler: numpy's global legacy RandomState, consumed in visiting order."""
+
+    release_prob = staticmethod(numpy_release_prob)
 
     def binomial(self, site, link, t, n, p):
         return np.random.binomial(n=n, p=p)
@@ -44,6 +51,8 @@ class NumpyDraws:
 
 class TableDraws:
     """Replay of recorded outcomes: {(site, link_id, t): value}."""
+
+    release_prob = staticmethod(numpy_release_prob)
 
     def __init__(self, table):
         self.table = table
@@ -195,7 +204,7 @@ class LtmOracle:
         original = flow
         if flow > 0:
             rel = np.clip(density / o.k_jam, 0, 1)                                     # :315
-            p_release = 0.7 + (0.85 - 0.7) * rel ** 0.8                                # :317
+            p_release = self.draws.release_prob(rel)                                   # :317
             if density <= o.k_critical:
                 spread = self._diffusion_outflow(o, t, tau)
                 if spread > 0:

@@ -1,0 +1,180 @@
+"""TEST INFRASTRUCTURE ONLY -- Python restatement of the device-side counter-based samplers.
+
+Mirrors pednstream_b200/csrc/pns_rng.cuh operation for operation in IEEE doubles (Python floats
+never contract multiply-adds), so device samples can be checked bit for bit:
+Philox4x32-10 (Salmon et al., SC'11), 53-bit uniforms, fdlibm-style log/exp/sin/cos kernels,
+chunked CDF-inversion binomial, Box-Muller normal.  There is no reference-side counterpart: the
+reference draws from numpy's sequential global stream (SURVEY.md "RNG ledger"); this mode replaces
+the generator, not the distributions.
+"""
+from __future__ import annotations
+
+import math
+import struct
+
+import numpy as np
+
+M32 = 0xFFFFFFFF
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    c = [c0 & M32, c1 & M32, c2 & M32, c3 & M32]
+    for _ in range(10):
+        p0 = 0xD2511F53 * c[0]
+        p1 = 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & M32, p1 & M32, ((p0 >> 32) ^ c[3] ^ k1) & M32, p0 & M32]
+        k0 = (k0 + 0x9E3779B9) & M32
+        k1 = (k1 + 0xBB67AE85) & M32
+    return c
+
+
+def u53(hi, lo):
+    return (float(hi >> 5) * 67108864.0 + float(lo >> 6)) / 9007199254740992.0
+
+
+def det_log(x):
+    Lg = (6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+          2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+          1.479819860511658591e-01)
+    ln2_hi, ln2_lo = 6.93147180369123816490e-01, 1.90821492927058770002e-10
+    bits = struct.unpack("<Q", struct.pack("<d", x))[0]
+    e = ((bits >> 52) & 0x7FF) - 1023
+    m = struct.unpack("<d", struct.pack("<Q", (bits & 0x000FFFFFFFFFFFFF) | 0x3FF0000000000000))[0]
+    if m > 1.4142135623730951:
+        m = m * 0.5
+        e += 1
+    f = m - 1.0
+    s = f / (2.0 + f)
+    z = s * s
+    w = z * z
+    t1 = w * (Lg[1] + w * (Lg[3] + w * Lg[5]))
+    t2 = z * (Lg[0] + w * (Lg[2] + w * (Lg[4] + w * Lg[6])))
+    R = t2 + t1
+    hfsq = (0.5 * f) * f
+    dk = float(e)
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f)
+
+
+def det_exp(x):
+    P = (1.66666666666666019037e-01, -2.77777777770155933842e-03, 6.61375632143793436117e-05,
+         -1.65339022054652515390e-06, 4.13813679705723846039e-08)
+    ln2_hi, ln2_lo = 6.93147180369123816490e-01, 1.90821492927058770002e-10
+    invln2 = 1.44269504088896338700e+00
+    if x < -700.0:
+        return 0.0
+    k = int(invln2 * x - 0.5)          # truncation toward zero, as the C cast
+    dk = float(k)
+    hi = x - dk * ln2_hi
+    lo = dk * ln2_lo
+    r = hi - lo
+    t = r * r
+    c = r - t * (P[0] + t * (P[1] + t * (P[2] + t * (P[3] + t * P[4]))))
+    y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi)
+    return y * struct.unpack("<d", struct.pack("<Q", (k + 1023) << 52))[0]
+
+
+def det_sin_k(x):
+    S = (-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+         2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10)
+    z = x * x
+    v = z * x
+    r = S[1] + z * (S[2] + z * (S[3] + z * (S[4] + z * S[5])))
+    return x + v * (S[0] + z * r)
+
+
+def det_cos_k(x):
+    Cc = (4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+          -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11)
+    z = x * x
+    r = z * (Cc[0] + z * (Cc[1] + z * (Cc[2] + z * (Cc[3] + z * (Cc[4] + z * Cc[5])))))
+    return (1.0 - 0.5 * z) + z * r
+
+
+def det_cos2pi(u):
+    half_pi = 1.5707963267948966
+    u4 = u * 4.0
+    q = int(u4)
+    f = u4 - float(q)
+    if f <= 0.5:
+        a = f * half_pi
+        c, s = det_cos_k(a), det_sin_k(a)
+    else:
+        a = (1.0 - f) * half_pi
+        c, s = det_sin_k(a), det_cos_k(a)
+    return (c, -s, -c, s)[q]
+
+
+def det_pow08(x32):
+    """float32 -> float32, x**0.8 on [0, 1]."""
+    x = float(x32)
+    if not x > 0.0:
+        return np.float32(0.0)
+    if x >= 1.0:
+        return np.float32(1.0)
+    return np.float32(det_exp(float(np.float32(0.8)) * det_log(x)))   # numpy demotes the exponent to float32
+
+
+def binomial_inversion(m, pp, u):
+    q = 1.0 - pp
+    ratio = pp / q
+    pk, b, e = 1.0, q, m
+    while e:
+        if e & 1:
+            pk = pk * b
+        b = b * b
+        e >>= 1
+    k = 0
+    while u > pk and k < m:
+        u = u - pk
+        k += 1
+        pk = ((pk * ratio) * float(m - k + 1)) / float(k)
+    return k
+
+
+def binomial_philox(seed, t, link, replica, site, n, p):
+    n = int(n)
+    p = float(p)
+    if n <= 0 or not p > 0.0:
+        return 0
+    if p >= 1.0:
+        return n
+    flip = p > 0.5
+    pp = 1.0 - p if flip else p
+    k0, k1 = seed & M32, (seed >> 32) & M32
+    total, left, chunk = 0, n, 0
+    while left > 0:
+        w = philox4x32_10(t, link, site | ((chunk >> 1) << 8), replica, k0, k1)
+        for h in range(2):
+            if left <= 0:
+                break
+            m = min(left, 512)
+            total += binomial_inversion(m, pp, u53(w[2 * h], w[2 * h + 1]))
+            left -= m
+            chunk += 1
+    return n - total if flip else total
+
+
+def normal_philox(seed, t, link, replica, site):
+    w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
+    u1 = 1.0 - u53(w[0], w[1])
+    u2 = u53(w[2], w[3])
+    return math.sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2)
+
+
+class PhiloxDraws:
+    """Draw provider for oracle.ltm_oracle.LtmOracle matching the kernels' PHILOX mode."""
+
+    def __init__(self, seed=0, replica=0):
+        self.seed, self.replica = int(seed), int(replica)
+
+    _SITE = {"R1": 1, "R2": 2, "R3": 3}
+
+    def release_prob(self, rel32):
+        return np.float32(0.7) + np.float32(0.15) * det_pow08(rel32)
+
+    def binomial(self, site, link, t, n, p):
+        # the kernels key the draw by the step being computed (= time index + 1)
+        return binomial_philox(self.seed, t + 1, link.col, self.replica, self._SITE[site], int(n), float(p))
+
+    def normal(self, link, t, sigma):
+        return sigma * normal_philox(self.seed, t, link.col, self.replica, 4)

@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI in include/pns_b200.h (library: pednstream_b200/lib/libpns_b200.so).
+
+There is no fallback: if the CUDA library has not been built (`python -c "import
+__graft_entry__ as g; g.build()"`) loading raises, and so does every simulation call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
+ABI_VERSION = 1
+
+RNG_TABLE, RNG_PHILOX, RNG_REQUEST = 0, 1, 2
+ERR_BITS = {1: "negative sending flow (reference link.py:346,366 ValueError)",
+            2: "negative node flow (reference node.py:194,219,238 Warning)",
+            4: "history index out of range (numpy IndexError in reference link.py:210-212)",
+            8: "zero travel-time lag: the reference result depends on node visiting order"}
+
+_p = C.c_void_p
+_i32 = C.c_int32
+
+
+class PnsNet(C.Structure):
+    _fields_ = (
+        [(n, _i32) for n in ("abi_version", "n_links", "n_nodes", "n_cols64", "sim_steps", "replicas",
+                             "window", "n_edges", "n_od", "n_demand_rows",
+                             "n_routed", "n_groups", "n_opts", "n_rows", "n_terms")]
+        + [("unit_time", C.c_double)]
+        + [(n, _p) for n in ("lk_length", "lk_width", "lk_vf", "lk_kc", "lk_kj", "lk_gamma", "lk_act",
+                             "lk_bi", "lk_sigma", "lk_tt0", "lk_fftau", "lk_swtau", "lk_flags",
+                             "nd_ptr", "nd_in_col", "nd_out_col", "nd_kind", "nd_dem_row", "nd_tf_ptr",
+                             "nd_routed",
+                             "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
+                             "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
+                             "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
+                             "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
+        + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
+    )
+
+
+class PnsState(C.Structure):
+    _fields_ = [(n, _p) for n in ("hist64", "hist32", "widths", "sep_np64", "runsum", "tf_static",
+                                  "tf_routed", "probs", "err")] + [("n_f64", _i32)]
+
+
+class PnsStepIO(C.Structure):
+    _fields_ = [("demand", _p), ("od_w", _p), ("draw_b", _p), ("draw_n", _p),
+                ("draw_row_stride", C.c_int64),
+                ("req_kind", _p), ("req_n1", _p), ("req_rf", _p), ("req_sval", _p), ("req_n3", _p),
+                ("seed", C.c_uint64)]
+
+
+EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
+           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_rng_selftest")
+
+_LIB = None
+
+
+def _declare(lib):
+    net_p, st_p, io_p = C.POINTER(PnsNet), C.POINTER(PnsState), C.POINTER(PnsStepIO)
+    lib.pns_abi_version.restype = C.c_int
+    lib.pns_last_error.restype = C.c_char_p
+    lib.pns_state_init.argtypes = [net_p, st_p, _p]
+    lib.pns_link_flows.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
+    lib.pns_route_probs.argtypes = [net_p, st_p, io_p, C.c_int, _p]
+    lib.pns_node_flows.argtypes = [net_p, st_p, io_p, C.c_int, _p]
+    lib.pns_link_update.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
+    lib.pns_step.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p]
+    lib.pns_step_profiled.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p, _p, _p]
+    lib.pns_rng_selftest.argtypes = [C.c_int, C.c_int, _p, _p, C.c_uint64, C.c_int, C.c_int, _p, _p, _p]
+    for name in EXPORTS[2:]:
+        getattr(lib, name).restype = C.c_int
+    return lib
+
+
+def load(path: str = None):
+    """Load (once) and return the native library; raises if it is missing or ABI-incompatible."""
+    global _LIB
+    if path is None and _LIB is not None:
+        return _LIB
+    target = path or LIB_PATH
+    if not os.path.exists(target):
+        raise RuntimeError(
+            f"pednstream_b200: native CUDA library not found at {target}. Build it with "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            f"There is no CPU fallback for the simulation step.")
+    lib = _declare(C.CDLL(target))
+    if lib.pns_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{target}: ABI version {lib.pns_abi_version()} != expected {ABI_VERSION}")
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def check(lib, rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib.pns_last_error().decode()}")

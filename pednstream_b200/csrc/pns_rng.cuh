@@ -1,0 +1,201 @@
+// Counter-based sampling for the on-device ("philox") draw mode.
+//
+// The reference draws from numpy's global MT19937 stream in node-visiting order
+// (SURVEY.md "RNG ledger": R1/R2 link.py:337,343,356; R3 link.py:382; R4 functions.py:133), which
+// cannot be generated in parallel.  The device mode replaces the *generator*, not the
+// distributions: every draw is an exact Binomial(n, p) / Normal(0, sigma) variate keyed by
+// (seed, replica; t, link, site), so results do not depend on thread scheduling.
+//
+// Every arithmetic step below is a single IEEE-754 operation (the library is compiled with
+// -fmad=false) and uses no libdevice transcendental, so `oracle/philox.py`, which restates the
+// same operation sequence in Python floats, reproduces the device samples bit for bit.
+#pragma once
+#include <stdint.h>
+
+namespace pns {
+
+struct Philox4 {
+    uint32_t v[4];
+};
+
+__host__ __device__ inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0, k1).
+__host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    Philox4 out;
+    out.v[0] = c[0]; out.v[1] = c[1]; out.v[2] = c[2]; out.v[3] = c[3];
+    return out;
+}
+
+// 53-bit uniform in [0, 1) from two words.
+__host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
+}
+
+// ---- deterministic elementary functions (fdlibm-style kernels, basic operations only) ------
+__host__ __device__ inline double det_log(double x) {  // x > 0, normal
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    union { double d; uint64_t u; } cv;
+    cv.d = x;
+    int e = (int)((cv.u >> 52) & 0x7ffu) - 1023;
+    cv.u = (cv.u & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double m = cv.d;  // [1, 2)
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    const double R = t2 + t1;
+    const double hfsq = (0.5 * f) * f;
+    const double dk = (double)e;
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+}
+
+__host__ __device__ inline double det_exp(double x) {  // x <= 0
+    const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+                 P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+                 P5 = 4.13813679705723846039e-08;
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double invln2 = 1.44269504088896338700e+00;
+    if (x < -700.0) return 0.0;
+    const int k = (int)(invln2 * x - 0.5);  // truncation toward zero of a negative number
+    const double dk = (double)k;
+    const double hi = x - dk * ln2_hi;
+    const double lo = dk * ln2_lo;
+    const double r = hi - lo;
+    const double t = r * r;
+    const double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    const double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+    union { double d; uint64_t u; } sc;
+    sc.u = (uint64_t)(k + 1023) << 52;  // 2^k, k >= -1010
+    return y * sc.d;
+}
+
+__host__ __device__ inline double det_sin_k(double x) {  // |x| <= pi/4
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double z = x * x;
+    const double v = z * x;
+    const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x + v * (S1 + z * r);
+}
+
+__host__ __device__ inline double det_cos_k(double x) {  // |x| <= pi/4
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double z = x * x;
+    const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    return (1.0 - 0.5 * z) + z * r;
+}
+
+// cos(2*pi*u), u in [0, 1)
+__host__ __device__ inline double det_cos2pi(double u) {
+    const double half_pi = 1.5707963267948966;
+    const double u4 = u * 4.0;
+    const int q = (int)u4;  // 0..3
+    const double f = u4 - (double)q;
+    double c, s;
+    if (f <= 0.5) {
+        const double a = f * half_pi;
+        c = det_cos_k(a);
+        s = det_sin_k(a);
+    } else {
+        const double a = (1.0 - f) * half_pi;
+        c = det_sin_k(a);
+        s = det_cos_k(a);
+    }
+    if (q == 0) return c;
+    if (q == 1) return -s;
+    if (q == 2) return -c;
+    return s;
+}
+
+// x**0.8 for the release probability (link.py:317), x in [0, 1] fp32
+__host__ __device__ inline float det_pow08(float x) {
+    if (!(x > 0.0f)) return 0.0f;
+    if (x >= 1.0f) return 1.0f;
+    return (float)det_exp((double)0.8f * det_log((double)x));   // numpy demotes the exponent to float32
+}
+
+// ---- samplers ---------------------------------------------------------------------------------
+struct DrawKey {
+    uint32_t t, link, replica, k0, k1;
+};
+
+// Binomial(m, pp) by CDF inversion, m <= 512, 0 < pp <= 0.5, u in [0, 1)
+__host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
+    const double q = 1.0 - pp;
+    const double ratio = pp / q;
+    double pk = 1.0, b = q;
+    for (int e = m; e; e >>= 1) {
+        if (e & 1) pk = pk * b;
+        b = b * b;
+    }
+    int k = 0;
+    while (u > pk && k < m) {
+        u = u - pk;
+        k += 1;
+        pk = ((pk * ratio) * (double)(m - k + 1)) / (double)k;
+    }
+    return k;
+}
+
+// Exact Binomial(n, p); chunks of 512 trials keep q^m representable (binomial additivity).
+__host__ __device__ inline int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double pp = flip ? 1.0 - p : p;
+    int total = 0, left = n;
+    uint32_t chunk = 0;
+    while (left > 0) {
+        const Philox4 w = philox4x32_10(key.t, key.link, site | ((chunk >> 1) << 8), key.replica, key.k0, key.k1);
+        for (int h = 0; h < 2 && left > 0; ++h) {
+            const int m = left < 512 ? left : 512;
+            total += binomial_inversion(m, pp, u53(w.v[2 * h], w.v[2 * h + 1]));
+            left -= m;
+            chunk += 1;
+        }
+    }
+    return flip ? n - total : total;
+}
+
+// Standard normal by Box-Muller on one Philox block.
+__host__ __device__ inline double normal_philox(const DrawKey& key, uint32_t site) {
+    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
+    const double u1 = 1.0 - u53(w.v[0], w.v[1]);  // (0, 1]
+    const double u2 = u53(w.v[2], w.v[3]);
+    double rad = -2.0 * det_log(u1);
+#ifdef __CUDA_ARCH__
+    rad = __dsqrt_rn(rad);
+#else
+    rad = __builtin_sqrt(rad);
+#endif
+    return rad * det_cos2pi(u2);
+}
+
+}  // namespace pns

@@ -1,0 +1,358 @@
+"""Device runtime: owns the torch tensors behind `pns_net` / `pns_state` and drives the step.
+
+Three draw modes (SURVEY.md "RNG ledger"):
+
+numpy   per step: REQUEST pass on the GPU -> the host draws the step's binomials/normals from
+        numpy's *global legacy* RNG in the reference's visiting order -> TABLE step on the GPU.
+        Same `np.random.seed` => bit-identical trajectory to the reference.  One host sync per step.
+table   outcomes for many steps supplied up front (replay); no host involvement per step.
+philox  counter-based sampling on the device; no host involvement per step.
+
+All physics runs in the CUDA kernels; the host only supplies random numbers (numpy mode), the
+demand row and width/fraction edits made between steps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native, ops
+from .state import F32_INDEX, F64_FIELDS, F64_INDEX
+
+_NET_ARRAYS = ("lk_length", "lk_width", "lk_vf", "lk_kc", "lk_kj", "lk_gamma", "lk_act", "lk_bi",
+               "lk_sigma", "lk_tt0", "lk_fftau", "lk_swtau", "lk_flags",
+               "nd_ptr", "nd_in_col", "nd_out_col", "nd_kind", "nd_dem_row", "nd_tf_ptr", "nd_routed",
+               "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
+               "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
+               "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
+               "rt_term_row_entry")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, plan: dict, replicas: int = 1, device=None, rng: str = "numpy", seed: int = 0,
+                 lib=None, emulation: bool = False):
+        self.plan = plan
+        self.R = int(replicas)
+        self.rng = rng
+        self.seed = int(seed)
+        if rng not in ("numpy", "philox", "table"):
+            raise ValueError(f"unknown rng mode {rng!r}")
+        self.lib = lib if lib is not None else _native.load()
+        if emulation:
+            self.device = torch.device("cpu")
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("pednstream_b200 needs a CUDA device: the LTM step has no CPU path")
+            self.device = torch.device(device if device is not None else "cuda")
+            if self.device.type != "cuda":
+                raise RuntimeError("pednstream_b200: device must be a CUDA device")
+        self.emulation = emulation
+        dev = self.device
+        p = plan
+        self.L, self.N, self.S = p["n_links"], p["n_nodes"], p["sim_steps"]
+        self.C64 = self.L + p["n_virtual"]
+        self.n_f64 = 8 if p["has_separators"] else 7
+        R, L, S = self.R, self.L, self.S
+
+        # ---- immutable plan ------------------------------------------------------------------
+        self._net_t = {k: torch.from_numpy(np.ascontiguousarray(p[k])).to(dev) for k in _NET_ARRAYS}
+        net = _native.PnsNet()
+        net.abi_version = _native.ABI_VERSION
+        net.n_links, net.n_nodes, net.n_cols64 = L, self.N, self.C64
+        net.sim_steps, net.replicas, net.window = S, R, p["window"]
+        net.n_edges, net.n_od, net.n_demand_rows = p["n_edges"], p["n_od"], p["n_demand_rows"]
+        net.n_routed = len(p["rt_routed_nodes"])
+        net.n_groups = len(p["rt_grp_node"])
+        net.n_opts = len(p["rt_opt_link"])
+        net.n_rows = len(p["rt_row_ptr"]) - 1
+        net.n_terms = len(p["rt_term_opt"])
+        net.unit_time = p["unit_time"]
+        for k in _NET_ARRAYS:
+            setattr(net, k, _ptr(self._net_t[k]))
+        net.rt_temp, net.rt_alpha, net.rt_beta, net.rt_omega, net.rt_eps = [float(x) for x in p["rt_scalars"]]
+        self.net = net
+
+        # ---- mutable state ---------------------------------------------------------------------
+        self.hist64 = torch.empty((self.n_f64, S + 1, self.C64 * R), dtype=torch.float64, device=dev)
+        self.hist32 = torch.empty((6, S + 1, L * R), dtype=torch.float32, device=dev)
+        self.widths = torch.zeros((3, L * R), dtype=torch.float64, device=dev)
+        self.sep_np64 = torch.zeros((L * R,), dtype=torch.int32, device=dev)
+        self.runsum = torch.zeros((L * R,), dtype=torch.float32, device=dev)
+        self.tf_static = torch.zeros((max(1, p["n_edges"]),), dtype=torch.float64, device=dev)
+        self.tf_routed = torch.zeros((max(1, p["n_edges"]) * R,), dtype=torch.float64, device=dev)
+        self.probs = torch.zeros((max(1, net.n_opts) * R,), dtype=torch.float64, device=dev)
+        self.err = torch.zeros((R,), dtype=torch.int32, device=dev)
+        st = _native.PnsState()
+        for k in ("hist64", "hist32", "widths", "sep_np64", "runsum", "tf_static", "tf_routed", "probs", "err"):
+            setattr(st, k, _ptr(getattr(self, k)))
+        st.n_f64 = self.n_f64
+        self.state = st
+
+        # ---- per-step inputs --------------------------------------------------------------------
+        rows = p["n_demand_rows"]
+        self.demand = torch.zeros((S + 1, max(1, rows) * R), dtype=torch.float64, device=dev)
+        self.od_w = torch.zeros((S + 1, max(1, p["n_od"])), dtype=torch.float64, device=dev)
+        n32 = L * R
+        # request block (device + pinned host mirror): kind, n1, n3 (int32) | rf (float32) | sval (float64)
+        self._req = torch.zeros((6 * n32,), dtype=torch.int32, device=dev)
+        self._req_host = torch.zeros((6 * n32,), dtype=torch.int32, pin_memory=not emulation)
+        # draw block: R1, R2, R3 outcomes (int32) + one pad row | noise (float64)
+        self._draw = torch.zeros((6 * n32,), dtype=torch.int32, device=dev)
+        self._draw_host = torch.zeros((6 * n32,), dtype=torch.int32, pin_memory=not emulation)
+        io = _native.PnsStepIO()
+        io.demand, io.od_w = _ptr(self.demand), _ptr(self.od_w)
+        b = self._req.data_ptr()
+        io.req_kind, io.req_n1, io.req_n3 = b, b + 4 * n32, b + 8 * n32
+        io.req_rf, io.req_sval = b + 12 * n32, b + 16 * n32
+        d = self._draw.data_ptr()
+        io.draw_b, io.draw_n = d, d + 16 * n32
+        io.draw_row_stride = 0
+        io.seed = self.seed
+        self.io = io
+        self._table_io = None
+
+        self.handle = ops.register_engine(self)
+        self.t_done = 0
+        self._net_ref = None
+        self._initialised = False
+
+    # ------------------------------------------------------------------ native calls
+    def _stream(self):
+        if self.emulation:
+            return C.c_void_p(0)
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _native_init(self):
+        _native.check(self.lib, self.lib.pns_state_init(C.byref(self.net), C.byref(self.state), self._stream()),
+                      "pns_state_init")
+
+    def _native_requests(self, t):
+        _native.check(self.lib, self.lib.pns_link_flows(C.byref(self.net), C.byref(self.state), C.byref(self.io),
+                                                        t, _native.RNG_REQUEST, self._stream()), "pns_link_flows")
+
+    def _native_step(self, t0, n_steps, rng_mode):
+        io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
+        _native.check(self.lib, self.lib.pns_step(C.byref(self.net), C.byref(self.state), C.byref(io),
+                                                  t0, n_steps, rng_mode, self._stream()), "pns_step")
+
+    def _guard(self):
+        return torch.cuda.device(self.device) if not self.emulation else _NullCtx()
+
+    # ------------------------------------------------------------------ setup
+    def initialise(self, widths: np.ndarray, sep_np64: np.ndarray = None, tf_static: np.ndarray = None,
+                   demand: np.ndarray = None, od_w: np.ndarray = None):
+        """widths [3, L] (broadcast over replicas) or [3, L*R]; demand [T, rows] or [T, rows*R]."""
+        with self._guard():
+            self.set_widths(widths, sep_np64)
+            if tf_static is not None and len(tf_static):
+                self.tf_static[: len(tf_static)].copy_(torch.from_numpy(np.ascontiguousarray(tf_static)))
+            if demand is not None:
+                self.set_demand(demand)
+            if od_w is not None and od_w.size:
+                self.od_w[: od_w.shape[0], : od_w.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(od_w)))
+            ops.ltm_state_init(self.hist64, self.hist32, self.runsum, self.err, self.handle)
+        self.t_done = 0
+        self._initialised = True
+
+    def set_widths(self, widths, sep_np64=None):
+        w = torch.from_numpy(np.ascontiguousarray(widths, dtype=np.float64))
+        if w.shape[1] == self.L and self.R > 1:
+            w = w.repeat_interleave(self.R, dim=1)
+        self.widths.copy_(w)
+        if sep_np64 is not None:
+            f = torch.from_numpy(np.ascontiguousarray(sep_np64, dtype=np.int32))
+            if f.shape[0] == self.L and self.R > 1:
+                f = f.repeat_interleave(self.R)
+            self.sep_np64.copy_(f)
+
+    def set_demand(self, demand):
+        d = torch.from_numpy(np.ascontiguousarray(demand, dtype=np.float64))
+        if d.shape[1] * self.R == self.demand.shape[1] and self.R > 1:
+            d = d.repeat_interleave(self.R, dim=1)
+        self.demand[: d.shape[0]].copy_(d)
+
+    # ------------------------------------------------------------------ single-network facade
+    def bind_network(self, net):
+        """Static visiting order of the reference's draws + host-side per-link constants."""
+        self._net_ref = net
+        links = list(net.links.values())
+        ev_link, ev_recv = [], []
+        for node in net.nodes.values():
+            for l in node.incoming_links:
+                if not l.is_virtual:
+                    ev_link.append(l.index); ev_recv.append(0)
+            for l in node.outgoing_links:
+                if not l.is_virtual and not l.is_separator:
+                    ev_link.append(l.index); ev_recv.append(1)
+        self._ev_link = np.asarray(ev_link, dtype=np.int64)
+        self._ev_recv = np.asarray(ev_recv, dtype=bool)
+        self._act = np.asarray([l.activity_probability for l in links], dtype=np.float64)
+        self._any_activity = bool((self._act > 0).any())
+        self._sigma = np.asarray([l.speed_noise_std for l in links], dtype=np.float64)
+        self._noisy = np.nonzero(self._sigma > 0)[0]
+        self._demand_nodes = self.plan["demand_nodes"]
+        self._od_arrays = ([net.od_manager.od_flows[k] for k in self.plan["od_keys"]]
+                           if net.od_manager is not None else [])
+        store = net._store
+        od_w = (np.stack(self._od_arrays, axis=1) if self._od_arrays else None)
+        self.initialise(store.widths, store.sep_np64, net._static_fractions(), None, od_w)
+        store.widths_dirty = False
+        net._fractions_dirty = False
+
+    def _push_host_edits(self, net, t):
+        store = net._store
+        if store.widths_dirty:
+            self.set_widths(store.widths, store.sep_np64)
+            store.widths_dirty = False
+        if net._fractions_dirty:
+            tf = net._static_fractions()
+            if len(tf):
+                self.tf_static[: len(tf)].copy_(torch.from_numpy(tf))
+            net._fractions_dirty = False
+        if self._demand_nodes:
+            row = np.array([float(n.demand[t - 1]) for n in self._demand_nodes], dtype=np.float64)
+            self.demand[t - 1, : len(row)].copy_(torch.from_numpy(row))
+        if self._od_arrays:
+            row = np.array([float(a[t]) for a in self._od_arrays], dtype=np.float64)
+            self.od_w[t, : len(row)].copy_(torch.from_numpy(row))
+
+    def step_network(self, net, t: int):
+        if not (1 <= t <= self.S):
+            raise IndexError(f"time step {t} outside [1, {self.S}]")
+        with self._guard():
+            self._push_host_edits(net, t)
+            if self.rng == "philox":
+                ops.ltm_step(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
+                             self.handle, t, 1, _native.RNG_PHILOX)
+            else:
+                self._numpy_draws(t)
+                ops.ltm_step(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
+                             self.handle, t, 1, _native.RNG_TABLE)
+        if t != self.t_done + 1:
+            net._store.invalidate()
+        self.t_done = t
+
+    def _numpy_draws(self, t):
+        """Draw this step's R1..R4 outcomes from np.random in the reference's order."""
+        n32 = self.L
+        ops.ltm_draw_requests(self.hist64, self.hist32, self._req, self.err, self.handle, t)
+        self._req_host.copy_(self._req, non_blocking=not self.emulation)
+        err = self.err.cpu() if self.emulation else self.err.to("cpu", non_blocking=False)
+        self._raise_on_error(err)
+        req = self._req_host.numpy()
+        kind, n1, n3 = req[:n32], req[n32:2 * n32], req[2 * n32:3 * n32]
+        rf = req[3 * n32:4 * n32].view(np.float32)
+        sval = req[4 * n32:6 * n32].view(np.float64)
+        out = self._draw_host.numpy()
+        d1, d2, d3 = out[:n32], out[n32:2 * n32], out[2 * n32:3 * n32]
+        noise = out[4 * n32:6 * n32].view(np.float64)
+        ev, recv = self._ev_link, self._ev_recv
+        if not self._any_activity:
+            need = recv | (kind[ev] == 2)
+            lk = ev[need]
+            is_r = recv[need]
+            n = np.where(is_r, n3[lk], n1[lk]).astype(np.int64)
+            p = np.full(len(lk), 0.9)
+            for i in np.nonzero(~is_r)[0]:
+                # same scalar expression as the reference (link.py:317): float32 powf
+                p[i] = 0.7 + (0.85 - 0.7) * rf[lk[i]] ** 0.8
+            if len(lk):
+                draws = np.random.binomial(n, p)
+                d3[lk[is_r]] = draws[is_r]
+                d1[lk[~is_r]] = draws[~is_r]
+        else:
+            act = self._act
+            for l, is_r in zip(ev.tolist(), recv.tolist()):
+                if is_r:
+                    d3[l] = np.random.binomial(n=int(n3[l]), p=0.9)
+                    continue
+                k = kind[l]
+                if k == 2:
+                    flow = np.random.binomial(n=int(n1[l]), p=0.7 + (0.85 - 0.7) * rf[l] ** 0.8)
+                    d1[l] = flow
+                else:
+                    flow = sval[l]
+                if act[l] > 0 and flow > 1:
+                    d2[l] = np.random.binomial(n=int(np.floor(flow)), p=act[l])
+        if len(self._noisy):
+            noise[self._noisy] = np.random.normal(0, self._sigma[self._noisy])
+        self._draw.copy_(self._draw_host, non_blocking=not self.emulation)
+
+    # ------------------------------------------------------------------ batched / multi-step driving
+    def run(self, t0: int, n_steps: int, rng_mode: int = _native.RNG_PHILOX):
+        """Advance n_steps without host involvement (PHILOX, or TABLE after `set_draw_table`)."""
+        with self._guard():
+            ops.ltm_step(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
+                         self.handle, t0, n_steps, rng_mode)
+        self.t_done = t0 + n_steps - 1
+
+    def run_profiled(self, t0: int, n_steps: int, rng_mode: int = _native.RNG_PHILOX):
+        """`run` with per-kernel CUDA-event timing; returns (ms[4], launches[4]) for the passes
+        link_flows, route_probs, node_flows, link_update.  Synchronises."""
+        ms = (C.c_double * 4)(0, 0, 0, 0)
+        cnt = (C.c_int64 * 4)(0, 0, 0, 0)
+        io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
+        with self._guard():
+            _native.check(self.lib, self.lib.pns_step_profiled(
+                C.byref(self.net), C.byref(self.state), C.byref(io), t0, n_steps, rng_mode, self._stream(),
+                ms, cnt), "pns_step_profiled")
+        self.t_done = t0 + n_steps - 1
+        return list(ms), list(cnt)
+
+    def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor):
+        """draw_b [rows, 3, L*R] int32, draw_n [rows, L*R] float64; row k serves step t0+k of `run`."""
+        self._table = (draw_b, draw_n)
+        io = _native.PnsStepIO()
+        C.memmove(C.byref(io), C.byref(self.io), C.sizeof(io))
+        io.draw_b, io.draw_n = draw_b.data_ptr(), draw_n.data_ptr()
+        io.draw_row_stride = 1
+        self._table_io = io
+
+    # ------------------------------------------------------------------ reading back
+    def _raise_on_error(self, err_host):
+        bits = int(np.bitwise_or.reduce(err_host.numpy())) if err_host.numel() else 0
+        if bits:
+            msgs = [m for b, m in _native.ERR_BITS.items() if bits & b]
+            raise ValueError("LTM step fault on device: " + "; ".join(msgs))
+
+    def check_errors(self):
+        self._raise_on_error(self.err.cpu())
+
+    def read_rows(self, field: str, lo: int, hi: int, out: np.ndarray):
+        """Copy rows lo..hi of one history field (replica 0 layout for R=1) into `out[lo:hi+1]`."""
+        if field in F64_INDEX:
+            f = F64_INDEX[field]
+            if f >= self.n_f64:
+                return
+            src = self.hist64[f, lo:hi + 1]
+        else:
+            src = self.hist32[F32_INDEX[field], lo:hi + 1]
+        out[lo:hi + 1] = src.cpu().numpy().reshape(hi + 1 - lo, -1)[:, : out.shape[1]]
+        self.check_errors()
+
+    def routed_fractions(self, node_index: int):
+        p = self.plan
+        if p["nd_routed"][node_index] < 0:
+            return None
+        a, b = p["nd_tf_ptr"][node_index], p["nd_tf_ptr"][node_index + 1]
+        return self.tf_routed.view(-1, self.R)[a:b, 0].cpu().numpy()
+
+    def history(self, field: str) -> torch.Tensor:
+        """Device view [S+1, columns, R] of one field."""
+        if field in F64_INDEX:
+            return self.hist64[F64_INDEX[field]].view(self.S + 1, self.C64, self.R)
+        return self.hist32[F32_INDEX[field]].view(self.S + 1, self.L, self.R)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,162 @@
+"""Sparse constructor for n x n lattice networks (BASELINE config 4: 512 x 512 nodes).
+
+The reference can only build a network from a dense adjacency matrix (src/LTM/network.py:151-152,
+194-248), which for 262 144 nodes would need ~550 GB.  This builder emits the same *plan* the
+generic path compiles (pednstream_b200/plan.py) -- node creation order, (i,j),(j,i) link pairs by
+ascending i then j, slot order "virtual first, then neighbours by ascending id", node classes of
+network.py:141-167 -- straight from the lattice rule of data/create_grid.py:3-21 (node id =
+row*size + col, edges to the right and down neighbour), without per-link Python objects.
+`tests/test_grid.py` checks it against the generic constructor on small lattices.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .link import FD_TYPES
+
+DEFAULT_LINK = dict(length=50, width=4, free_flow_speed=1.1, k_critical=2, k_jam=6, gamma=0.01,
+                    speed_noise_std=0.05, fd_type="yperman", activity_probability=0, bi_factor=1)
+
+
+def grid_adjacency(size: int) -> np.ndarray:
+    """Dense adjacency of the lattice (small sizes only; used by tests and examples)."""
+    n = size * size
+    adj = np.zeros((n, n), dtype=int)
+    for r in range(size):
+        for c in range(size):
+            i = r * size + c
+            if c < size - 1:
+                adj[i, i + 1] = adj[i + 1, i] = 1
+            if r < size - 1:
+                adj[i, i + size] = adj[i + size, i] = 1
+    return adj
+
+
+def default_origins(size: int, stride: int = 64):
+    """The 4 corners plus every `stride`-th node of the boundary walk."""
+    n = size
+    walk = ([(0, c) for c in range(n)] + [(r, n - 1) for r in range(1, n)] +
+            [(n - 1, c) for c in range(n - 2, -1, -1)] + [(r, 0) for r in range(n - 2, 0, -1)])
+    picked = {0, n - 1, (n - 1) * n, n * n - 1}
+    picked.update(r * n + c for (r, c) in walk[::stride])
+    return sorted(picked)
+
+
+def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=None,
+                    peak_lambda=50, base_lambda=30, demand_seed=0):
+    """Returns (plan, widths[3, L], tf_static[n_edges], demand[S, rows]) for `Engine`."""
+    lk = dict(DEFAULT_LINK)
+    lk.update(link or {})
+    n = size
+    N = n * n
+    origins = default_origins(n) if origins is None else sorted(origins)
+    is_origin = np.zeros(N, dtype=bool)
+    is_origin[origins] = True
+
+    ids = np.arange(N)
+    r, c = ids // n, ids % n
+    has_right, has_down = c < n - 1, r < n - 1
+    # pair index of edge (i, i+1) / (i, i+n): pairs are enumerated by ascending i, right before down
+    n_pairs_at = has_right.astype(np.int64) + has_down.astype(np.int64)
+    first_pair = np.concatenate([[0], np.cumsum(n_pairs_at)[:-1]])
+    pair_right = np.where(has_right, first_pair, -1)
+    pair_down = np.where(has_down, first_pair + has_right, -1)
+    P = int(n_pairs_at.sum())
+    L = 2 * P
+
+    # node creation order of init_nodes_and_links: i, then its not-yet-created neighbours j > i
+    order = np.empty(N, dtype=np.int64)
+    seen = np.zeros(N, dtype=bool)
+    k = 0
+    for i in range(N):
+        if not seen[i]:
+            seen[i] = True; order[k] = i; k += 1
+        if has_right[i] and not seen[i + 1]:
+            seen[i + 1] = True; order[k] = i + 1; k += 1
+        if has_down[i] and not seen[i + n]:
+            seen[i + n] = True; order[k] = i + n; k += 1
+    assert k == N
+
+    degree = (r > 0).astype(int) + (c > 0) + has_right + has_down
+    # network.py:141-167: degree 2 -> one-to-one unless O/D; degree 1 -> one-to-one + virtual; else regular
+    virtual = is_origin | (degree == 1)
+    kind = np.where((degree == 2) & ~is_origin, 0, np.where(degree == 1, 0, 1)).astype(np.int32)
+    vrank = np.full(N, -1, dtype=np.int64)           # rank among virtual-link owners, creation order
+    vo = order[virtual[order]]
+    vrank[vo] = np.arange(len(vo))
+
+    m = degree + virtual
+    m_o = m[order]
+    nd_ptr = np.concatenate([[0], np.cumsum(m_o)]).astype(np.int32)
+    in_col = np.empty(nd_ptr[-1], dtype=np.int32)
+    out_col = np.empty(nd_ptr[-1], dtype=np.int32)
+    # neighbour slots in ascending id: up (i-n), left (i-1), right (i+1), down (i+n)
+    up_pair = np.where(r > 0, pair_down[np.maximum(ids - n, 0)], -1)
+    left_pair = np.where(c > 0, pair_right[np.maximum(ids - 1, 0)], -1)
+    cursor = nd_ptr[:-1].astype(np.int64).copy()
+    sel = virtual[order]
+    in_col[cursor[sel]] = L + 2 * vrank[order[sel]]
+    out_col[cursor[sel]] = L + 2 * vrank[order[sel]] + 1
+    cursor[sel] += 1
+    # (pair, node is the larger id of the pair?)  forward link 2p runs small->large id
+    for pair_of, node_is_large in ((up_pair, True), (left_pair, True), (pair_right, False), (pair_down, False)):
+        pp = pair_of[order]
+        sel = pp >= 0
+        fwd = 2 * pp[sel]
+        if node_is_large:      # incoming = forward (nbr -> i), outgoing = reverse (i -> nbr)
+            in_col[cursor[sel]] = fwd
+            out_col[cursor[sel]] = fwd + 1
+        else:                  # incoming = reverse (nbr -> i), outgoing = forward
+            in_col[cursor[sel]] = fwd + 1
+            out_col[cursor[sel]] = fwd
+        cursor[sel] += 1
+    assert (cursor == nd_ptr[1:]).all()
+
+    dem_row = np.where(virtual[order], vrank[order], -1).astype(np.int32)
+    edges = (m_o * (m_o - 1)).astype(np.int64)
+    tf_ptr = np.concatenate([[0], np.cumsum(edges)]).astype(np.int32)
+
+    f64 = lambda v: np.full(L, float(v), dtype=np.float64)
+    length, vf, kc, kj = lk["length"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"]
+    tt0 = np.float32(min(length / vf, length / 0.05))
+    shock = (vf * kc) / (kj - kc)
+    plan = dict(
+        n_links=L, n_nodes=N, sim_steps=int(sim_steps), unit_time=float(unit_time),
+        window=int(round(100 / unit_time)),
+        lk_length=f64(length), lk_width=f64(lk["width"]), lk_vf=f64(vf), lk_kc=f64(kc), lk_kj=f64(kj),
+        lk_gamma=f64(lk["gamma"]), lk_act=f64(lk["activity_probability"]), lk_bi=f64(lk["bi_factor"]),
+        lk_sigma=f64(lk["speed_noise_std"]), lk_tt0=np.full(L, tt0, dtype=np.float32),
+        lk_fftau=np.full(L, round(tt0 / unit_time), dtype=np.int32),
+        lk_swtau=np.full(L, round(length / (shock * unit_time)), dtype=np.int32),
+        lk_flags=np.full(L, FD_TYPES[lk["fd_type"]] << 1, dtype=np.int32),
+        has_separators=False,
+        nd_ptr=nd_ptr, nd_in_col=in_col, nd_out_col=out_col, nd_kind=kind[order].astype(np.int32),
+        nd_dem_row=dem_row, nd_tf_ptr=tf_ptr, nd_routed=np.full(N, -1, dtype=np.int32),
+        n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
+        n_od=0, od_keys=[], demand_nodes=[], node_order=order,
+    )
+    i32 = lambda a: np.asarray(a, dtype=np.int32)
+    for key in ("routed_nodes", "routed_edge0", "routed_row0", "grp_node", "grp_up", "grp_od",
+                "grp_has_virtual", "opt_link", "opt_slot", "row_od", "term_opt", "term_row_entry"):
+        plan["rt_" + key] = i32([])
+    for key in ("opt_ptr", "row_ptr", "term_ptr"):
+        plan["rt_" + key] = i32([0])
+    plan["rt_opt_dist"] = np.zeros(0)
+    plan["rt_scalars"] = np.array([0.1, 1.0, 0.05, 0.05, 0.0])
+
+    widths = np.tile(f64(lk["width"]), (3, 1))
+    tf_static = np.repeat(1.0 / np.maximum(m_o - 1, 1), edges)      # uniform 1/(m-1), network.py:269-271
+
+    # demand rows in virtual-owner creation order; Poisson around two gaussian peaks
+    # (od_manager.py:145-155), drawn from the global numpy RNG in node creation order like the reference
+    S = int(sim_steps)
+    demand = np.zeros((S, int(virtual.sum())), dtype=np.float64)
+    tgrid = np.arange(S)
+    width2 = 2 * (S / 20) ** 2
+    lam = (base_lambda + peak_lambda * np.exp(-(tgrid - S / 4) ** 2 / width2)
+           + peak_lambda * np.exp(-(tgrid - 3 * S / 4) ** 2 / width2))
+    np.random.seed(demand_seed)
+    for node in vo:
+        if is_origin[node]:
+            demand[:, vrank[node]] = np.random.poisson(lam=lam)
+    return plan, widths, tf_static, demand

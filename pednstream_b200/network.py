@@ -194,7 +194,7 @@ class Network:
                            tt0=[l.travel_time0 for l in links],
                            window=round(100 / self.unit_time),
                            bgw0=[l._width for l in links],
-                           has_separators=any(l.is_separator for l in links))
+                           is_separator=[l.is_separator for l in links])
 
     # ------------------------------------------------------------------ fractions
     def update_turning_fractions_per_node(self, node_ids: List[int], new_turning_fractions):

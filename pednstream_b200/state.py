@@ -41,13 +41,14 @@ class StateStore:
         assert index == len(self._width_rows)
         self._width_rows.append(tuple(row))
 
-    def freeze(self, n_links, n_virtual, tt0, window, bgw0, has_separators):
+    def freeze(self, n_links, n_virtual, tt0, window, bgw0, is_separator):
         self.n_links, self.n_virtual = n_links, n_virtual
         self.widths = np.array(self._width_rows, dtype=np.float64).T.copy().reshape(3, n_links)
         self.sep_np64 = np.zeros(n_links, dtype=np.int32)
         self._init = dict(tt0=np.asarray(tt0, dtype=np.float32), window=int(window),
                           bgw0=np.asarray(bgw0, dtype=np.float64))
-        self.has_separators = bool(has_separators)
+        self.is_separator = np.asarray(is_separator, dtype=bool)
+        self.has_separators = bool(self.is_separator.any())
 
     # ---- widths ---------------------------------------------------------------------------
     def get_width(self, which, index):
@@ -67,10 +68,6 @@ class StateStore:
         self.widths_dirty = True
 
     # ---- history views ----------------------------------------------------------------------
-    def n_cols(self, field):
-        return self.n_links + self.n_virtual if field in F64_INDEX and field not in (
-            "back_gate_width_data", "separator_width_data") else self.n_links
-
     def _initial(self, field):
         S, L = self.S, self.n_links
         if field in F64_INDEX:
@@ -80,7 +77,7 @@ class StateStore:
             if field == "back_gate_width_data":
                 a = np.zeros((S + 1, C)); a[:, :L] = self._init["bgw0"][None, :]; return a
             if field == "separator_width_data":
-                a = np.zeros((S + 1, C)); a[:, :L] = self.widths[2][None, :]; return a
+                a = np.zeros((S + 1, C)); a[:, :L] = np.where(self.is_separator, self._init["bgw0"] / 2, 0.0)[None, :]; return a
             return np.zeros((S + 1, C))
         a = np.zeros((S + 1, L), dtype=np.float32)
         if field == "travel_time":
