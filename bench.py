@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
@@ -158,7 +158,10 @@ def run_ours(args):
 
     K, W = args.steps, max(args.warmup, 3)
     size = args.grid
-    S = 2 * (W + K) + 2                                  # two timed regions (value, e2e) + headroom
+    Kp, Ke = min(K, 50), min(K, 100)                     # profiled / end-to-end region lengths
+    S = W + K + Kp + Ke + 2                              # history rows: 80 B x links x (S+1) of HBM
+    if 80.0 * (S + 1) * (2 * 2 * size * (size - 1)) > 150e9:
+        raise SystemExit(f"--steps {K}: the {size}x{size} history would not fit in HBM; use <= 1500 steps")
     plan, widths, tf, demand = build_grid_plan(size, S, demand_seed=rank)
     L = plan["n_links"]
     eng = Engine(plan, replicas=1, rng="philox", seed=rank, device=dev)
@@ -185,7 +188,6 @@ def run_ours(args):
     t_next = W + K + 1
 
     # ---- per-kernel durations (CUDA events on the launching stream, inside the library) --------
-    Kp = min(K, 50)
     k_ms, k_cnt = eng.run_profiled(t_next, Kp)
     t_next += Kp
     names = ("link_flows", "route_probs", "node_flows", "link_update")
@@ -193,7 +195,6 @@ def run_ours(args):
 
     # ---- end to end through the public call, host buffers: every step copies its demand row from
     # pinned host memory, launches the step, and reads the network-wide pedestrian count back ----
-    Ke = min(K, S - t_next - 1)
     pinned = torch.from_numpy(np.ascontiguousarray(demand)).pin_memory()
     result_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     num_hist = eng.history("num_pedestrians")
