@@ -28,10 +28,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 B_ALG = 176.0            # algorithmic bytes per link-timestep, SURVEY.md section 8(d)
-# split of B_ALG by pass (DESIGN.md "kernels"; sums to 176): link_flows = 92 B lagged/previous-row reads
-# + 16 B sending/receiving writes; node_flows = 32 B flow/cumulative-count writes; link_update = 4 B
-# lagged read + 32 B state writes.  Intermediate re-reads between passes are not algorithmic bytes.
-B_ALG_PASS = {"link_flows": 108.0, "route_probs": 0.0, "node_flows": 32.0, "link_update": 36.0}
+# split of B_ALG by kernel (DESIGN.md "kernels"; sums to 176): the fused link-pair kernel carries the
+# 96 B of lagged / previous-row reads and 48 B of link-state + sending/receiving writes, the node kernel
+# the 32 B of flow / cumulative-count writes.  Intermediate re-reads between kernels are not algorithmic.
+B_ALG_PASS = {"link_pair": 144.0, "route_probs": 0.0, "node_flows": 32.0}
 GRID_SIZE = 512
 REF_SAMPLE_SIZE = 32
 
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def stop(self):
         self._halt.set()
@@ -162,10 +162,10 @@ def run_ours(args):
     S = W + K + Kp + Ke + 2                              # history rows: 80 B x links x (S+1) of HBM
     if 80.0 * (S + 1) * (2 * 2 * size * (size - 1)) > 150e9:
         raise SystemExit(f"--steps {K}: the {size}x{size} history would not fit in HBM; use <= 1500 steps")
-    plan, widths, tf, demand = build_grid_plan(size, S, demand_seed=rank)
+    plan, gate, tf, demand = build_grid_plan(size, S, demand_seed=rank, locality_order=True)
     L = plan["n_links"]
     eng = Engine(plan, replicas=1, rng="philox", seed=rank, device=dev)
-    eng.initialise(widths, None, tf, demand, None)
+    eng.initialise(gate, None, tf, demand, None)
     torch.cuda.synchronize()
 
     def barrier():
@@ -190,7 +190,7 @@ def run_ours(args):
     # ---- per-kernel durations (CUDA events on the launching stream, inside the library) --------
     k_ms, k_cnt = eng.run_profiled(t_next, Kp)
     t_next += Kp
-    names = ("link_flows", "route_probs", "node_flows", "link_update")
+    names = ("link_pair", "route_probs", "node_flows")
     per_kernel = {n: (k_ms[i] / k_cnt[i] if k_cnt[i] else None) for i, n in enumerate(names)}
 
     # ---- end to end through the public call, host buffers: every step copies its demand row from
@@ -241,7 +241,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(pinned.shape[1] * 8), "d2h_bytes_per_step": 4,
                     "note": "per step: H2D of the demand row from pinned memory, one native step call, "
                             "D2H of the network-wide pedestrian count (host sync every step)"},
-            "gpu_launches": int(3 * K + (K if plan["rt_grp_node"].size else 0)),
+            "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak,
                          "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
@@ -263,7 +263,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_SIZE)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 1
+#define PNS_ABI_VERSION 2
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -69,25 +69,44 @@ enum {
     PNS_ERR_ZERO_LAG = 8         /* tau == 0: the reference result depends on node visiting order */
 };
 
+/* One parameter class of links (reference src/LTM/link.py:52-100): networks have few distinct
+ * parameter sets, so links carry a class index and the table stays L1-resident.  Every derived
+ * constant is evaluated on the host with the reference's own expression order and stored in the
+ * precision the reference uses it in (numpy demotes Python scalars to float32 next to a float32). */
+typedef struct pns_link_class {
+    double length, area, space; /* area = length*width (link.py:131), space = k_jam*area (link.py:386) */
+    double kc, vf, kj, act, sigma;
+    float kc32, kj32, kj_minus_kc32, gamma32, bi32, area32, length32;
+    float yp_coef32;   /* (kc*vf)/(kj-kc)   functions.py:123 */
+    float neg_vf32;    /* -vf               functions.py:118 */
+    float vf32;        /* vf                functions.py:126 */
+    float sm_gamma32;  /* vf*kc             functions.py:128 */
+    float inv_kj32;    /* 1/kj              functions.py:128 */
+    float max_tt32;    /* length/0.05       link.py:63 */
+    float tt0;         /* travel_time[0]    link.py:83 */
+    int32_t fftau, swtau; /* free-flow lag (link.py:86), shock-wave lag (link.py:380) */
+    int32_t flags;        /* bit0 separator, bits1-2 fd type (0 yperman 1 greenshields 2 smulders) */
+    int32_t pad_;
+} pns_link_class;
+
 /* Immutable network description.  All pointers are device pointers. */
 typedef struct pns_net {
     int32_t abi_version;
     int32_t n_links, n_nodes, n_cols64, sim_steps, replicas, window, n_edges, n_od, n_demand_rows;
-    int32_t n_routed, n_groups, n_opts, n_rows, n_terms;
+    int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes;
     double unit_time;
-    /* link table [n_links] -- parameters of src/LTM/link.py:52-100 */
-    const double *lk_length, *lk_width, *lk_vf, *lk_kc, *lk_kj, *lk_gamma, *lk_act, *lk_bi, *lk_sigma;
-    const float *lk_tt0;                 /* travel_time[0], fp32 (link.py:83) */
-    const int32_t *lk_fftau, *lk_swtau;  /* free-flow lag (link.py:86), shock-wave lag (link.py:380) */
-    const int32_t *lk_flags;             /* bit0 separator, bits1-2 fd type (0 yperman 1 greenshields 2 smulders) */
-    /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id) */
-    const int32_t *nd_ptr;      /* [n_nodes+1] */
+    const pns_link_class *classes; /* [n_classes] */
+    const int32_t *lk_class;       /* [n_links] */
+    const double *lk_width;        /* [n_links] corridor width `_width` (link.py:53): initial gate / lane widths */
+    /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id).
+     * The outgoing link of a slot is the reverse of its incoming link: out column = in column ^ 1
+     * (physical pairs are adjacent, virtual in/out links are allocated as adjacent columns). */
+    const int32_t *nd_meta;     /* [n_nodes][4]: slot offset, m | kind<<8 | tf_mode<<16, demand row (-1 none),
+                                   offset of the node's m(m-1) turning fractions.
+                                   kind: 0 one-to-one (node.py:230), 1 regular/classic (node.py:272);
+                                   tf_mode: 0 uniform 1/(m-1) (network.py:269-271), 1 tf_static, 2 routed */
     const int32_t *nd_in_col;   /* [slots] history column of the incoming link of each slot */
-    const int32_t *nd_out_col;  /* [slots] history column of the outgoing link of each slot */
-    const int32_t *nd_kind;     /* 0 one-to-one (node.py:230), 1 regular/classic (node.py:272) */
-    const int32_t *nd_dem_row;  /* row of the demand table, -1 if the node has no virtual links */
-    const int32_t *nd_tf_ptr;   /* [n_nodes+1] offset of the node's m(m-1) turning fractions */
-    const int32_t *nd_routed;   /* index into the routed-node arrays, -1 = static fractions */
+    const int32_t *nd_routed;   /* [n_nodes] index into the routed-node arrays, -1 = none */
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
@@ -101,7 +120,10 @@ typedef struct pns_net {
 typedef struct pns_state {
     double *hist64;      /* [n_f64][sim_steps+1][n_cols64*R] */
     float *hist32;       /* [6][sim_steps+1][n_links*R] */
-    double *widths;      /* [3][n_links*R]: front gate, back gate, separator width (link.py:54-55, 422) */
+    double *gate;        /* [n_links*R] back gate width of plain links / separator width of separators.
+                            The other widths follow from the reference's setters (link.py:110-126, 462-478):
+                            front_gate(l) = gate[l^1] for a plain link, = gate[l] for a separator;
+                            a separator's back gate and lane width are both gate[l]. */
     int32_t *sep_np64;   /* [n_links*R] separator width was set from a numpy float64 (dtype ledger) */
     float *runsum;       /* [n_links*R] fp32 running sum of travel times (link.py:84,183-186) */
     double *tf_static;   /* [n_edges] host-owned turning fractions (uniform default / user supplied) */
@@ -132,13 +154,15 @@ const char *pns_last_error(void);
 
 /* Initial state of every history field, width table and running sum
  * (reference Link.__init__/Separator.__init__, link.py:12-17, 32-100, 420-425).
- * `widths` must already hold the initial widths. */
+ * `gate` must already hold the initial widths. */
 int pns_state_init(const pns_net *net, const pns_state *st, void *stream);
 
 /* Link demand/supply pass for step t (time index tau = t-1), one thread per link pair and replica:
  * Link.cal_sending_flow (link.py:216-370) incl. get_outflow (:199-214) and
  * Link/Separator.cal_receiving_flow_with_reverse (:372-416, :480-512).
- * Writes sending_flow[tau], receiving_flow[tau] (or the draw requests in REQUEST mode). */
+ * Writes sending_flow[tau], receiving_flow[tau] (or the draw requests in REQUEST mode).
+ * Inside pns_step this pass for step t+1 is fused with pns_link_update of step t (same thread,
+ * state kept in registers). */
 int pns_link_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
                    void *stream);
 
@@ -163,8 +187,8 @@ int pns_step(const pns_net *net, const pns_state *st, const pns_step_io *io, int
              int rng_mode, void *stream);
 
 /* pns_step with CUDA-event timing of every launch on `stream` (bench/roofline instrumentation):
- * adds the elapsed milliseconds of each pass to ms[0..3] (link_flows, route_probs, node_flows,
- * link_update) and the launch counts to launches[0..3].  Synchronises the stream before returning. */
+ * adds the elapsed milliseconds of each pass to ms[0..2] (link-pair kernel, route_probs, node_flows;
+ * ms[3] is unused) and the launch counts to launches[0..2].  Synchronises the stream before returning. */
 int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
                       int rng_mode, void *stream, double *ms, int64_t *launches);
 

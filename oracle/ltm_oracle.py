@@ -41,6 +41,7 @@ class NumpyDraws:
     """The reference's own sampler: numpy's global legacy RandomState, consumed in visiting order."""
 
     release_prob = staticmethod(numpy_release_prob)
+    exp = staticmethod(np.exp)
 
     def binomial(self, site, link, t, n, p):
         return np.random.binomial(n=n, p=p)
@@ -53,6 +54,7 @@ class TableDraws:
     """Replay of recorded outcomes: {(site, link_id, t): value}."""
 
     release_prob = staticmethod(numpy_release_prob)
+    exp = staticmethod(np.exp)
 
     def __init__(self, table):
         self.table = table
@@ -283,7 +285,7 @@ class LtmOracle:
             util = (pf.alpha * np.array(dist) / (np.sum(dist) + 1e-6)
                     + pf.beta * crowd
                     - pf.omega * np.array(caps) / (np.sum(caps) + 1e-6)) + pf.epsilon
-            e = np.exp(-pf.temp * util)
+            e = self.draws.exp(-pf.temp * util)
             store.update(dict(zip(turns, e / np.sum(e))))
         return store
 

@@ -62,7 +62,9 @@ def det_exp(x):
     invln2 = 1.44269504088896338700e+00
     if x < -700.0:
         return 0.0
-    k = int(invln2 * x - 0.5)          # truncation toward zero, as the C cast
+    if x > 700.0:
+        x = 700.0
+    k = int(invln2 * x + (-0.5 if x < 0.0 else 0.5))          # truncation toward zero, as the C cast
     dk = float(k)
     hi = x - dk * ln2_hi
     lo = dk * ln2_lo
@@ -88,6 +90,21 @@ def det_cos_k(x):
     z = x * x
     r = z * (Cc[0] + z * (Cc[1] + z * (Cc[2] + z * (Cc[3] + z * (Cc[4] + z * Cc[5])))))
     return (1.0 - 0.5 * z) + z * r
+
+
+def det_sincos2pi(u):
+    """(cos, sin)(2*pi*u)."""
+    half_pi = 1.5707963267948966
+    u4 = u * 4.0
+    q = int(u4)
+    f = u4 - float(q)
+    if f <= 0.5:
+        a = f * half_pi
+        c, s = det_cos_k(a), det_sin_k(a)
+    else:
+        a = (1.0 - f) * half_pi
+        c, s = det_sin_k(a), det_cos_k(a)
+    return ((c, s), (-s, c), (-c, -s), (s, -c))[q]
 
 
 def det_cos2pi(u):
@@ -161,6 +178,16 @@ def normal_philox(seed, t, link, replica, site):
     return math.sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2)
 
 
+def normal_pair_philox(seed, t, link, replica, site):
+    """Two independent standard normals from one block: (cosine branch, sine branch)."""
+    w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
+    u1 = 1.0 - u53(w[0], w[1])
+    u2 = u53(w[2], w[3])
+    rad = math.sqrt(-2.0 * det_log(u1))
+    cs, sn = det_sincos2pi(u2)
+    return rad * cs, rad * sn
+
+
 class PhiloxDraws:
     """Draw provider for oracle.ltm_oracle.LtmOracle matching the kernels' PHILOX mode."""
 
@@ -172,9 +199,15 @@ class PhiloxDraws:
     def release_prob(self, rel32):
         return np.float32(0.7) + np.float32(0.15) * det_pow08(rel32)
 
+    def exp(self, values):
+        """Logit exponentials of the route-choice kernel in PHILOX mode (det_exp, not numpy's exp)."""
+        return np.array([det_exp(float(v)) for v in values], dtype=np.float64)
+
     def binomial(self, site, link, t, n, p):
         # the kernels key the draw by the step being computed (= time index + 1)
         return binomial_philox(self.seed, t + 1, link.col, self.replica, self._SITE[site], int(n), float(p))
 
     def normal(self, link, t, sigma):
-        return sigma * normal_philox(self.seed, t, link.col, self.replica, 4)
+        # the two directions of a corridor share one block keyed by the even link of the pair
+        pair = normal_pair_philox(self.seed, t, link.col & ~1, self.replica, 4)
+        return sigma * pair[link.col & 1]

@@ -1,17 +1,23 @@
 // B200 (sm_100a) kernels of the Link-Transmission-Model timestep + their C-ABI launchers.
 //
-// One simulation step t (reference Network.network_loading, src/LTM/network.py:266-287) is four
-// passes; all state is time-major structure-of-arrays history in HBM (include/pns_b200.h):
+// One simulation step t (reference Network.network_loading, src/LTM/network.py:266-287) is
 //
-//   k_link_flows   one thread per (link pair, replica)   sending + receiving flow at tau = t-1
-//   k_route_probs  one thread per (route group, replica) logit P(down | up, od)
-//   k_node_flows   one thread per (node, replica)        turning fractions, node model, cum. counts
-//   k_link_update  one thread per (link pair, replica)   pedestrians, density, speed, travel time
+//   k_link_pair    one thread per (link pair, replica)   FLOWS : sending + receiving flow at tau = t-1
+//                                                         UPDATE: pedestrians, density, speed, travel time at t
+//   k_route_probs  one thread per (route group, replica) logit P(down | up, od)           (routed nets only)
+//   k_node_flows   one thread per (node, replica)        turning fractions, node model, cumulative counts
 //
-// Nodes are mutually independent within a step (every read is of rows <= t-1 or of values the
-// same pass produced for the same link pair), which is what makes the
-// step data-parallel.  The replica index is the fastest-varying one, so for batched replicas a
-// warp touches 32 consecutive elements of every row it reads or writes.
+// and inside a multi-step call the UPDATE of step t and the FLOWS of step t+1 run in the same
+// thread (the link state stays in registers), so a step costs two launches:
+//
+//   FLOWS(t0) | node(t0) | UPDATE(t0)+FLOWS(t0+1) | node(t0+1) | ... | UPDATE(t0+n-1)
+//
+// Nodes are mutually independent within a step (every read is of rows <= t-1 or of values the same
+// pass produced for the same link pair), which is what makes the step
+// data-parallel.  All state is time-major structure-of-arrays history in HBM (include/pns_b200.h);
+// the replica index is the fastest-varying one, so for batched replicas a warp touches 32
+// consecutive elements of every row; for a single replica a thread owns the two adjacent columns of
+// a link pair.  Per-link parameters come from a small class table that stays in L1.
 //
 // Numerics: the reference mixes float32 history with float64 counters under numpy-2 scalar
 // promotion; every expression below states its precision explicitly and the file is compiled
@@ -44,25 +50,28 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 }
 
 constexpr int kBlock = 128;
+constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
 struct Ctx {
     pns_net n;
     pns_state s;
     pns_step_io io;
-    int t;      // step being computed
-    int mode;   // PNS_RNG_*
-    const int32_t* draw_b;  // row of this step (TABLE)
-    const double* draw_n;
+    int t;        // UPDATE acts on row t; route/node kernels compute step t
+    int t_flows;  // FLOWS computes the flows of step t_flows (time index t_flows-1)
+    int phase;    // PH_* mask
+    int mode;     // PNS_RNG_*
+    const int32_t* draw_b;  // TABLE: R1..R3 outcomes for step t_flows
+    const double* draw_n;   // TABLE: R4 noise for step t
+    size_t row64, row32;    // elements per history row
+    size_t fld64, fld32;    // elements per history field
 };
 
 // ---- addressing ---------------------------------------------------------------------------------
-__device__ __forceinline__ size_t row64(const Ctx& c) { return (size_t)c.n.n_cols64 * c.n.replicas; }
-__device__ __forceinline__ size_t row32(const Ctx& c) { return (size_t)c.n.n_links * c.n.replicas; }
 __device__ __forceinline__ double* H64(const Ctx& c, int f, int t) {
-    return c.s.hist64 + ((size_t)f * (c.n.sim_steps + 1) + t) * row64(c);
+    return c.s.hist64 + (size_t)f * c.fld64 + (size_t)t * c.row64;
 }
 __device__ __forceinline__ float* H32(const Ctx& c, int f, int t) {
-    return c.s.hist32 + ((size_t)f * (c.n.sim_steps + 1) + t) * row32(c);
+    return c.s.hist32 + (size_t)f * c.fld32 + (size_t)t * c.row32;
 }
 // numpy-style index of a length-(S+1) series: negative wraps once, anything else is an IndexError
 __device__ __forceinline__ int wrap_index(const Ctx& c, int i, int replica) {
@@ -75,41 +84,31 @@ __device__ __forceinline__ int wrap_index(const Ctx& c, int i, int replica) {
     return i;
 }
 
-struct LinkP {
-    double length, width, vf, kc, kj, gamma, act, bi, sigma;
-    int fftau, swtau, flags;
-};
-__device__ __forceinline__ LinkP load_link(const Ctx& c, int l) {
-    LinkP p;
-    p.length = __ldg(c.n.lk_length + l);
-    p.width = __ldg(c.n.lk_width + l);
-    p.vf = __ldg(c.n.lk_vf + l);
-    p.kc = __ldg(c.n.lk_kc + l);
-    p.kj = __ldg(c.n.lk_kj + l);
-    p.gamma = __ldg(c.n.lk_gamma + l);
-    p.act = __ldg(c.n.lk_act + l);
-    p.bi = __ldg(c.n.lk_bi + l);
-    p.sigma = __ldg(c.n.lk_sigma + l);
-    p.fftau = __ldg(c.n.lk_fftau + l);
-    p.swtau = __ldg(c.n.lk_swtau + l);
-    p.flags = __ldg(c.n.lk_flags + l);
-    return p;
-}
+typedef pns_link_class LinkP;
 __device__ __forceinline__ bool is_sep(const LinkP& p) { return p.flags & 1; }
 
-// area of the walkable surface (link.py:128-131, 454-456); `f64` tells whether the reference
-// holds it as a numpy float64 (a separator width assigned from np.clip) -- then density is a
-// double-precision divide, otherwise the area is demoted to float32 first.
-__device__ __forceinline__ double link_area(const Ctx& c, const LinkP& p, size_t e, bool* f64) {
+// Walkable area (link.py:128-131, 454-456).  For a separator it follows the lane width; `f64`
+// tells whether the reference holds that width as a numpy float64 (assigned from np.clip), in
+// which case density is a double-precision divide instead of a float32 one.
+struct Area {
+    double area, space;
+    float area32;
+    bool f64;
+};
+__device__ __forceinline__ Area link_area(const Ctx& c, const LinkP& p, size_t e, double gate) {
+    Area a;
     if (is_sep(p)) {
-        *f64 = c.s.sep_np64[e] != 0;
-        return p.length * c.s.widths[2 * row32(c) + e];
+        a.area = p.length * gate;
+        a.space = p.kj * a.area;
+        a.area32 = (float)a.area;
+        a.f64 = c.s.sep_np64[e] != 0;
+    } else {
+        a.area = p.area; a.space = p.space; a.area32 = p.area32; a.f64 = false;
     }
-    *f64 = false;
-    return p.length * p.width;
+    return a;
 }
-__device__ __forceinline__ float div_by_area(float x, double area, bool f64) {
-    return f64 ? (float)((double)x / area) : x / (float)area;
+__device__ __forceinline__ float div_by_area(float x, const Area& a) {
+    return a.f64 ? (float)((double)x / a.area) : x / a.area32;
 }
 
 // Python min/max on scalars: min(a, b) -> b if b < a else a ; max(a, b) -> b if b > a else a
@@ -119,16 +118,16 @@ __device__ __forceinline__ float clip01(float x) { return fminf(fmaxf(x, 0.0f), 
 
 struct SendOut {
     double flow;   // sending_flow[tau]
-    int kind;      // request kind
+    double sval;   // REQUEST: flow after the release stage when no R1 draw is needed
+    int kind;      // REQUEST: 0 nothing to draw, 1 diffusion branch, 2 binomial R1
     int n1;
     float rf;
-    double sval;
 };
 
-// Link.get_outflow (link.py:199-214)
-__device__ double diffusion_outflow(const Ctx& c, const LinkP& p, size_t e, int tau_idx, int tau, float avg_tt,
-                                    int replica) {
-    const float F = 1.0f / (1.0f + (float)p.gamma * avg_tt);
+// Link.get_outflow (link.py:199-214): 4-tap geometric smoothing of lagged inflow
+__device__ __noinline__ double diffusion_outflow(const Ctx& c, const LinkP& p, size_t e, int tau, int lag,
+                                                 float avg_tt, int replica) {
+    const float F = 1.0f / (1.0f + p.gamma32 * avg_tt);
     const float u = 1.0f - F;
     const float c1 = F * u;
     const float c2 = F * (float)((double)u * (double)u);                 // powf(u, 2)
@@ -136,7 +135,7 @@ __device__ double diffusion_outflow(const Ctx& c, const LinkP& p, size_t e, int 
     double in[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int i = wrap_index(c, tau_idx - tau - k, replica);
+        const int i = wrap_index(c, tau - lag - k, replica);
         in[k] = i >= 0 ? H64(c, PNS_F64_INFLOW, i)[e] : 0.0;
     }
     const double total = (((double)F * in[0] + (double)c1 * in[1]) + (double)c2 * in[2]) + (double)c3 * in[3];
@@ -144,34 +143,34 @@ __device__ double diffusion_outflow(const Ctx& c, const LinkP& p, size_t e, int 
     return 0.0 > up ? 0.0 : up;
 }
 
+struct LinkNow {      // state of one link at time index tau, either just computed or loaded
+    float num, dens, avg_tt;
+};
+
 // Link.cal_sending_flow at time index tau (link.py:216-370)
-__device__ SendOut sending_flow(const Ctx& c, const LinkP& p, int l, size_t e, int tau, float num_self,
-                                float num_rev, int replica, const pns::DrawKey& key) {
+__device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, size_t e, int tau, const LinkNow& me,
+                                                float num_rev, const Area& ar, double front_gate, double cum_out_tau,
+                                                double snd_prev, int replica, const pns::DrawKey& key) {
     SendOut o;
     o.kind = 0; o.n1 = 0; o.rf = 0.0f; o.sval = 0.0; o.flow = 0.0;
-    const float dens_self = H32(c, PNS_F32_DENSITY, tau)[e];
-    bool a64;
-    const double area = link_area(c, p, e, &a64);
-    const float dens = is_sep(p) ? dens_self : div_by_area(num_self + num_rev, area, a64);
-    const float avg_tt = H32(c, PNS_F32_AVG_TRAVEL_TIME, tau)[e];
-    const int lag = __float2int_rn(avg_tt / (float)c.n.unit_time);        // round(), half to even
     if (tau < p.fftau) return o;                                          // link.py:267-269
+    const float dens = is_sep(p) ? me.dens : div_by_area(me.num + num_rev, ar);
+    const int lag = __float2int_rn(me.avg_tt / (float)c.n.unit_time);     // round(), half to even (link.py:260)
     if (lag == 0) atomicOr(c.s.err + replica, PNS_ERR_ZERO_LAG);
     const int idx = max(0, tau + 1 - lag);
-    const float cong = clip01((dens_self - (float)p.kc) / (float)(p.kj - p.kc));
-    const double arrived_raw = H64(c, PNS_F64_CUM_INFLOW, idx)[e] - H64(c, PNS_F64_CUM_OUTFLOW, tau)[e];
+    const float cong = clip01((me.dens - p.kc32) / p.kj_minus_kc32);
+    const double arrived_raw = H64(c, PNS_F64_CUM_INFLOW, idx)[e] - cum_out_tau;
     const double arrived = arrived_raw > 0.0 ? arrived_raw : 0.0;
-    const double boundary = (double)(cong * num_self) + (double)(1.0f - cong) * arrived;
-    const double fgw = c.s.widths[e];
-    const double gate_cap = ((fgw * p.kc) * p.vf) * c.n.unit_time;
+    const double boundary = (double)(cong * me.num) + (double)(1.0f - cong) * arrived;
+    const double gate_cap = ((front_gate * p.kc) * p.vf) * c.n.unit_time;
     double flow = pymin(boundary, gate_cap);
     const double original = flow;
     if (flow > 0.0) {
-        const float rf = clip01(dens / (float)p.kj);
+        const float rf = clip01(dens / p.kj32);
         o.rf = rf;
         bool draw = true;
-        if (dens <= (float)p.kc) {
-            const double spread = diffusion_outflow(c, p, e, tau, lag, avg_tt, replica);
+        if (dens <= p.kc32) {
+            const double spread = diffusion_outflow(c, p, e, tau, lag, me.avg_tt, replica);
             if (spread > 0.0) {
                 flow = floor(pymin(0.8 * spread + 0.19999999999999996 * flow, flow));   // link.py:330
                 draw = false;
@@ -197,14 +196,12 @@ __device__ SendOut sending_flow(const Ctx& c, const LinkP& p, int l, size_t e, i
     if (p.act > 0.0 && flow > 1.0) {                                       // link.py:351-358
         const int trials = (int)floor(flow);
         int stay;
-        if (c.mode == PNS_RNG_TABLE) stay = c.draw_b[row32(c) + e];
+        if (c.mode == PNS_RNG_TABLE) stay = c.draw_b[c.row32 + e];
         else stay = pns::binomial_philox(key, 2u, trials, p.act);
         flow = flow - (double)stay;
     }
     flow = flow > 0.0 ? flow : 0.0;
-    const int prev_i = wrap_index(c, tau - 1, replica);
-    const double prev = H64(c, PNS_F64_SENDING, prev_i)[e];
-    flow = pymin(floor(0.8 * flow + 0.2 * prev), original);               // link.py:363-364
+    flow = pymin(floor(0.8 * flow + 0.2 * snd_prev), original);           // link.py:363-364
     if (flow < 0.0) atomicOr(c.s.err + replica, PNS_ERR_NEG_SENDING);
     o.flow = flow;
     return o;
@@ -212,85 +209,226 @@ __device__ SendOut sending_flow(const Ctx& c, const LinkP& p, int l, size_t e, i
 
 // Link/Separator.cal_receiving_flow at tau, before the reverse sending flow is subtracted
 // (link.py:372-405, 480-507)
-__device__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev, int replica,
-                                 const pns::DrawKey& key, int* n3) {
-    bool a64;
-    const double area = link_area(c, p, e, &a64);
-    const double space = p.kj * area;
+__device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev,
+                                                 const Area& ar, double back_gate, double cum_in_tau,
+                                                 double rcv_prev, const pns::DrawKey& key, int* n3) {
     const int lag_i = tau + 1 - p.swtau;
     double bound;
     if (is_sep(p)) {
         *n3 = -1;
-        if (lag_i < 0) bound = space;
-        else bound = (H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + space) - H64(c, PNS_F64_CUM_INFLOW, tau)[e];
+        if (lag_i < 0) bound = ar.space;
+        else bound = (H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + ar.space) - cum_in_tau;
     } else {
         const int trials = (int)num_rev;        // numpy casts the float32 count to int64 (truncation)
         *n3 = trials;
         int blockers = 0;
-        if (c.mode == PNS_RNG_TABLE) blockers = c.draw_b[2 * row32(c) + e];
+        if (c.mode == PNS_RNG_TABLE) blockers = c.draw_b[2 * c.row32 + e];
         else if (c.mode == PNS_RNG_PHILOX) blockers = pns::binomial_philox(key, 3u, trials, 0.9);
         else return 0.0;
         if (lag_i < 0) {
-            bound = space - (double)blockers;
+            bound = ar.space - (double)blockers;
         } else {
-            const double x = ((H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + space) - (double)blockers) -
-                             H64(c, PNS_F64_CUM_INFLOW, tau)[e];
+            const double x = ((H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + ar.space) - (double)blockers) - cum_in_tau;
             bound = x > 0.0 ? x : 0.0;
         }
     }
     if (c.mode == PNS_RNG_REQUEST) return 0.0;
-    const double bgw = c.s.widths[row32(c) + e];
-    const double gate_cap = ((bgw * p.kc) * p.vf) * c.n.unit_time;
+    const double gate_cap = ((back_gate * p.kc) * p.vf) * c.n.unit_time;
     double flow = pymin(bound, gate_cap);
     flow = pymax(flow, 0.0);
-    const int prev_i = wrap_index(c, tau - 1, replica);
-    const double prev = H64(c, PNS_F64_RECEIVING, prev_i)[e];
-    if (prev >= 0.0) flow = pymin(floor(flow * 0.8 + prev * 0.2), flow);   // link.py:400-401
+    if (rcv_prev >= 0.0) flow = pymin(floor(flow * 0.8 + rcv_prev * 0.2), flow);   // link.py:400-401
     return flow;
 }
 
+// BiDirectionalFd.__call__ (src/utils/functions.py:112-134) + travel time (link.py:176-177).
+// Returns the float32 value stored in speed[t]; *tt is the float32 stored in travel_time[t].
+__device__ __forceinline__ float speed_and_travel_time(const LinkP& p, float k_self, float k_opp, bool have_noise,
+                                                       double z, float* tt) {
+    const float k_eff = k_self + p.bi32 * k_opp;
+    const int fd = (p.flags >> 1) & 3;
+    // the speed is a Python double in the free-flow branch (and after `0 + noise`), a float32 otherwise
+    bool is_f64 = false, is_zero = false;
+    double v64 = 0.0;
+    float v32 = 0.0f;
+    const bool free_flow = k_eff <= p.kc32;
+    if (fd == 2) {                                    // smulders
+        if (free_flow) v32 = p.vf32 * (1.0f - k_eff / p.kj32);
+        else {
+            v32 = p.sm_gamma32 * (1.0f / k_eff - p.inv_kj32);
+            if (!(v32 > 0.0f)) is_zero = true;
+        }
+    } else if (free_flow) {
+        is_f64 = true;
+        v64 = p.vf;
+    } else if (fd == 0) {                             // yperman
+        v32 = p.yp_coef32 * (p.kj32 / k_eff - 1.0f);
+        if (!(v32 > 0.0f)) is_zero = true;
+    } else {                                          // greenshields
+        v32 = (p.neg_vf32 * (k_eff - p.kj32)) / p.kj_minus_kc32;
+        if (!(v32 > 0.0f)) is_zero = true;
+    }
+    if (have_noise) {
+        if (is_zero) { is_f64 = true; is_zero = false; v64 = 0.0 + z; }
+        else if (is_f64) v64 = v64 + z;
+        else v32 = v32 + (float)z;
+    }
+    if (is_zero) { *tt = p.max_tt32; return 0.0f; }
+    if (is_f64) {
+        if (!(v64 > 0.0)) { *tt = p.max_tt32; return 0.0f; }
+        *tt = (float)(p.length / v64);
+        return (float)v64;
+    }
+    if (!(v32 > 0.0f)) { *tt = p.max_tt32; return 0.0f; }
+    *tt = p.length32 / v32;
+    return v32;
+}
+
 // =================================================================================================
-__global__ void __launch_bounds__(kBlock) k_link_flows(const __grid_constant__ Ctx c) {
+// UPDATE: Link.update_link_density_flow + update_speeds at row t (link.py:133-188; Separator :430-452)
+// FLOWS : sending/receiving flows of step t_flows (time index t_flows-1)
+__global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__ Ctx c) {
     const int R = c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_pairs = (size_t)(c.n.n_links / 2);
     if (gid >= n_pairs * R) return;
     const int pair = (int)(gid / R);
     const int rep = (int)(gid % R);
-    const int tau = c.t - 1;
-    const int l0 = 2 * pair, l1 = l0 + 1;
-    const size_t e0 = (size_t)l0 * R + rep, e1 = e0 + R;
-    const LinkP p0 = load_link(c, l0), p1 = load_link(c, l1);
-    const float* num = H32(c, PNS_F32_NUM_PED, tau);
-    const float n0 = num[e0], n1 = num[e1];
-    pns::DrawKey k0, k1;
-    k0.t = (uint32_t)c.t; k0.link = (uint32_t)l0; k0.replica = (uint32_t)rep;
-    k0.k0 = (uint32_t)c.io.seed; k0.k1 = (uint32_t)(c.io.seed >> 32);
-    k1 = k0; k1.link = (uint32_t)l1;
+    const int l0 = 2 * pair;
+    const size_t e[2] = {(size_t)l0 * R + rep, (size_t)(l0 + 1) * R + rep};
+    const LinkP* const pp[2] = {c.n.classes + __ldg(c.n.lk_class + l0), c.n.classes + __ldg(c.n.lk_class + l0 + 1)};
+    const double gate[2] = {c.s.gate[e[0]], c.s.gate[e[1]]};
+    Area ar[2];
+    ar[0] = link_area(c, *pp[0], e[0], gate[0]);
+    ar[1] = link_area(c, *pp[1], e[1], gate[1]);
+    const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
 
-    const SendOut s0 = sending_flow(c, p0, l0, e0, tau, n0, n1, rep, k0);
-    const SendOut s1 = sending_flow(c, p1, l1, e1, tau, n1, n0, rep, k1);
-    int n3_0, n3_1;
-    const double r0 = receiving_flow(c, p0, e0, tau, n1, rep, k0, &n3_0);
-    const double r1 = receiving_flow(c, p1, e1, tau, n0, rep, k1, &n3_1);
+    LinkNow now[2];
+    if (c.phase & PH_UPDATE) {
+        const int t = c.t;
+        const double* inflow = H64(c, PNS_F64_INFLOW, t);
+        const double* outflow = H64(c, PNS_F64_OUTFLOW, t);
+        const float* num_prev = H32(c, PNS_F32_NUM_PED, t - 1);
+        const double din[2] = {inflow[e[0]], inflow[e[1]]};
+        const double dout[2] = {outflow[e[0]], outflow[e[1]]};
+        const float np_[2] = {num_prev[e[0]], num_prev[e[1]]};
+        const float rs[2] = {c.s.runsum[e[0]], c.s.runsum[e[1]]};
+        float tt_old[2] = {0.0f, 0.0f};
+        const bool windowed = t >= c.n.window;
+        if (windowed) {
+            const float* tt_w = H32(c, PNS_F32_TRAVEL_TIME, t - c.n.window);
+            tt_old[0] = tt_w[e[0]];
+            tt_old[1] = tt_w[e[1]];
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            now[a].num = (float)((double)np_[a] + (din[a] - dout[a]));    // link.py:134-135
+            now[a].dens = div_by_area(now[a].num, ar[a]);                  // link.py:136
+        }
+        // speed noise (functions.py:132-133): one Philox block serves both directions of the pair
+        double z[2] = {0.0, 0.0};
+        const bool noisy[2] = {pp[0]->sigma > 0.0, pp[1]->sigma > 0.0};
+        if (noisy[0] | noisy[1]) {
+            if (c.mode == PNS_RNG_TABLE) {
+                if (noisy[0]) z[0] = c.draw_n[e[0]];
+                if (noisy[1]) z[1] = c.draw_n[e[1]];
+            } else {
+                pns::DrawKey key;
+                key.t = (uint32_t)t; key.link = (uint32_t)l0; key.replica = (uint32_t)rep; key.k0 = k0; key.k1 = k1;
+                double g0, g1;
+                pns::normal_pair_philox(key, 4u, &g0, &g1);
+                z[0] = pp[0]->sigma * g0;
+                z[1] = pp[1]->sigma * g1;
+            }
+        }
+        float* num_t = H32(c, PNS_F32_NUM_PED, t);
+        float* dens_t = H32(c, PNS_F32_DENSITY, t);
+        float* speed_t = H32(c, PNS_F32_SPEED, t);
+        float* tt_t = H32(c, PNS_F32_TRAVEL_TIME, t);
+        float* flow_t = H32(c, PNS_F32_LINK_FLOW, t);
+        float* avg_t = H32(c, PNS_F32_AVG_TRAVEL_TIME, t);
+        double* bgw_t = H64(c, PNS_F64_BACK_GATE, t);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const LinkP& p = *pp[a];
+            const bool sep = is_sep(p);
+            float tt;
+            const float v = speed_and_travel_time(p, now[a].dens, sep ? 0.0f : now[1 - a].dens, noisy[a], z[a], &tt);
+            num_t[e[a]] = now[a].num;
+            dens_t[e[a]] = now[a].dens;
+            speed_t[e[a]] = v;
+            tt_t[e[a]] = tt;
+            flow_t[e[a]] = v * now[a].dens;                                // functions.py:97-101
+            float sum = rs[a] + tt;                                        // link.py:183-186
+            if (windowed) {
+                sum = sum - tt_old[a];
+                now[a].avg_tt = sum / (float)c.n.window;
+                avg_t[e[a]] = now[a].avg_tt;
+            } else {
+                now[a].avg_tt = p.tt0;                                     // rows < window keep travel_time[0]
+            }
+            c.s.runsum[e[a]] = sum;
+            bgw_t[e[a]] = gate[a];                                         // link.py:188, 451-452
+            if (sep) H64(c, PNS_F64_SEP_WIDTH, t)[e[a]] = gate[a];
+        }
+    }
+    if (!(c.phase & PH_FLOWS)) return;
 
+    const int tau = c.t_flows - 1;
+    if (!(c.phase & PH_UPDATE)) {
+        const float* num = H32(c, PNS_F32_NUM_PED, tau);
+        const float* den = H32(c, PNS_F32_DENSITY, tau);
+        const float* avg = H32(c, PNS_F32_AVG_TRAVEL_TIME, tau);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            now[a].num = num[e[a]];
+            now[a].dens = den[e[a]];
+            now[a].avg_tt = avg[e[a]];
+        }
+    }
+    const double* cin = H64(c, PNS_F64_CUM_INFLOW, tau);
+    const double* cou = H64(c, PNS_F64_CUM_OUTFLOW, tau);
+    const int prev_i = wrap_index(c, tau - 1, rep);
+    const double* sndp = H64(c, PNS_F64_SENDING, prev_i);
+    const double* rcvp = H64(c, PNS_F64_RECEIVING, prev_i);
+    const double cin_tau[2] = {cin[e[0]], cin[e[1]]};
+    const double cou_tau[2] = {cou[e[0]], cou[e[1]]};
+    const double snd_prev[2] = {sndp[e[0]], sndp[e[1]]};
+    const double rcv_prev[2] = {rcvp[e[0]], rcvp[e[1]]};
+
+    SendOut s[2];
+    double r[2];
+    int n3[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const LinkP& p = *pp[a];
+        pns::DrawKey key;
+        key.t = (uint32_t)c.t_flows; key.link = (uint32_t)(l0 + a); key.replica = (uint32_t)rep; key.k0 = k0; key.k1 = k1;
+        // front gate of a plain link is the back gate of its reverse (link.py:110-126); a separator's
+        // gates both equal its lane width (link.py:462-478)
+        const double front = is_sep(p) ? gate[a] : gate[1 - a];
+        s[a] = sending_flow(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep, key);
+        r[a] = receiving_flow(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], rcv_prev[a], key, &n3[a]);
+    }
     if (c.mode == PNS_RNG_REQUEST) {
-        c.io.req_kind[e0] = s0.kind; c.io.req_kind[e1] = s1.kind;
-        c.io.req_n1[e0] = s0.n1;     c.io.req_n1[e1] = s1.n1;
-        c.io.req_rf[e0] = s0.rf;     c.io.req_rf[e1] = s1.rf;
-        c.io.req_sval[e0] = s0.sval; c.io.req_sval[e1] = s1.sval;
-        c.io.req_n3[e0] = n3_0;      c.io.req_n3[e1] = n3_1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            c.io.req_kind[e[a]] = s[a].kind;
+            c.io.req_n1[e[a]] = s[a].n1;
+            c.io.req_rf[e[a]] = s[a].rf;
+            c.io.req_sval[e[a]] = s[a].sval;
+            c.io.req_n3[e[a]] = n3[a];
+        }
         return;
     }
     double* snd = H64(c, PNS_F64_SENDING, tau);
     double* rcv = H64(c, PNS_F64_RECEIVING, tau);
-    snd[e0] = s0.flow;
-    snd[e1] = s1.flow;
-    // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
-    const double q0 = is_sep(p0) ? r0 : r0 - s1.flow;
-    const double q1 = is_sep(p1) ? r1 : r1 - s0.flow;
-    rcv[e0] = pymax(q0, 0.0);
-    rcv[e1] = pymax(q1, 0.0);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        snd[e[a]] = s[a].flow;
+        // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
+        const double q = is_sep(*pp[a]) ? r[a] : r[a] - s[1 - a].flow;
+        rcv[e[a]] = pymax(q, 0.0);
+    }
 }
 
 // =================================================================================================
@@ -317,17 +455,17 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
         const int l = c.n.rt_opt_link[o0 + k];
         sum_d = k == 0 ? c.n.rt_opt_dist[o0] : sum_d + c.n.rt_opt_dist[o0 + k];
         if (l >= 0) {
-            const LinkP p = load_link(c, l);
+            const LinkP& p = c.n.classes[c.n.lk_class[l]];
             const size_t e = (size_t)l * R + rep;
+            const double gate = c.s.gate[e];
             if (is_sep(p)) {
                 dens[k] = dens_row[e];
             } else {
-                bool a64;
-                const double area = link_area(c, p, e, &a64);
-                dens[k] = div_by_area(num[e] + num[(size_t)(l ^ 1) * R + rep], area, a64);
+                const Area ar = link_area(c, p, e, gate);
+                dens[k] = div_by_area(num[e] + num[(size_t)(l ^ 1) * R + rep], ar);
             }
             const double last = rcv[e];
-            cap[k] = last >= 0.0 ? last : ((c.s.widths[row32(c) + e] * p.vf) * p.kc) * c.n.unit_time;
+            cap[k] = last >= 0.0 ? last : ((gate * p.vf) * p.kc) * c.n.unit_time;
         } else {
             dens[k] = 0.0f;
             cap[k] = 100.0;
@@ -347,248 +485,174 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
         }
         const double util = (((c.n.rt_alpha * c.n.rt_opt_dist[o0 + k]) / (sum_d + 1e-6) + crowd_term) -
                              (c.n.rt_omega * cap[k]) / (sum_c + 1e-6)) + c.n.rt_eps;
-        ex[k] = exp(-c.n.rt_temp * util);
+        // numpy's exp in the reference-compatible modes; the operation-exact restatement when the
+        // whole step is counter-based (so oracle/philox.py can reproduce it bit for bit anywhere)
+        ex[k] = c.mode == PNS_RNG_PHILOX ? pns::det_exp(-c.n.rt_temp * util) : exp(-c.n.rt_temp * util);
         sum_e = k == 0 ? ex[0] : sum_e + ex[k];
     }
     for (int k = 0; k < n; ++k) c.s.probs[(size_t)(o0 + k) * R + rep] = ex[k] / sum_e;
 }
 
 // =================================================================================================
-// Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
-// (path_finder.py:591-715)
-__global__ void __launch_bounds__(kBlock) k_node_flows(const __grid_constant__ Ctx c) {
+// PathFinder.update_turning_fractions + check_fractions (path_finder.py:591-715) for one routed node;
+// writes the node's m(m-1) fractions to tf_routed (element k at out[k*R]).
+__device__ __noinline__ void routed_fractions(const Ctx& c, int routed, int m, int t, int rep, double* out) {
     const int R = c.n.replicas;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)c.n.n_nodes * R) return;
-    const int node = (int)(gid / R);
-    const int rep = (int)(gid % R);
-    const int base = c.n.nd_ptr[node];
-    const int m = c.n.nd_ptr[node + 1] - base;
-    if (m == 0) return;
+    const int row0 = c.n.rt_routed_row0[routed];
+    const int edge0 = c.n.rt_routed_edge0[routed];
+    const double* w = c.io.od_w + (size_t)t * c.n.n_od;
+    int k = 0;
+    for (int i = 0; i < m; ++i) {
+        const int ra = c.n.rt_row_ptr[row0 + i], rb = c.n.rt_row_ptr[row0 + i + 1];
+        double total = 0.0;
+        for (int x = ra; x < rb; ++x) total = total + w[c.n.rt_row_od[x]];
+        const double uniform = rb > ra ? 1.0 / (double)(rb - ra) : 0.0;
+        double row_sum = 0.0;
+        for (int j = 0; j < m - 1; ++j, ++k) {
+            const int ta = c.n.rt_term_ptr[edge0 + k], tb = c.n.rt_term_ptr[edge0 + k + 1];
+            double acc = 0.0;
+            for (int x = ta; x < tb; ++x) {
+                const double od_p = total > 0.0 ? w[c.n.rt_row_od[c.n.rt_term_row_entry[x]]] / total : uniform;
+                acc = acc + c.s.probs[(size_t)c.n.rt_term_opt[x] * R + rep] * od_p;
+            }
+            out[(size_t)k * R] = acc;
+            row_sum = j == 0 ? acc : row_sum + acc;
+        }
+        if (fabs(row_sum - 1.0) > 1e-3) {                                  // check_fractions
+            double* rowp = out + (size_t)(k - (m - 1)) * R;
+            if (row_sum > 1e-6) {
+                for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = rowp[(size_t)j * R] / row_sum;
+            } else {
+                for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = 1.0 / (double)(m - 1);
+            }
+        }
+    }
+}
+
+// One node: gather s/r over its slots, node model, scatter flows and cumulative counts.
+// M > 0: slot count known at compile time (loops unrolled, everything in registers);
+// M == 0: generic path for rare high-degree nodes (arrays in local memory).
+template <int M>
+__device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int base, int kind,
+                                          int tf_mode, int dem_row, int tf_ptr) {
+    constexpr int CAP = M ? M : PNS_MAX_DEGREE;
+    const int m = M ? M : m_dyn;
+    const int R = c.n.replicas;
     const int t = c.t, tau = c.t - 1;
     const int L = c.n.n_links;
-
-    double s[PNS_MAX_DEGREE], r[PNS_MAX_DEGREE];
-    int icol[PNS_MAX_DEGREE], ocol[PNS_MAX_DEGREE];
+    int icol[CAP];
+#pragma unroll
+    for (int i = 0; i < m; ++i) icol[i] = __ldg(c.n.nd_in_col + base + i);
     const double* snd = H64(c, PNS_F64_SENDING, tau);
     const double* rcv = H64(c, PNS_F64_RECEIVING, tau);
-    bool negative = false;
+    const double* cout_p = H64(c, PNS_F64_CUM_OUTFLOW, tau);
+    const double* cin_p = H64(c, PNS_F64_CUM_INFLOW, tau);
+    double s[CAP], r[CAP], co[CAP], ci[CAP];
+#pragma unroll
     for (int i = 0; i < m; ++i) {
-        icol[i] = c.n.nd_in_col[base + i];
-        ocol[i] = c.n.nd_out_col[base + i];
+        const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
         if (icol[i] >= L) {
-            const int row = c.n.nd_dem_row[node];
-            s[i] = c.io.demand[(size_t)tau * c.n.n_demand_rows * R + (size_t)row * R + rep];   // node.py:176
+            s[i] = c.io.demand[((size_t)tau * c.n.n_demand_rows + dem_row) * R + rep];      // node.py:176
+            r[i] = 1e6;                                                                       // node.py:186
         } else {
-            s[i] = snd[(size_t)icol[i] * R + rep];
+            s[i] = snd[ei];
+            r[i] = rcv[eo];
         }
-        r[i] = ocol[i] >= L ? 1e6 : rcv[(size_t)ocol[i] * R + rep];                            // node.py:186
-        negative |= (s[i] < 0.0) | (r[i] < 0.0);
+        co[i] = cout_p[ei];
+        ci[i] = cin_p[eo];
     }
+    bool negative = false;
+#pragma unroll
+    for (int i = 0; i < m; ++i) negative |= (s[i] < 0.0) | (r[i] < 0.0);
     if (negative) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
 
-    double q_out[PNS_MAX_DEGREE], q_in[PNS_MAX_DEGREE];
-    if (c.n.nd_kind[node] == 0) {
-        // OneToOneNode.solve (node.py:230-242)
-        const double a = fmin(s[0], r[1]), b = fmin(s[1], r[0]);
-        q_out[0] = a; q_out[1] = b; q_in[0] = b; q_in[1] = a;
+    double q_out[CAP], q_in[CAP];
+    if (kind == 0) {
+        // OneToOneNode.solve (node.py:230-242): exactly two slots
+        const double a = fmin(s[0], r[CAP > 1 ? 1 : 0]), b = fmin(s[CAP > 1 ? 1 : 0], r[0]);
+        q_out[0] = a; q_out[CAP > 1 ? 1 : 0] = b;
+        q_in[0] = b;  q_in[CAP > 1 ? 1 : 0] = a;
     } else {
-        const int e0 = c.n.nd_tf_ptr[node];
-        const double* tf;
-        const int routed = c.n.nd_routed[node];
-        if (routed >= 0) {
-            // PathFinder.update_turning_fractions (path_finder.py:591-689)
-            double* out = c.s.tf_routed + (size_t)e0 * R + rep;   // element k at out[k*R]
-            const int row0 = c.n.rt_routed_row0[routed];
-            const int edge0 = c.n.rt_routed_edge0[routed];
-            const double* w = c.io.od_w + (size_t)t * c.n.n_od;
-            int k = 0;
-            for (int i = 0; i < m; ++i) {
-                const int ra = c.n.rt_row_ptr[row0 + i], rb = c.n.rt_row_ptr[row0 + i + 1];
-                double total = 0.0;
-                for (int x = ra; x < rb; ++x) total = total + w[c.n.rt_row_od[x]];
-                const double uniform = rb > ra ? 1.0 / (double)(rb - ra) : 0.0;
-                double row_sum = 0.0;
-                for (int j = 0; j < m - 1; ++j, ++k) {
-                    const int ta = c.n.rt_term_ptr[edge0 + k], tb = c.n.rt_term_ptr[edge0 + k + 1];
-                    double acc = 0.0;
-                    for (int x = ta; x < tb; ++x) {
-                        const double od_p = total > 0.0 ? w[c.n.rt_row_od[c.n.rt_term_row_entry[x]]] / total : uniform;
-                        acc = acc + c.s.probs[(size_t)c.n.rt_term_opt[x] * R + rep] * od_p;
-                    }
-                    out[(size_t)k * R] = acc;
-                    row_sum = j == 0 ? acc : row_sum + acc;
-                }
-                // PathFinder.check_fractions (path_finder.py:691-715)
-                if (fabs(row_sum - 1.0) > 1e-3) {
-                    double* rowp = out + (size_t)(k - (m - 1)) * R;
-                    if (row_sum > 1e-6) {
-                        for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = rowp[(size_t)j * R] / row_sum;
-                    } else {
-                        for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = 1.0 / (double)(m - 1);
-                    }
-                }
-            }
+        // RegularNode.solve, 'classic' (node.py:272-300).  P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)];
+        // tf_mode 0 means uniform 1/(m-1) (network.py:269-271).
+        const double* tf = nullptr;
+        size_t ts = 1;
+        if (tf_mode == 2) {
+            double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
+            routed_fractions(c, __ldg(c.n.nd_routed + node), m, t, rep, out);
             tf = out;
-        } else {
-            tf = c.s.tf_static + e0;
+            ts = (size_t)R;
+        } else if (tf_mode == 1) {
+            tf = c.s.tf_static + tf_ptr;
         }
-        const size_t tstride = routed >= 0 ? (size_t)R : 1;
-        // RegularNode.solve, 'classic' (node.py:272-300).  P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)]
-        double D[PNS_MAX_DEGREE];
+        const double phi = 1.0 / (double)(m - 1);
+        double D[CAP];
+#pragma unroll
         for (int j = 0; j < m; ++j) {
-            double acc = 0.0;
+            double acc = 0.0;          // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
+#pragma unroll
             for (int i = 0; i < m; ++i) {
-                const double pij = i == j ? 0.0 : tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * tstride];
-                const double wij = pij * s[i];
-                acc = i == 0 ? wij : acc + wij;      // np.sum(axis=0): rows added in order
+                if (i == j) continue;
+                const double pij = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] : phi;
+                acc = acc + pij * s[i];
             }
             D[j] = acc != 0.0 ? acc : 1e-5;
             q_in[j] = 0.0;
         }
+#pragma unroll
         for (int i = 0; i < m; ++i) {
             double out_i = 0.0;
+#pragma unroll
             for (int j = 0; j < m; ++j) {
                 if (i == j) continue;
-                const double pij = tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * tstride];
+                const double pij = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] : phi;
                 const double wij = pij * s[i];
                 const double supply = r[j] * (wij / D[j]);
                 const double f = floor(pymin(wij, supply));
                 out_i += f;
                 q_in[j] += f;
             }
-            q_out[i] = out_i;
+            q_out[i] = fmax(0.0, out_i);
         }
-        for (int i = 0; i < m; ++i) {
-            q_out[i] = fmax(0.0, q_out[i]);
-            q_in[i] = fmax(0.0, q_in[i]);
-        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) q_in[j] = fmax(0.0, q_in[j]);
     }
     // Node.update_links (node.py:146-162, link.py:19-25)
     double* outflow = H64(c, PNS_F64_OUTFLOW, t);
     double* inflow = H64(c, PNS_F64_INFLOW, t);
     double* cout_t = H64(c, PNS_F64_CUM_OUTFLOW, t);
     double* cin_t = H64(c, PNS_F64_CUM_INFLOW, t);
-    const double* cout_p = H64(c, PNS_F64_CUM_OUTFLOW, tau);
-    const double* cin_p = H64(c, PNS_F64_CUM_INFLOW, tau);
+#pragma unroll
     for (int i = 0; i < m; ++i) {
-        const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)ocol[i] * R + rep;
+        const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
         outflow[ei] = q_out[i];
-        cout_t[ei] = cout_p[ei] + q_out[i];
+        cout_t[ei] = co[i] + q_out[i];
         inflow[eo] = q_in[i];
-        cin_t[eo] = cin_p[eo] + q_in[i];
+        cin_t[eo] = ci[i] + q_in[i];
     }
 }
 
-// =================================================================================================
-// BiDirectionalFd.__call__ (src/utils/functions.py:112-134) + travel time (link.py:176-177).
-// Returns the float32 value stored in speed[t]; *tt is the float32 stored in travel_time[t].
-__device__ float speed_and_travel_time(const LinkP& p, float k_self, float k_opp, bool have_noise, double z,
-                                       float* tt) {
-    const float k_eff = k_self + (float)p.bi * k_opp;
-    const int fd = (p.flags >> 1) & 3;
-    // the speed is a Python double in the free-flow branch (and after `0 + noise`), a float32 otherwise
-    bool is_f64 = false, is_zero = false;
-    double v64 = 0.0;
-    float v32 = 0.0f;
-    const bool free_flow = k_eff <= (float)p.kc;
-    if (fd == 2) {                                    // smulders
-        if (free_flow) v32 = (float)p.vf * (1.0f - k_eff / (float)p.kj);
-        else {
-            v32 = (float)(p.vf * p.kc) * (1.0f / k_eff - (float)(1.0 / p.kj));
-            if (!(v32 > 0.0f)) is_zero = true;
-        }
-    } else if (free_flow) {
-        is_f64 = true;
-        v64 = p.vf;
-    } else if (fd == 0) {                             // yperman
-        v32 = (float)((p.kc * p.vf) / (p.kj - p.kc)) * ((float)p.kj / k_eff - 1.0f);
-        if (!(v32 > 0.0f)) is_zero = true;
-    } else {                                          // greenshields
-        v32 = ((float)(-p.vf) * (k_eff - (float)p.kj)) / (float)(p.kj - p.kc);
-        if (!(v32 > 0.0f)) is_zero = true;
-    }
-    if (have_noise) {
-        if (is_zero) { is_f64 = true; is_zero = false; v64 = 0.0 + z; }
-        else if (is_f64) v64 = v64 + z;
-        else v32 = v32 + (float)z;
-    }
-    if (is_zero) { *tt = (float)(p.length / 0.05); return 0.0f; }
-    if (is_f64) {
-        if (!(v64 > 0.0)) { *tt = (float)(p.length / 0.05); return 0.0f; }
-        *tt = (float)(p.length / v64);
-        return (float)v64;
-    }
-    if (!(v32 > 0.0f)) { *tt = (float)(p.length / 0.05); return 0.0f; }
-    *tt = (float)p.length / v32;
-    return v32;
+__device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int base, int kind,
+                                               int tf_mode, int dem_row, int tf_ptr) {
+    node_body<0>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr);
 }
 
-// Link.update_link_density_flow + update_speeds (link.py:133-188; Separator :430-452)
-__global__ void __launch_bounds__(kBlock) k_link_update(const __grid_constant__ Ctx c) {
+// Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
+__global__ void __launch_bounds__(kBlock, 4) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n_pairs = (size_t)(c.n.n_links / 2);
-    if (gid >= n_pairs * R) return;
-    const int pair = (int)(gid / R);
+    if (gid >= (size_t)c.n.n_nodes * R) return;
+    const int node = (int)(gid / R);
     const int rep = (int)(gid % R);
-    const int t = c.t, tau = c.t - 1;
-    const int l0 = 2 * pair;
-    const size_t e[2] = {(size_t)l0 * R + rep, (size_t)(l0 + 1) * R + rep};
-    const LinkP p[2] = {load_link(c, l0), load_link(c, l0 + 1)};
-    const double* inflow = H64(c, PNS_F64_INFLOW, t);
-    const double* outflow = H64(c, PNS_F64_OUTFLOW, t);
-    const float* num_prev = H32(c, PNS_F32_NUM_PED, tau);
-    float num[2], dens[2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const double delta = inflow[e[a]] - outflow[e[a]];
-        num[a] = (float)((double)num_prev[e[a]] + delta);
-        bool a64;
-        const double area = link_area(c, p[a], e[a], &a64);
-        dens[a] = div_by_area(num[a], area, a64);
-    }
-    float* num_t = H32(c, PNS_F32_NUM_PED, t);
-    float* dens_t = H32(c, PNS_F32_DENSITY, t);
-    float* speed_t = H32(c, PNS_F32_SPEED, t);
-    float* tt_t = H32(c, PNS_F32_TRAVEL_TIME, t);
-    float* flow_t = H32(c, PNS_F32_LINK_FLOW, t);
-    float* avg_t = H32(c, PNS_F32_AVG_TRAVEL_TIME, t);
-    double* bgw_t = H64(c, PNS_F64_BACK_GATE, t);
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const bool sep = is_sep(p[a]);
-        const bool noisy = p[a].sigma > 0.0;
-        double z = 0.0;
-        if (noisy) {
-            if (c.mode == PNS_RNG_TABLE) z = c.draw_n[e[a]];
-            else {
-                pns::DrawKey key;
-                key.t = (uint32_t)t; key.link = (uint32_t)(l0 + a); key.replica = (uint32_t)rep;
-                key.k0 = (uint32_t)c.io.seed; key.k1 = (uint32_t)(c.io.seed >> 32);
-                z = p[a].sigma * pns::normal_philox(key, 4u);
-            }
-        }
-        float tt;
-        const float v = speed_and_travel_time(p[a], dens[a], sep ? 0.0f : dens[1 - a], noisy, z, &tt);
-        num_t[e[a]] = num[a];
-        dens_t[e[a]] = dens[a];
-        speed_t[e[a]] = v;
-        tt_t[e[a]] = tt;
-        flow_t[e[a]] = v * dens[a];
-        float rs = c.s.runsum[e[a]] + tt;                                   // link.py:183-186
-        if (t >= c.n.window) {
-            rs = rs - H32(c, PNS_F32_TRAVEL_TIME, t - c.n.window)[e[a]];
-            avg_t[e[a]] = rs / (float)c.n.window;
-        }
-        c.s.runsum[e[a]] = rs;
-        if (sep) {
-            const double w = c.s.widths[2 * row32(c) + e[a]];
-            bgw_t[e[a]] = w;
-            H64(c, PNS_F64_SEP_WIDTH, t)[e[a]] = w;
-        } else {
-            bgw_t[e[a]] = c.s.widths[row32(c) + e[a]];
-        }
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);
+    const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
+    switch (m) {
+        case 0: case 1: break;   // isolated node / dead end without any turn
+        case 2: node_body<2>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 3: node_body<3>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 4: node_body<4>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 5: node_body<5>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        default: node_body_generic(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w); break;
     }
 }
 
@@ -596,7 +660,7 @@ __global__ void __launch_bounds__(kBlock) k_link_update(const __grid_constant__ 
 // Initial state (link.py:12-17, 56, 82-97, 425)
 __global__ void k_state_init(const __grid_constant__ Ctx c) {
     const int R = c.n.replicas;
-    const size_t n64 = row64(c), n32 = row32(c);
+    const size_t n64 = c.row64, n32 = c.row32;
     const int T = c.n.sim_steps + 1;
     const size_t total = (size_t)T * n64;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -605,15 +669,16 @@ __global__ void k_state_init(const __grid_constant__ Ctx c) {
         const size_t e = i % n64;
         const bool physical = e < n32;
         const int l = physical ? (int)(e / R) : 0;
+        const LinkP* p = physical ? c.n.classes + c.n.lk_class[l] : nullptr;
         for (int f = 0; f < c.s.n_f64; ++f) {
             double v = 0.0;
             if (f == PNS_F64_SENDING || f == PNS_F64_RECEIVING) v = -1.0;
-            else if (f == PNS_F64_BACK_GATE && physical) v = c.n.lk_width[l];
-            else if (f == PNS_F64_SEP_WIDTH && physical && (c.n.lk_flags[l] & 1)) v = c.n.lk_width[l] / 2;   // link.py:425
+            else if (f == PNS_F64_BACK_GATE && physical) v = c.n.lk_width[l];                  // link.py:56
+            else if (f == PNS_F64_SEP_WIDTH && physical && is_sep(*p)) v = c.n.lk_width[l] / 2;  // link.py:425
             H64(c, f, t)[e] = v;
         }
         if (physical) {
-            const float tt0 = c.n.lk_tt0[l];
+            const float tt0 = p->tt0;
             H32(c, PNS_F32_NUM_PED, t)[e] = 0.0f;
             H32(c, PNS_F32_DENSITY, t)[e] = 0.0f;
             H32(c, PNS_F32_SPEED, t)[e] = 0.0f;
@@ -633,22 +698,34 @@ __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const d
     key.t = (uint32_t)t; key.link = (uint32_t)i; key.replica = 0;
     key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
     if (kind == 0) out_i[i] = pns::binomial_philox(key, (uint32_t)site, n_trials[i], p[i]);
-    else if (kind == 1) out_d[i] = pns::normal_philox(key, (uint32_t)site);
-    else out_d[i] = (double)pns::det_pow08((float)p[i]);
+    else if (kind == 1) {
+        double g0, g1;
+        pns::normal_pair_philox(key, (uint32_t)site, &g0, &g1);
+        out_d[2 * i] = g0;
+        out_d[2 * i + 1] = g1;
+    } else out_d[i] = (double)pns::det_pow08((float)p[i]);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, int mode, int step_no) {
+// row_update / row_flows: draw-table rows (relative to the first step of the call) of the UPDATE
+// step and of the FLOWS step
+Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int phase, int t, int t_flows,
+             int mode, int row_update, int row_flows) {
     Ctx c;
     c.n = *net;
     c.s = *st;
     if (io) c.io = *io; else memset(&c.io, 0, sizeof c.io);
     c.t = t;
+    c.t_flows = t_flows;
+    c.phase = phase;
     c.mode = mode;
-    const size_t n32 = (size_t)net->n_links * net->replicas;
-    const int64_t row = io ? io->draw_row_stride * step_no : 0;
-    c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)row * 3 * n32 : nullptr;
-    c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)row * n32 : nullptr;
+    c.row64 = (size_t)net->n_cols64 * net->replicas;
+    c.row32 = (size_t)net->n_links * net->replicas;
+    c.fld64 = c.row64 * (size_t)(net->sim_steps + 1);
+    c.fld32 = c.row32 * (size_t)(net->sim_steps + 1);
+    const int64_t stride = io ? io->draw_row_stride : 0;
+    c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
+    c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
     return c;
 }
 
@@ -667,6 +744,77 @@ int launched(const char* what) {
     return e == cudaSuccess ? 0 : fail(what, e);
 }
 
+int check_step_io(const pns_net* net, const pns_step_io* io, int rng_mode) {
+    if (rng_mode != PNS_RNG_TABLE && rng_mode != PNS_RNG_PHILOX) return fail("TABLE or PHILOX mode only");
+    if (rng_mode == PNS_RNG_TABLE && !(io && io->draw_b)) return fail("TABLE mode needs draw_b");
+    if (net->n_demand_rows > 0 && !(io && io->demand)) return fail("demand table missing");
+    if (net->n_routed > 0 && !(io && io->od_w)) return fail("od weight table missing");
+    return 0;
+}
+
+struct StepSizes { size_t n_pair, n_grp, n_node; };
+StepSizes sizes_of(const pns_net* net) {
+    StepSizes z;
+    z.n_pair = (size_t)(net->n_links / 2) * net->replicas;
+    z.n_grp = (size_t)net->n_groups * net->replicas;
+    z.n_node = (size_t)net->n_nodes * net->replicas;
+    return z;
+}
+
+int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps, int rng_mode,
+              cudaStream_t s, double* ms, int64_t* launches) {
+    if (n_steps <= 0) return 0;
+    if (check_common(net, st, t0) || check_common(net, st, t0 + n_steps - 1)) return 1;
+    if (check_step_io(net, io, rng_mode)) return 1;
+    const StepSizes z = sizes_of(net);
+#ifndef PNS_HOST_EMULATION
+    cudaEvent_t* ev = nullptr;
+    const int per_step = 4;   // before pair | after pair | after route | after node
+    if (ms) {
+        ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * (per_step * (n_steps + 1)));
+        for (int i = 0; i < per_step * (n_steps + 1); ++i) cudaEventCreate(&ev[i]);
+    }
+#define PNS_MARK(k, j) do { if (ev) cudaEventRecord(ev[per_step * (k) + (j)], s); } while (0)
+#else
+    (void)ms; (void)launches;
+#define PNS_MARK(k, j) do { } while (0)
+#endif
+    // launch k (0..n_steps): pair kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
+    for (int k = 0; k <= n_steps; ++k) {
+        const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
+        const Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
+        PNS_MARK(k, 0);
+        if (z.n_pair) PNS_LAUNCH(k_link_pair, blocks_for(z.n_pair), kBlock, s, cp);
+        PNS_MARK(k, 1);
+        if (k == n_steps) break;
+        const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
+        if (z.n_grp) PNS_LAUNCH(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
+        PNS_MARK(k, 2);
+        if (z.n_node) PNS_LAUNCH(k_node_flows, blocks_for(z.n_node), kBlock, s, cn);
+        PNS_MARK(k, 3);
+    }
+#undef PNS_MARK
+#ifndef PNS_HOST_EMULATION
+    if (ev) {
+        const cudaError_t err = cudaStreamSynchronize(s);
+        for (int k = 0; k <= n_steps && err == cudaSuccess; ++k) {
+            float dt = 0.f;
+            cudaEventElapsedTime(&dt, ev[per_step * k], ev[per_step * k + 1]);
+            if (z.n_pair) { ms[0] += dt; launches[0] += 1; }
+            if (k == n_steps) break;
+            cudaEventElapsedTime(&dt, ev[per_step * k + 1], ev[per_step * k + 2]);
+            if (z.n_grp) { ms[1] += dt; launches[1] += 1; }
+            cudaEventElapsedTime(&dt, ev[per_step * k + 2], ev[per_step * k + 3]);
+            if (z.n_node) { ms[2] += dt; launches[2] += 1; }
+        }
+        for (int i = 0; i < per_step * (n_steps + 1); ++i) cudaEventDestroy(ev[i]);
+        free(ev);
+        if (err != cudaSuccess) return fail("pns_step_profiled", err);
+    }
+#endif
+    return launched("pns_step");
+}
+
 }  // namespace
 
 extern "C" {
@@ -676,9 +824,10 @@ const char* pns_last_error(void) { return g_err; }
 
 int pns_state_init(const pns_net* net, const pns_state* st, void* stream) {
     if (!net || !st) return fail("null net/state");
+    if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
     if (cudaMemsetAsync(st->err, 0, sizeof(int32_t) * net->replicas, (cudaStream_t)stream) != cudaSuccess)
         return fail("memset err", cudaGetLastError());
-    Ctx c = make_ctx(net, st, nullptr, 1, PNS_RNG_TABLE, 0);
+    const Ctx c = make_ctx(net, st, nullptr, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
     PNS_LAUNCH(k_state_init, 148 * 8, 256, (cudaStream_t)stream, c);
     return launched("k_state_init");
 }
@@ -686,32 +835,33 @@ int pns_state_init(const pns_net* net, const pns_state* st, void* stream) {
 int pns_link_flows(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, int rng_mode,
                    void* stream) {
     if (check_common(net, st, t)) return 1;
-    if (rng_mode == PNS_RNG_TABLE && !io->draw_b) return fail("TABLE mode needs draw_b");
-    if (rng_mode == PNS_RNG_REQUEST && !(io->req_kind && io->req_n1 && io->req_rf && io->req_sval && io->req_n3))
+    if (rng_mode == PNS_RNG_TABLE && !(io && io->draw_b)) return fail("TABLE mode needs draw_b");
+    if (rng_mode == PNS_RNG_REQUEST &&
+        !(io && io->req_kind && io->req_n1 && io->req_rf && io->req_sval && io->req_n3))
         return fail("REQUEST mode needs the req_* buffers");
-    const size_t n = (size_t)(net->n_links / 2) * net->replicas;
+    const size_t n = sizes_of(net).n_pair;
     if (n == 0) return 0;
-    const Ctx c = make_ctx(net, st, io, t, rng_mode, 0);
-    PNS_LAUNCH(k_link_flows, blocks_for(n), kBlock, (cudaStream_t)stream, c);
-    return launched("k_link_flows");
+    const Ctx c = make_ctx(net, st, io, PH_FLOWS, t, t, rng_mode, 0, 0);
+    PNS_LAUNCH(k_link_pair, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    return launched("k_link_pair[flows]");
 }
 
 int pns_route_probs(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, void* stream) {
     if (check_common(net, st, t)) return 1;
-    const size_t n = (size_t)net->n_groups * net->replicas;
+    const size_t n = sizes_of(net).n_grp;
     if (n == 0) return 0;
-    const Ctx c = make_ctx(net, st, io, t, PNS_RNG_TABLE, 0);
+    const Ctx c = make_ctx(net, st, io, 0, t, t, PNS_RNG_TABLE, 0, 0);
     PNS_LAUNCH(k_route_probs, blocks_for(n), kBlock, (cudaStream_t)stream, c);
     return launched("k_route_probs");
 }
 
 int pns_node_flows(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, void* stream) {
     if (check_common(net, st, t)) return 1;
-    if (net->n_demand_rows > 0 && !io->demand) return fail("demand table missing");
-    if (net->n_routed > 0 && !io->od_w) return fail("od weight table missing");
-    const size_t n = (size_t)net->n_nodes * net->replicas;
+    if (net->n_demand_rows > 0 && !(io && io->demand)) return fail("demand table missing");
+    if (net->n_routed > 0 && !(io && io->od_w)) return fail("od weight table missing");
+    const size_t n = sizes_of(net).n_node;
     if (n == 0) return 0;
-    const Ctx c = make_ctx(net, st, io, t, PNS_RNG_TABLE, 0);
+    const Ctx c = make_ctx(net, st, io, 0, t, t, PNS_RNG_TABLE, 0, 0);
     PNS_LAUNCH(k_node_flows, blocks_for(n), kBlock, (cudaStream_t)stream, c);
     return launched("k_node_flows");
 }
@@ -719,83 +869,28 @@ int pns_node_flows(const pns_net* net, const pns_state* st, const pns_step_io* i
 int pns_link_update(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, int rng_mode,
                     void* stream) {
     if (check_common(net, st, t)) return 1;
-    const size_t n = (size_t)(net->n_links / 2) * net->replicas;
+    const size_t n = sizes_of(net).n_pair;
     if (n == 0) return 0;
-    const Ctx c = make_ctx(net, st, io, t, rng_mode, 0);
-    PNS_LAUNCH(k_link_update, blocks_for(n), kBlock, (cudaStream_t)stream, c);
-    return launched("k_link_update");
+    const Ctx c = make_ctx(net, st, io, PH_UPDATE, t, t, rng_mode, 0, 0);
+    PNS_LAUNCH(k_link_pair, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    return launched("k_link_pair[update]");
 }
 
 int pns_step(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps, int rng_mode,
              void* stream) {
-    if (rng_mode != PNS_RNG_TABLE && rng_mode != PNS_RNG_PHILOX) return fail("pns_step: TABLE or PHILOX mode only");
-    if (check_common(net, st, t0) || check_common(net, st, t0 + n_steps - 1)) return 1;
-    if (rng_mode == PNS_RNG_TABLE && !io->draw_b) return fail("TABLE mode needs draw_b");
-    if (net->n_demand_rows > 0 && !io->demand) return fail("demand table missing");
-    if (net->n_routed > 0 && !io->od_w) return fail("od weight table missing");
-    const cudaStream_t s = (cudaStream_t)stream;
-    const size_t n_pair = (size_t)(net->n_links / 2) * net->replicas;
-    const size_t n_grp = (size_t)net->n_groups * net->replicas;
-    const size_t n_node = (size_t)net->n_nodes * net->replicas;
-    for (int k = 0; k < n_steps; ++k) {
-        const Ctx c = make_ctx(net, st, io, t0 + k, rng_mode, k);
-        if (n_pair) PNS_LAUNCH(k_link_flows, blocks_for(n_pair), kBlock, s, c);
-        if (n_grp) PNS_LAUNCH(k_route_probs, blocks_for(n_grp), kBlock, s, c);
-        if (n_node) PNS_LAUNCH(k_node_flows, blocks_for(n_node), kBlock, s, c);
-        if (n_pair) PNS_LAUNCH(k_link_update, blocks_for(n_pair), kBlock, s, c);
-    }
-    return launched("pns_step");
+    return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 int pns_step_profiled(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps,
                       int rng_mode, void* stream, double* ms, int64_t* launches) {
-#ifdef PNS_HOST_EMULATION
-    (void)ms; (void)launches;
-    return pns_step(net, st, io, t0, n_steps, rng_mode, stream);
-#else
-    if (rng_mode != PNS_RNG_TABLE && rng_mode != PNS_RNG_PHILOX) return fail("pns_step_profiled: TABLE or PHILOX mode only");
-    if (check_common(net, st, t0) || check_common(net, st, t0 + n_steps - 1)) return 1;
-    const cudaStream_t s = (cudaStream_t)stream;
-    const size_t n_pair = (size_t)(net->n_links / 2) * net->replicas;
-    const size_t n_grp = (size_t)net->n_groups * net->replicas;
-    const size_t n_node = (size_t)net->n_nodes * net->replicas;
-    const int per_step = 5;
-    const int n_ev = per_step * n_steps;
-    cudaEvent_t* ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * n_ev);
-    for (int i = 0; i < n_ev; ++i) cudaEventCreate(&ev[i]);
-    for (int k = 0; k < n_steps; ++k) {
-        const Ctx c = make_ctx(net, st, io, t0 + k, rng_mode, k);
-        cudaEvent_t* e = ev + per_step * k;
-        cudaEventRecord(e[0], s);
-        if (n_pair) PNS_LAUNCH(k_link_flows, blocks_for(n_pair), kBlock, s, c);
-        cudaEventRecord(e[1], s);
-        if (n_grp) PNS_LAUNCH(k_route_probs, blocks_for(n_grp), kBlock, s, c);
-        cudaEventRecord(e[2], s);
-        if (n_node) PNS_LAUNCH(k_node_flows, blocks_for(n_node), kBlock, s, c);
-        cudaEventRecord(e[3], s);
-        if (n_pair) PNS_LAUNCH(k_link_update, blocks_for(n_pair), kBlock, s, c);
-        cudaEventRecord(e[4], s);
-    }
-    cudaError_t err = cudaStreamSynchronize(s);
-    const size_t counts[4] = {n_pair, n_grp, n_node, n_pair};
-    for (int k = 0; k < n_steps && err == cudaSuccess; ++k)
-        for (int j = 0; j < 4; ++j) {
-            float t = 0.f;
-            cudaEventElapsedTime(&t, ev[per_step * k + j], ev[per_step * k + j + 1]);
-            if (counts[j]) { ms[j] += t; launches[j] += 1; }
-        }
-    for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
-    free(ev);
-    if (err != cudaSuccess) return fail("pns_step_profiled", err);
-    return launched("pns_step_profiled");
-#endif
+    return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, ms, launches);
 }
 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,
                      int32_t* out_i, double* out_d, void* stream) {
     if (n <= 0) return 0;
     PNS_LAUNCH(k_rng_selftest, (n + 127) / 128, 128, (cudaStream_t)stream, kind, n, n_trials, p, seed, t, site, out_i,
-                                                                       out_d);
+               out_d);
     return launched("k_rng_selftest");
 }
 

@@ -45,7 +45,7 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 
 // 53-bit uniform in [0, 1) from two words.
 __host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
-    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);   // exact: power of two
 }
 
 // ---- deterministic elementary functions (fdlibm-style kernels, basic operations only) ------
@@ -73,14 +73,15 @@ __host__ __device__ inline double det_log(double x) {  // x > 0, normal
     return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
 }
 
-__host__ __device__ inline double det_exp(double x) {  // x <= 0
+__host__ __device__ inline double det_exp(double x) {  // |x| < 700
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
                  P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
                  P5 = 4.13813679705723846039e-08;
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double invln2 = 1.44269504088896338700e+00;
     if (x < -700.0) return 0.0;
-    const int k = (int)(invln2 * x - 0.5);  // truncation toward zero of a negative number
+    if (x > 700.0) x = 700.0;
+    const int k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));  // nearest integer (C cast truncates)
     const double dk = (double)k;
     const double hi = x - dk * ln2_hi;
     const double lo = dk * ln2_lo;
@@ -89,7 +90,7 @@ __host__ __device__ inline double det_exp(double x) {  // x <= 0
     const double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
     const double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
     union { double d; uint64_t u; } sc;
-    sc.u = (uint64_t)(k + 1023) << 52;  // 2^k, k >= -1010
+    sc.u = (uint64_t)(k + 1023) << 52;  // 2^k, |k| <= 1010
     return y * sc.d;
 }
 
@@ -110,6 +111,28 @@ __host__ __device__ inline double det_cos_k(double x) {  // |x| <= pi/4
     const double z = x * x;
     const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
     return (1.0 - 0.5 * z) + z * r;
+}
+
+// (cos, sin)(2*pi*u), u in [0, 1)
+__host__ __device__ inline void det_sincos2pi(double u, double* cos_out, double* sin_out) {
+    const double half_pi = 1.5707963267948966;
+    const double u4 = u * 4.0;
+    const int q = (int)u4;  // 0..3
+    const double f = u4 - (double)q;
+    double c, s;
+    if (f <= 0.5) {
+        const double a = f * half_pi;
+        c = det_cos_k(a);
+        s = det_sin_k(a);
+    } else {
+        const double a = (1.0 - f) * half_pi;
+        c = det_sin_k(a);
+        s = det_cos_k(a);
+    }
+    if (q == 0) { *cos_out = c; *sin_out = s; }
+    else if (q == 1) { *cos_out = -s; *sin_out = c; }
+    else if (q == 2) { *cos_out = -c; *sin_out = -s; }
+    else { *cos_out = s; *sin_out = -c; }
 }
 
 // cos(2*pi*u), u in [0, 1)
@@ -165,7 +188,12 @@ __host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
 }
 
 // Exact Binomial(n, p); chunks of 512 trials keep q^m representable (binomial additivity).
-__host__ __device__ inline int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+inline
+#endif
+int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
     if (n <= 0 || !(p > 0.0)) return 0;
     if (p >= 1.0) return n;
     const bool flip = p > 0.5;
@@ -196,6 +224,24 @@ __host__ __device__ inline double normal_philox(const DrawKey& key, uint32_t sit
     rad = __builtin_sqrt(rad);
 #endif
     return rad * det_cos2pi(u2);
+}
+
+// Two independent standard normals from one Philox block (Box-Muller, both branches): the two
+// directions of a link pair share the block, the even link takes the cosine branch.
+__host__ __device__ inline void normal_pair_philox(const DrawKey& key, uint32_t site, double* g0, double* g1) {
+    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
+    const double u1 = 1.0 - u53(w.v[0], w.v[1]);  // (0, 1]
+    const double u2 = u53(w.v[2], w.v[3]);
+    double rad = -2.0 * det_log(u1);
+#ifdef __CUDA_ARCH__
+    rad = __dsqrt_rn(rad);
+#else
+    rad = __builtin_sqrt(rad);
+#endif
+    double cs, sn;
+    det_sincos2pi(u2, &cs, &sn);
+    *g0 = rad * cs;
+    *g1 = rad * sn;
 }
 
 }  // namespace pns

@@ -21,9 +21,7 @@ import torch
 from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
-_NET_ARRAYS = ("lk_length", "lk_width", "lk_vf", "lk_kc", "lk_kj", "lk_gamma", "lk_act", "lk_bi",
-               "lk_sigma", "lk_tt0", "lk_fftau", "lk_swtau", "lk_flags",
-               "nd_ptr", "nd_in_col", "nd_out_col", "nd_kind", "nd_dem_row", "nd_tf_ptr", "nd_routed",
+_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed",
                "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
@@ -62,6 +60,9 @@ class Engine:
 
         # ---- immutable plan ------------------------------------------------------------------
         self._net_t = {k: torch.from_numpy(np.ascontiguousarray(p[k])).to(dev) for k in _NET_ARRAYS}
+        cls_bytes = np.ascontiguousarray(p["classes"]).view(np.uint8).reshape(-1)
+        self._net_t["classes"] = torch.from_numpy(cls_bytes.copy()).to(dev)
+        self._meta_host = np.ascontiguousarray(p["nd_meta"]).copy()
         net = _native.PnsNet()
         net.abi_version = _native.ABI_VERSION
         net.n_links, net.n_nodes, net.n_cols64 = L, self.N, self.C64
@@ -72,8 +73,9 @@ class Engine:
         net.n_opts = len(p["rt_opt_link"])
         net.n_rows = len(p["rt_row_ptr"]) - 1
         net.n_terms = len(p["rt_term_opt"])
+        net.n_classes = len(p["classes"])
         net.unit_time = p["unit_time"]
-        for k in _NET_ARRAYS:
+        for k in _NET_ARRAYS + ("classes",):
             setattr(net, k, _ptr(self._net_t[k]))
         net.rt_temp, net.rt_alpha, net.rt_beta, net.rt_omega, net.rt_eps = [float(x) for x in p["rt_scalars"]]
         self.net = net
@@ -81,7 +83,7 @@ class Engine:
         # ---- mutable state ---------------------------------------------------------------------
         self.hist64 = torch.empty((self.n_f64, S + 1, self.C64 * R), dtype=torch.float64, device=dev)
         self.hist32 = torch.empty((6, S + 1, L * R), dtype=torch.float32, device=dev)
-        self.widths = torch.zeros((3, L * R), dtype=torch.float64, device=dev)
+        self.gate = torch.zeros((L * R,), dtype=torch.float64, device=dev)
         self.sep_np64 = torch.zeros((L * R,), dtype=torch.int32, device=dev)
         self.runsum = torch.zeros((L * R,), dtype=torch.float32, device=dev)
         self.tf_static = torch.zeros((max(1, p["n_edges"]),), dtype=torch.float64, device=dev)
@@ -89,7 +91,7 @@ class Engine:
         self.probs = torch.zeros((max(1, net.n_opts) * R,), dtype=torch.float64, device=dev)
         self.err = torch.zeros((R,), dtype=torch.int32, device=dev)
         st = _native.PnsState()
-        for k in ("hist64", "hist32", "widths", "sep_np64", "runsum", "tf_static", "tf_routed", "probs", "err"):
+        for k in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static", "tf_routed", "probs", "err"):
             setattr(st, k, _ptr(getattr(self, k)))
         st.n_f64 = self.n_f64
         self.state = st
@@ -145,13 +147,14 @@ class Engine:
         return torch.cuda.device(self.device) if not self.emulation else _NullCtx()
 
     # ------------------------------------------------------------------ setup
-    def initialise(self, widths: np.ndarray, sep_np64: np.ndarray = None, tf_static: np.ndarray = None,
-                   demand: np.ndarray = None, od_w: np.ndarray = None):
-        """widths [3, L] (broadcast over replicas) or [3, L*R]; demand [T, rows] or [T, rows*R]."""
+    def initialise(self, gate: np.ndarray, sep_np64: np.ndarray = None, tf_static: np.ndarray = None,
+                   demand: np.ndarray = None, od_w: np.ndarray = None, tf_supplied: np.ndarray = None):
+        """gate [L] (broadcast over replicas) or [L*R]: back gate width of plain links / lane width of
+        separators; tf_static [n_edges] with tf_supplied[node] marking user-supplied fractions;
+        demand [T, rows] or [T, rows*R]."""
         with self._guard():
-            self.set_widths(widths, sep_np64)
-            if tf_static is not None and len(tf_static):
-                self.tf_static[: len(tf_static)].copy_(torch.from_numpy(np.ascontiguousarray(tf_static)))
+            self.set_gate(gate, sep_np64)
+            self.set_static_fractions(tf_static, tf_supplied)
             if demand is not None:
                 self.set_demand(demand)
             if od_w is not None and od_w.size:
@@ -160,16 +163,28 @@ class Engine:
         self.t_done = 0
         self._initialised = True
 
-    def set_widths(self, widths, sep_np64=None):
-        w = torch.from_numpy(np.ascontiguousarray(widths, dtype=np.float64))
-        if w.shape[1] == self.L and self.R > 1:
-            w = w.repeat_interleave(self.R, dim=1)
-        self.widths.copy_(w)
+    def set_gate(self, gate, sep_np64=None):
+        g = torch.from_numpy(np.ascontiguousarray(gate, dtype=np.float64).reshape(-1))
+        if g.shape[0] == self.L and self.R > 1:
+            g = g.repeat_interleave(self.R)
+        self.gate.copy_(g)
         if sep_np64 is not None:
             f = torch.from_numpy(np.ascontiguousarray(sep_np64, dtype=np.int32))
             if f.shape[0] == self.L and self.R > 1:
                 f = f.repeat_interleave(self.R)
             self.sep_np64.copy_(f)
+
+    def set_static_fractions(self, tf_static, tf_supplied=None):
+        """Host-owned turning fractions.  Nodes flagged in tf_supplied read them (tf_mode 1); the
+        others use uniform 1/(m-1) computed in the kernel (tf_mode 0); routed nodes keep tf_mode 2."""
+        if tf_static is not None and len(tf_static):
+            self.tf_static[: len(tf_static)].copy_(torch.from_numpy(np.ascontiguousarray(tf_static, dtype=np.float64)))
+        if tf_supplied is not None:
+            meta = self._meta_host
+            mode = (meta[:, 1] >> 16) & 0xff
+            new_mode = np.where(mode == 2, 2, np.where(np.asarray(tf_supplied, dtype=bool), 1, 0))
+            meta[:, 1] = (meta[:, 1] & 0xffff) | (new_mode.astype(np.int32) << 16)
+            self._net_t["nd_meta"].copy_(torch.from_numpy(meta))
 
     def set_demand(self, demand):
         d = torch.from_numpy(np.ascontiguousarray(demand, dtype=np.float64))
@@ -201,19 +216,19 @@ class Engine:
                            if net.od_manager is not None else [])
         store = net._store
         od_w = (np.stack(self._od_arrays, axis=1) if self._od_arrays else None)
-        self.initialise(store.widths, store.sep_np64, net._static_fractions(), None, od_w)
+        tf, supplied = net._static_fractions()
+        self.initialise(store.gate, store.sep_np64, tf, None, od_w, supplied)
         store.widths_dirty = False
         net._fractions_dirty = False
 
     def _push_host_edits(self, net, t):
         store = net._store
         if store.widths_dirty:
-            self.set_widths(store.widths, store.sep_np64)
+            self.set_gate(store.gate, store.sep_np64)
             store.widths_dirty = False
         if net._fractions_dirty:
-            tf = net._static_fractions()
-            if len(tf):
-                self.tf_static[: len(tf)].copy_(torch.from_numpy(tf))
+            tf, supplied = net._static_fractions()
+            self.set_static_fractions(tf, supplied)
             net._fractions_dirty = False
         if self._demand_nodes:
             row = np.array([float(n.demand[t - 1]) for n in self._demand_nodes], dtype=np.float64)
@@ -293,8 +308,8 @@ class Engine:
         self.t_done = t0 + n_steps - 1
 
     def run_profiled(self, t0: int, n_steps: int, rng_mode: int = _native.RNG_PHILOX):
-        """`run` with per-kernel CUDA-event timing; returns (ms[4], launches[4]) for the passes
-        link_flows, route_probs, node_flows, link_update.  Synchronises."""
+        """`run` with per-kernel CUDA-event timing; returns (ms[4], launches[4]) for the kernels
+        link_pair, route_probs, node_flows (slot 3 unused).  Synchronises."""
         ms = (C.c_double * 4)(0, 0, 0, 0)
         cnt = (C.c_int64 * 4)(0, 0, 0, 0)
         io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
@@ -340,8 +355,10 @@ class Engine:
         p = self.plan
         if p["nd_routed"][node_index] < 0:
             return None
-        a, b = p["nd_tf_ptr"][node_index], p["nd_tf_ptr"][node_index + 1]
-        return self.tf_routed.view(-1, self.R)[a:b, 0].cpu().numpy()
+        meta = p["nd_meta"][node_index]
+        m = int(meta[1]) & 0xff
+        a = int(meta[3])
+        return self.tf_routed.view(-1, self.R)[a:a + m * (m - 1), 0].cpu().numpy()
 
     def history(self, field: str) -> torch.Tensor:
         """Device view [S+1, columns, R] of one field."""

@@ -43,8 +43,9 @@ def default_origins(size: int, stride: int = 64):
 
 
 def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=None,
-                    peak_lambda=50, base_lambda=30, demand_seed=0):
-    """Returns (plan, widths[3, L], tf_static[n_edges], demand[S, rows]) for `Engine`."""
+                    peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False):
+    """Returns (plan, gate[L], tf_static[n_edges], demand[S, rows]) for `Engine`.
+    locality_order=True lists nodes by id instead of the reference's creation order."""
     lk = dict(DEFAULT_LINK)
     lk.update(link or {})
     n = size
@@ -76,6 +77,11 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         if has_down[i] and not seen[i + n]:
             seen[i + n] = True; order[k] = i + n; k += 1
     assert k == N
+    if locality_order:
+        # Node order only fixes the visiting order of the reference's sequential RNG; with
+        # counter-based draws any order gives the same result, and id order keeps the links of
+        # neighbouring threads adjacent in memory.
+        order = ids.copy()
 
     degree = (r > 0).astype(int) + (c > 0) + has_right + has_down
     # network.py:141-167: degree 2 -> one-to-one unless O/D; degree 1 -> one-to-one + virtual; else regular
@@ -115,23 +121,20 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     dem_row = np.where(virtual[order], vrank[order], -1).astype(np.int32)
     edges = (m_o * (m_o - 1)).astype(np.int64)
     tf_ptr = np.concatenate([[0], np.cumsum(edges)]).astype(np.int32)
+    assert (out_col == (in_col ^ 1)).all()
+    meta = np.stack([nd_ptr[:-1], (m_o | (kind[order].astype(np.int64) << 8)).astype(np.int32),
+                     dem_row, tf_ptr[:-1]], axis=1).astype(np.int32)
 
-    f64 = lambda v: np.full(L, float(v), dtype=np.float64)
-    length, vf, kc, kj = lk["length"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"]
-    tt0 = np.float32(min(length / vf, length / 0.05))
-    shock = (vf * kc) / (kj - kc)
+    from .plan import class_record, CLASS_DTYPE
+    rec = class_record(lk["length"], lk["width"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"],
+                       lk["gamma"], lk["activity_probability"], lk["bi_factor"], lk["speed_noise_std"],
+                       lk["fd_type"], False, unit_time)
     plan = dict(
         n_links=L, n_nodes=N, sim_steps=int(sim_steps), unit_time=float(unit_time),
         window=int(round(100 / unit_time)),
-        lk_length=f64(length), lk_width=f64(lk["width"]), lk_vf=f64(vf), lk_kc=f64(kc), lk_kj=f64(kj),
-        lk_gamma=f64(lk["gamma"]), lk_act=f64(lk["activity_probability"]), lk_bi=f64(lk["bi_factor"]),
-        lk_sigma=f64(lk["speed_noise_std"]), lk_tt0=np.full(L, tt0, dtype=np.float32),
-        lk_fftau=np.full(L, round(tt0 / unit_time), dtype=np.int32),
-        lk_swtau=np.full(L, round(length / (shock * unit_time)), dtype=np.int32),
-        lk_flags=np.full(L, FD_TYPES[lk["fd_type"]] << 1, dtype=np.int32),
-        has_separators=False,
-        nd_ptr=nd_ptr, nd_in_col=in_col, nd_out_col=out_col, nd_kind=kind[order].astype(np.int32),
-        nd_dem_row=dem_row, nd_tf_ptr=tf_ptr, nd_routed=np.full(N, -1, dtype=np.int32),
+        classes=np.array([rec], dtype=CLASS_DTYPE).reshape(1), lk_class=np.zeros(L, dtype=np.int32),
+        lk_width=np.full(L, float(lk["width"])), has_separators=False,
+        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32),
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,
     )
@@ -144,7 +147,7 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     plan["rt_opt_dist"] = np.zeros(0)
     plan["rt_scalars"] = np.array([0.1, 1.0, 0.05, 0.05, 0.0])
 
-    widths = np.tile(f64(lk["width"]), (3, 1))
+    gate = np.full(L, float(lk["width"]))
     tf_static = np.repeat(1.0 / np.maximum(m_o - 1, 1), edges)      # uniform 1/(m-1), network.py:269-271
 
     # demand rows in virtual-owner creation order; Poisson around two gaussian peaks
@@ -159,4 +162,4 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     for node in vo:
         if is_origin[node]:
             demand[:, vrank[node]] = np.random.poisson(lam=lam)
-    return plan, widths, tf_static, demand
+    return plan, gate, tf_static, demand

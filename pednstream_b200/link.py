@@ -88,31 +88,34 @@ class Link(BaseLink):
         self.free_flow_tau = round(self.travel_time0 / unit_time)
         self.avg_travel_time_window = round(100 / unit_time)
         self.shockwave_tau = round(self.length / (self.shockwave_speed * unit_time))
-        store.set_width_row(index, self._initial_widths())
+        store.add_link_gate(index, self._initial_gate(), self.is_separator)
 
-    def _initial_widths(self):
-        return (self._width, self._width, self._width)   # front gate, back gate, (unused) separator
+    def _initial_gate(self):
+        return self._width
 
-    # --- widths -----------------------------------------------------------------------
+    # --- widths ------------------------------------------------------------------------
+    # One value per directed link lives in the store (and on the device): the back gate width.
+    # The reference's setters keep front_gate(l) == back_gate(reverse(l)) (link.py:110-126), so the
+    # front gate is read from / written to the reverse link's entry.
     @property
     def width(self):
         return self._width
 
     @property
-    def _front_gate_width(self):
-        return self._store.get_width(0, self.index)
-
-    @_front_gate_width.setter
-    def _front_gate_width(self, value):
-        self._store.set_width(0, self.index, value)
-
-    @property
     def _back_gate_width(self):
-        return self._store.get_width(1, self.index)
+        return self._store.get_gate(self.index)
 
     @_back_gate_width.setter
     def _back_gate_width(self, value):
-        self._store.set_width(1, self.index, value)
+        self._store.set_gate(self.index, value)
+
+    @property
+    def _front_gate_width(self):
+        return self._store.get_gate(self.index ^ 1)
+
+    @_front_gate_width.setter
+    def _front_gate_width(self, value):
+        self._store.set_gate(self.index ^ 1, value)
 
     @property
     def front_gate_width(self):
@@ -121,8 +124,6 @@ class Link(BaseLink):
     @front_gate_width.setter
     def front_gate_width(self, value):
         self._front_gate_width = value
-        if self.reverse_link:
-            self.reverse_link._back_gate_width = value
 
     @property
     def back_gate_width(self):
@@ -131,8 +132,6 @@ class Link(BaseLink):
     @back_gate_width.setter
     def back_gate_width(self, value):
         self._back_gate_width = value
-        if self.reverse_link:
-            self.reverse_link._front_gate_width = value
 
     @property
     def area(self):
@@ -155,19 +154,31 @@ class Separator(Link):
 
     is_separator = True
 
-    def _initial_widths(self):
-        half = self._width / 2
-        return (half, half, half)
+    def _initial_gate(self):
+        return self._width / 2
 
     separator_width_data = _series_property("separator_width_data")
 
+    # A separator's lane width, front gate and back gate are one value (link.py:462-478); the
+    # reverse direction holds the rest of the corridor.
     @property
     def _separator_width(self):
-        return self._store.get_width(2, self.index)
+        return self._store.get_gate(self.index)
 
     @_separator_width.setter
     def _separator_width(self, value):
-        self._store.set_width(2, self.index, value)
+        self._store.set_gate(self.index, value)
+
+    _front_gate_width = _separator_width
+    _back_gate_width = _separator_width
+
+    @property
+    def front_gate_width(self):
+        return self._separator_width
+
+    @property
+    def back_gate_width(self):
+        return self._separator_width
 
     @property
     def area(self):
@@ -180,14 +191,8 @@ class Separator(Link):
     @separator_width.setter
     def separator_width(self, value):
         self._separator_width = value
-        self._front_gate_width = value
-        self._back_gate_width = value
-        other = self.reverse_link
-        if other:
-            rest = self._width - value
-            other._separator_width = rest
-            other._front_gate_width = rest
-            other._back_gate_width = rest
+        if self.reverse_link:
+            self.reverse_link._separator_width = self._width - value
 
     def get_density(self, time_step: int):
         return self.density[time_step]

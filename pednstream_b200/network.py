@@ -193,8 +193,7 @@ class Network:
         self._store.freeze(L, len(self._virtual_cols),
                            tt0=[l.travel_time0 for l in links],
                            window=round(100 / self.unit_time),
-                           bgw0=[l._width for l in links],
-                           is_separator=[l.is_separator for l in links])
+                           bgw0=[l._width for l in links])
 
     # ------------------------------------------------------------------ fractions
     def update_turning_fractions_per_node(self, node_ids: List[int], new_turning_fractions):
@@ -204,26 +203,27 @@ class Network:
     def _mark_fractions_dirty(self):
         self._fractions_dirty = True
 
+    def _stepped(self):
+        return self._engine is not None and self._engine.t_done > 0
+
     def _routed_fractions(self, node):
         if self._engine is None or self._engine.t_done == 0:
             return None
         return self._engine.routed_fractions(node.index)
 
-    def _static_fractions(self) -> np.ndarray:
-        """Concatenated per-node fractions; None => uniform 1/(m-1) (network.py:269-271)."""
-        out = []
+    def _static_fractions(self):
+        """(concatenated per-node fractions, per-node flag 'user supplied').  Nodes without
+        supplied fractions use uniform 1/(m-1) (network.py:269-271), evaluated on the device."""
+        out, supplied = [], []
         for node in self.nodes.values():
             tf = node._tf_static
+            supplied.append(tf is not None)
             if tf is None:
-                if node.edge_num > 0:
-                    tf = np.ones(node.edge_num) * (1 / (node.dest_num - 1))
-                else:
-                    tf = np.zeros(0)
-                node._tf_static = tf
+                tf = (np.ones(node.edge_num) * (1 / (node.dest_num - 1))) if node.edge_num > 0 else np.zeros(0)
             if len(tf) != node.edge_num:
                 raise ValueError(f"node {node.node_id}: expected {node.edge_num} turning fractions")
-            out.append(tf)
-        return np.concatenate(out) if out else np.zeros(0)
+            out.append(np.asarray(tf, dtype=np.float64))
+        return (np.concatenate(out) if out else np.zeros(0)), np.asarray(supplied, dtype=bool)
 
     # ------------------------------------------------------------------ device runtime
     @property

@@ -40,6 +40,8 @@ class Node:
             live = self._net._routed_fractions(self)
             if live is not None:
                 return live
+            if self._tf_static is None and self._net._stepped() and self.edge_num:
+                return np.ones(self.edge_num) * (1 / (self.dest_num - 1))     # network.py:269-271
         return self._tf_static
 
     @turning_fractions.setter

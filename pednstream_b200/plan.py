@@ -28,6 +28,57 @@ def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
 
+CLASS_DTYPE = np.dtype([
+    ("length", "f8"), ("area", "f8"), ("space", "f8"), ("kc", "f8"), ("vf", "f8"), ("kj", "f8"),
+    ("act", "f8"), ("sigma", "f8"),
+    ("kc32", "f4"), ("kj32", "f4"), ("kj_minus_kc32", "f4"), ("gamma32", "f4"), ("bi32", "f4"),
+    ("area32", "f4"), ("length32", "f4"), ("yp_coef32", "f4"), ("neg_vf32", "f4"), ("vf32", "f4"),
+    ("sm_gamma32", "f4"), ("inv_kj32", "f4"), ("max_tt32", "f4"), ("tt0", "f4"),
+    ("fftau", "i4"), ("swtau", "i4"), ("flags", "i4"), ("pad_", "i4")], align=True)   # = pns_link_class
+
+
+def class_record(length, width, vf, kc, kj, gamma, act, bi, sigma, fd_type, is_sep, unit_time):
+    """One pns_link_class row.  Every derived constant is evaluated here with the reference's own
+    Python expression (operand types and order as in src/LTM/link.py / src/utils/functions.py) and
+    stored in the precision numpy would use it in next to a float32 history value."""
+    f32 = np.float32
+    rec = np.zeros((), dtype=CLASS_DTYPE)
+    area = length * width                                   # link.py:131
+    tt0 = f32(min(length / vf, length / 0.05))              # link.py:63,83
+    shock = (vf * kc) / (kj - kc)                           # link.py:58,61
+    rec["length"], rec["area"], rec["space"] = length, area, kj * area          # link.py:386
+    rec["kc"], rec["vf"], rec["kj"], rec["act"], rec["sigma"] = kc, vf, kj, act, sigma
+    rec["kc32"], rec["kj32"], rec["kj_minus_kc32"] = f32(kc), f32(kj), f32(kj - kc)
+    rec["gamma32"], rec["bi32"], rec["area32"], rec["length32"] = f32(gamma), f32(bi), f32(area), f32(length)
+    rec["yp_coef32"] = f32((kc * vf) / (kj - kc))           # functions.py:123
+    rec["neg_vf32"] = f32(-vf)                              # functions.py:118
+    rec["vf32"] = f32(vf)                                   # functions.py:126
+    rec["sm_gamma32"] = f32(vf * kc)                        # functions.py:108,128
+    rec["inv_kj32"] = f32(1 / kj)                           # functions.py:128
+    rec["max_tt32"] = f32(length / 0.05)                    # link.py:63,177
+    rec["tt0"] = tt0
+    rec["fftau"] = round(tt0 / unit_time)                   # link.py:86
+    rec["swtau"] = round(length / (shock * unit_time))      # link.py:380
+    rec["flags"] = (1 if is_sep else 0) | (FD_TYPES[fd_type] << 1)
+    return rec
+
+
+def link_classes(links, unit_time):
+    """Deduplicate link parameter sets: returns (classes[CLASS_DTYPE], lk_class[int32])."""
+    seen, rows, idx = {}, [], []
+    for l in links:
+        key = (l.length, l._width, l.free_flow_speed, l.k_critical, l.k_jam, l.gamma,
+               l.activity_probability, l.bi_factor, l.speed_noise_std, l.fd_type, bool(l.is_separator))
+        k = seen.get(key)
+        if k is None:
+            k = seen[key] = len(rows)
+            rec = class_record(*key, unit_time)
+            assert int(rec["fftau"]) == l.free_flow_tau and int(rec["swtau"]) == l.shockwave_tau
+            rows.append(rec)
+        idx.append(k)
+    return np.array(rows, dtype=CLASS_DTYPE).reshape(len(rows)), _i32(idx)
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -42,27 +93,21 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     p["unit_time"] = float(unit_time)
     p["window"] = int(round(100 / unit_time))
 
-    # ---- link table -------------------------------------------------------------------
-    p["lk_length"] = _f64([l.length for l in links])
+    # ---- link classes + per-link class index ------------------------------------------------
+    classes, lk_class = link_classes(links, unit_time)
+    p["classes"] = classes
+    p["lk_class"] = lk_class
     p["lk_width"] = _f64([l._width for l in links])
-    p["lk_vf"] = _f64([l.free_flow_speed for l in links])
-    p["lk_kc"] = _f64([l.k_critical for l in links])
-    p["lk_kj"] = _f64([l.k_jam for l in links])
-    p["lk_gamma"] = _f64([l.gamma for l in links])
-    p["lk_act"] = _f64([l.activity_probability for l in links])
-    p["lk_bi"] = _f64([l.bi_factor for l in links])
-    p["lk_sigma"] = _f64([l.speed_noise_std for l in links])
-    p["lk_tt0"] = np.asarray([l.travel_time0 for l in links], dtype=np.float32)
-    p["lk_fftau"] = _i32([l.free_flow_tau for l in links])
-    p["lk_swtau"] = _i32([l.shockwave_tau for l in links])
-    # bit0 separator, bits 1-2 fundamental diagram
-    p["lk_flags"] = _i32([(1 if l.is_separator else 0) | (FD_TYPES[l.fd_type] << 1) for l in links])
     p["has_separators"] = any(l.is_separator for l in links)
 
     # ---- node table -------------------------------------------------------------------
-    node_ptr, in_col, out_col, kind, dem_row, tf_ptr = [0], [], [], [], [], [0]
+    slot0, in_col, meta, tf_ptr = 0, [], [], 0
     n_virtual_nodes = 0
     demand_nodes = []
+    routed_ids = set()
+    if path_finder is not None:
+        routed_ids = {n.node_id for n in nodes
+                      if n.node_id in path_finder.nodes_in_paths and n.source_num > 2}
     for n in nodes:
         m = n.source_num
         if m != n.dest_num:
@@ -71,31 +116,26 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
             raise ValueError(f"node {n.node_id} has {m} link slots; the node kernel handles <= {MAX_DEGREE}")
         if n.kind == 0 and m != 2:
             raise ValueError(f"one-to-one node {n.node_id} must have exactly 2 slots, has {m}")
-        has_virtual = n.virtual_incoming_link is not None
         for lin, lout in zip(n.incoming_links, n.outgoing_links):
+            assert lout._col == lin._col ^ 1, "outgoing link of a slot must be the reverse of its incoming link"
             in_col.append(lin._col)
-            out_col.append(lout._col)
-        if has_virtual:
+        dem_row = -1
+        if n.virtual_incoming_link is not None:
             assert n.incoming_links[0] is n.virtual_incoming_link
             assert n.outgoing_links[0] is n.virtual_outgoing_link
-            dem_row.append(len(demand_nodes))
+            dem_row = len(demand_nodes)
             demand_nodes.append(n)
             n_virtual_nodes += 1
-        else:
-            dem_row.append(-1)
-        kind.append(n.kind)
-        node_ptr.append(len(in_col))
-        tf_ptr.append(tf_ptr[-1] + m * (m - 1))
-    p["nd_ptr"] = _i32(node_ptr)
+        tf_mode = 2 if n.node_id in routed_ids else 0
+        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr))
+        slot0 += m
+        tf_ptr += m * (m - 1)
+    p["nd_meta"] = _i32(meta).reshape(-1, 4)
     p["nd_in_col"] = _i32(in_col)
-    p["nd_out_col"] = _i32(out_col)
-    p["nd_kind"] = _i32(kind)
-    p["nd_dem_row"] = _i32(dem_row)
-    p["nd_tf_ptr"] = _i32(tf_ptr)
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
-    p["n_edges"] = tf_ptr[-1]
+    p["n_edges"] = tf_ptr
 
     # ---- route plan -------------------------------------------------------------------
     if path_finder is not None:
@@ -123,4 +163,5 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     routed_of = np.full(len(nodes), -1, dtype=np.int32)
     routed_of[p["rt_routed_nodes"]] = np.arange(len(p["rt_routed_nodes"]), dtype=np.int32)
     p["nd_routed"] = routed_of
+    assert set(np.nonzero(routed_of >= 0)[0].tolist()) == {n.index for n in nodes if n.node_id in routed_ids}
     return p

@@ -27,8 +27,9 @@ class StateStore:
         self.S = simulation_steps
         self.n_links = 0           # physical links (columns 0..L-1)
         self.n_virtual = 0         # virtual links (columns L..L+V-1 of the fp64 fields)
-        self._width_rows = []      # [front, back, separator] per physical link
-        self.widths = None         # float64 [3, L] once frozen
+        self._gate_rows = []       # back gate width / separator lane width per physical link
+        self._sep_rows = []
+        self.gate = None           # float64 [L] once frozen
         self.sep_np64 = None       # separator width was assigned a numpy float64 (dtype ledger)
         self.widths_dirty = True
         self._host = {}            # field -> ndarray
@@ -37,33 +38,32 @@ class StateStore:
         self._init = None          # per-link initial values (set by freeze)
 
     # ---- construction -------------------------------------------------------------------
-    def set_width_row(self, index, row):
-        assert index == len(self._width_rows)
-        self._width_rows.append(tuple(row))
+    def add_link_gate(self, index, value, is_separator):
+        assert index == len(self._gate_rows)
+        self._gate_rows.append(value)
+        self._sep_rows.append(bool(is_separator))
 
-    def freeze(self, n_links, n_virtual, tt0, window, bgw0, is_separator):
+    def freeze(self, n_links, n_virtual, tt0, window, bgw0):
         self.n_links, self.n_virtual = n_links, n_virtual
-        self.widths = np.array(self._width_rows, dtype=np.float64).T.copy().reshape(3, n_links)
+        self.gate = np.asarray(self._gate_rows, dtype=np.float64).reshape(n_links)
+        self.is_separator = np.asarray(self._sep_rows, dtype=bool).reshape(n_links)
+        self.has_separators = bool(self.is_separator.any())
         self.sep_np64 = np.zeros(n_links, dtype=np.int32)
         self._init = dict(tt0=np.asarray(tt0, dtype=np.float32), window=int(window),
                           bgw0=np.asarray(bgw0, dtype=np.float64))
-        self.is_separator = np.asarray(is_separator, dtype=bool)
-        self.has_separators = bool(self.is_separator.any())
 
     # ---- widths ---------------------------------------------------------------------------
-    def get_width(self, which, index):
-        if self.widths is None:
-            return self._width_rows[index][which]
-        v = self.widths[which, index]
-        return float(v)
+    def get_gate(self, index):
+        if self.gate is None:
+            return self._gate_rows[index]
+        return float(self.gate[index])
 
-    def set_width(self, which, index, value):
-        if self.widths is None:
-            row = list(self._width_rows[index]); row[which] = value
-            self._width_rows[index] = tuple(row)
+    def set_gate(self, index, value):
+        if self.gate is None:
+            self._gate_rows[index] = value
             return
-        self.widths[which, index] = value
-        if which == 2:
+        self.gate[index] = value
+        if self.is_separator[index]:
             self.sep_np64[index] = 1 if isinstance(value, np.floating) else 0
         self.widths_dirty = True
 

@@ -16,6 +16,8 @@
 #define __forceinline__ inline
 #define __launch_bounds__(x)
 #define __grid_constant__
+#define __noinline__
+struct int4 { int x, y, z, w; };
 
 struct emu_dim3 { unsigned x, y, z; };
 static thread_local emu_dim3 blockIdx, threadIdx, blockDim, gridDim;

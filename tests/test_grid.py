@@ -15,14 +15,15 @@ def test_grid_plan_equals_generic_plan(size, origins):
     np.random.seed(0)
     net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
     want = net.plan
-    got, widths, tf, demand = build_grid_plan(size, S, origins=origins, demand_seed=0)
+    got, gate, tf, demand = build_grid_plan(size, S, origins=origins, demand_seed=0)
     assert list(net.nodes.keys()) == got["node_order"].tolist()
     for k, v in want.items():
         if isinstance(v, np.ndarray):
-            assert np.array_equal(v, got[k]), k
+            assert v.dtype == got[k].dtype and np.array_equal(v, got[k]), k
     for k in ("n_links", "n_nodes", "n_virtual", "n_demand_rows", "n_edges", "window", "unit_time"):
         assert want[k] == got[k], k
-    assert np.array_equal(net._store.widths, widths)
-    assert np.array_equal(net._static_fractions(), tf)
+    assert np.array_equal(net._store.gate, gate)
+    assert np.array_equal(net._static_fractions()[0], tf)
+    assert not net._static_fractions()[1].any()
     for row, node in enumerate(want["demand_nodes"]):
         assert np.array_equal(np.asarray(node.demand, dtype=np.float64)[:S], demand[:, row]), node.node_id

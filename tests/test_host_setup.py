@@ -32,10 +32,15 @@ def test_build_and_plan(name):
                 assert lout.is_virtual
             else:
                 assert lin.reverse_link is lout
-    assert p["nd_ptr"][-1] == len(p["nd_in_col"]) == len(p["nd_out_col"])
+    meta = p["nd_meta"]
+    assert meta.shape == (len(net.nodes), 4)
+    assert int((meta[:, 1] & 0xff).sum()) == len(p["nd_in_col"])
+    assert len(p["classes"]) >= 1 and p["lk_class"].max() < len(p["classes"])
     assert p["rt_opt_ptr"][-1] == len(p["rt_opt_link"])
     assert p["rt_term_ptr"][-1] == len(p["rt_term_opt"])
-    assert len(p["rt_term_ptr"]) - 1 == sum(p["nd_tf_ptr"][n + 1] - p["nd_tf_ptr"][n] for n in p["rt_routed_nodes"])
+    m = meta[:, 1] & 0xff
+    assert len(p["rt_term_ptr"]) - 1 == int(sum(m[n] * (m[n] - 1) for n in p["rt_routed_nodes"]))
+    assert ((meta[:, 1] >> 16 == 2) == (p["nd_routed"] >= 0)).all()
 
 
 def test_long_corridor_node_kinds_and_separators():
@@ -46,6 +51,7 @@ def test_long_corridor_node_kinds_and_separators():
     assert type(net.links[(0, 1)]) is Link
     sep = net.links[(2, 3)]
     assert sep.separator_width == 2.0 and sep.front_gate_width == 2.0 and sep.area == 200.0
+    assert sep.back_gate_width == 2.0 and net.links[(3, 2)].separator_width == 2.0
     sep.separator_width = 2.5
     assert net.links[(3, 2)].separator_width == 1.5 and net.links[(3, 2)].back_gate_width == 1.5
     assert len(sep.separator_width_data) == 601 and sep.separator_width_data[0] == 2.0
