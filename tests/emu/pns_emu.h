@@ -14,7 +14,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __grid_constant__
 #define __noinline__
 struct int4 { int x, y, z, w; };
