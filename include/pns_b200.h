@@ -147,7 +147,31 @@ typedef struct pns_step_io {
     double *req_sval;       /* sending flow after the release stage when kind != 2 */
     int32_t *req_n3;        /* trials of R3 (-1: separator, no draw) */
     uint64_t seed;          /* PHILOX */
+    uint32_t replica_base;  /* PHILOX: global index of local replica 0 (replicas sharded over GPUs) */
+    uint32_t pad_;
 } pns_step_io;
+
+/* Control environment over R replicas (reference rl/pz_pednet_env.py, rl/builders.py, rl/discovery.py).
+ * Actions and observations are replica-major: actions[r][n_act], obs[r][n_obs], reward[r]. */
+enum { /* observation sources (rl/builders.py:119-177) */
+    PNS_OBS_INFLOW = 0, PNS_OBS_OUTFLOW = 1, PNS_OBS_REV_INFLOW = 2, PNS_OBS_REV_OUTFLOW = 3,
+    PNS_OBS_SHARED_DENSITY = 4,        /* link.get_density(t) */
+    PNS_OBS_SHARED_DENSITY_OVER_KJ = 5,/* link.get_density(t) / k_jam */
+    PNS_OBS_SPEED = 6, PNS_OBS_GATE = 7 /* link.back_gate_width */
+};
+typedef struct pns_env {
+    int32_t n_act, n_obs, n_reward_links, pad_;
+    const int32_t *act_link;   /* [n_act] controlled link (a separator agent lists its forward link) */
+    const int32_t *act_sep;    /* [n_act] 1 = separator action (also sets the reverse lane to W - v) */
+    const double *act_lo, *act_hi;     /* [n_act] clip bounds: gate [0, width]; separator [w_min, W - w_min] */
+    const double *act_max_delta;       /* [n_act] per-env-step rate limit (rl/builders.py:281-311) */
+    const double *act_total_width;     /* [n_act] corridor width W (separator actions) */
+    const int32_t *obs_link;   /* [n_obs] */
+    const int32_t *obs_src;    /* [n_obs] PNS_OBS_* */
+    const float *obs_div;      /* [n_obs] fixed normalisation divisor (1 = none, rl/builders.py:179-238) */
+    const int32_t *reward_link;/* [n_reward_links] controlled links of the first agent when it is a gate agent
+                                  (the reference rewards only that agent, pz_pednet_env.py:548-581) */
+} pns_env;
 
 int pns_abi_version(void);
 const char *pns_last_error(void);
@@ -191,6 +215,15 @@ int pns_step(const pns_net *net, const pns_state *st, const pns_step_io *io, int
  * ms[3] is unused) and the launch counts to launches[0..2].  Synchronises the stream before returning. */
 int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
                       int rng_mode, void *stream, double *ms, int64_t *launches);
+
+/* ActionApplier.apply_all_actions (rl/builders.py:264-352): rate-limit, clip, write the gate table. */
+int pns_env_apply_actions(const pns_net *net, const pns_state *st, const pns_env *env, const float *actions,
+                          void *stream);
+
+/* ObservationBuilder.build_observation for every agent (rl/builders.py:68-177) and
+ * PedNetParallelEnv._compute_rewards (rl/pz_pednet_env.py:548-581) at simulation row t. */
+int pns_env_observe(const pns_net *net, const pns_state *st, const pns_env *env, int t, float *obs,
+                    float *reward, void *stream);
 
 /* Draw `n` samples with the on-device Philox samplers (test hook for oracle/philox.py):
  * kind 0: binomial(n_trials[i], p[i]) -> out_i; kind 1: standard normal -> out_d. */

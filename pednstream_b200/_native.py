@@ -46,11 +46,21 @@ class PnsStepIO(C.Structure):
     _fields_ = [("demand", _p), ("od_w", _p), ("draw_b", _p), ("draw_n", _p),
                 ("draw_row_stride", C.c_int64),
                 ("req_kind", _p), ("req_n1", _p), ("req_rf", _p), ("req_sval", _p), ("req_n3", _p),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("pad_", C.c_uint32)]
+
+
+class PnsEnv(C.Structure):
+    _fields_ = [("n_act", _i32), ("n_obs", _i32), ("n_reward_links", _i32), ("pad_", _i32)] + \
+               [(k, _p) for k in ("act_link", "act_sep", "act_lo", "act_hi", "act_max_delta", "act_total_width",
+                                  "obs_link", "obs_src", "obs_div", "reward_link")]
+
+
+OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens": 4, "gdens/kjam": 5,
+           "speed": 6, "gate": 7}
 
 
 EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
-           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_rng_selftest")
+           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_env_apply_actions", "pns_env_observe", "pns_rng_selftest")
 
 _LIB = None
 
@@ -66,6 +76,9 @@ def _declare(lib):
     lib.pns_link_update.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
     lib.pns_step.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p]
     lib.pns_step_profiled.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p, _p, _p]
+    env_p = C.POINTER(PnsEnv)
+    lib.pns_env_apply_actions.argtypes = [net_p, st_p, env_p, _p, _p]
+    lib.pns_env_observe.argtypes = [net_p, st_p, env_p, C.c_int, _p, _p, _p]
     lib.pns_rng_selftest.argtypes = [C.c_int, C.c_int, _p, _p, C.c_uint64, C.c_int, C.c_int, _p, _p, _p]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
                 if (noisy[1]) z[1] = c.draw_n[e[1]];
             } else {
                 pns::DrawKey key;
-                key.t = (uint32_t)t; key.link = (uint32_t)l0; key.replica = (uint32_t)rep; key.k0 = k0; key.k1 = k1;
+                key.t = (uint32_t)t; key.link = (uint32_t)l0; key.replica = (uint32_t)rep + c.io.replica_base; key.k0 = k0; key.k1 = k1;
                 double g0, g1;
                 pns::normal_pair_philox(key, 4u, &g0, &g1);
                 z[0] = pp[0]->sigma * g0;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
     for (int a = 0; a < 2; ++a) {
         const LinkP& p = *pp[a];
         pns::DrawKey key;
-        key.t = (uint32_t)c.t_flows; key.link = (uint32_t)(l0 + a); key.replica = (uint32_t)rep; key.k0 = k0; key.k1 = k1;
+        key.t = (uint32_t)c.t_flows; key.link = (uint32_t)(l0 + a); key.replica = (uint32_t)rep + c.io.replica_base; key.k0 = k0; key.k1 = k1;
         // front gate of a plain link is the back gate of its reverse (link.py:110-126); a separator's
         // gates both equal its lane width (link.py:462-478)
         const double front = is_sep(p) ? gate[a] : gate[1 - a];
@@ -656,6 +656,105 @@ __global__ void __launch_bounds__(kBlock, 4) k_node_flows(const __grid_constant_
     }
 }
 
+
+// =================================================================================================
+// Control environment (reference rl/builders.py, rl/pz_pednet_env.py)
+struct EnvCtx {
+    Ctx c;
+    pns_env env;
+    const float* actions;
+    float* obs;
+    float* reward;
+};
+
+// ActionApplier.clip_gater_action_value / clip_separator_action_value + setters
+// (rl/builders.py:281-352; link.py:121-126, 462-478)
+__global__ void __launch_bounds__(kBlock) k_env_actions(const __grid_constant__ EnvCtx x) {
+    const Ctx& c = x.c;
+    const int R = c.n.replicas;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)x.env.n_act * R) return;
+    const int a = (int)(gid / R), rep = (int)(gid % R);
+    const int l = x.env.act_link[a];
+    const size_t e = (size_t)l * R + rep;
+    double v = (double)x.actions[(size_t)rep * x.env.n_act + a];       // float(action[i])
+    const double cur = c.s.gate[e];
+    const double md = x.env.act_max_delta[a];
+    if (fabs(v - cur) > md) {
+        const double d = fmin(fmax(v - cur, -md), md);                   // np.clip
+        v = cur + d;
+    }
+    v = fmin(fmax(v, x.env.act_lo[a]), x.env.act_hi[a]);
+    c.s.gate[e] = v;
+    if (x.env.act_sep[a]) {
+        const size_t er = (size_t)(l ^ 1) * R + rep;
+        c.s.gate[er] = x.env.act_total_width[a] - v;
+        c.s.sep_np64[e] = 1;       // np.clip returns numpy float64: the lane area becomes a float64
+        c.s.sep_np64[er] = 1;
+    }
+}
+
+__device__ __forceinline__ float shared_density(const Ctx& c, int l, int rep, int t) {
+    const int R = c.n.replicas;
+    const LinkP& p = c.n.classes[c.n.lk_class[l]];
+    const size_t e = (size_t)l * R + rep;
+    if (is_sep(p)) return H32(c, PNS_F32_DENSITY, t)[e];
+    const float* num = H32(c, PNS_F32_NUM_PED, t);
+    const Area ar = link_area(c, p, e, 0.0);
+    return div_by_area(num[e] + num[(size_t)(l ^ 1) * R + rep], ar);
+}
+
+__global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ EnvCtx x) {
+    const Ctx& c = x.c;
+    const int R = c.n.replicas;
+    const int t = c.t;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_obs_threads = (size_t)x.env.n_obs * R;
+    if (gid < n_obs_threads) {
+        const int k = (int)(gid / R), rep = (int)(gid % R);
+        const int l = x.env.obs_link[k];
+        const size_t e = (size_t)l * R + rep, er = (size_t)(l ^ 1) * R + rep;
+        float v;
+        switch (x.env.obs_src[k]) {
+            case PNS_OBS_INFLOW: v = (float)H64(c, PNS_F64_INFLOW, t)[e]; break;
+            case PNS_OBS_OUTFLOW: v = (float)H64(c, PNS_F64_OUTFLOW, t)[e]; break;
+            case PNS_OBS_REV_INFLOW: v = (float)H64(c, PNS_F64_INFLOW, t)[er]; break;
+            case PNS_OBS_REV_OUTFLOW: v = (float)H64(c, PNS_F64_OUTFLOW, t)[er]; break;
+            case PNS_OBS_SHARED_DENSITY: v = shared_density(c, l, rep, t); break;
+            case PNS_OBS_SHARED_DENSITY_OVER_KJ: v = shared_density(c, l, rep, t) / c.n.classes[c.n.lk_class[l]].kj32; break;
+            case PNS_OBS_SPEED: v = H32(c, PNS_F32_SPEED, t)[e]; break;
+            default: v = (float)c.s.gate[e]; break;
+        }
+        const float d = x.env.obs_div[k];
+        if (d != 1.0f) v = v / d;
+        x.obs[(size_t)rep * x.env.n_obs + k] = v;
+        return;
+    }
+    // reward: one thread per replica (pz_pednet_env.py:548-581, float32 arithmetic as numpy does it)
+    const size_t rid = gid - n_obs_threads;
+    if (rid >= (size_t)R) return;
+    const int rep = (int)rid;
+    const int n = x.env.n_reward_links;
+    float total = 0.0f, rho[PNS_MAX_DEGREE];
+    for (int i = 0; i < n; ++i) {
+        const int l = x.env.reward_link[i];
+        const size_t e = (size_t)l * R + rep, er = (size_t)(l ^ 1) * R + rep;
+        rho[i] = shared_density(c, l, rep, t);
+        const float* tt = H32(c, PNS_F32_TRAVEL_TIME, t);
+        total = total - (tt[e] + tt[er]);
+        if (rho[i] > 4.0f) total = total - 10.0f * (rho[i] - c.n.classes[c.n.lk_class[l]].kc32);
+    }
+    if (n > 1) {
+        float s = rho[0];
+        for (int i = 1; i < n; ++i) s = s + rho[i];
+        const float mean = s / (float)n;
+        float d = fabsf(rho[0] - mean);
+        for (int i = 1; i < n; ++i) d = d + fabsf(rho[i] - mean);
+        total = total - 10.0f * (d / (float)n);
+    }
+    x.reward[rep] = total;
+}
+
 // =================================================================================================
 // Initial state (link.py:12-17, 56, 82-97, 425)
 __global__ void k_state_init(const __grid_constant__ Ctx c) {
@@ -884,6 +983,33 @@ int pns_step(const pns_net* net, const pns_state* st, const pns_step_io* io, int
 int pns_step_profiled(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps,
                       int rng_mode, void* stream, double* ms, int64_t* launches) {
     return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, ms, launches);
+}
+
+int pns_env_apply_actions(const pns_net* net, const pns_state* st, const pns_env* env, const float* actions,
+                          void* stream) {
+    if (!net || !st || !env || !actions) return fail("pns_env_apply_actions: null argument");
+    if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
+    const size_t n = (size_t)env->n_act * net->replicas;
+    if (n == 0) return 0;
+    EnvCtx x;
+    x.c = make_ctx(net, st, nullptr, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
+    x.env = *env; x.actions = actions; x.obs = nullptr; x.reward = nullptr;
+    PNS_LAUNCH(k_env_actions, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    return launched("k_env_actions");
+}
+
+int pns_env_observe(const pns_net* net, const pns_state* st, const pns_env* env, int t, float* obs, float* reward,
+                    void* stream) {
+    if (!net || !st || !env || !obs || !reward) return fail("pns_env_observe: null argument");
+    if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
+    if (t < 0 || t > net->sim_steps) return fail("pns_env_observe: row out of range");
+    if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_observe: too many reward links");
+    const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
+    EnvCtx x;
+    x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
+    x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward;
+    PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    return launched("k_env_observe");
 }
 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,
