@@ -90,7 +90,7 @@ def load(path: str = None):
     global _LIB
     if path is None and _LIB is not None:
         return _LIB
-    target = path or LIB_PATH
+    target = path or os.environ.get("PNS_B200_LIB") or LIB_PATH     # env override: kernel tuning builds
     if not os.path.exists(target):
         raise RuntimeError(
             f"pednstream_b200: native CUDA library not found at {target}. Build it with "

@@ -50,6 +50,9 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 }
 
 constexpr int kBlock = 128;
+#ifndef PNS_MIN_BLOCKS
+#define PNS_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (tuning knob)
+#endif
 constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
 struct Ctx {
@@ -64,6 +67,38 @@ struct Ctx {
     const double* draw_n;   // TABLE: R4 noise for step t
     size_t row64, row32;    // elements per history row
     size_t fld64, fld32;    // elements per history field
+    // rows known at launch time, resolved on the host (saves 64-bit index arithmetic per access)
+    const double *u_inflow, *u_outflow;                 // UPDATE inputs, row t
+    const float *u_num_prev, *u_tt_old;                 // row t-1; row t-window (null while t < window)
+    float *u_num, *u_dens, *u_speed, *u_tt, *u_flow, *u_avg;   // UPDATE outputs, row t
+    double *u_bgw, *u_sepw;
+    const float *f_num, *f_dens, *f_avg;                // FLOWS inputs, row tau = t_flows-1
+    const double *f_cin, *f_cou, *f_sndp, *f_rcvp;      // rows tau, tau, tau-1 (wrapped), tau-1
+    double *f_snd, *f_rcv;                              // FLOWS outputs, row tau
+    const double *n_snd, *n_rcv, *n_coutp, *n_cinp, *n_demand;   // node inputs, row t-1
+    double *n_outflow, *n_inflow, *n_cout, *n_cin;      // node outputs, row t
+};
+
+template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
+template <> struct Lanes<true> {   // single replica: adjacent columns -> one vector access
+    static __device__ __forceinline__ void ld(const double* row, size_t e0, size_t, double* o) {
+        const double2 v = *reinterpret_cast<const double2*>(row + e0); o[0] = v.x; o[1] = v.y;
+    }
+    static __device__ __forceinline__ void ld(const float* row, size_t e0, size_t, float* o) {
+        const float2 v = *reinterpret_cast<const float2*>(row + e0); o[0] = v.x; o[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(double* row, size_t e0, size_t, double a, double b) {
+        double2 v; v.x = a; v.y = b; *reinterpret_cast<double2*>(row + e0) = v;
+    }
+    static __device__ __forceinline__ void st(float* row, size_t e0, size_t, float a, float b) {
+        float2 v; v.x = a; v.y = b; *reinterpret_cast<float2*>(row + e0) = v;
+    }
+};
+template <> struct Lanes<false> {  // batched replicas: the two links are R elements apart
+    static __device__ __forceinline__ void ld(const double* row, size_t e0, size_t e1, double* o) { o[0] = row[e0]; o[1] = row[e1]; }
+    static __device__ __forceinline__ void ld(const float* row, size_t e0, size_t e1, float* o) { o[0] = row[e0]; o[1] = row[e1]; }
+    static __device__ __forceinline__ void st(double* row, size_t e0, size_t e1, double a, double b) { row[e0] = a; row[e1] = b; }
+    static __device__ __forceinline__ void st(float* row, size_t e0, size_t e1, float a, float b) { row[e0] = a; row[e1] = b; }
 };
 
 // ---- addressing ---------------------------------------------------------------------------------
@@ -108,6 +143,7 @@ __device__ __forceinline__ Area link_area(const Ctx& c, const LinkP& p, size_t e
     return a;
 }
 __device__ __forceinline__ float div_by_area(float x, const Area& a) {
+    if (x == 0.0f) return 0.0f;   // exact (areas are positive); keeps empty links off the division slow path
     return a.f64 ? (float)((double)x / a.area) : x / a.area32;
 }
 
@@ -166,7 +202,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
     double flow = pymin(boundary, gate_cap);
     const double original = flow;
     if (flow > 0.0) {
-        const float rf = clip01(dens / p.kj32);
+        const float rf = dens == 0.0f ? 0.0f : clip01(dens / p.kj32);
         o.rf = rf;
         bool draw = true;
         if (dens <= p.kc32) {
@@ -211,13 +247,14 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
 // (link.py:372-405, 480-507)
 __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev,
                                                  const Area& ar, double back_gate, double cum_in_tau,
-                                                 double rcv_prev, const pns::DrawKey& key, int* n3) {
-    const int lag_i = tau + 1 - p.swtau;
+                                                 double cum_out_lag, double rcv_prev, const pns::DrawKey& key,
+                                                 int* n3) {
+    const int lag_i = tau + 1 - p.swtau;   // cum_out_lag = cumulative_outflow[lag_i] when lag_i >= 0
     double bound;
     if (is_sep(p)) {
         *n3 = -1;
         if (lag_i < 0) bound = ar.space;
-        else bound = (H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + ar.space) - cum_in_tau;
+        else bound = (cum_out_lag + ar.space) - cum_in_tau;
     } else {
         const int trials = (int)num_rev;        // numpy casts the float32 count to int64 (truncation)
         *n3 = trials;
@@ -228,7 +265,7 @@ __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, s
         if (lag_i < 0) {
             bound = ar.space - (double)blockers;
         } else {
-            const double x = ((H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e] + ar.space) - (double)blockers) - cum_in_tau;
+            const double x = ((cum_out_lag + ar.space) - (double)blockers) - cum_in_tau;
             bound = x > 0.0 ? x : 0.0;
         }
     }
@@ -286,39 +323,62 @@ __device__ __forceinline__ float speed_and_travel_time(const LinkP& p, float k_s
 // =================================================================================================
 // UPDATE: Link.update_link_density_flow + update_speeds at row t (link.py:133-188; Separator :430-452)
 // FLOWS : sending/receiving flows of step t_flows (time index t_flows-1)
-__global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__ Ctx c) {
-    const int R = c.n.replicas;
+// Every load that does not depend on a computed lag is issued before the first arithmetic so the
+// whole batch is in flight at once; only cumulative_inflow[idx] and the diffusion taps are dependent.
+template <bool R1>
+__device__ __forceinline__ void link_pair_body(const Ctx& c) {
+    const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_pairs = (size_t)(c.n.n_links / 2);
     if (gid >= n_pairs * R) return;
-    const int pair = (int)(gid / R);
-    const int rep = (int)(gid % R);
+    const int pair = R1 ? (int)gid : (int)(gid / R);
+    const int rep = R1 ? 0 : (int)(gid % R);
     const int l0 = 2 * pair;
     const size_t e[2] = {(size_t)l0 * R + rep, (size_t)(l0 + 1) * R + rep};
+    typedef Lanes<R1> V;
+    const bool upd = c.phase & PH_UPDATE, flw = c.phase & PH_FLOWS;
+    const int tau = c.t_flows - 1;
+
     const LinkP* const pp[2] = {c.n.classes + __ldg(c.n.lk_class + l0), c.n.classes + __ldg(c.n.lk_class + l0 + 1)};
-    const double gate[2] = {c.s.gate[e[0]], c.s.gate[e[1]]};
+    double gate[2];
+    V::ld(c.s.gate, e[0], e[1], gate);
+    // ---- batch of independent loads --------------------------------------------------------
+    double din[2] = {0, 0}, dout[2] = {0, 0};
+    float np_[2] = {0, 0}, rs[2] = {0, 0}, tt_old[2] = {0, 0};
+    const bool windowed = c.u_tt_old != nullptr;
+    if (upd) {
+        V::ld(c.u_inflow, e[0], e[1], din);
+        V::ld(c.u_outflow, e[0], e[1], dout);
+        V::ld(c.u_num_prev, e[0], e[1], np_);
+        V::ld(c.s.runsum, e[0], e[1], rs);
+        if (windowed) V::ld(c.u_tt_old, e[0], e[1], tt_old);
+    }
+    double cin_tau[2] = {0, 0}, cou_tau[2] = {0, 0}, snd_prev[2] = {0, 0}, rcv_prev[2] = {0, 0}, cou_lag[2] = {0, 0};
+    float ld_num[2] = {0, 0}, ld_dens[2] = {0, 0}, ld_avg[2] = {0, 0};
+    if (flw) {
+        V::ld(c.f_cin, e[0], e[1], cin_tau);
+        V::ld(c.f_cou, e[0], e[1], cou_tau);
+        V::ld(c.f_sndp, e[0], e[1], snd_prev);
+        V::ld(c.f_rcvp, e[0], e[1], rcv_prev);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int lag_i = tau + 1 - pp[a]->swtau;                      // static shock-wave lag (link.py:380)
+            if (lag_i >= 0) cou_lag[a] = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e[a]];
+        }
+        if (!upd) {
+            V::ld(c.f_num, e[0], e[1], ld_num);
+            V::ld(c.f_dens, e[0], e[1], ld_dens);
+            V::ld(c.f_avg, e[0], e[1], ld_avg);
+        }
+    }
     Area ar[2];
     ar[0] = link_area(c, *pp[0], e[0], gate[0]);
     ar[1] = link_area(c, *pp[1], e[1], gate[1]);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
 
     LinkNow now[2];
-    if (c.phase & PH_UPDATE) {
+    if (upd) {
         const int t = c.t;
-        const double* inflow = H64(c, PNS_F64_INFLOW, t);
-        const double* outflow = H64(c, PNS_F64_OUTFLOW, t);
-        const float* num_prev = H32(c, PNS_F32_NUM_PED, t - 1);
-        const double din[2] = {inflow[e[0]], inflow[e[1]]};
-        const double dout[2] = {outflow[e[0]], outflow[e[1]]};
-        const float np_[2] = {num_prev[e[0]], num_prev[e[1]]};
-        const float rs[2] = {c.s.runsum[e[0]], c.s.runsum[e[1]]};
-        float tt_old[2] = {0.0f, 0.0f};
-        const bool windowed = t >= c.n.window;
-        if (windowed) {
-            const float* tt_w = H32(c, PNS_F32_TRAVEL_TIME, t - c.n.window);
-            tt_old[0] = tt_w[e[0]];
-            tt_old[1] = tt_w[e[1]];
-        }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             now[a].num = (float)((double)np_[a] + (din[a] - dout[a]));    // link.py:134-135
@@ -329,8 +389,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
         const bool noisy[2] = {pp[0]->sigma > 0.0, pp[1]->sigma > 0.0};
         if (noisy[0] | noisy[1]) {
             if (c.mode == PNS_RNG_TABLE) {
-                if (noisy[0]) z[0] = c.draw_n[e[0]];
-                if (noisy[1]) z[1] = c.draw_n[e[1]];
+                V::ld(c.draw_n, e[0], e[1], z);
             } else {
                 pns::DrawKey key;
                 key.t = (uint32_t)t; key.link = (uint32_t)l0; key.replica = (uint32_t)rep + c.io.replica_base; key.k0 = k0; key.k1 = k1;
@@ -340,61 +399,42 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
                 z[1] = pp[1]->sigma * g1;
             }
         }
-        float* num_t = H32(c, PNS_F32_NUM_PED, t);
-        float* dens_t = H32(c, PNS_F32_DENSITY, t);
-        float* speed_t = H32(c, PNS_F32_SPEED, t);
-        float* tt_t = H32(c, PNS_F32_TRAVEL_TIME, t);
-        float* flow_t = H32(c, PNS_F32_LINK_FLOW, t);
-        float* avg_t = H32(c, PNS_F32_AVG_TRAVEL_TIME, t);
-        double* bgw_t = H64(c, PNS_F64_BACK_GATE, t);
+        float v[2], tt[2], sum[2], lf[2];
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const LinkP& p = *pp[a];
-            const bool sep = is_sep(p);
-            float tt;
-            const float v = speed_and_travel_time(p, now[a].dens, sep ? 0.0f : now[1 - a].dens, noisy[a], z[a], &tt);
-            num_t[e[a]] = now[a].num;
-            dens_t[e[a]] = now[a].dens;
-            speed_t[e[a]] = v;
-            tt_t[e[a]] = tt;
-            flow_t[e[a]] = v * now[a].dens;                                // functions.py:97-101
-            float sum = rs[a] + tt;                                        // link.py:183-186
+            v[a] = speed_and_travel_time(p, now[a].dens, is_sep(p) ? 0.0f : now[1 - a].dens, noisy[a], z[a], &tt[a]);
+            lf[a] = v[a] * now[a].dens;                                    // functions.py:97-101
+            sum[a] = rs[a] + tt[a];                                        // link.py:183-186
             if (windowed) {
-                sum = sum - tt_old[a];
-                now[a].avg_tt = sum / (float)c.n.window;
-                avg_t[e[a]] = now[a].avg_tt;
+                sum[a] = sum[a] - tt_old[a];
+                now[a].avg_tt = sum[a] / (float)c.n.window;
             } else {
                 now[a].avg_tt = p.tt0;                                     // rows < window keep travel_time[0]
             }
-            c.s.runsum[e[a]] = sum;
-            bgw_t[e[a]] = gate[a];                                         // link.py:188, 451-452
-            if (sep) H64(c, PNS_F64_SEP_WIDTH, t)[e[a]] = gate[a];
         }
+        V::st(c.u_num, e[0], e[1], now[0].num, now[1].num);
+        V::st(c.u_dens, e[0], e[1], now[0].dens, now[1].dens);
+        V::st(c.u_speed, e[0], e[1], v[0], v[1]);
+        V::st(c.u_tt, e[0], e[1], tt[0], tt[1]);
+        V::st(c.u_flow, e[0], e[1], lf[0], lf[1]);
+        if (windowed) V::st(c.u_avg, e[0], e[1], now[0].avg_tt, now[1].avg_tt);
+        V::st(c.s.runsum, e[0], e[1], sum[0], sum[1]);
+        V::st(c.u_bgw, e[0], e[1], gate[0], gate[1]);                      // link.py:188, 451-452
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+            if (is_sep(*pp[a])) c.u_sepw[e[a]] = gate[a];
     }
-    if (!(c.phase & PH_FLOWS)) return;
+    if (!flw) return;
 
-    const int tau = c.t_flows - 1;
-    if (!(c.phase & PH_UPDATE)) {
-        const float* num = H32(c, PNS_F32_NUM_PED, tau);
-        const float* den = H32(c, PNS_F32_DENSITY, tau);
-        const float* avg = H32(c, PNS_F32_AVG_TRAVEL_TIME, tau);
+    if (!upd) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-            now[a].num = num[e[a]];
-            now[a].dens = den[e[a]];
-            now[a].avg_tt = avg[e[a]];
+            now[a].num = ld_num[a];
+            now[a].dens = ld_dens[a];
+            now[a].avg_tt = ld_avg[a];
         }
     }
-    const double* cin = H64(c, PNS_F64_CUM_INFLOW, tau);
-    const double* cou = H64(c, PNS_F64_CUM_OUTFLOW, tau);
-    const int prev_i = wrap_index(c, tau - 1, rep);
-    const double* sndp = H64(c, PNS_F64_SENDING, prev_i);
-    const double* rcvp = H64(c, PNS_F64_RECEIVING, prev_i);
-    const double cin_tau[2] = {cin[e[0]], cin[e[1]]};
-    const double cou_tau[2] = {cou[e[0]], cou[e[1]]};
-    const double snd_prev[2] = {sndp[e[0]], sndp[e[1]]};
-    const double rcv_prev[2] = {rcvp[e[0]], rcvp[e[1]]};
-
     SendOut s[2];
     double r[2];
     int n3[2];
@@ -407,7 +447,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
         // gates both equal its lane width (link.py:462-478)
         const double front = is_sep(p) ? gate[a] : gate[1 - a];
         s[a] = sending_flow(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep, key);
-        r[a] = receiving_flow(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], rcv_prev[a], key, &n3[a]);
+        r[a] = receiving_flow(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], cou_lag[a], rcv_prev[a], key,
+                              &n3[a]);
     }
     if (c.mode == PNS_RNG_REQUEST) {
 #pragma unroll
@@ -420,16 +461,15 @@ __global__ void __launch_bounds__(kBlock, 4) k_link_pair(const __grid_constant__
         }
         return;
     }
-    double* snd = H64(c, PNS_F64_SENDING, tau);
-    double* rcv = H64(c, PNS_F64_RECEIVING, tau);
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        snd[e[a]] = s[a].flow;
-        // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
-        const double q = is_sep(*pp[a]) ? r[a] : r[a] - s[1 - a].flow;
-        rcv[e[a]] = pymax(q, 0.0);
-    }
+    // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
+    const double q0 = is_sep(*pp[0]) ? r[0] : r[0] - s[1].flow;
+    const double q1 = is_sep(*pp[1]) ? r[1] : r[1] - s[0].flow;
+    V::st(c.f_snd, e[0], e[1], s[0].flow, s[1].flow);
+    V::st(c.f_rcv, e[0], e[1], pymax(q0, 0.0), pymax(q1, 0.0));
 }
+
+template <bool R1>
+__global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_link_pair(const __grid_constant__ Ctx c) { link_pair_body<R1>(c); }
 
 // =================================================================================================
 // PathFinder.update_node_turn_probs (path_finder.py:561-589)
@@ -529,37 +569,42 @@ __device__ __noinline__ void routed_fractions(const Ctx& c, int routed, int m, i
     }
 }
 
+// floor(min(w, r * (w / D))) of node.py:296-298 with two exact shortcuts that avoid the IEEE division:
+//  * w == 0  ->  0/D = 0, r*0 = 0, min(0, 0) = 0;
+//  * r >= 2D ->  r*(w/D) >= 2w(1 - 2^-52) > w for w > 0, so the minimum is w itself.
+// Otherwise the division is evaluated as the reference does (quotient first, then the product).
+__device__ __forceinline__ double turn_flow(double w, double r, double D) {
+    if (w == 0.0) return 0.0;
+    if (w > 0.0 && D > 0.0 && r >= 2.0 * D && r < 1e300) return floor(w);
+    return floor(pymin(w, r * (w / D)));
+}
+
 // One node: gather s/r over its slots, node model, scatter flows and cumulative counts.
 // M > 0: slot count known at compile time (loops unrolled, everything in registers);
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
-template <int M>
+template <int M, bool R1>
 __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int base, int kind,
                                           int tf_mode, int dem_row, int tf_ptr) {
     constexpr int CAP = M ? M : PNS_MAX_DEGREE;
     const int m = M ? M : m_dyn;
-    const int R = c.n.replicas;
-    const int t = c.t, tau = c.t - 1;
+    const int R = R1 ? 1 : c.n.replicas;
     const int L = c.n.n_links;
     int icol[CAP];
 #pragma unroll
     for (int i = 0; i < m; ++i) icol[i] = __ldg(c.n.nd_in_col + base + i);
-    const double* snd = H64(c, PNS_F64_SENDING, tau);
-    const double* rcv = H64(c, PNS_F64_RECEIVING, tau);
-    const double* cout_p = H64(c, PNS_F64_CUM_OUTFLOW, tau);
-    const double* cin_p = H64(c, PNS_F64_CUM_INFLOW, tau);
     double s[CAP], r[CAP], co[CAP], ci[CAP];
 #pragma unroll
     for (int i = 0; i < m; ++i) {
         const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
         if (icol[i] >= L) {
-            s[i] = c.io.demand[((size_t)tau * c.n.n_demand_rows + dem_row) * R + rep];      // node.py:176
-            r[i] = 1e6;                                                                       // node.py:186
+            s[i] = c.n_demand[(size_t)dem_row * R + rep];                  // node.py:176
+            r[i] = 1e6;                                                     // node.py:186
         } else {
-            s[i] = snd[ei];
-            r[i] = rcv[eo];
+            s[i] = c.n_snd[ei];
+            r[i] = c.n_rcv[eo];
         }
-        co[i] = cout_p[ei];
-        ci[i] = cin_p[eo];
+        co[i] = c.n_coutp[ei];
+        ci[i] = c.n_cinp[eo];
     }
     bool negative = false;
 #pragma unroll
@@ -572,29 +617,56 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         const double a = fmin(s[0], r[CAP > 1 ? 1 : 0]), b = fmin(s[CAP > 1 ? 1 : 0], r[0]);
         q_out[0] = a; q_out[CAP > 1 ? 1 : 0] = b;
         q_in[0] = b;  q_in[CAP > 1 ? 1 : 0] = a;
-    } else {
-        // RegularNode.solve, 'classic' (node.py:272-300).  P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)];
-        // tf_mode 0 means uniform 1/(m-1) (network.py:269-271).
-        const double* tf = nullptr;
-        size_t ts = 1;
-        if (tf_mode == 2) {
-            double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
-            routed_fractions(c, __ldg(c.n.nd_routed + node), m, t, rep, out);
-            tf = out;
-            ts = (size_t)R;
-        } else if (tf_mode == 1) {
-            tf = c.s.tf_static + tf_ptr;
-        }
+    } else if (tf_mode == 0) {
+        // RegularNode.solve, 'classic' (node.py:272-300) with the default uniform fractions
+        // phi = 1/(m-1) (network.py:269-271): W[i][j] = phi*s[i] for every j != i
         const double phi = 1.0 / (double)(m - 1);
-        double D[CAP];
+        double w[CAP], D[CAP];
+#pragma unroll
+        for (int i = 0; i < m; ++i) w[i] = phi * s[i];
 #pragma unroll
         for (int j = 0; j < m; ++j) {
             double acc = 0.0;          // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
 #pragma unroll
+            for (int i = 0; i < m; ++i)
+                if (i != j) acc = acc + w[i];
+            D[j] = acc != 0.0 ? acc : 1e-5;
+            q_in[j] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+            double out_i = 0.0;
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                if (i == j) continue;
+                const double f = turn_flow(w[i], r[j], D[j]);
+                out_i += f;
+                q_in[j] += f;
+            }
+            q_out[i] = fmax(0.0, out_i);
+        }
+#pragma unroll
+        for (int j = 0; j < m; ++j) q_in[j] = fmax(0.0, q_in[j]);
+    } else {
+        // general fractions: P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)]
+        const double* tf;
+        size_t ts = 1;
+        if (tf_mode == 2) {
+            double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
+            routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
+            tf = out;
+            ts = (size_t)R;
+        } else {
+            tf = c.s.tf_static + tf_ptr;
+        }
+        double D[CAP];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            double acc = 0.0;
+#pragma unroll
             for (int i = 0; i < m; ++i) {
                 if (i == j) continue;
-                const double pij = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] : phi;
-                acc = acc + pij * s[i];
+                acc = acc + tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i];
             }
             D[j] = acc != 0.0 ? acc : 1e-5;
             q_in[j] = 0.0;
@@ -605,10 +677,8 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
 #pragma unroll
             for (int j = 0; j < m; ++j) {
                 if (i == j) continue;
-                const double pij = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] : phi;
-                const double wij = pij * s[i];
-                const double supply = r[j] * (wij / D[j]);
-                const double f = floor(pymin(wij, supply));
+                const double wij = tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i];
+                const double f = turn_flow(wij, r[j], D[j]);
                 out_i += f;
                 q_in[j] += f;
             }
@@ -618,44 +688,41 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         for (int j = 0; j < m; ++j) q_in[j] = fmax(0.0, q_in[j]);
     }
     // Node.update_links (node.py:146-162, link.py:19-25)
-    double* outflow = H64(c, PNS_F64_OUTFLOW, t);
-    double* inflow = H64(c, PNS_F64_INFLOW, t);
-    double* cout_t = H64(c, PNS_F64_CUM_OUTFLOW, t);
-    double* cin_t = H64(c, PNS_F64_CUM_INFLOW, t);
 #pragma unroll
     for (int i = 0; i < m; ++i) {
         const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
-        outflow[ei] = q_out[i];
-        cout_t[ei] = co[i] + q_out[i];
-        inflow[eo] = q_in[i];
-        cin_t[eo] = ci[i] + q_in[i];
+        c.n_outflow[ei] = q_out[i];
+        c.n_cout[ei] = co[i] + q_out[i];
+        c.n_inflow[eo] = q_in[i];
+        c.n_cin[eo] = ci[i] + q_in[i];
     }
 }
 
+template <bool R1>
 __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int base, int kind,
                                                int tf_mode, int dem_row, int tf_ptr) {
-    node_body<0>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr);
+    node_body<0, R1>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr);
 }
 
 // Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
-__global__ void __launch_bounds__(kBlock, 4) k_node_flows(const __grid_constant__ Ctx c) {
-    const int R = c.n.replicas;
+template <bool R1>
+__global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
+    const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)c.n.n_nodes * R) return;
-    const int node = (int)(gid / R);
-    const int rep = (int)(gid % R);
+    const int node = R1 ? (int)gid : (int)(gid / R);
+    const int rep = R1 ? 0 : (int)(gid % R);
     const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
-        case 2: node_body<2>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 3: node_body<3>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 4: node_body<4>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 5: node_body<5>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        default: node_body_generic(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 2: node_body<2, R1>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 3: node_body<3, R1>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 4: node_body<4, R1>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 5: node_body<5, R1>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        default: node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w); break;
     }
 }
-
 
 // =================================================================================================
 // Control environment (reference rl/builders.py, rl/pz_pednet_env.py)
@@ -822,6 +889,33 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
     c.row32 = (size_t)net->n_links * net->replicas;
     c.fld64 = c.row64 * (size_t)(net->sim_steps + 1);
     c.fld32 = c.row32 * (size_t)(net->sim_steps + 1);
+    {   // rows known at launch time
+        const int S1 = net->sim_steps + 1;
+        auto h64 = [&](int f, int row) { return st->hist64 + (size_t)f * c.fld64 + (size_t)row * c.row64; };
+        auto h32 = [&](int f, int row) { return st->hist32 + (size_t)f * c.fld32 + (size_t)row * c.row32; };
+        const int tu = t >= 1 && t < S1 ? t : 1;                 // UPDATE / node row (clamped when unused)
+        c.u_inflow = h64(PNS_F64_INFLOW, tu); c.u_outflow = h64(PNS_F64_OUTFLOW, tu);
+        c.u_num_prev = h32(PNS_F32_NUM_PED, tu - 1);
+        c.u_tt_old = tu >= net->window ? h32(PNS_F32_TRAVEL_TIME, tu - net->window) : nullptr;
+        c.u_num = h32(PNS_F32_NUM_PED, tu); c.u_dens = h32(PNS_F32_DENSITY, tu); c.u_speed = h32(PNS_F32_SPEED, tu);
+        c.u_tt = h32(PNS_F32_TRAVEL_TIME, tu); c.u_flow = h32(PNS_F32_LINK_FLOW, tu);
+        c.u_avg = h32(PNS_F32_AVG_TRAVEL_TIME, tu);
+        c.u_bgw = h64(PNS_F64_BACK_GATE, tu);
+        c.u_sepw = st->n_f64 > PNS_F64_SEP_WIDTH ? h64(PNS_F64_SEP_WIDTH, tu) : nullptr;
+        const int tf_ = t_flows >= 1 && t_flows <= S1 ? t_flows : 1;
+        const int tau = tf_ - 1;
+        const int prev = tau - 1 < 0 ? tau - 1 + S1 : tau - 1;   // numpy wrap of index -1 (link.py:364, 400)
+        c.f_num = h32(PNS_F32_NUM_PED, tau); c.f_dens = h32(PNS_F32_DENSITY, tau);
+        c.f_avg = h32(PNS_F32_AVG_TRAVEL_TIME, tau);
+        c.f_cin = h64(PNS_F64_CUM_INFLOW, tau); c.f_cou = h64(PNS_F64_CUM_OUTFLOW, tau);
+        c.f_sndp = h64(PNS_F64_SENDING, prev); c.f_rcvp = h64(PNS_F64_RECEIVING, prev);
+        c.f_snd = h64(PNS_F64_SENDING, tau); c.f_rcv = h64(PNS_F64_RECEIVING, tau);
+        c.n_snd = h64(PNS_F64_SENDING, tu - 1); c.n_rcv = h64(PNS_F64_RECEIVING, tu - 1);
+        c.n_coutp = h64(PNS_F64_CUM_OUTFLOW, tu - 1); c.n_cinp = h64(PNS_F64_CUM_INFLOW, tu - 1);
+        c.n_outflow = h64(PNS_F64_OUTFLOW, tu); c.n_inflow = h64(PNS_F64_INFLOW, tu);
+        c.n_cout = h64(PNS_F64_CUM_OUTFLOW, tu); c.n_cin = h64(PNS_F64_CUM_INFLOW, tu);
+        c.n_demand = (io && io->demand) ? io->demand + (size_t)(tu - 1) * net->n_demand_rows * net->replicas : nullptr;
+    }
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
     c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
@@ -849,6 +943,15 @@ int check_step_io(const pns_net* net, const pns_step_io* io, int rng_mode) {
     if (net->n_demand_rows > 0 && !(io && io->demand)) return fail("demand table missing");
     if (net->n_routed > 0 && !(io && io->od_w)) return fail("od weight table missing");
     return 0;
+}
+
+void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
+    if (net->replicas == 1) PNS_LAUNCH(k_link_pair<true>, blocks_for(n), kBlock, s, c);
+    else PNS_LAUNCH(k_link_pair<false>, blocks_for(n), kBlock, s, c);
+}
+void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
+    if (net->replicas == 1) PNS_LAUNCH(k_node_flows<true>, blocks_for(n), kBlock, s, c);
+    else PNS_LAUNCH(k_node_flows<false>, blocks_for(n), kBlock, s, c);
 }
 
 struct StepSizes { size_t n_pair, n_grp, n_node; };
@@ -883,13 +986,13 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
         const Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
         PNS_MARK(k, 0);
-        if (z.n_pair) PNS_LAUNCH(k_link_pair, blocks_for(z.n_pair), kBlock, s, cp);
+        if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
         if (z.n_grp) PNS_LAUNCH(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
         PNS_MARK(k, 2);
-        if (z.n_node) PNS_LAUNCH(k_node_flows, blocks_for(z.n_node), kBlock, s, cn);
+        if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
     }
 #undef PNS_MARK
@@ -941,7 +1044,7 @@ int pns_link_flows(const pns_net* net, const pns_state* st, const pns_step_io* i
     const size_t n = sizes_of(net).n_pair;
     if (n == 0) return 0;
     const Ctx c = make_ctx(net, st, io, PH_FLOWS, t, t, rng_mode, 0, 0);
-    PNS_LAUNCH(k_link_pair, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    launch_pair(net, n, (cudaStream_t)stream, c);
     return launched("k_link_pair[flows]");
 }
 
@@ -961,7 +1064,7 @@ int pns_node_flows(const pns_net* net, const pns_state* st, const pns_step_io* i
     const size_t n = sizes_of(net).n_node;
     if (n == 0) return 0;
     const Ctx c = make_ctx(net, st, io, 0, t, t, PNS_RNG_TABLE, 0, 0);
-    PNS_LAUNCH(k_node_flows, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    launch_node(net, n, (cudaStream_t)stream, c);
     return launched("k_node_flows");
 }
 
@@ -971,7 +1074,7 @@ int pns_link_update(const pns_net* net, const pns_state* st, const pns_step_io* 
     const size_t n = sizes_of(net).n_pair;
     if (n == 0) return 0;
     const Ctx c = make_ctx(net, st, io, PH_UPDATE, t, t, rng_mode, 0, 0);
-    PNS_LAUNCH(k_link_pair, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    launch_pair(net, n, (cudaStream_t)stream, c);
     return launched("k_link_pair[update]");
 }
 

@@ -1,0 +1,201 @@
+"""`BatchedPedNetEnv`: R independent replicas of one scenario stepped per launch.
+
+The per-replica semantics are those of the reference's `PedNetParallelEnv`
+(rl/pz_pednet_env.py:143-254): actions are absolute widths (rate-limited, clipped,
+rl/builders.py:264-352), one `network_loading` per env step (`action_gap` = 1), observations in
+the reference's link-major layout (rl/builders.py:68-177), the first agent's reward
+(pz_pednet_env.py:548-581), termination after S env steps.  Everything per step -- action
+application, the LTM step with on-device Philox draws, observation and reward -- is a CUDA kernel
+over the replica-fastest state, so a warp is 32 replicas of the same link or node.
+
+Tensors: `actions [R, n_act] float32` (agents concatenated in `possible_agents` order),
+`obs [R, n_obs] float32`, `reward [R] float32`, `done [R] bool`.  Replicas are sharded over
+GPUs by the caller (`replica_base` is the global index of local replica 0); no collective is
+needed inside a step.  Demand is pre-drawn on the host per replica (`np.random.RandomState(seed +
+replica)`), Poisson around the scenario's gaussian peaks (od_manager.py:145-155).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..engine import Engine, _ptr
+from ..env_loader import NetworkEnvGenerator
+from .builders import DENSITY_NORM, FLOW_NORM, OBS_LAYOUT
+from .discovery import AgentManager
+
+
+def _gater_divisors(obs_mode, k):
+    """Per-feature divisor of the reference's fixed-constant normalisation (rl/builders.py:206-238)."""
+    d = [1.0] * k
+    if obs_mode in ("option1", "option2"):
+        d[0] = d[1] = FLOW_NORM
+    elif obs_mode in ("option3", "option4"):
+        if k < 3:
+            raise IndexError("normalize_obs with this obs_mode indexes past the observation vector "
+                             "(the reference raises IndexError too)")
+        d[0], d[1], d[2] = DENSITY_NORM, FLOW_NORM, FLOW_NORM
+    return d
+
+
+class BatchedPedNetEnv:
+    def __init__(self, dataset: str, replicas: int, obs_mode: str = "option3", normalize_obs: bool = False,
+                 seed: int = 0, replica_base: int = 0, device=None, data_dir="data",
+                 _lib=None, _emulation: bool = False):
+        if obs_mode not in OBS_LAYOUT:
+            raise ValueError(f"obs_mode must be one of {list(OBS_LAYOUT)}, got: {obs_mode}")
+        self.dataset, self.R, self.obs_mode, self.seed = dataset, int(replicas), obs_mode, int(seed)
+        self.replica_base = int(replica_base)
+        state = np.random.get_state()                 # building the template must not disturb the caller's stream
+        np.random.seed(self.seed)
+        self.network = NetworkEnvGenerator(data_dir).create_network(dataset, verbose=False)
+        np.random.set_state(state)
+        net = self.network
+        self.simulation_steps = S = net.simulation_steps
+        self.agent_manager = am = AgentManager(net)
+        self.possible_agents = am.get_all_agent_ids()
+        unit_time = net.params["unit_time"]
+        max_delta = 0.25 * unit_time                   # pz_pednet_env.py:84-85
+        min_sep = 1.5                                  # pz_pednet_env.py:86
+
+        # ---- action / observation / reward programs (agents in possible_agents order) ----------
+        act_link, act_sep, act_lo, act_hi, act_md, act_w = [], [], [], [], [], []
+        obs_link, obs_src, obs_div = [], [], []
+        self.action_slices, self.obs_slices = {}, {}
+        for aid in self.possible_agents:
+            a0, o0 = len(act_link), len(obs_link)
+            if am.get_agent_type(aid) == "sep":
+                fwd, rev = am.get_separator_links(aid)
+                act_link.append(fwd.index); act_sep.append(1)
+                act_lo.append(min_sep); act_hi.append(fwd.width - min_sep)
+                act_md.append(max_delta); act_w.append(fwd._width)
+                for l, src in ((fwd, "inflow"), (fwd, "outflow"), (rev, "inflow"), (rev, "outflow")):
+                    obs_link.append(l.index); obs_src.append(_native.OBS_SRC[src])
+                if normalize_obs:
+                    if obs_mode in ("option3", "option4"):
+                        raise IndexError("normalize_obs with this obs_mode indexes past the separator "
+                                         "observation (the reference raises IndexError too)")
+                    obs_div += [FLOW_NORM] * 4 if obs_mode in ("option1", "option2") else [1.0] * 4
+                else:
+                    obs_div += [1.0] * 4
+            else:
+                feats = OBS_LAYOUT[obs_mode]
+                div = _gater_divisors(obs_mode, len(feats)) if normalize_obs else [1.0] * len(feats)
+                for link in am.get_gater_outgoing_links(aid):
+                    act_link.append(link.index); act_sep.append(0)
+                    act_lo.append(0.0); act_hi.append(link.width)
+                    act_md.append(max_delta); act_w.append(link._width)
+                    for f, d in zip(feats, div):
+                        obs_link.append(link.index); obs_src.append(_native.OBS_SRC[f]); obs_div.append(d)
+            self.action_slices[aid] = slice(a0, len(act_link))
+            self.obs_slices[aid] = slice(o0, len(obs_link))
+        first = self.possible_agents[0] if self.possible_agents else None
+        reward_links = ([l.index for l in am.get_gater_outgoing_links(first)]
+                        if first is not None and am.get_agent_type(first) == "gate" else [])
+        self.n_act, self.n_obs = len(act_link), len(obs_link)
+
+        # ---- device runtime --------------------------------------------------------------------
+        self.engine = eng = Engine(net.plan, replicas=self.R, device=device, rng="philox", seed=self.seed,
+                                   lib=_lib, emulation=_emulation)
+        eng.io.replica_base = self.replica_base
+        dev = eng.device
+        self.device = dev
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to(dev)
+        self._env_t = dict(act_link=to(act_link, np.int32), act_sep=to(act_sep, np.int32),
+                           act_lo=to(act_lo, np.float64), act_hi=to(act_hi, np.float64),
+                           act_max_delta=to(act_md, np.float64), act_total_width=to(act_w, np.float64),
+                           obs_link=to(obs_link, np.int32), obs_src=to(obs_src, np.int32),
+                           obs_div=to(obs_div, np.float32), reward_link=to(reward_links, np.int32))
+        env = _native.PnsEnv()
+        env.n_act, env.n_obs, env.n_reward_links = self.n_act, self.n_obs, len(reward_links)
+        for k, t in self._env_t.items():
+            setattr(env, k, _ptr(t))
+        self._env = env
+        self.obs = torch.zeros((self.R, max(1, self.n_obs)), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((self.R,), dtype=torch.float32, device=dev)
+        self.cumulative_reward = torch.zeros((self.R,), dtype=torch.float32, device=dev)
+        self._tf, self._supplied = net._static_fractions()
+        self._od_w = (np.stack([net.od_manager.od_flows[k] for k in net.plan["od_keys"]], axis=1)
+                      if net.od_manager is not None else None)
+        self.episode = 0
+        self.sim_step = 1
+        self.reset()
+
+    # ------------------------------------------------------------------ demand
+    def _draw_demand(self, episode: int) -> np.ndarray:
+        """[S+1, rows * R] demand, replica fastest; replica r uses RandomState(seed + global r) and
+        draws its origins in node creation order, like the reference's setup does."""
+        net, S, R = self.network, self.simulation_steps, self.R
+        rows = net.plan["demand_nodes"]
+        out = np.zeros((S + 1, max(1, len(rows)), R), dtype=np.float64)
+        gen = net.demand_generator
+        t = np.arange(S)
+        width = 2 * (S / 20) ** 2
+        lams = {}
+        for k, node in enumerate(rows):
+            if node.node_id not in net.origin_nodes:
+                continue
+            cfg = gen._get_demand_config(node.node_id)
+            if cfg.pattern != "gaussian_peaks":
+                raise NotImplementedError("batched demand supports the gaussian_peaks pattern")
+            lams[k] = (cfg.base_lambda + cfg.peak_lambda * np.exp(-(t - S / 4) ** 2 / width)
+                       + cfg.peak_lambda * np.exp(-(t - 3 * S / 4) ** 2 / width))
+        for r in range(R):
+            rs = np.random.RandomState((self.seed + self.replica_base + r + 1_000_003 * episode) % (2 ** 32))
+            for k, lam in lams.items():
+                out[:S, k, r] = rs.poisson(lam)
+        return out.reshape(S + 1, -1)
+
+    # ------------------------------------------------------------------ API
+    def reset(self):
+        """Start a new episode in every replica; returns obs [R, n_obs] at step 1 (all zeros + widths)."""
+        eng, net = self.engine, self.network
+        eng.io.seed = (self.seed + 0x9E3779B97F4A7C15 * self.episode) % (2 ** 64)
+        eng.initialise(net._store.gate, net._store.sep_np64, self._tf, self._draw_demand(self.episode),
+                       self._od_w, self._supplied)
+        self.sim_step = 1
+        self.cumulative_reward.zero_()
+        self.episode += 1
+        self._observe(self.sim_step)
+        return self.obs
+
+    def _stream(self):
+        return self.engine._stream()
+
+    def _observe(self, row):
+        eng = self.engine
+        with eng._guard():
+            _native.check(eng.lib, eng.lib.pns_env_observe(C.byref(eng.net), C.byref(eng.state), C.byref(self._env),
+                                                           int(row), _ptr(self.obs), _ptr(self.reward),
+                                                           self._stream()), "pns_env_observe")
+
+    def step(self, actions: torch.Tensor):
+        """actions [R, n_act] float32 on the env's device.  Returns (obs, reward, done, info)."""
+        eng = self.engine
+        if self.sim_step > self.simulation_steps:
+            raise RuntimeError("episode finished: call reset()")
+        if actions is not None and self.n_act:
+            if actions.shape != (self.R, self.n_act) or actions.dtype != torch.float32:
+                raise ValueError(f"actions must be float32 [{self.R}, {self.n_act}]")
+            actions = actions.contiguous()
+            with eng._guard():
+                _native.check(eng.lib, eng.lib.pns_env_apply_actions(
+                    C.byref(eng.net), C.byref(eng.state), C.byref(self._env), _ptr(actions), self._stream()),
+                    "pns_env_apply_actions")
+        eng.run(self.sim_step, 1, _native.RNG_PHILOX)
+        self._observe(self.sim_step)
+        self.cumulative_reward += self.reward
+        done = self.sim_step >= self.simulation_steps           # tested before the increment (quirk Q8)
+        self.sim_step += 1
+        return self.obs, self.reward, done, {"step": self.sim_step - 1}
+
+    def split_obs(self, obs=None):
+        obs = self.obs if obs is None else obs
+        return {a: obs[:, s] for a, s in self.obs_slices.items()}
+
+    def launches_per_step(self):
+        routed = 1 if len(self.network.plan["rt_grp_node"]) else 0
+        return 1 + 3 + routed + 1      # actions, flows | [route] | node | update, observe+reward

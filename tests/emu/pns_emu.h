@@ -18,6 +18,8 @@
 #define __grid_constant__
 #define __noinline__
 struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
+struct float2 { float x, y; };
 
 struct emu_dim3 { unsigned x, y, z; };
 static thread_local emu_dim3 blockIdx, threadIdx, blockDim, gridDim;
