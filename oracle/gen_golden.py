@@ -100,6 +100,68 @@ def generate(name):
           f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+# ---- control-environment fixtures (reference rl/pz_pednet_env.py with scripted actions) -----------
+ENV_CASES = {
+    "env_nine_intersections": dict(dataset="nine_intersections", obs_mode="option3", normalize_obs=False,
+                                   seed=123, steps=300),
+    "env_45_intersections": dict(dataset="45_intersections", obs_mode="option3", normalize_obs=False,
+                                 seed=123, steps=250),
+    "env_long_corridor": dict(dataset="long_corridor", obs_mode="option1", normalize_obs=False,
+                              seed=5, steps=300),
+    "env_nine_intersections_opt2n": dict(dataset="nine_intersections", obs_mode="option2", normalize_obs=True,
+                                         seed=9, steps=120),
+    "env_butterfly_opt5": dict(dataset="butterfly_scA", obs_mode="option5", normalize_obs=False, seed=3, steps=200),
+}
+
+
+def scripted_actions(env, steps, seed=7):
+    """[steps, n_act] float32: uniform over each agent's action box from a private RandomState
+    (the environment's own global stream is left alone)."""
+    rs = np.random.RandomState(seed)
+    rows = []
+    for _ in range(steps):
+        row = []
+        for a in env.possible_agents:
+            sp = env.action_space(a)
+            row.append(rs.uniform(sp.low, sp.high).astype(np.float32))
+        rows.append(np.concatenate(row) if row else np.zeros(0, dtype=np.float32))
+    return np.stack(rows)
+
+
+def generate_env(name):
+    case = ENV_CASES[name]
+    env = rh.make_reference_env(case["dataset"], obs_mode=case["obs_mode"], normalize_obs=case["normalize_obs"],
+                                seed=case["seed"])
+    obs0, _ = env.reset()
+    steps = case["steps"]
+    actions = scripted_actions(env, steps)
+    agents = list(env.possible_agents)
+    widths = [env.action_space(a).shape[0] for a in agents]
+    obs_rows, rew_rows, done_rows = [], [], []
+    for k in range(steps):
+        off, act = 0, {}
+        for a, w in zip(agents, widths):
+            act[a] = actions[k, off:off + w]
+            off += w
+        obs, rew, term, trunc, info = env.step(act)
+        obs_rows.append(np.concatenate([obs[a] for a in agents]))
+        rew_rows.append(np.array([float(rew.get(a, 0.0)) for a in agents], dtype=np.float64))
+        done_rows.append(bool(term[agents[0]]))
+    arrays = rh.collect_link_arrays(env.network)
+    out = {"steps_run": np.int64(steps), "seed": np.int64(case["seed"]), "actions": actions,
+           "agents": np.array(agents), "action_widths": np.array(widths, dtype=np.int64),
+           "obs0": np.concatenate([obs0[a] for a in agents]), "obs": np.stack(obs_rows),
+           "rewards": np.stack(rew_rows), "done": np.array(done_rows),
+           "n_links": np.int64(arrays["inflow"].shape[1]), "sample_links": np.asarray([0, 1], dtype=np.int64)}
+    for f in rh.LINK_FIELDS:
+        out["rows_" + f] = row_digests(arrays[f])
+        out["sample_" + f] = arrays[f][:, [0, 1]]
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {len(agents)} agents {agents}, {steps} env steps -> {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or list(CASES)):
-        generate(nm)
+    for nm in (sys.argv[1:] or list(CASES) + list(ENV_CASES)):
+        (generate_env if nm in ENV_CASES else generate)(nm)

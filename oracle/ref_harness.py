@@ -35,21 +35,36 @@ def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM"))
 
 
+class _Anything:
+    """Stand-in for any plotting class/function the reference imports but the hot path never calls."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+    def __getattr__(self, name):
+        return _Anything()
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything
+
+
 def _install_stubs():
     if "matplotlib" not in sys.modules:
-        mpl = types.ModuleType("matplotlib")
+        mpl = _StubModule("matplotlib")
         mpl.use = lambda *a, **k: None
-        plt = types.ModuleType("matplotlib.pyplot")
-        anim = types.ModuleType("matplotlib.animation")
-        anim.PillowWriter = type("PillowWriter", (), {})
-        anim.FuncAnimation = type("FuncAnimation", (), {})
-        for name in ("cm", "colors", "patches", "lines", "collections", "gridspec", "ticker"):
-            sub = types.ModuleType(f"matplotlib.{name}")
+        sys.modules["matplotlib"] = mpl
+        for name in ("pyplot", "animation", "cm", "colors", "patches", "lines", "collections", "gridspec",
+                     "ticker", "colorbar", "figure", "axes"):
+            sub = _StubModule(f"matplotlib.{name}")
             setattr(mpl, name, sub)
             sys.modules[f"matplotlib.{name}"] = sub
-        mpl.pyplot, mpl.animation = plt, anim
-        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt,
-                            "matplotlib.animation": anim})
     if "pettingzoo" not in sys.modules:
         pz = types.ModuleType("pettingzoo")
         pz.ParallelEnv = type("ParallelEnv", (), {"__init__": lambda self, *a, **k: None})
@@ -101,6 +116,26 @@ def import_reference():
     from src.utils.env_loader import NetworkEnvGenerator  # noqa
     logging.getLogger("src.LTM.network").setLevel(logging.ERROR)
     return Network, NetworkEnvGenerator
+
+
+def make_reference_env(dataset, **kw):
+    """reference rl/pz_pednet_env.PedNetParallelEnv with the `verbose` kwarg shim."""
+    import logging
+    _, Gen = import_reference()
+    log = logging.getLogger("src.LTM.network")
+    if not log.handlers:
+        log.addHandler(logging.NullHandler())     # keeps Network.setup_logger from resetting the level
+    log.setLevel(logging.ERROR)
+    if not getattr(Gen.create_network, "_accepts_verbose", False):
+        orig = Gen.create_network
+
+        def create_network(self, yaml_file_path, *a, verbose=True, **k):
+            return orig(self, yaml_file_path, *a, **k)
+
+        create_network._accepts_verbose = True
+        Gen.create_network = create_network
+    from rl.pz_pednet_env import PedNetParallelEnv
+    return PedNetParallelEnv(dataset, **kw)
 
 
 def create_network(name: str, steps_override: int | None = None, verbose: bool = True, **kw):

@@ -42,7 +42,7 @@ class Network:
                  destination_nodes: list = [], demand_pattern: List[Callable] = None,
                  od_flows: dict = None, pos: dict = None,
                  log_level: int = logging.INFO, verbose: bool = True,
-                 rng: str = "numpy", seed: int = 0, device=None):
+                 rng: str = "numpy", seed: int = 0, device=None, _lib=None, _emulation: bool = False):
         """rng: 'numpy'  -- in-step draws come from numpy's global legacy RNG in the reference's
                             order (same seed => same trajectory as the reference);
                 'philox' -- counter-based on-device sampling keyed (seed, t, link, site)."""
@@ -69,6 +69,7 @@ class Network:
         self.rng_mode = rng
         self.seed = seed
         self._device = device
+        self._lib, self._emulation = _lib, _emulation      # test hooks (tests/emu host build of the kernels)
         self._engine = None
         self._plan = None
         self._fractions_dirty = True
@@ -239,7 +240,7 @@ class Network:
         if self._engine is None:
             from .engine import Engine       # imports torch + the native library; fails loudly
             self._engine = Engine(self.plan, replicas=1, device=self._device,
-                                  rng=self.rng_mode, seed=self.seed)
+                                  rng=self.rng_mode, seed=self.seed, lib=self._lib, emulation=self._emulation)
             self._engine.bind_network(self)
             self._store.engine = self._engine
         return self._engine

@@ -134,19 +134,29 @@ class BatchedPedNetEnv:
         gen = net.demand_generator
         t = np.arange(S)
         width = 2 * (S / 20) ** 2
-        lams = {}
+        specs = {}
         for k, node in enumerate(rows):
             if node.node_id not in net.origin_nodes:
                 continue
             cfg = gen._get_demand_config(node.node_id)
-            if cfg.pattern != "gaussian_peaks":
-                raise NotImplementedError("batched demand supports the gaussian_peaks pattern")
-            lams[k] = (cfg.base_lambda + cfg.peak_lambda * np.exp(-(t - S / 4) ** 2 / width)
-                       + cfg.peak_lambda * np.exp(-(t - 3 * S / 4) ** 2 / width))
+            pattern = net.params.get("demand", {}).get(f"origin_{node.node_id}", {}).get("pattern", "gaussian_peaks")
+            if pattern not in ("gaussian_peaks", "sudden_demand", "constant"):
+                raise NotImplementedError(f"batched demand does not support the custom pattern {pattern!r}")
+            lam = (cfg.base_lambda + cfg.peak_lambda * np.exp(-(t - S / 4) ** 2 / width)
+                   + cfg.peak_lambda * np.exp(-(t - 3 * S / 4) ** 2 / width))
+            specs[k] = (pattern, lam, cfg.base_lambda)
         for r in range(R):
             rs = np.random.RandomState((self.seed + self.replica_base + r + 1_000_003 * episode) % (2 ** 32))
-            for k, lam in lams.items():
-                out[:S, k, r] = rs.poisson(lam)
+            for k, (pattern, lam, base) in specs.items():
+                if pattern == "constant":                                  # od_manager.py:106-109
+                    out[:, k, r] = base
+                    continue
+                d = rs.poisson(lam).astype(np.float64)
+                if pattern == "sudden_demand":                             # od_manager.py:111-123
+                    period = rs.randint(10, 20)
+                    start = rs.randint(0, max(1, S - period))
+                    d[start:start + period] += rs.randint(20, 50)
+                out[:S, k, r] = d
         return out.reshape(S + 1, -1)
 
     # ------------------------------------------------------------------ API

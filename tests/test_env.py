@@ -1,0 +1,146 @@
+"""Control environments: the single-network facade vs fixtures recorded from the reference's own
+PedNetParallelEnv (scripted actions), and the batched device environment vs the facade."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_matches_golden, load_golden
+from oracle.ltm_oracle import F32_FIELDS, F64_FIELDS
+from pednstream_b200.rl import BatchedPedNetEnv, PedNetParallelEnv
+
+ENV_CASES = {"env_nine_intersections": ("nine_intersections", "option3", False),
+             "env_45_intersections": ("45_intersections", "option3", False),
+             "env_long_corridor": ("long_corridor", "option1", False),
+             "env_nine_intersections_opt2n": ("nine_intersections", "option2", True),
+             "env_butterfly_opt5": ("butterfly_scA", "option5", False)}
+
+
+def run_env_case(name, **engine_kw):
+    dataset, obs_mode, norm = ENV_CASES[name]
+    gold = load_golden(name)
+    env = PedNetParallelEnv(dataset, obs_mode=obs_mode, normalize_obs=norm, seed=int(gold["seed"]), **engine_kw)
+    agents = list(env.possible_agents)
+    assert agents == gold["agents"].tolist()
+    widths = gold["action_widths"].tolist()
+    assert [env.action_space(a).shape[0] for a in agents] == widths
+    obs0, _ = env.reset()
+    assert np.array_equal(np.concatenate([obs0[a] for a in agents]), gold["obs0"])
+    steps = int(gold["steps_run"])
+    for k in range(steps):
+        off, act = 0, {}
+        for a, w in zip(agents, widths):
+            act[a] = gold["actions"][k, off:off + w]
+            off += w
+        obs, rew, term, trunc, info = env.step(act)
+        got = np.concatenate([obs[a] for a in agents])
+        assert got.dtype == np.float32
+        assert np.array_equal(got, gold["obs"][k]), f"observation differs at env step {k + 1}"
+        r = np.array([float(rew.get(a, 0.0)) for a in agents])
+        assert np.array_equal(r, gold["rewards"][k]), f"reward differs at env step {k + 1}: {r} vs {gold['rewards'][k]}"
+        assert bool(term[agents[0]]) == bool(gold["done"][k]) and not any(trunc.values())
+        assert info[agents[0]]["step"] == k + 1
+    fields = {f: env.network._store.field(f) for f in F64_FIELDS[:7] + F32_FIELDS}
+    assert_matches_golden(gold, fields, steps, int(gold["n_links"]))
+    return env
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_env_matches_reference_env_emulated(name, emu_lib):
+    run_env_case(name, _lib=emu_lib, _emulation=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_env_matches_reference_env_cuda(name):
+    run_env_case(name, device="cuda:0")
+
+
+def test_env_api_surface(emu_lib):
+    env = PedNetParallelEnv("nine_intersections", obs_mode="option3", seed=1, _lib=emu_lib, _emulation=True)
+    assert env.possible_agents == ["gate_3", "gate_4", "gate_7"] and env.agents == env.possible_agents
+    assert env.observation_space("gate_4").shape == (20,) and env.action_space("gate_4").shape == (4,)
+    assert float(env.action_space("gate_4").high[0]) == 4.0
+    with pytest.raises(ValueError):
+        env.step({"gate_99": np.zeros(3, dtype=np.float32)})
+    with pytest.raises(ValueError):
+        env.observation_space("nope")
+    with pytest.raises(ValueError):
+        PedNetParallelEnv("nine_intersections", obs_mode="bogus", _lib=emu_lib, _emulation=True)
+
+
+# ---------------------------------------------------------------------------------- batched
+def _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, lib=None, emulation=False, device=None):
+    """Replica r of the batched environment must equal a single-network facade run that uses the
+    same demand, the same actions and the Philox key of replica r."""
+    kw = dict(_lib=lib, _emulation=emulation) if emulation else dict(device=device)
+    benv = BatchedPedNetEnv(dataset, replicas=R, obs_mode=obs_mode, normalize_obs=norm, seed=21, **kw)
+    dev = benv.device
+    rs = np.random.RandomState(4)
+    lo = benv._env_t["act_lo"].cpu().numpy()
+    hi = benv._env_t["act_hi"].cpu().numpy()
+    acts = rs.uniform(lo - 0.5, hi + 0.5, size=(steps, R, benv.n_act)).astype(np.float32)
+    demand = benv.engine.demand.cpu().numpy().reshape(benv.simulation_steps + 1, -1, R)
+    obs_b = [benv.obs.cpu().numpy().copy()]
+    rew_b, done_b = [], []
+    for k in range(steps):
+        o, r, d, _ = benv.step(torch.from_numpy(acts[k]).to(dev))
+        obs_b.append(o.cpu().numpy().copy())
+        rew_b.append(r.cpu().numpy().copy())
+        done_b.append(d)
+    benv.engine.check_errors()
+    for rep in picks:
+        fkw = dict(_lib=lib, _emulation=True) if emulation else dict(device=device)
+        env = PedNetParallelEnv(dataset, obs_mode=obs_mode, normalize_obs=norm, seed=21, rng="philox", **fkw)
+        env.reset()
+        for row, node in enumerate(env.network.plan["demand_nodes"]):
+            node.demand = demand[:, row, rep].copy()
+        eng = env.network.engine
+        eng.io.seed = benv.engine.io.seed
+        eng.io.replica_base = rep
+        agents = env.possible_agents
+        first = np.concatenate([env._get_observations()[a] for a in agents])
+        assert np.array_equal(first, obs_b[0][rep])
+        for k in range(steps):
+            act = {a: acts[k, rep, benv.action_slices[a]] for a in agents}
+            obs, rew, term, _, _ = env.step(act)
+            assert np.array_equal(np.concatenate([obs[a] for a in agents]), obs_b[k + 1][rep]), (rep, k)
+            assert np.float32(rew.get(agents[0], 0.0)) == rew_b[k][rep], (rep, k)
+        for f in F64_FIELDS[:7] + F32_FIELDS:
+            want = env.network._store.field(f)
+            got = benv.engine.history(f)[:, :, rep].cpu().numpy()
+            assert np.array_equal(want[: steps + 1], got[: steps + 1]), (f, rep)
+
+
+def test_batched_env_matches_facade_emulated(emu_lib):
+    _batched_vs_facade("nine_intersections", "option3", False, 40, 3, (0, 2), lib=emu_lib, emulation=True)
+
+
+def test_batched_env_separator_emulated(emu_lib):
+    _batched_vs_facade("long_corridor", "option1", False, 60, 2, (1,), lib=emu_lib, emulation=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dataset,obs_mode,norm,steps,R,picks", [
+    ("45_intersections", "option3", False, 80, 64, (0, 33, 63)),
+    ("nine_intersections", "option2", True, 60, 40, (7,)),
+    ("long_corridor", "option1", False, 80, 33, (32,))])
+def test_batched_env_matches_facade_cuda(dataset, obs_mode, norm, steps, R, picks):
+    _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, device="cuda:0")
+
+
+@pytest.mark.gpu
+def test_batched_env_full_episode_and_reset():
+    env = BatchedPedNetEnv("45_intersections", replicas=256, obs_mode="option3", seed=2, device="cuda:0")
+    assert env.n_act == 4 and env.n_obs == 20
+    a = torch.full((256, 4), 2.0, dtype=torch.float32, device=env.device)
+    done = False
+    n = 0
+    while not done:
+        obs, rew, done, info = env.step(a)
+        n += 1
+    assert n == env.simulation_steps == 700
+    env.engine.check_errors()
+    assert torch.isfinite(obs).all() and torch.isfinite(env.cumulative_reward).all()
+    assert float(env.cumulative_reward.std()) > 0          # replicas differ (independent demand / draws)
+    first = env.reset()
+    assert env.sim_step == 1 and float(first[:, :4].abs().sum()) == 0.0 and float(first[0, 4]) == 4.0
