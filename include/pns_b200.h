@@ -101,8 +101,10 @@ typedef struct pns_net {
     /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id).
      * The outgoing link of a slot is the reverse of its incoming link: out column = in column ^ 1
      * (physical pairs are adjacent, virtual in/out links are allocated as adjacent columns). */
-    const int32_t *nd_meta;     /* [n_nodes][4]: slot offset, m | kind<<8 | tf_mode<<16, demand row (-1 none),
-                                   offset of the node's m(m-1) turning fractions.
+    const int32_t *nd_meta;     /* [n_nodes][8] (32-byte records): slot offset, m | kind<<8 | tf_mode<<16,
+                                   demand row (-1 none), offset of the node's m(m-1) turning fractions, then the
+                                   in-columns of slots 0..3 (copies of nd_in_col, so that one record fetch serves
+                                   nodes with up to four slots).
                                    kind: 0 one-to-one (node.py:230), 1 regular/classic (node.py:272);
                                    tf_mode: 0 uniform 1/(m-1) (network.py:269-271), 1 tf_static, 2 routed */
     const int32_t *nd_in_col;   /* [slots] history column of the incoming link of each slot */

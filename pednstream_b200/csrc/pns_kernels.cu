@@ -584,14 +584,15 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
 template <int M, bool R1>
 __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int base, int kind,
-                                          int tf_mode, int dem_row, int tf_ptr) {
+                                          int tf_mode, int dem_row, int tf_ptr, const int4& first4) {
     constexpr int CAP = M ? M : PNS_MAX_DEGREE;
     const int m = M ? M : m_dyn;
     const int R = R1 ? 1 : c.n.replicas;
     const int L = c.n.n_links;
     int icol[CAP];
+    const int inl[4] = {first4.x, first4.y, first4.z, first4.w};     // slots 0..3 come with the node record
 #pragma unroll
-    for (int i = 0; i < m; ++i) icol[i] = __ldg(c.n.nd_in_col + base + i);
+    for (int i = 0; i < m; ++i) icol[i] = i < 4 ? inl[i < 4 ? i : 0] : __ldg(c.n.nd_in_col + base + i);
     double s[CAP], r[CAP], co[CAP], ci[CAP];
 #pragma unroll
     for (int i = 0; i < m; ++i) {
@@ -700,8 +701,8 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
 
 template <bool R1>
 __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int base, int kind,
-                                               int tf_mode, int dem_row, int tf_ptr) {
-    node_body<0, R1>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr);
+                                               int tf_mode, int dem_row, int tf_ptr, const int4& first4) {
+    node_body<0, R1>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr, first4);
 }
 
 // Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
@@ -712,15 +713,16 @@ __global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_node_flows(const __g
     if (gid >= (size_t)c.n.n_nodes * R) return;
     const int node = R1 ? (int)gid : (int)(gid / R);
     const int rep = R1 ? 0 : (int)(gid % R);
-    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);
+    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
+    const int4 meta = __ldg(rec), cols = __ldg(rec + 1);
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
-        case 2: node_body<2, R1>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 3: node_body<3, R1>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 4: node_body<4, R1>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        case 5: node_body<5, R1>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w); break;
-        default: node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w); break;
+        case 2: node_body<2, R1>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
+        case 3: node_body<3, R1>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
+        case 4: node_body<4, R1>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
+        case 5: node_body<5, R1>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
+        default: node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
     }
 }
 

@@ -122,8 +122,14 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     edges = (m_o * (m_o - 1)).astype(np.int64)
     tf_ptr = np.concatenate([[0], np.cumsum(edges)]).astype(np.int32)
     assert (out_col == (in_col ^ 1)).all()
-    meta = np.stack([nd_ptr[:-1], (m_o | (kind[order].astype(np.int64) << 8)).astype(np.int32),
-                     dem_row, tf_ptr[:-1]], axis=1).astype(np.int32)
+    meta = np.zeros((N, 8), dtype=np.int32)
+    meta[:, 0] = nd_ptr[:-1]
+    meta[:, 1] = (m_o | (kind[order].astype(np.int64) << 8)).astype(np.int32)
+    meta[:, 2] = dem_row
+    meta[:, 3] = tf_ptr[:-1]
+    for k in range(4):                       # in-columns of the first four slots, inline
+        has = m_o > k
+        meta[has, 4 + k] = in_col[nd_ptr[:-1][has] + k]
 
     from .plan import class_record, CLASS_DTYPE
     rec = class_record(lk["length"], lk["width"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"],

@@ -127,10 +127,11 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
             demand_nodes.append(n)
             n_virtual_nodes += 1
         tf_mode = 2 if n.node_id in routed_ids else 0
-        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr))
+        first4 = [l._col for l in n.incoming_links[:4]] + [0] * (4 - min(m, 4))
+        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr, *first4))
         slot0 += m
         tf_ptr += m * (m - 1)
-    p["nd_meta"] = _i32(meta).reshape(-1, 4)
+    p["nd_meta"] = _i32(meta).reshape(-1, 8)
     p["nd_in_col"] = _i32(in_col)
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
