@@ -139,6 +139,66 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------- batched env (config 5)
+def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup):
+    """BASELINE config 5: data/45_intersections, batched replicas with random gate actions in [0, 4] m,
+    obs_mode option3, action_gap 1.  Returns (env-steps/s device-resident, env-steps/s end-to-end with the
+    actions coming from pinned host memory and observations + rewards copied back every step)."""
+    from pednstream_b200.rl import BatchedPedNetEnv
+    env = BatchedPedNetEnv("45_intersections", replicas=replicas, obs_mode="option3", seed=1000 + rank,
+                           replica_base=rank * replicas, device=dev)
+    R, A = env.R, env.n_act
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank)
+    actions = torch.rand((warmup + 2 * steps, R, A), generator=gen, device=dev, dtype=torch.float32) * 4.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(warmup):
+        env.step(actions[k])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        env.step(actions[warmup + k])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    host_actions = actions[warmup + steps:].cpu().pin_memory()
+    host_obs = torch.zeros((R, env.n_obs), dtype=torch.float32).pin_memory()
+    host_rew = torch.zeros((R,), dtype=torch.float32).pin_memory()
+    dev_act = torch.zeros((R, A), dtype=torch.float32, device=dev)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for k in range(steps):
+        dev_act.copy_(host_actions[k], non_blocking=True)
+        obs, rew, done, _ = env.step(dev_act)
+        host_obs.copy_(obs, non_blocking=True)
+        host_rew.copy_(rew, non_blocking=False)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    env.engine.check_errors()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    links = env.engine.L
+    return {"env_steps_per_s": world * R * steps / (ms * 1e-3),
+            "env_steps_per_s_e2e": world * R * steps / (ms_e2e * 1e-3),
+            "link_timesteps_per_s": world * R * links * steps / (ms * 1e-3),
+            "replicas_per_gpu": R, "replicas_total": world * R, "env_steps": steps, "ms_per_env_step": ms / steps,
+            "launches_per_env_step": env.launches_per_step(), "links": links,
+            "h2d_bytes_per_step": R * A * 4, "d2h_bytes_per_step": R * (env.n_obs + 1) * 4,
+            "workload": "config 5: data/45_intersections, obs option3, uniform random gate actions, philox draws, "
+                        "per-replica pre-drawn demand",
+            "mean_reward_last_step": float(host_rew.mean())}
+
+
 # --------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import numpy as np
@@ -162,7 +222,10 @@ def run_ours(args):
     S = W + K + Kp + Ke + 2                              # history rows: 80 B x links x (S+1) of HBM
     if 80.0 * (S + 1) * (2 * 2 * size * (size - 1)) > 150e9:
         raise SystemExit(f"--steps {K}: the {size}x{size} history would not fit in HBM; use <= 1500 steps")
-    plan, gate, tf, demand = build_grid_plan(size, S, demand_seed=rank, locality_order=True)
+    link_over = {"speed_noise_std": args.sigma} if args.sigma is not None else None
+    from pednstream_b200.grid import default_origins
+    plan, gate, tf, demand = build_grid_plan(size, S, demand_seed=rank, locality_order=True, link=link_over,
+                                             origins=default_origins(size, args.origin_stride))
     L = plan["n_links"]
     eng = Engine(plan, replicas=1, rng="philox", seed=rank, device=dev)
     eng.initialise(gate, None, tf, demand, None)
@@ -216,6 +279,14 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
 
+    # free the lattice history before the batched environment allocates its own
+    del num_hist, pinned
+    eng = None
+    torch.cuda.empty_cache()
+    env_stats = None
+    if not args.no_env:
+        env_stats = bench_env45(torch, dist, world, rank, dev, args.env_replicas, min(K, 300), 10)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         value = world * L * K / (ms * 1e-3)
@@ -250,6 +321,8 @@ def run_ours(args):
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak, "alg_bytes_per_link_step": B_ALG}},
             "check": {"pedestrians_on_links_last_step": total_peds},
         }
+        if env_stats is not None:
+            line["batched_env"] = env_stats
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "link-timesteps/s", "cores": 1, "kind": "port",
                                     "sample": f"Python oracle, {REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({cpu_L} links), "
@@ -268,6 +341,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sigma", type=float, default=None, help="override speed_noise_std of the lattice (experiments)")
+    ap.add_argument("--origin-stride", type=int, default=64, help="every n-th boundary node is an origin")
+    ap.add_argument("--no-env", action="store_true", help="skip the batched 45_intersections environment section")
+    ap.add_argument("--env-replicas", type=int, default=1024, help="replicas per GPU of the batched environment")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
