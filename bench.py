@@ -280,6 +280,7 @@ def run_ours(args):
     ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
 
     # free the lattice history before the batched environment allocates its own
+    h2d_bytes = int(pinned.shape[1] * 8)
     del num_hist, pinned
     eng = None
     torch.cuda.empty_cache()
@@ -309,7 +310,7 @@ def run_ours(args):
                                     f"{B_ALG * L / 1e6:.0f} MB of history",
                        "multi_gpu": "replicas only: one independent grid per rank, no data-path collective"},
             "e2e": {"value": e2e, "unit": "link-timesteps/s", "steps": Ke,
-                    "h2d_bytes_per_step": int(pinned.shape[1] * 8), "d2h_bytes_per_step": 4,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "note": "per step: H2D of the demand row from pinned memory, one native step call, "
                             "D2H of the network-wide pedestrian count (host sync every step)"},
             "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
