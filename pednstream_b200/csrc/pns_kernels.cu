@@ -184,6 +184,7 @@ struct LinkNow {      // state of one link at time index tau, either just comput
 };
 
 // Link.cal_sending_flow at time index tau (link.py:216-370)
+template <int MODE>
 __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, size_t e, int tau, const LinkNow& me,
                                                 float num_rev, const Area& ar, double front_gate, double cum_out_tau,
                                                 double snd_prev, int replica, const pns::DrawKey& key) {
@@ -217,9 +218,9 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
             const int trials = (int)floor(flow);
             o.kind = 2;
             o.n1 = trials;
-            if (c.mode == PNS_RNG_TABLE) {
+            if (MODE == PNS_RNG_TABLE) {
                 flow = (double)c.draw_b[e];
-            } else if (c.mode == PNS_RNG_PHILOX) {
+            } else if (MODE == PNS_RNG_PHILOX) {
                 const float p32 = 0.7f + 0.15f * pns::det_pow08(rf);
                 flow = (double)pns::binomial_philox(key, 1u, trials, (double)p32);
             } else {
@@ -228,11 +229,11 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
         }
     }
     o.sval = flow;
-    if (c.mode == PNS_RNG_REQUEST) return o;
+    if (MODE == PNS_RNG_REQUEST) return o;
     if (p.act > 0.0 && flow > 1.0) {                                       // link.py:351-358
         const int trials = (int)floor(flow);
         int stay;
-        if (c.mode == PNS_RNG_TABLE) stay = c.draw_b[c.row32 + e];
+        if (MODE == PNS_RNG_TABLE) stay = c.draw_b[c.row32 + e];
         else stay = pns::binomial_philox(key, 2u, trials, p.act);
         flow = flow - (double)stay;
     }
@@ -245,6 +246,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
 
 // Link/Separator.cal_receiving_flow at tau, before the reverse sending flow is subtracted
 // (link.py:372-405, 480-507)
+template <int MODE>
 __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev,
                                                  const Area& ar, double back_gate, double cum_in_tau,
                                                  double cum_out_lag, double rcv_prev, const pns::DrawKey& key,
@@ -259,8 +261,8 @@ __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, s
         const int trials = (int)num_rev;        // numpy casts the float32 count to int64 (truncation)
         *n3 = trials;
         int blockers = 0;
-        if (c.mode == PNS_RNG_TABLE) blockers = c.draw_b[2 * c.row32 + e];
-        else if (c.mode == PNS_RNG_PHILOX) blockers = pns::binomial_philox(key, 3u, trials, 0.9);
+        if (MODE == PNS_RNG_TABLE) blockers = c.draw_b[2 * c.row32 + e];
+        else if (MODE == PNS_RNG_PHILOX) blockers = pns::binomial_philox(key, 3u, trials, 0.9);
         else return 0.0;
         if (lag_i < 0) {
             bound = ar.space - (double)blockers;
@@ -269,7 +271,7 @@ __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, s
             bound = x > 0.0 ? x : 0.0;
         }
     }
-    if (c.mode == PNS_RNG_REQUEST) return 0.0;
+    if (MODE == PNS_RNG_REQUEST) return 0.0;
     const double gate_cap = ((back_gate * p.kc) * p.vf) * c.n.unit_time;
     double flow = pymin(bound, gate_cap);
     flow = pymax(flow, 0.0);
@@ -325,7 +327,7 @@ __device__ __forceinline__ float speed_and_travel_time(const LinkP& p, float k_s
 // FLOWS : sending/receiving flows of step t_flows (time index t_flows-1)
 // Every load that does not depend on a computed lag is issued before the first arithmetic so the
 // whole batch is in flight at once; only cumulative_inflow[idx] and the diffusion taps are dependent.
-template <bool R1>
+template <bool R1, int PHASE, int MODE>
 __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,10 +338,13 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     const int l0 = 2 * pair;
     const size_t e[2] = {(size_t)l0 * R + rep, (size_t)(l0 + 1) * R + rep};
     typedef Lanes<R1> V;
-    const bool upd = c.phase & PH_UPDATE, flw = c.phase & PH_FLOWS;
+    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     const int tau = c.t_flows - 1;
 
-    const LinkP* const pp[2] = {c.n.classes + __ldg(c.n.lk_class + l0), c.n.classes + __ldg(c.n.lk_class + l0 + 1)};
+    // networks with a single parameter class (lattices, the shipped 45_intersections) skip the index load
+    const bool one_class = c.n.n_classes == 1;
+    const LinkP* const pp[2] = {c.n.classes + (one_class ? 0 : __ldg(c.n.lk_class + l0)),
+                                c.n.classes + (one_class ? 0 : __ldg(c.n.lk_class + l0 + 1))};
     double gate[2];
     V::ld(c.s.gate, e[0], e[1], gate);
     // ---- batch of independent loads --------------------------------------------------------
@@ -388,7 +393,7 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
         double z[2] = {0.0, 0.0};
         const bool noisy[2] = {pp[0]->sigma > 0.0, pp[1]->sigma > 0.0};
         if (noisy[0] | noisy[1]) {
-            if (c.mode == PNS_RNG_TABLE) {
+            if (MODE == PNS_RNG_TABLE) {
                 V::ld(c.draw_n, e[0], e[1], z);
             } else {
                 pns::DrawKey key;
@@ -446,11 +451,12 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
         // front gate of a plain link is the back gate of its reverse (link.py:110-126); a separator's
         // gates both equal its lane width (link.py:462-478)
         const double front = is_sep(p) ? gate[a] : gate[1 - a];
-        s[a] = sending_flow(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep, key);
-        r[a] = receiving_flow(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], cou_lag[a], rcv_prev[a], key,
-                              &n3[a]);
+        s[a] = sending_flow<MODE>(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep,
+                                  key);
+        r[a] = receiving_flow<MODE>(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], cou_lag[a],
+                                    rcv_prev[a], key, &n3[a]);
     }
-    if (c.mode == PNS_RNG_REQUEST) {
+    if (MODE == PNS_RNG_REQUEST) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             c.io.req_kind[e[a]] = s[a].kind;
@@ -468,8 +474,10 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     V::st(c.f_rcv, e[0], e[1], pymax(q0, 0.0), pymax(q1, 0.0));
 }
 
-template <bool R1>
-__global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_link_pair(const __grid_constant__ Ctx c) { link_pair_body<R1>(c); }
+template <bool R1, int PHASE, int MODE>
+__global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_link_pair(const __grid_constant__ Ctx c) {
+    link_pair_body<R1, PHASE, MODE>(c);
+}
 
 // =================================================================================================
 // PathFinder.update_node_turn_probs (path_finder.py:561-589)
@@ -947,9 +955,21 @@ int check_step_io(const pns_net* net, const pns_step_io* io, int rng_mode) {
     return 0;
 }
 
+template <bool R1, int PHASE>
+void launch_pair_mode(size_t n, cudaStream_t s, const Ctx& c) {
+    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_PHILOX>), blocks_for(n), kBlock, s, c);
+    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_TABLE>), blocks_for(n), kBlock, s, c);
+    else PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_REQUEST>), blocks_for(n), kBlock, s, c);
+}
+template <bool R1>
+void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
+    if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_pair_mode<R1, PH_UPDATE | PH_FLOWS>(n, s, c);
+    else if (c.phase == PH_UPDATE) launch_pair_mode<R1, PH_UPDATE>(n, s, c);
+    else if (c.phase == PH_FLOWS) launch_pair_mode<R1, PH_FLOWS>(n, s, c);
+}
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
-    if (net->replicas == 1) PNS_LAUNCH(k_link_pair<true>, blocks_for(n), kBlock, s, c);
-    else PNS_LAUNCH(k_link_pair<false>, blocks_for(n), kBlock, s, c);
+    if (net->replicas == 1) launch_pair_phase<true>(n, s, c);
+    else launch_pair_phase<false>(n, s, c);
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     if (net->replicas == 1) PNS_LAUNCH(k_node_flows<true>, blocks_for(n), kBlock, s, c);

@@ -187,21 +187,22 @@ __host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
     return k;
 }
 
-// Exact Binomial(n, p); chunks of 512 trials keep q^m representable (binomial additivity).
+// Exact Binomial(n, p), 0 < p < 1, n > 0; chunks of 512 trials keep q^m representable (binomial
+// additivity).  Out of line and with scalar arguments: it is called on a minority of the links and
+// must not bloat the callers' register footprint.
 #ifdef __CUDACC__
 __device__ __noinline__
 #else
 inline
 #endif
-int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
-    if (n <= 0 || !(p > 0.0)) return 0;
-    if (p >= 1.0) return n;
+int binomial_philox_core(uint32_t t, uint32_t link, uint32_t replica, uint32_t k0, uint32_t k1, uint32_t site,
+                         int n, double p) {
     const bool flip = p > 0.5;
     const double pp = flip ? 1.0 - p : p;
     int total = 0, left = n;
     uint32_t chunk = 0;
     while (left > 0) {
-        const Philox4 w = philox4x32_10(key.t, key.link, site | ((chunk >> 1) << 8), key.replica, key.k0, key.k1);
+        const Philox4 w = philox4x32_10(t, link, site | ((chunk >> 1) << 8), replica, k0, k1);
         for (int h = 0; h < 2 && left > 0; ++h) {
             const int m = left < 512 ? left : 512;
             total += binomial_inversion(m, pp, u53(w.v[2 * h], w.v[2 * h + 1]));
@@ -210,6 +211,17 @@ int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
         }
     }
     return flip ? n - total : total;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__
+#else
+inline
+#endif
+int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    return binomial_philox_core(key.t, key.link, key.replica, key.k0, key.k1, site, n, p);
 }
 
 // Standard normal by Box-Muller on one Philox block.
