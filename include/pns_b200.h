@@ -93,7 +93,7 @@ typedef struct pns_link_class {
 typedef struct pns_net {
     int32_t abi_version;
     int32_t n_links, n_nodes, n_cols64, sim_steps, replicas, window, n_edges, n_od, n_demand_rows;
-    int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes;
+    int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes, max_degree, pad_;
     double unit_time;
     const pns_link_class *classes; /* [n_classes] */
     const int32_t *lk_class;       /* [n_links] */

@@ -26,7 +26,7 @@ class PnsNet(C.Structure):
     _fields_ = (
         [(n, _i32) for n in ("abi_version", "n_links", "n_nodes", "n_cols64", "sim_steps", "replicas",
                              "window", "n_edges", "n_od", "n_demand_rows",
-                             "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes")]
+                             "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes", "max_degree", "pad_")]
         + [("unit_time", C.c_double)]
         + [(n, _p) for n in ("classes", "lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed",
                              "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",

@@ -63,6 +63,7 @@ struct Ctx {
     int t_flows;  // FLOWS computes the flows of step t_flows (time index t_flows-1)
     int phase;    // PH_* mask
     int mode;     // PNS_RNG_*
+    int max_degree;   // largest slot count of any node (selects the node kernel's group size)
     const int32_t* draw_b;  // TABLE: R1..R3 outcomes for step t_flows
     const double* draw_n;   // TABLE: R4 noise for step t
     size_t row64, row32;    // elements per history row
@@ -734,6 +735,202 @@ __global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_node_flows(const __g
     }
 }
 
+
+#ifndef PNS_HOST_EMULATION
+// =================================================================================================
+// Single-replica fast path: one thread per *directed link*; the two directions of a corridor sit
+// in adjacent lanes and trade the three values they need from each other (pedestrians, density,
+// sending flow) with warp shuffles.  Same arithmetic as link_pair_body, half the critical path
+// per thread and no cross-direction state to keep in registers.  (The host-emulation test build
+// runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
+template <int PHASE, int MODE>
+__global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__ Ctx c) {
+    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
+    const int l = valid ? (int)gid : 0;
+    const size_t e = (size_t)l;
+    const int tau = c.t_flows - 1;
+    const bool one_class = c.n.n_classes == 1;
+    const LinkP& p = c.n.classes[one_class ? 0 : __ldg(c.n.lk_class + l)];
+    const double gate = c.s.gate[e];
+    // ---- batch of independent loads --------------------------------------------------------
+    double din = 0, dout = 0;
+    float np_ = 0, rs = 0, tt_old = 0;
+    const bool windowed = c.u_tt_old != nullptr;
+    if (upd) {
+        din = c.u_inflow[e]; dout = c.u_outflow[e]; np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
+        if (windowed) tt_old = c.u_tt_old[e];
+    }
+    double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
+    LinkNow me;
+    me.num = 0; me.dens = 0; me.avg_tt = 0;
+    if (flw) {
+        cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
+        const int lag_i = tau + 1 - p.swtau;
+        if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
+        if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
+    }
+    const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
+    const Area ar = link_area(c, p, e, gate);
+    const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
+
+    if (upd) {
+        const int t = c.t;
+        me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
+        me.dens = div_by_area(me.num, ar);                                  // link.py:136
+        const float dens_rev = __shfl_xor_sync(FULL, me.dens, 1);
+        const bool noisy = p.sigma > 0.0;
+        double z = 0.0;
+        if (noisy) {
+            if (MODE == PNS_RNG_TABLE) z = c.draw_n[e];
+            else {
+                // both directions evaluate the pair's Philox block; the even link takes the cosine branch
+                pns::DrawKey key;
+                key.t = (uint32_t)t; key.link = (uint32_t)(l & ~1); key.replica = c.io.replica_base; key.k0 = k0; key.k1 = k1;
+                double g0, g1;
+                pns::normal_pair_philox(key, 4u, &g0, &g1);
+                z = p.sigma * ((l & 1) ? g1 : g0);
+            }
+        }
+        float tt;
+        const float v = speed_and_travel_time(p, me.dens, is_sep(p) ? 0.0f : dens_rev, noisy, z, &tt);
+        float sum = rs + tt;                                                // link.py:183-186
+        if (windowed) {
+            sum = sum - tt_old;
+            me.avg_tt = sum / (float)c.n.window;
+        } else {
+            me.avg_tt = p.tt0;
+        }
+        if (valid) {
+            c.u_num[e] = me.num; c.u_dens[e] = me.dens; c.u_speed[e] = v; c.u_tt[e] = tt;
+            c.u_flow[e] = v * me.dens;                                      // functions.py:97-101
+            if (windowed) c.u_avg[e] = me.avg_tt;
+            c.s.runsum[e] = sum;
+            c.u_bgw[e] = gate;                                              // link.py:188, 451-452
+            if (is_sep(p)) c.u_sepw[e] = gate;
+        }
+    }
+    if (!flw) return;
+    const float num_rev = __shfl_xor_sync(FULL, me.num, 1);
+    pns::DrawKey key;
+    key.t = (uint32_t)c.t_flows; key.link = (uint32_t)l; key.replica = c.io.replica_base; key.k0 = k0; key.k1 = k1;
+    const double front = is_sep(p) ? gate : gate_rev;                       // link.py:110-126, 462-478
+    SendOut s;
+    double r = 0.0;
+    int n3 = -1;
+    if (valid) {
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key);
+        r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
+    } else {
+        s.flow = 0; s.sval = 0; s.kind = 0; s.n1 = 0; s.rf = 0;
+    }
+    if (MODE == PNS_RNG_REQUEST) {
+        if (valid) {
+            c.io.req_kind[e] = s.kind; c.io.req_n1[e] = s.n1; c.io.req_rf[e] = s.rf;
+            c.io.req_sval[e] = s.sval; c.io.req_n3[e] = n3;
+        }
+        return;
+    }
+    const double s_rev = __shfl_xor_sync(FULL, s.flow, 1);
+    if (valid) {
+        c.f_snd[e] = s.flow;
+        // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
+        c.f_rcv[e] = pymax(is_sep(p) ? r : r - s_rev, 0.0);
+    }
+}
+
+// Single-replica node pass with one thread per (node, slot): the GS lanes of a node each own one
+// incoming/outgoing link pair, gather the sending flows of the whole node with shuffles, solve
+// their own *column* of the classic node model (all turns into their outgoing link) and reduce the
+// row sums (outflow of each incoming link) across the group.  Sums of floor()ed flows are integers,
+// so the reduction order does not matter; the demand sums D[j] keep the reference's order.
+template <int GS>
+__global__ void __launch_bounds__(kBlock, 8) k_node_slot(const __grid_constant__ Ctx c) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned node_u = gid / GS;
+    const int k = (int)(gid % GS);                        // my slot
+    const bool in_range = node_u < (unsigned)c.n.n_nodes;
+    const int node = in_range ? (int)node_u : 0;
+    const int lane = threadIdx.x & 31;
+    const int g0 = lane & ~(GS - 1);                      // first lane of my group
+    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
+    const int4 meta = __ldg(rec);
+    const int m = in_range ? (meta.y & 0xff) : 0;
+    const int kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
+    const bool mine = k < m;                              // this lane owns a slot
+    const int L = c.n.n_links;
+    int icol = 0;
+    if (mine) icol = k < 4 ? reinterpret_cast<const int*>(rec + 1)[k] : __ldg(c.n.nd_in_col + meta.x + k);
+    const size_t ei = (size_t)icol, eo = (size_t)(icol ^ 1);
+    double s = 0.0, r = 0.0, co = 0.0, ci = 0.0;
+    if (mine) {
+        if (icol >= L) { s = c.n_demand[meta.z]; r = 1e6; }                 // node.py:176, 186
+        else { s = c.n_snd[ei]; r = c.n_rcv[eo]; }
+        co = c.n_coutp[ei];
+        ci = c.n_cinp[eo];
+        if ((s < 0.0) | (r < 0.0)) atomicOr(c.s.err, PNS_ERR_NEG_NODE_FLOW);
+    }
+    // routed nodes: lane i evaluates row i of the turning fractions, the group then reads columns
+    const double* tf = nullptr;
+    if (tf_mode == 2) {
+        if (k == 0 && m > 0) routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, 0, c.s.tf_routed + meta.w);
+        tf = c.s.tf_routed + meta.w;
+    } else if (tf_mode == 1) {
+        tf = c.s.tf_static + meta.w;
+    }
+    __syncwarp();
+    double s_all[GS];
+#pragma unroll
+    for (int i = 0; i < GS; ++i) s_all[i] = __shfl_sync(FULL, s, g0 + i);
+    double q_in = 0.0;
+    double f[GS];
+#pragma unroll
+    for (int i = 0; i < GS; ++i) f[i] = 0.0;
+    if (kind == 0) {
+        // OneToOneNode.solve (node.py:230-242): q_out[0] = q_in[1] = min(s0, r1), q_out[1] = q_in[0] = min(s1, r0)
+        if (mine) { f[1 - k] = fmin(s_all[1 - k], r); q_in = f[1 - k]; }
+    } else if (mine) {
+        // my column j = k of RegularNode.solve 'classic' (node.py:272-300)
+        const double phi = 1.0 / (double)(m - 1);
+        double w[GS];
+        double D = 0.0;
+#pragma unroll
+        for (int i = 0; i < GS; ++i) {
+            w[i] = 0.0;
+            if (i < m && i != k) {
+                const double pij = tf ? tf[i * (m - 1) + (k < i ? k : k - 1)] : phi;
+                w[i] = pij * s_all[i];
+                D = D + w[i];                          // np.sum(axis=0): rows added in order
+            }
+        }
+        D = D != 0.0 ? D : 1e-5;
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+            if (i < m && i != k) { f[i] = turn_flow(w[i], r, D); q_in += f[i]; }
+        q_in = fmax(0.0, q_in);
+    }
+    // outflow of incoming link i = sum over columns of f[i][.]
+    double q_out = 0.0;
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+        double v = f[i];
+#pragma unroll
+        for (int d = 1; d < GS; d <<= 1) v += __shfl_xor_sync(FULL, v, d);
+        if (i == k) q_out = v;
+    }
+    if (kind != 0) q_out = fmax(0.0, q_out);
+    if (mine) {                                            // Node.update_links (node.py:146-162)
+        c.n_outflow[ei] = q_out;
+        c.n_cout[ei] = co + q_out;
+        c.n_inflow[eo] = q_in;
+        c.n_cin[eo] = ci + q_in;
+    }
+}
+#endif  // !PNS_HOST_EMULATION
+
 // =================================================================================================
 // Control environment (reference rl/builders.py, rl/pz_pednet_env.py)
 struct EnvCtx {
@@ -895,6 +1092,7 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
     c.t_flows = t_flows;
     c.phase = phase;
     c.mode = mode;
+    c.max_degree = net->max_degree;
     c.row64 = (size_t)net->n_cols64 * net->replicas;
     c.row32 = (size_t)net->n_links * net->replicas;
     c.fld64 = c.row64 * (size_t)(net->sim_steps + 1);
@@ -967,11 +1165,35 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
     else if (c.phase == PH_UPDATE) launch_pair_mode<R1, PH_UPDATE>(n, s, c);
     else if (c.phase == PH_FLOWS) launch_pair_mode<R1, PH_FLOWS>(n, s, c);
 }
+#ifndef PNS_HOST_EMULATION
+template <int PHASE>
+void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
+    const unsigned nb = blocks_for(n_links);
+    if (c.mode == PNS_RNG_PHILOX) k_link_lane<PHASE, PNS_RNG_PHILOX><<<nb, kBlock, 0, s>>>(c);
+    else if (c.mode == PNS_RNG_TABLE) k_link_lane<PHASE, PNS_RNG_TABLE><<<nb, kBlock, 0, s>>>(c);
+    else k_link_lane<PHASE, PNS_RNG_REQUEST><<<nb, kBlock, 0, s>>>(c);
+}
+#endif
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
+#ifndef PNS_HOST_EMULATION
+    if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
+        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
+        else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
+        else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, c);
+        return;
+    }
+#endif
     if (net->replicas == 1) launch_pair_phase<true>(n, s, c);
     else launch_pair_phase<false>(n, s, c);
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
+#ifndef PNS_HOST_EMULATION
+    if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per (node, slot)
+        if (c.max_degree <= 4) k_node_slot<4><<<blocks_for(4 * n), kBlock, 0, s>>>(c);
+        else k_node_slot<8><<<blocks_for(8 * n), kBlock, 0, s>>>(c);
+        return;
+    }
+#endif
     if (net->replicas == 1) PNS_LAUNCH(k_node_flows<true>, blocks_for(n), kBlock, s, c);
     else PNS_LAUNCH(k_node_flows<false>, blocks_for(n), kBlock, s, c);
 }

@@ -74,6 +74,7 @@ class Engine:
         net.n_rows = len(p["rt_row_ptr"]) - 1
         net.n_terms = len(p["rt_term_opt"])
         net.n_classes = len(p["classes"])
+        net.max_degree = int((np.asarray(p["nd_meta"])[:, 1] & 0xff).max()) if len(p["nd_meta"]) else 0
         net.unit_time = p["unit_time"]
         for k in _NET_ARRAYS + ("classes",):
             setattr(net, k, _ptr(self._net_t[k]))
