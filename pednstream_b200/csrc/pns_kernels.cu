@@ -188,7 +188,9 @@ struct LinkNow {      // state of one link at time index tau, either just comput
 template <int MODE>
 __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, size_t e, int tau, const LinkNow& me,
                                                 float num_rev, const Area& ar, double front_gate, double cum_out_tau,
-                                                double snd_prev, int replica, const pns::DrawKey& key) {
+                                                double snd_prev, int replica, const pns::DrawKey& key,
+                                                int pre_idx0 = -1, double pre_val0 = 0.0, int pre_idx1 = -1,
+                                                double pre_val1 = 0.0) {
     SendOut o;
     o.kind = 0; o.n1 = 0; o.rf = 0.0f; o.sval = 0.0; o.flow = 0.0;
     if (tau < p.fftau) return o;                                          // link.py:267-269
@@ -197,7 +199,9 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
     if (lag == 0) atomicOr(c.s.err + replica, PNS_ERR_ZERO_LAG);
     const int idx = max(0, tau + 1 - lag);
     const float cong = clip01((me.dens - p.kc32) / p.kj_minus_kc32);
-    const double arrived_raw = H64(c, PNS_F64_CUM_INFLOW, idx)[e] - cum_out_tau;
+    // cumulative_inflow[idx]: the caller may have fetched the rows of the two most likely lags early
+    const double cin_idx = idx == pre_idx0 ? pre_val0 : idx == pre_idx1 ? pre_val1 : H64(c, PNS_F64_CUM_INFLOW, idx)[e];
+    const double arrived_raw = cin_idx - cum_out_tau;
     const double arrived = arrived_raw > 0.0 ? arrived_raw : 0.0;
     const double boundary = (double)(cong * me.num) + (double)(1.0f - cong) * arrived;
     const double gate_cap = ((front_gate * p.kc) * p.vf) * c.n.unit_time;
@@ -772,6 +776,19 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
         if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
         if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
     }
+    // The arrival row cumulative_inflow[tau+1-lag] depends on the travel-time lag computed below; in
+    // free flow the lag is the free-flow lag or one less (speed noise), so fetch both rows now and
+    // fall back to a dependent load only when the link is congested.
+    int pre_i0 = -1, pre_i1 = -1;
+    double pre_v0 = 0.0, pre_v1 = 0.0;
+    if (flw && tau >= p.fftau) {
+        pre_i0 = max(0, tau + 1 - p.fftau);
+        pre_v0 = H64(c, PNS_F64_CUM_INFLOW, pre_i0)[e];
+        if (p.fftau > 1) {
+            pre_i1 = max(0, tau + 2 - p.fftau);
+            pre_v1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1)[e];
+        }
+    }
     const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
     const Area ar = link_area(c, p, e, gate);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
@@ -821,7 +838,8 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     double r = 0.0;
     int n3 = -1;
     if (valid) {
-        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key);
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, pre_i0, pre_v0, pre_i1,
+                               pre_v1);
         r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
     } else {
         s.flow = 0; s.sval = 0; s.kind = 0; s.n1 = 0; s.rf = 0;
@@ -1188,7 +1206,7 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
-    if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per (node, slot)
+    if (net->replicas == 1 && getenv("PNS_NODE_SLOT")) {          // experimental: one thread per (node, slot)
         if (c.max_degree <= 4) k_node_slot<4><<<blocks_for(4 * n), kBlock, 0, s>>>(c);
         else k_node_slot<8><<<blocks_for(8 * n), kBlock, 0, s>>>(c);
         return;

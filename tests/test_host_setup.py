@@ -100,3 +100,14 @@ def test_optimal_mode_is_rejected():
 def test_missing_scenario_raises():
     with pytest.raises(FileNotFoundError):
         NetworkEnvGenerator().create_network("no_such_scenario")
+
+
+def test_reference_import_paths_resolve_to_this_package():
+    """A script written against the reference (`from src.LTM.network import Network`) runs unchanged."""
+    import importlib
+    import pednstream_b200
+    for mod, names in (("src.LTM.network", ["Network"]), ("src.LTM.link", ["Link", "Separator"]),
+                       ("src.utils.env_loader", ["NetworkEnvGenerator"]), ("src.utils.config", ["load_config"])):
+        m = importlib.import_module(mod)
+        for n in names:
+            assert getattr(m, n) is getattr(pednstream_b200, n)
