@@ -268,7 +268,7 @@ def run_ours(args):
     for k, t in enumerate(range(t_next, t_next + Ke)):
         eng.demand[t - 1, : pinned.shape[1]].copy_(pinned[t - 1], non_blocking=True)     # H2D, this step's input
         eng.run(t, 1)                                                                    # the public step call
-        torch.sum(num_hist[t], out=result_dev[k])                                        # the step's metric
+        result_dev[k: k + 1].copy_(num_hist[t].sum().reshape(1))                         # the step's metric
         result_host[k: k + 1].copy_(result_dev[k: k + 1], non_blocking=True)             # D2H, every step
     e3.record()
     barrier()
