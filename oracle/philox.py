@@ -178,14 +178,80 @@ def normal_philox(seed, t, link, replica, site):
     return math.sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2)
 
 
+# ---- float32 Box-Muller with exact fused multiply-adds (mirrors pns_rng.cuh) -----------------------
+from fractions import Fraction
+
+F32 = np.float32
+
+
+def _round_f32(fr: Fraction) -> np.float32:
+    """Correctly rounded (nearest, ties to even) float32 of an exact rational."""
+    if fr == 0:
+        return F32(0.0)
+    guess = F32(float(fr))                       # may be off by one ulp through double rounding
+    cands = {guess, np.nextafter(guess, F32(np.inf)), np.nextafter(guess, F32(-np.inf))}
+    best = None
+    for c in cands:
+        if not np.isfinite(c):
+            continue
+        err = abs(Fraction(float(c)) - fr)
+        key = (err, int(np.float32(c).view(np.uint32)) & 1)      # ties -> even mantissa
+        if best is None or key < best[0]:
+            best = (key, c)
+    return F32(best[1])
+
+
+def fmaf(a, b, c) -> np.float32:
+    return _round_f32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def det_logf(x):
+    x = F32(x)
+    bits = int(x.view(np.uint32))
+    e = ((bits >> 23) & 0xFF) - 127
+    m = np.uint32((bits & 0x007FFFFF) | 0x3F800000).view(np.float32)
+    if m > F32(1.41421356):
+        m = m * F32(0.5)
+        e += 1
+    f = m - F32(1.0)
+    z = f * f
+    y = F32(7.0376836292e-2)
+    for coef in (-1.1514610310e-1, 1.1676998740e-1, -1.2420140846e-1, 1.4249322787e-1, -1.6668057665e-1,
+                 2.0000714765e-1, -2.4999993993e-1, 3.3333331174e-1):
+        y = fmaf(y, f, F32(coef))
+    y = (y * f) * z
+    fe = F32(e)
+    y = fmaf(F32(-2.12194440e-4), fe, y)
+    y = fmaf(F32(-0.5), z, y)
+    return fmaf(F32(0.693359375), fe, f + y)
+
+
+def det_sincos2pif(u):
+    u = F32(u)
+    u4 = u * F32(4.0)
+    q = int(u4)
+    f = u4 - F32(q)
+    lo = f <= F32(0.5)
+    a = (f if lo else F32(1.0) - f) * F32(1.57079632679)
+    z = a * a
+    ps = fmaf(F32(-1.9515295891e-4), z, F32(8.3321608736e-3))
+    ps = fmaf(ps, z, F32(-1.6666654611e-1))
+    sn = fmaf(ps * z, a, a)
+    pc = fmaf(F32(2.443315711809948e-5), z, F32(-1.388731625493765e-3))
+    pc = fmaf(pc, z, F32(4.166664568298827e-2))
+    cs = fmaf(pc * z, z, fmaf(F32(-0.5), z, F32(1.0)))
+    c, s = (cs, sn) if lo else (sn, cs)
+    return ((c, s), (-s, c), (-c, -s), (s, -c))[q]
+
+
 def normal_pair_philox(seed, t, link, replica, site):
-    """Two independent standard normals from one block: (cosine branch, sine branch)."""
+    """Two independent standard normals from one block: (cosine branch, sine branch), float32 math."""
     w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
-    u1 = 1.0 - u53(w[0], w[1])
-    u2 = u53(w[2], w[3])
-    rad = math.sqrt(-2.0 * det_log(u1))
-    cs, sn = det_sincos2pi(u2)
-    return rad * cs, rad * sn
+    u1 = F32((w[0] >> 8) + 1) * F32(5.9604644775390625e-8)
+    u2 = F32(w[1] >> 8) * F32(5.9604644775390625e-8)
+    rad = np.sqrt(F32(-2.0) * det_logf(u1))
+    cs, sn = det_sincos2pif(u2)
+    return float(rad * cs), float(rad * sn)
 
 
 class PhiloxDraws:

@@ -53,6 +53,9 @@ constexpr int kBlock = 128;
 #ifndef PNS_MIN_BLOCKS
 #define PNS_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (tuning knob)
 #endif
+#ifndef PNS_NODE_MIN_BLOCKS
+#define PNS_NODE_MIN_BLOCKS 4
+#endif
 constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
 struct Ctx {
@@ -720,7 +723,7 @@ __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, 
 
 // Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
 template <bool R1>
-__global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
+__global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)c.n.n_nodes * R) return;

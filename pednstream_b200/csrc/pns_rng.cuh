@@ -238,22 +238,84 @@ __host__ __device__ inline double normal_philox(const DrawKey& key, uint32_t sit
     return rad * det_cos2pi(u2);
 }
 
+// ---- float32 Box-Muller (speed noise, functions.py:132-133) ---------------------------------------
+// The noise sample feeds a float32 history value (speed[t]), so it is generated in float32: one
+// Philox block -> two 24-bit uniforms -> (radius, angle) -> two independent standard normals.
+// Polynomials are the Cephes single-precision kernels, evaluated with explicit fused
+// multiply-adds (one rounding each) so that oracle/philox.py can restate them exactly.
+__host__ __device__ inline float pns_fmaf(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+__host__ __device__ inline float pns_sqrtf(float x) {
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(x);
+#else
+    return __builtin_sqrtf(x);
+#endif
+}
+
+__host__ __device__ inline float det_logf(float x) {   // x in (0, 1], normal
+    union { float f; uint32_t u; } cv;
+    cv.f = x;
+    int e = (int)((cv.u >> 23) & 0xffu) - 127;
+    cv.u = (cv.u & 0x007fffffu) | 0x3f800000u;
+    float m = cv.f;                                      // [1, 2)
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    const float f = m - 1.0f;
+    const float z = f * f;
+    float y = 7.0376836292e-2f;
+    y = pns_fmaf(y, f, -1.1514610310e-1f);
+    y = pns_fmaf(y, f, 1.1676998740e-1f);
+    y = pns_fmaf(y, f, -1.2420140846e-1f);
+    y = pns_fmaf(y, f, 1.4249322787e-1f);
+    y = pns_fmaf(y, f, -1.6668057665e-1f);
+    y = pns_fmaf(y, f, 2.0000714765e-1f);
+    y = pns_fmaf(y, f, -2.4999993993e-1f);
+    y = pns_fmaf(y, f, 3.3333331174e-1f);
+    y = (y * f) * z;
+    const float fe = (float)e;
+    y = pns_fmaf(-2.12194440e-4f, fe, y);
+    y = pns_fmaf(-0.5f, z, y);
+    return pns_fmaf(0.693359375f, fe, f + y);
+}
+
+// (cos, sin)(2*pi*u), u in [0, 1), float32
+__host__ __device__ inline void det_sincos2pif(float u, float* cos_out, float* sin_out) {
+    const float half_pi = 1.57079632679f;
+    const float u4 = u * 4.0f;
+    const int q = (int)u4;                               // 0..3
+    const float f = u4 - (float)q;
+    const bool lo = f <= 0.5f;
+    const float a = (lo ? f : 1.0f - f) * half_pi;       // [0, pi/4]
+    const float z = a * a;
+    float ps = pns_fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = pns_fmaf(ps, z, -1.6666654611e-1f);
+    const float sn = pns_fmaf(ps * z, a, a);
+    float pc = pns_fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = pns_fmaf(pc, z, 4.166664568298827e-2f);
+    const float cs = pns_fmaf(pc * z, z, pns_fmaf(-0.5f, z, 1.0f));
+    const float c = lo ? cs : sn, s = lo ? sn : cs;
+    if (q == 0) { *cos_out = c; *sin_out = s; }
+    else if (q == 1) { *cos_out = -s; *sin_out = c; }
+    else if (q == 2) { *cos_out = -c; *sin_out = -s; }
+    else { *cos_out = s; *sin_out = -c; }
+}
+
 // Two independent standard normals from one Philox block (Box-Muller, both branches): the two
 // directions of a link pair share the block, the even link takes the cosine branch.
 __host__ __device__ inline void normal_pair_philox(const DrawKey& key, uint32_t site, double* g0, double* g1) {
     const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
-    const double u1 = 1.0 - u53(w.v[0], w.v[1]);  // (0, 1]
-    const double u2 = u53(w.v[2], w.v[3]);
-    double rad = -2.0 * det_log(u1);
-#ifdef __CUDA_ARCH__
-    rad = __dsqrt_rn(rad);
-#else
-    rad = __builtin_sqrt(rad);
-#endif
-    double cs, sn;
-    det_sincos2pi(u2, &cs, &sn);
-    *g0 = rad * cs;
-    *g1 = rad * sn;
+    const float u1 = (float)((w.v[0] >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1], 24 bits
+    const float u2 = (float)(w.v[1] >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+    const float rad = pns_sqrtf(-2.0f * det_logf(u1));
+    float cs, sn;
+    det_sincos2pif(u2, &cs, &sn);
+    *g0 = (double)(rad * cs);
+    *g1 = (double)(rad * sn);
 }
 
 }  // namespace pns

@@ -131,6 +131,9 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         has = m_o > k
         meta[has, 4 + k] = in_col[nd_ptr[:-1][has] + k]
 
+    from .plan import link_solve_records
+    lk_solve = link_solve_records(meta, in_col, L)
+
     from .plan import class_record, CLASS_DTYPE
     rec = class_record(lk["length"], lk["width"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"],
                        lk["gamma"], lk["activity_probability"], lk["bi_factor"], lk["speed_noise_std"],
@@ -140,7 +143,7 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         window=int(round(100 / unit_time)),
         classes=np.array([rec], dtype=CLASS_DTYPE).reshape(1), lk_class=np.zeros(L, dtype=np.int32),
         lk_width=np.full(L, float(lk["width"])), has_separators=False,
-        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32),
+        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_solve=lk_solve,
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,
     )

@@ -79,6 +79,28 @@ def link_classes(links, unit_time):
     return np.array(rows, dtype=CLASS_DTYPE).reshape(len(rows)), _i32(idx)
 
 
+def link_solve_records(nd_meta, nd_in_col, n_links):
+    """[n_links, 12] int32: what a link needs to evaluate its own row/column of the node model at
+    its two ends without a separate node pass (`link_solve` in csrc/pns_kernels.cu):
+      [0] m | kind<<8 | tf_mode<<16 | slot<<24 of the END node (slot = position of the link in the
+          node's incoming list), [1] that node's tf offset, [2..5] in-columns of its slots 0..3;
+      [6..11] the same for the START node (slot = position in the outgoing list, which is the slot of
+          the link's reverse in the incoming list).
+    Only meaningful when no node has more than four slots."""
+    nd_meta = np.asarray(nd_meta)
+    m = nd_meta[:, 1] & 0xff
+    node_of_slot = np.repeat(np.arange(len(nd_meta)), m)
+    slot = np.arange(len(nd_in_col)) - np.repeat(nd_meta[:, 0], m)
+    phys = np.asarray(nd_in_col) < n_links
+    cols, node, k = np.asarray(nd_in_col)[phys], node_of_slot[phys], slot[phys]
+    rec = np.zeros((n_links, 12), dtype=np.int32)
+    for off, target in ((0, cols), (6, cols ^ 1)):      # incoming link ends here; its reverse starts here
+        rec[target, off] = nd_meta[node, 1] | (k << 24)
+        rec[target, off + 1] = nd_meta[node, 3]
+        rec[target, off + 2: off + 6] = nd_meta[node, 4:8]
+    return rec
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -133,6 +155,7 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
         tf_ptr += m * (m - 1)
     p["nd_meta"] = _i32(meta).reshape(-1, 8)
     p["nd_in_col"] = _i32(in_col)
+    p["lk_solve"] = link_solve_records(p["nd_meta"], p["nd_in_col"], L)
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
