@@ -109,6 +109,10 @@ typedef struct pns_net {
                                    tf_mode: 0 uniform 1/(m-1) (network.py:269-271), 1 tf_static, 2 routed */
     const int32_t *nd_in_col;   /* [slots] history column of the incoming link of each slot */
     const int32_t *nd_routed;   /* [n_nodes] index into the routed-node arrays, -1 = none */
+    const int32_t *lk_solve;    /* [n_links][12] per-link view of the node model at both ends of the link (may be
+                                   null): {m | kind<<8 | tf_mode<<16 | slot<<24, tf offset, in-columns of slots 0..3}
+                                   of the END node, then the same of the START node; used when max_degree <= 4 */
+    const int32_t *dem_node;    /* [n_demand_rows] node index owning each demand row (= each virtual link pair) */
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;

@@ -28,7 +28,7 @@ class PnsNet(C.Structure):
                              "window", "n_edges", "n_od", "n_demand_rows",
                              "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes", "max_degree", "pad_")]
         + [("unit_time", C.c_double)]
-        + [(n, _p) for n in ("classes", "lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed",
+        + [(n, _p) for n in ("classes", "lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed", "lk_solve", "dem_node",
                              "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",

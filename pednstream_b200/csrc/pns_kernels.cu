@@ -56,7 +56,7 @@ constexpr int kBlock = 128;
 #ifndef PNS_NODE_MIN_BLOCKS
 #define PNS_NODE_MIN_BLOCKS 4
 #endif
-constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
+constexpr int PH_UPDATE = 1, PH_FLOWS = 2, PH_SOLVE = 4;   // SOLVE: node model evaluated per link, fused in front of UPDATE
 
 struct Ctx {
     pns_net n;
@@ -743,6 +743,153 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
 }
 
 
+
+// =================================================================================================
+// Per-link evaluation of the node model (networks whose nodes have at most four slots).
+// A directed link l = (a -> b) needs two numbers from the node pass: its outflow q_out (row of l
+// in the solve at its end node b) and its inflow q_in (column of l in the solve at its start node
+// a).  Both are functions of the sending/receiving flows around the two nodes only, so the link's
+// own thread can evaluate them from the per-link record `lk_solve` instead of waiting for a node
+// kernel to scatter them -- the turns are recomputed by every link that needs them, with the same
+// operations in the same order as RegularNode.solve / OneToOneNode.solve (node.py:230-300).
+
+// sending flow entering the node through slot x (virtual origin link: the demand row)
+template <bool R1>
+__device__ __forceinline__ double slot_sending(const Ctx& c, int col, int rep) {
+    const int R = R1 ? 1 : c.n.replicas;
+    if (col >= c.n.n_links) return c.n_demand[(size_t)((col - c.n.n_links) >> 1) * R + rep];   // node.py:176
+    return c.n_snd[(size_t)col * R + rep];
+}
+// receiving flow of the outgoing link of slot x (virtual destination link: M = 1e6, node.py:186)
+template <bool R1>
+__device__ __forceinline__ double slot_receiving(const Ctx& c, int col, int rep) {
+    const int R = R1 ? 1 : c.n.replicas;
+    if (col >= c.n.n_links) return 1e6;
+    return c.n_rcv[(size_t)(col ^ 1) * R + rep];
+}
+
+template <bool R1>
+__device__ __forceinline__ void link_solve(const Ctx& c, int l, int rep, double* q_out, double* q_in) {
+    const int R = R1 ? 1 : c.n.replicas;
+    const int4* rec = reinterpret_cast<const int4*>(c.n.lk_solve) + 3 * (size_t)l;
+    const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+    const int hdr[2] = {r0.x, r1.z};
+    const int tfp[2] = {r0.y, r1.w};
+    const int cols[2][4] = {{r0.z, r0.w, r1.x, r1.y}, {r2.x, r2.y, r2.z, r2.w}};
+    bool negative = false;
+#pragma unroll
+    for (int end = 0; end < 2; ++end) {       // 0: end node (row of l -> q_out); 1: start node (column of l -> q_in)
+        const int m = hdr[end] & 0xff, kind = (hdr[end] >> 8) & 0xff, tf_mode = (hdr[end] >> 16) & 0xff;
+        const int k = (hdr[end] >> 24) & 0xff;
+        double s[4], r[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            s[x] = 0.0; r[x] = 0.0;
+            if (x < m) {
+                s[x] = slot_sending<R1>(c, cols[end][x], rep);
+                // the row needs every receiving flow, the column only its own
+                if (end == 0 || x == k) r[x] = slot_receiving<R1>(c, cols[end][x], rep);
+                negative |= (s[x] < 0.0) | (r[x] < 0.0);
+            }
+        }
+        double q = 0.0;
+        if (kind == 0) {
+            // OneToOneNode.solve: q_out[i] = min(s[i], r[1-i]); q_in[j] = min(s[1-j], r[j])
+            q = end == 0 ? fmin(s[k & 1], r[1 - (k & 1)]) : fmin(s[1 - (k & 1)], r[k & 1]);
+        } else {
+            const double* tf = nullptr;
+            size_t ts = 1;
+            if (tf_mode == 2) { tf = c.s.tf_routed + (size_t)tfp[end] * R + rep; ts = (size_t)R; }
+            else if (tf_mode == 1) tf = c.s.tf_static + tfp[end];
+            const double phi = 1.0 / (double)(m - 1);
+            // w(x, j) = P[x][j] * s[x]; D[j] = sum over x != j in slot order
+            if (end == 1) {
+                double D = 0.0, w[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    w[x] = 0.0;
+                    if (x < m && x != k) {
+                        w[x] = (tf ? tf[(size_t)(x * (m - 1) + (k < x ? k : k - 1)) * ts] : phi) * s[x];
+                        D = D + w[x];
+                    }
+                }
+                D = D != 0.0 ? D : 1e-5;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (x < m && x != k) q += turn_flow(w[x], r[k], D);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= m || j == k) continue;
+                    double D = 0.0, wk = 0.0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        if (x < m && x != j) {
+                            const double w = (tf ? tf[(size_t)(x * (m - 1) + (j < x ? j : j - 1)) * ts] : phi) * s[x];
+                            D = D + w;
+                            if (x == k) wk = w;
+                        }
+                    }
+                    D = D != 0.0 ? D : 1e-5;
+                    q += turn_flow(wk, r[j], D);
+                }
+            }
+            q = fmax(0.0, q);
+        }
+        if (end == 0) *q_out = q; else *q_in = q;
+    }
+    if (negative) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
+}
+
+// Turning fractions of every routed node for step t (PathFinder.update_turning_fractions +
+// check_fractions), needed up front when the node model is evaluated per link.
+template <bool R1>
+__global__ void __launch_bounds__(kBlock) k_route_tf(const __grid_constant__ Ctx c) {
+    const int R = R1 ? 1 : c.n.replicas;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)c.n.n_routed * R) return;
+    const int routed = R1 ? (int)gid : (int)(gid / R);
+    const int rep = R1 ? 0 : (int)(gid % R);
+    const int node = c.n.rt_routed_nodes[routed];
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node);
+    routed_fractions(c, routed, meta.y & 0xff, c.t, rep, c.s.tf_routed + (size_t)meta.w * R + rep);
+}
+
+// Stand-alone form of the per-link node pass: writes inflow/outflow/cumulative counts of the
+// physical links at row t.  (The single-replica lane kernel evaluates link_solve in registers
+// instead; this kernel is what the host-emulation tests and the batched path can run.)
+template <bool R1>
+__global__ void __launch_bounds__(kBlock) k_link_solve(const __grid_constant__ Ctx c) {
+    const int R = R1 ? 1 : c.n.replicas;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)c.n.n_links * R) return;
+    const int l = R1 ? (int)gid : (int)(gid / R);
+    const int rep = R1 ? 0 : (int)(gid % R);
+    const size_t e = (size_t)l * R + rep;
+    double q_out, q_in;
+    link_solve<R1>(c, l, rep, &q_out, &q_in);
+    c.n_outflow[e] = q_out;
+    c.n_cout[e] = c.n_coutp[e] + q_out;
+    c.n_inflow[e] = q_in;
+    c.n_cin[e] = c.n_cinp[e] + q_in;
+}
+
+// Virtual origin/destination links have no link thread: their node runs the full node model and
+// only the counters of the virtual columns are kept from it.
+template <bool R1>
+__global__ void __launch_bounds__(kBlock) k_virtual_flows(const __grid_constant__ Ctx c) {
+    const int R = R1 ? 1 : c.n.replicas;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)c.n.n_demand_rows * R) return;
+    const int row = R1 ? (int)gid : (int)(gid / R);
+    const int rep = R1 ? 0 : (int)(gid % R);
+    const int node = c.n.dem_node[row];
+    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
+    const int4 meta = __ldg(rec), cols = __ldg(rec + 1);
+    const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
+    node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w, cols);
+}
+
 #ifndef PNS_HOST_EMULATION
 // =================================================================================================
 // Single-replica fast path: one thread per *directed link*; the two directions of a corridor sit
@@ -752,7 +899,7 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
 template <int PHASE, int MODE>
 __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__ Ctx c) {
-    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
+    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0, slv = (PHASE & PH_SOLVE) != 0;
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
@@ -766,15 +913,19 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     double din = 0, dout = 0;
     float np_ = 0, rs = 0, tt_old = 0;
     const bool windowed = c.u_tt_old != nullptr;
+    double cin_prev = 0, cou_prev = 0;
     if (upd) {
-        din = c.u_inflow[e]; dout = c.u_outflow[e]; np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
+        if (slv) { cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e]; }
+        else { din = c.u_inflow[e]; dout = c.u_outflow[e]; }
+        np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
         if (windowed) tt_old = c.u_tt_old[e];
     }
     double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
     LinkNow me;
     me.num = 0; me.dens = 0; me.avg_tt = 0;
     if (flw) {
-        cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
+        if (!slv) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
+        snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
         const int lag_i = tau + 1 - p.swtau;
         if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
         if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
@@ -796,6 +947,16 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     const Area ar = link_area(c, p, e, gate);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
 
+    if (slv) {
+        // node pass of step t for this link: its inflow/outflow and cumulative counts (node.py:146-162)
+        if (valid) {
+            link_solve<true>(c, l, 0, &dout, &din);
+            cin_tau = cin_prev + din;
+            cou_tau = cou_prev + dout;
+            c.n_outflow[e] = dout; c.n_cout[e] = cou_tau;
+            c.n_inflow[e] = din;   c.n_cin[e] = cin_tau;
+        }
+    }
     if (upd) {
         const int t = c.t;
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
@@ -1198,7 +1359,9 @@ void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
-        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
+        if (c.phase == (PH_SOLVE | PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_SOLVE | PH_UPDATE | PH_FLOWS>(2 * n, s, c);
+        else if (c.phase == (PH_SOLVE | PH_UPDATE)) launch_lane_mode<PH_SOLVE | PH_UPDATE>(2 * n, s, c);
+        else if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
         else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
         else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, c);
         return;
@@ -1207,7 +1370,36 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     if (net->replicas == 1) launch_pair_phase<true>(n, s, c);
     else launch_pair_phase<false>(n, s, c);
 }
+bool use_fused_solve(const pns_net* net) {
+#ifdef PNS_HOST_EMULATION
+    (void)net;
+    return false;
+#else
+    static const bool off = getenv("PNS_NO_FUSE") != nullptr || getenv("PNS_PAIR_THREADS") != nullptr;
+    return !off && net->replicas == 1 && net->lk_solve && net->dem_node && net->max_degree <= 4;
+#endif
+}
+bool use_link_solve(const pns_net* net) {
+    static const bool want = getenv("PNS_LINK_SOLVE") != nullptr;
+    return want && net->lk_solve && net->dem_node && net->max_degree <= 4;
+}
+// node pass evaluated per link (+ the few nodes that own virtual links, + routed fractions first)
+void launch_link_solve(const pns_net* net, cudaStream_t s, const Ctx& c) {
+    const size_t R = net->replicas;
+    const size_t n_rt = (size_t)net->n_routed * R, n_lk = (size_t)net->n_links * R, n_v = (size_t)net->n_demand_rows * R;
+    if (net->replicas == 1) {
+        if (n_rt) PNS_LAUNCH(k_route_tf<true>, blocks_for(n_rt), kBlock, s, c);
+        if (n_lk) PNS_LAUNCH(k_link_solve<true>, blocks_for(n_lk), kBlock, s, c);
+        if (n_v) PNS_LAUNCH(k_virtual_flows<true>, blocks_for(n_v), kBlock, s, c);
+    } else {
+        if (n_rt) PNS_LAUNCH(k_route_tf<false>, blocks_for(n_rt), kBlock, s, c);
+        if (n_lk) PNS_LAUNCH(k_link_solve<false>, blocks_for(n_lk), kBlock, s, c);
+        if (n_v) PNS_LAUNCH(k_virtual_flows<false>, blocks_for(n_v), kBlock, s, c);
+    }
+}
+
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
+    if (use_link_solve(net)) { launch_link_solve(net, s, c); return; }
 #ifndef PNS_HOST_EMULATION
     if (net->replicas == 1 && getenv("PNS_NODE_SLOT")) {          // experimental: one thread per (node, slot)
         if (c.max_degree <= 4) k_node_slot<4><<<blocks_for(4 * n), kBlock, 0, s>>>(c);
@@ -1246,6 +1438,29 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     (void)ms; (void)launches;
 #define PNS_MARK(k, j) do { } while (0)
 #endif
+    if (use_fused_solve(net)) {
+        // single replica, nodes of degree <= 4: the node model is evaluated inside the link kernel
+        //   FLOWS(t0) | [route(t) | virtual(t) | SOLVE+UPDATE(t)+FLOWS(t+1)] ... | SOLVE+UPDATE(t_last)
+        for (int k = 0; k <= n_steps; ++k) {
+            const int t = t0 + k - 1;
+            if (k > 0) {
+                const Ctx cn = make_ctx(net, st, io, 0, t, t, rng_mode, k - 1, k - 1);
+                PNS_MARK(k - 1, 1);
+                if (z.n_grp) {
+                    PNS_LAUNCH(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
+                    PNS_LAUNCH(k_route_tf<true>, blocks_for((size_t)net->n_routed), kBlock, s, cn);
+                }
+                PNS_MARK(k - 1, 2);
+                if (net->n_demand_rows) PNS_LAUNCH(k_virtual_flows<true>, blocks_for((size_t)net->n_demand_rows), kBlock, s, cn);
+                PNS_MARK(k - 1, 3);
+            }
+            const int phase = (k > 0 ? (PH_SOLVE | PH_UPDATE) : 0) | (k < n_steps ? PH_FLOWS : 0);
+            const Ctx cp = make_ctx(net, st, io, phase, t, t0 + k, rng_mode, k - 1, k);
+            PNS_MARK(k, 0);
+            if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
+            if (k == n_steps) PNS_MARK(k, 1);
+        }
+    } else {
     // launch k (0..n_steps): pair kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
     for (int k = 0; k <= n_steps; ++k) {
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
@@ -1259,6 +1474,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
+    }
     }
 #undef PNS_MARK
 #ifndef PNS_HOST_EMULATION

@@ -21,7 +21,7 @@ import torch
 from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
-_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed",
+_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed", "lk_solve", "dem_node",
                "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",

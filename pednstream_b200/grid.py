@@ -143,7 +143,7 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         window=int(round(100 / unit_time)),
         classes=np.array([rec], dtype=CLASS_DTYPE).reshape(1), lk_class=np.zeros(L, dtype=np.int32),
         lk_width=np.full(L, float(lk["width"])), has_separators=False,
-        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_solve=lk_solve,
+        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_solve=lk_solve, dem_node=np.nonzero(virtual[order])[0].astype(np.int32),
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,
     )

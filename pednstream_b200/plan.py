@@ -159,6 +159,7 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
+    p["dem_node"] = _i32([n.index for n in demand_nodes])
     p["n_edges"] = tf_ptr
 
     # ---- route plan -------------------------------------------------------------------
