@@ -1375,8 +1375,11 @@ bool use_fused_solve(const pns_net* net) {
     (void)net;
     return false;
 #else
-    static const bool off = getenv("PNS_NO_FUSE") != nullptr || getenv("PNS_PAIR_THREADS") != nullptr;
-    return !off && net->replicas == 1 && net->lk_solve && net->dem_node && net->max_degree <= 4;
+    // Measured on B200 (profiles/r1_e_*): recomputing the turns per link triples the scattered 8-byte
+    // loads of sending/receiving flows and loses to the node kernel (118 vs 71 us per 512x512 step), so
+    // the fused SOLVE phase is an opt-in experiment, not the default.
+    static const bool on = getenv("PNS_FUSE_SOLVE") != nullptr && getenv("PNS_PAIR_THREADS") == nullptr;
+    return on && net->replicas == 1 && net->lk_solve && net->dem_node && net->max_degree <= 4;
 #endif
 }
 bool use_link_solve(const pns_net* net) {
