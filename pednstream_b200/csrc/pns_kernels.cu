@@ -609,19 +609,19 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     const int inl[4] = {first4.x, first4.y, first4.z, first4.w};     // slots 0..3 come with the node record
 #pragma unroll
     for (int i = 0; i < m; ++i) icol[i] = i < 4 ? inl[i < 4 ? i : 0] : __ldg(c.n.nd_in_col + base + i);
-    double s[CAP], r[CAP], co[CAP], ci[CAP];
+    // Register diet (the kernel is latency bound, so resident warps matter more than early loads):
+    // only the sending/receiving flows live through the solve; the previous cumulative counts are
+    // fetched right before the stores.
+    double s[CAP], r[CAP];
 #pragma unroll
     for (int i = 0; i < m; ++i) {
-        const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
         if (icol[i] >= L) {
             s[i] = c.n_demand[(size_t)dem_row * R + rep];                  // node.py:176
             r[i] = 1e6;                                                     // node.py:186
         } else {
-            s[i] = c.n_snd[ei];
-            r[i] = c.n_rcv[eo];
+            s[i] = c.n_snd[(size_t)icol[i] * R + rep];
+            r[i] = c.n_rcv[(size_t)(icol[i] ^ 1) * R + rep];
         }
-        co[i] = c.n_coutp[ei];
-        ci[i] = c.n_cinp[eo];
     }
     bool negative = false;
 #pragma unroll
@@ -634,84 +634,61 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         const double a = fmin(s[0], r[CAP > 1 ? 1 : 0]), b = fmin(s[CAP > 1 ? 1 : 0], r[0]);
         q_out[0] = a; q_out[CAP > 1 ? 1 : 0] = b;
         q_in[0] = b;  q_in[CAP > 1 ? 1 : 0] = a;
-    } else if (tf_mode == 0) {
-        // RegularNode.solve, 'classic' (node.py:272-300) with the default uniform fractions
-        // phi = 1/(m-1) (network.py:269-271): W[i][j] = phi*s[i] for every j != i
-        const double phi = 1.0 / (double)(m - 1);
-        double w[CAP], D[CAP];
-#pragma unroll
-        for (int i = 0; i < m; ++i) w[i] = phi * s[i];
-#pragma unroll
-        for (int j = 0; j < m; ++j) {
-            double acc = 0.0;          // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
-#pragma unroll
-            for (int i = 0; i < m; ++i)
-                if (i != j) acc = acc + w[i];
-            D[j] = acc != 0.0 ? acc : 1e-5;
-            q_in[j] = 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < m; ++i) {
-            double out_i = 0.0;
-#pragma unroll
-            for (int j = 0; j < m; ++j) {
-                if (i == j) continue;
-                const double f = turn_flow(w[i], r[j], D[j]);
-                out_i += f;
-                q_in[j] += f;
-            }
-            q_out[i] = fmax(0.0, out_i);
-        }
-#pragma unroll
-        for (int j = 0; j < m; ++j) q_in[j] = fmax(0.0, q_in[j]);
     } else {
-        // general fractions: P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)]
-        const double* tf;
+        // RegularNode.solve, 'classic' (node.py:272-300), one column (outgoing slot j) at a time:
+        // W[i][j] = P[i][j]*s[i], D[j] = sum_i W[i][j] in slot order, f = floor(min(W, r[j]*(W/D[j]))).
+        // tf_mode 0: P = phi = 1/(m-1) (network.py:269-271); otherwise P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)].
+        const double* tf = nullptr;
         size_t ts = 1;
         if (tf_mode == 2) {
             double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
             routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
             tf = out;
             ts = (size_t)R;
-        } else {
+        } else if (tf_mode == 1) {
             tf = c.s.tf_static + tf_ptr;
         }
-        double D[CAP];
+        const double phi = 1.0 / (double)(m - 1);
+        if (tf == nullptr) {
+#pragma unroll
+            for (int i = 0; i < m; ++i) s[i] = phi * s[i];        // from here on s[] holds W[i][*]
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) q_out[i] = 0.0;
 #pragma unroll
         for (int j = 0; j < m; ++j) {
-            double acc = 0.0;
+            double w[CAP];
+            double D = 0.0;               // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                w[i] = 0.0;
+                if (i == j) continue;
+                w[i] = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i] : s[i];
+                D = D + w[i];
+            }
+            D = D != 0.0 ? D : 1e-5;
+            double in_j = 0.0;
 #pragma unroll
             for (int i = 0; i < m; ++i) {
                 if (i == j) continue;
-                acc = acc + tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i];
+                const double f = turn_flow(w[i], r[j], D);
+                q_out[i] += f;
+                in_j += f;
             }
-            D[j] = acc != 0.0 ? acc : 1e-5;
-            q_in[j] = 0.0;
+            q_in[j] = fmax(0.0, in_j);
         }
 #pragma unroll
-        for (int i = 0; i < m; ++i) {
-            double out_i = 0.0;
-#pragma unroll
-            for (int j = 0; j < m; ++j) {
-                if (i == j) continue;
-                const double wij = tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i];
-                const double f = turn_flow(wij, r[j], D[j]);
-                out_i += f;
-                q_in[j] += f;
-            }
-            q_out[i] = fmax(0.0, out_i);
-        }
-#pragma unroll
-        for (int j = 0; j < m; ++j) q_in[j] = fmax(0.0, q_in[j]);
+        for (int i = 0; i < m; ++i) q_out[i] = fmax(0.0, q_out[i]);
     }
     // Node.update_links (node.py:146-162, link.py:19-25)
 #pragma unroll
     for (int i = 0; i < m; ++i) {
         const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
+        const double co = c.n_coutp[ei], ci = c.n_cinp[eo];
         c.n_outflow[ei] = q_out[i];
-        c.n_cout[ei] = co[i] + q_out[i];
+        c.n_cout[ei] = co + q_out[i];
         c.n_inflow[eo] = q_in[i];
-        c.n_cin[eo] = ci[i] + q_in[i];
+        c.n_cin[eo] = ci + q_in[i];
     }
 }
 
@@ -737,7 +714,6 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
         case 2: node_body<2, R1>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
         case 3: node_body<3, R1>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
         case 4: node_body<4, R1>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
-        case 5: node_body<5, R1>(c, node, rep, 5, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
         default: node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
     }
 }
