@@ -50,6 +50,8 @@ class Engine:
             self.device = torch.device(device if device is not None else "cuda")
             if self.device.type != "cuda":
                 raise RuntimeError("pednstream_b200: device must be a CUDA device")
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
         self.emulation = emulation
         dev = self.device
         p = plan
@@ -131,6 +133,12 @@ class Engine:
             return C.c_void_p(0)
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _guard(self):
+        """Make the engine's device current for the native launches (no-op when it already is)."""
+        if self.emulation or torch.cuda.current_device() == self.device.index:
+            return _NULL
+        return torch.cuda.device(self.device)
+
     def _native_init(self):
         _native.check(self.lib, self.lib.pns_state_init(C.byref(self.net), C.byref(self.state), self._stream()),
                       "pns_state_init")
@@ -143,9 +151,6 @@ class Engine:
         io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
         _native.check(self.lib, self.lib.pns_step(C.byref(self.net), C.byref(self.state), C.byref(io),
                                                   t0, n_steps, rng_mode, self._stream()), "pns_step")
-
-    def _guard(self):
-        return torch.cuda.device(self.device) if not self.emulation else _NullCtx()
 
     # ------------------------------------------------------------------ setup
     def initialise(self, gate: np.ndarray, sep_np64: np.ndarray = None, tf_static: np.ndarray = None,
@@ -374,3 +379,6 @@ class _NullCtx:
 
     def __exit__(self, *a):
         return False
+
+
+_NULL = _NullCtx()
