@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 2
+#define PNS_ABI_VERSION 3
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -93,7 +93,7 @@ typedef struct pns_link_class {
 typedef struct pns_net {
     int32_t abi_version;
     int32_t n_links, n_nodes, n_cols64, sim_steps, replicas, window, n_edges, n_od, n_demand_rows;
-    int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes, max_degree, pad_;
+    int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes, max_degree, nd_stride; /* nd_stride: 4 or 8 */
     double unit_time;
     const pns_link_class *classes; /* [n_classes] */
     const int32_t *lk_class;       /* [n_links] */
@@ -101,18 +101,16 @@ typedef struct pns_net {
     /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id).
      * The outgoing link of a slot is the reverse of its incoming link: out column = in column ^ 1
      * (physical pairs are adjacent, virtual in/out links are allocated as adjacent columns). */
-    const int32_t *nd_meta;     /* [n_nodes][8] (32-byte records): slot offset, m | kind<<8 | tf_mode<<16,
-                                   demand row (-1 none), offset of the node's m(m-1) turning fractions, then the
-                                   in-columns of slots 0..3 (copies of nd_in_col, so that one record fetch serves
-                                   nodes with up to four slots).
+    const int32_t *nd_meta;     /* [n_nodes][4]: slot offset (host use), m | kind<<8 | tf_mode<<16, demand row
+                                   (-1 none; the node's virtual in/out links are columns n_links + 2*row, +1),
+                                   offset of the node's m(m-1) turning fractions.
                                    kind: 0 one-to-one (node.py:230), 1 regular/classic (node.py:272);
                                    tf_mode: 0 uniform 1/(m-1) (network.py:269-271), 1 tf_static, 2 routed */
-    const int32_t *nd_in_col;   /* [slots] history column of the incoming link of each slot */
     const int32_t *nd_routed;   /* [n_nodes] index into the routed-node arrays, -1 = none */
-    const int32_t *lk_solve;    /* [n_links][12] per-link view of the node model at both ends of the link (may be
-                                   null): {m | kind<<8 | tf_mode<<16 | slot<<24, tf offset, in-columns of slots 0..3}
-                                   of the END node, then the same of the START node; used when max_degree <= 4 */
-    const int32_t *dem_node;    /* [n_demand_rows] node index owning each demand row (= each virtual link pair) */
+    const int32_t *lk_slots;    /* [n_links][2] node-major exchange slots of each link: where its sending flow goes
+                                   (end node * nd_stride + its slot there) and where its receiving flow goes
+                                   (start node * nd_stride + its slot there); the node pass answers in the same
+                                   slots with the link's outflow (nm_qo) and inflow (nm_qi) */
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
@@ -135,6 +133,8 @@ typedef struct pns_state {
     double *tf_static;   /* [n_edges] host-owned turning fractions (uniform default / user supplied) */
     double *tf_routed;   /* [n_edges*R] fractions computed this step for routed nodes */
     double *probs;       /* [n_opts*R] scratch: P(down | up, od) of this step */
+    double *nm_s, *nm_r;   /* [n_nodes*nd_stride*R] node-major sending / receiving flows of the step (link -> node) */
+    double *nm_qo, *nm_qi; /* [n_nodes*nd_stride*R] node-major outflow / inflow of the step (node -> link) */
     int32_t *err;        /* [R] error bits */
     int32_t n_f64;       /* 7, or 8 when the network has separators */
 } pns_state;

@@ -56,7 +56,7 @@ constexpr int kBlock = 128;
 #ifndef PNS_NODE_MIN_BLOCKS
 #define PNS_NODE_MIN_BLOCKS 4
 #endif
-constexpr int PH_UPDATE = 1, PH_FLOWS = 2, PH_SOLVE = 4;   // SOLVE: node model evaluated per link, fused in front of UPDATE
+constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
 struct Ctx {
     pns_net n;
@@ -356,12 +356,18 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     double gate[2];
     V::ld(c.s.gate, e[0], e[1], gate);
     // ---- batch of independent loads --------------------------------------------------------
-    double din[2] = {0, 0}, dout[2] = {0, 0};
+    double din[2] = {0, 0}, dout[2] = {0, 0}, cin_p[2] = {0, 0}, cou_p[2] = {0, 0};
     float np_[2] = {0, 0}, rs[2] = {0, 0}, tt_old[2] = {0, 0};
     const bool windowed = c.u_tt_old != nullptr;
+    // where this pair's flows live in the node-major exchange arrays (see k_node_flows)
+    const int4 slots = __ldg(reinterpret_cast<const int4*>(c.n.lk_slots) + pair);   // {s0, r0, s1, r1}
     if (upd) {
-        V::ld(c.u_inflow, e[0], e[1], din);
-        V::ld(c.u_outflow, e[0], e[1], dout);
+        // Node.update_links for this pair (node.py:146-162): the node pass left the flows in node-major
+        // order; fetch ours and extend the cumulative counts
+        dout[0] = c.s.nm_qo[(size_t)slots.x * R + rep]; din[0] = c.s.nm_qi[(size_t)slots.y * R + rep];
+        dout[1] = c.s.nm_qo[(size_t)slots.z * R + rep]; din[1] = c.s.nm_qi[(size_t)slots.w * R + rep];
+        V::ld(c.n_cinp, e[0], e[1], cin_p);
+        V::ld(c.n_coutp, e[0], e[1], cou_p);
         V::ld(c.u_num_prev, e[0], e[1], np_);
         V::ld(c.s.runsum, e[0], e[1], rs);
         if (windowed) V::ld(c.u_tt_old, e[0], e[1], tt_old);
@@ -369,8 +375,10 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     double cin_tau[2] = {0, 0}, cou_tau[2] = {0, 0}, snd_prev[2] = {0, 0}, rcv_prev[2] = {0, 0}, cou_lag[2] = {0, 0};
     float ld_num[2] = {0, 0}, ld_dens[2] = {0, 0}, ld_avg[2] = {0, 0};
     if (flw) {
-        V::ld(c.f_cin, e[0], e[1], cin_tau);
-        V::ld(c.f_cou, e[0], e[1], cou_tau);
+        if (!upd) {                     // fused launches carry the cumulative counts in registers
+            V::ld(c.f_cin, e[0], e[1], cin_tau);
+            V::ld(c.f_cou, e[0], e[1], cou_tau);
+        }
         V::ld(c.f_sndp, e[0], e[1], snd_prev);
         V::ld(c.f_rcvp, e[0], e[1], rcv_prev);
 #pragma unroll
@@ -392,6 +400,15 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     LinkNow now[2];
     if (upd) {
         const int t = c.t;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {                                      // link.py:19-25
+            cin_tau[a] = cin_p[a] + din[a];
+            cou_tau[a] = cou_p[a] + dout[a];
+        }
+        V::st(c.n_inflow, e[0], e[1], din[0], din[1]);
+        V::st(c.n_outflow, e[0], e[1], dout[0], dout[1]);
+        V::st(c.n_cin, e[0], e[1], cin_tau[0], cin_tau[1]);
+        V::st(c.n_cout, e[0], e[1], cou_tau[0], cou_tau[1]);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             now[a].num = (float)((double)np_[a] + (din[a] - dout[a]));    // link.py:134-135
@@ -476,10 +493,13 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
         return;
     }
     // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
-    const double q0 = is_sep(*pp[0]) ? r[0] : r[0] - s[1].flow;
-    const double q1 = is_sep(*pp[1]) ? r[1] : r[1] - s[0].flow;
+    const double q0 = pymax(is_sep(*pp[0]) ? r[0] : r[0] - s[1].flow, 0.0);
+    const double q1 = pymax(is_sep(*pp[1]) ? r[1] : r[1] - s[0].flow, 0.0);
     V::st(c.f_snd, e[0], e[1], s[0].flow, s[1].flow);
-    V::st(c.f_rcv, e[0], e[1], pymax(q0, 0.0), pymax(q1, 0.0));
+    V::st(c.f_rcv, e[0], e[1], q0, q1);
+    // hand the flows to the node pass in node-major order (slot of each link at its end / start node)
+    c.s.nm_s[(size_t)slots.x * R + rep] = s[0].flow; c.s.nm_r[(size_t)slots.y * R + rep] = q0;
+    c.s.nm_s[(size_t)slots.z * R + rep] = s[1].flow; c.s.nm_r[(size_t)slots.w * R + rep] = q1;
 }
 
 template <bool R1, int PHASE, int MODE>
@@ -595,33 +615,36 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
     return floor(pymin(w, r * (w / D)));
 }
 
-// One node: gather s/r over its slots, node model, scatter flows and cumulative counts.
+// One node.  The link kernels hand over sending/receiving flows in *node-major* order
+// (nm_s / nm_r: slot k of node n at index n*stride + k, replica fastest) and pick the resulting
+// flows up from nm_qo / nm_qi, so this pass reads and writes contiguous, coalesced records and
+// all scatter/gather over the link<->node incidence happens once per link in the link kernels.
 // M > 0: slot count known at compile time (loops unrolled, everything in registers);
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
 template <int M, bool R1>
-__device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int base, int kind,
-                                          int tf_mode, int dem_row, int tf_ptr, const int4& first4) {
+__device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int kind, int tf_mode,
+                                          int dem_row, int tf_ptr) {
     constexpr int CAP = M ? M : PNS_MAX_DEGREE;
     const int m = M ? M : m_dyn;
     const int R = R1 ? 1 : c.n.replicas;
-    const int L = c.n.n_links;
-    int icol[CAP];
-    const int inl[4] = {first4.x, first4.y, first4.z, first4.w};     // slots 0..3 come with the node record
-#pragma unroll
-    for (int i = 0; i < m; ++i) icol[i] = i < 4 ? inl[i < 4 ? i : 0] : __ldg(c.n.nd_in_col + base + i);
-    // Register diet (the kernel is latency bound, so resident warps matter more than early loads):
-    // only the sending/receiving flows live through the solve; the previous cumulative counts are
-    // fetched right before the stores.
+    const size_t base = (size_t)node * c.n.nd_stride;
     double s[CAP], r[CAP];
+    if (R1 && M == 4) {
+        const double2* ps = reinterpret_cast<const double2*>(c.s.nm_s + base);
+        const double2* pr = reinterpret_cast<const double2*>(c.s.nm_r + base);
+        const double2 a0 = ps[0], a1 = ps[1], b0 = pr[0], b1 = pr[1];
+        s[0] = a0.x; s[1 % CAP] = a0.y; s[2 % CAP] = a1.x; s[3 % CAP] = a1.y;
+        r[0] = b0.x; r[1 % CAP] = b0.y; r[2 % CAP] = b1.x; r[3 % CAP] = b1.y;
+    } else {
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-        if (icol[i] >= L) {
-            s[i] = c.n_demand[(size_t)dem_row * R + rep];                  // node.py:176
-            r[i] = 1e6;                                                     // node.py:186
-        } else {
-            s[i] = c.n_snd[(size_t)icol[i] * R + rep];
-            r[i] = c.n_rcv[(size_t)(icol[i] ^ 1) * R + rep];
+        for (int i = 0; i < m; ++i) {
+            s[i] = c.s.nm_s[(base + i) * R + rep];
+            r[i] = c.s.nm_r[(base + i) * R + rep];
         }
+    }
+    if (dem_row >= 0) {                                                     // slot 0 is the virtual O/D link pair
+        s[0] = c.n_demand[(size_t)dem_row * R + rep];                       // node.py:176
+        r[0] = 1e6;                                                         // node.py:186
     }
     bool negative = false;
 #pragma unroll
@@ -680,25 +703,38 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
 #pragma unroll
         for (int i = 0; i < m; ++i) q_out[i] = fmax(0.0, q_out[i]);
     }
-    // Node.update_links (node.py:146-162, link.py:19-25)
+    if (R1 && M == 4) {
+        double2* po = reinterpret_cast<double2*>(c.s.nm_qo + base);
+        double2* pi = reinterpret_cast<double2*>(c.s.nm_qi + base);
+        double2 v;
+        v.x = q_out[0]; v.y = q_out[1 % CAP]; po[0] = v;
+        v.x = q_out[2 % CAP]; v.y = q_out[3 % CAP]; po[1] = v;
+        v.x = q_in[0]; v.y = q_in[1 % CAP]; pi[0] = v;
+        v.x = q_in[2 % CAP]; v.y = q_in[3 % CAP]; pi[1] = v;
+    } else {
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-        const size_t ei = (size_t)icol[i] * R + rep, eo = (size_t)(icol[i] ^ 1) * R + rep;
-        const double co = c.n_coutp[ei], ci = c.n_cinp[eo];
-        c.n_outflow[ei] = q_out[i];
-        c.n_cout[ei] = co + q_out[i];
-        c.n_inflow[eo] = q_in[i];
-        c.n_cin[eo] = ci + q_in[i];
+        for (int i = 0; i < m; ++i) {
+            c.s.nm_qo[(base + i) * R + rep] = q_out[i];
+            c.s.nm_qi[(base + i) * R + rep] = q_in[i];
+        }
+    }
+    if (dem_row >= 0) {
+        // the virtual links have no link thread: keep their counters here (node.py:154-161, link.py:19-25)
+        const size_t vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep, vout = vin + R;
+        c.n_outflow[vin] = q_out[0];
+        c.n_cout[vin] = c.n_coutp[vin] + q_out[0];
+        c.n_inflow[vout] = q_in[0];
+        c.n_cin[vout] = c.n_cinp[vout] + q_in[0];
     }
 }
 
 template <bool R1>
-__device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int base, int kind,
-                                               int tf_mode, int dem_row, int tf_ptr, const int4& first4) {
-    node_body<0, R1>(c, node, rep, m, base, kind, tf_mode, dem_row, tf_ptr, first4);
+__device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int kind, int tf_mode,
+                                               int dem_row, int tf_ptr) {
+    node_body<0, R1>(c, node, rep, m, kind, tf_mode, dem_row, tf_ptr);
 }
 
-// Node.assign_flows / solve / update_links (node.py:146-300) + turning fractions
+// Node.assign_flows / solve (node.py:164-300) + turning fractions (path_finder.py:591-715)
 template <bool R1>
 __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
@@ -706,164 +742,15 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
     if (gid >= (size_t)c.n.n_nodes * R) return;
     const int node = R1 ? (int)gid : (int)(gid / R);
     const int rep = R1 ? 0 : (int)(gid % R);
-    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
-    const int4 meta = __ldg(rec), cols = __ldg(rec + 1);
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
-        case 2: node_body<2, R1>(c, node, rep, 2, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
-        case 3: node_body<3, R1>(c, node, rep, 3, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
-        case 4: node_body<4, R1>(c, node, rep, 4, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
-        default: node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w, cols); break;
+        case 2: node_body<2, R1>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w); break;
+        case 3: node_body<3, R1>(c, node, rep, 3, kind, tf_mode, meta.z, meta.w); break;
+        case 4: node_body<4, R1>(c, node, rep, 4, kind, tf_mode, meta.z, meta.w); break;
+        default: node_body_generic<R1>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
     }
-}
-
-
-
-// =================================================================================================
-// Per-link evaluation of the node model (networks whose nodes have at most four slots).
-// A directed link l = (a -> b) needs two numbers from the node pass: its outflow q_out (row of l
-// in the solve at its end node b) and its inflow q_in (column of l in the solve at its start node
-// a).  Both are functions of the sending/receiving flows around the two nodes only, so the link's
-// own thread can evaluate them from the per-link record `lk_solve` instead of waiting for a node
-// kernel to scatter them -- the turns are recomputed by every link that needs them, with the same
-// operations in the same order as RegularNode.solve / OneToOneNode.solve (node.py:230-300).
-
-// sending flow entering the node through slot x (virtual origin link: the demand row)
-template <bool R1>
-__device__ __forceinline__ double slot_sending(const Ctx& c, int col, int rep) {
-    const int R = R1 ? 1 : c.n.replicas;
-    if (col >= c.n.n_links) return c.n_demand[(size_t)((col - c.n.n_links) >> 1) * R + rep];   // node.py:176
-    return c.n_snd[(size_t)col * R + rep];
-}
-// receiving flow of the outgoing link of slot x (virtual destination link: M = 1e6, node.py:186)
-template <bool R1>
-__device__ __forceinline__ double slot_receiving(const Ctx& c, int col, int rep) {
-    const int R = R1 ? 1 : c.n.replicas;
-    if (col >= c.n.n_links) return 1e6;
-    return c.n_rcv[(size_t)(col ^ 1) * R + rep];
-}
-
-template <bool R1>
-__device__ __forceinline__ void link_solve(const Ctx& c, int l, int rep, double* q_out, double* q_in) {
-    const int R = R1 ? 1 : c.n.replicas;
-    const int4* rec = reinterpret_cast<const int4*>(c.n.lk_solve) + 3 * (size_t)l;
-    const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-    const int hdr[2] = {r0.x, r1.z};
-    const int tfp[2] = {r0.y, r1.w};
-    const int cols[2][4] = {{r0.z, r0.w, r1.x, r1.y}, {r2.x, r2.y, r2.z, r2.w}};
-    bool negative = false;
-#pragma unroll
-    for (int end = 0; end < 2; ++end) {       // 0: end node (row of l -> q_out); 1: start node (column of l -> q_in)
-        const int m = hdr[end] & 0xff, kind = (hdr[end] >> 8) & 0xff, tf_mode = (hdr[end] >> 16) & 0xff;
-        const int k = (hdr[end] >> 24) & 0xff;
-        double s[4], r[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            s[x] = 0.0; r[x] = 0.0;
-            if (x < m) {
-                s[x] = slot_sending<R1>(c, cols[end][x], rep);
-                // the row needs every receiving flow, the column only its own
-                if (end == 0 || x == k) r[x] = slot_receiving<R1>(c, cols[end][x], rep);
-                negative |= (s[x] < 0.0) | (r[x] < 0.0);
-            }
-        }
-        double q = 0.0;
-        if (kind == 0) {
-            // OneToOneNode.solve: q_out[i] = min(s[i], r[1-i]); q_in[j] = min(s[1-j], r[j])
-            q = end == 0 ? fmin(s[k & 1], r[1 - (k & 1)]) : fmin(s[1 - (k & 1)], r[k & 1]);
-        } else {
-            const double* tf = nullptr;
-            size_t ts = 1;
-            if (tf_mode == 2) { tf = c.s.tf_routed + (size_t)tfp[end] * R + rep; ts = (size_t)R; }
-            else if (tf_mode == 1) tf = c.s.tf_static + tfp[end];
-            const double phi = 1.0 / (double)(m - 1);
-            // w(x, j) = P[x][j] * s[x]; D[j] = sum over x != j in slot order
-            if (end == 1) {
-                double D = 0.0, w[4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    w[x] = 0.0;
-                    if (x < m && x != k) {
-                        w[x] = (tf ? tf[(size_t)(x * (m - 1) + (k < x ? k : k - 1)) * ts] : phi) * s[x];
-                        D = D + w[x];
-                    }
-                }
-                D = D != 0.0 ? D : 1e-5;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (x < m && x != k) q += turn_flow(w[x], r[k], D);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j >= m || j == k) continue;
-                    double D = 0.0, wk = 0.0;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        if (x < m && x != j) {
-                            const double w = (tf ? tf[(size_t)(x * (m - 1) + (j < x ? j : j - 1)) * ts] : phi) * s[x];
-                            D = D + w;
-                            if (x == k) wk = w;
-                        }
-                    }
-                    D = D != 0.0 ? D : 1e-5;
-                    q += turn_flow(wk, r[j], D);
-                }
-            }
-            q = fmax(0.0, q);
-        }
-        if (end == 0) *q_out = q; else *q_in = q;
-    }
-    if (negative) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
-}
-
-// Turning fractions of every routed node for step t (PathFinder.update_turning_fractions +
-// check_fractions), needed up front when the node model is evaluated per link.
-template <bool R1>
-__global__ void __launch_bounds__(kBlock) k_route_tf(const __grid_constant__ Ctx c) {
-    const int R = R1 ? 1 : c.n.replicas;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)c.n.n_routed * R) return;
-    const int routed = R1 ? (int)gid : (int)(gid / R);
-    const int rep = R1 ? 0 : (int)(gid % R);
-    const int node = c.n.rt_routed_nodes[routed];
-    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node);
-    routed_fractions(c, routed, meta.y & 0xff, c.t, rep, c.s.tf_routed + (size_t)meta.w * R + rep);
-}
-
-// Stand-alone form of the per-link node pass: writes inflow/outflow/cumulative counts of the
-// physical links at row t.  (The single-replica lane kernel evaluates link_solve in registers
-// instead; this kernel is what the host-emulation tests and the batched path can run.)
-template <bool R1>
-__global__ void __launch_bounds__(kBlock) k_link_solve(const __grid_constant__ Ctx c) {
-    const int R = R1 ? 1 : c.n.replicas;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)c.n.n_links * R) return;
-    const int l = R1 ? (int)gid : (int)(gid / R);
-    const int rep = R1 ? 0 : (int)(gid % R);
-    const size_t e = (size_t)l * R + rep;
-    double q_out, q_in;
-    link_solve<R1>(c, l, rep, &q_out, &q_in);
-    c.n_outflow[e] = q_out;
-    c.n_cout[e] = c.n_coutp[e] + q_out;
-    c.n_inflow[e] = q_in;
-    c.n_cin[e] = c.n_cinp[e] + q_in;
-}
-
-// Virtual origin/destination links have no link thread: their node runs the full node model and
-// only the counters of the virtual columns are kept from it.
-template <bool R1>
-__global__ void __launch_bounds__(kBlock) k_virtual_flows(const __grid_constant__ Ctx c) {
-    const int R = R1 ? 1 : c.n.replicas;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)c.n.n_demand_rows * R) return;
-    const int row = R1 ? (int)gid : (int)(gid / R);
-    const int rep = R1 ? 0 : (int)(gid % R);
-    const int node = c.n.dem_node[row];
-    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
-    const int4 meta = __ldg(rec), cols = __ldg(rec + 1);
-    const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
-    node_body_generic<R1>(c, node, rep, m, meta.x, kind, tf_mode, meta.z, meta.w, cols);
 }
 
 #ifndef PNS_HOST_EMULATION
@@ -875,7 +762,7 @@ __global__ void __launch_bounds__(kBlock) k_virtual_flows(const __grid_constant_
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
 template <int PHASE, int MODE>
 __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__ Ctx c) {
-    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0, slv = (PHASE & PH_SOLVE) != 0;
+    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
@@ -890,9 +777,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     float np_ = 0, rs = 0, tt_old = 0;
     const bool windowed = c.u_tt_old != nullptr;
     double cin_prev = 0, cou_prev = 0;
+    const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
     if (upd) {
-        if (slv) { cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e]; }
-        else { din = c.u_inflow[e]; dout = c.u_outflow[e]; }
+        // Node.update_links for this link (node.py:146-162): flows come from the node-major exchange arrays
+        dout = c.s.nm_qo[slots.x]; din = c.s.nm_qi[slots.y];
+        cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e];
         np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
         if (windowed) tt_old = c.u_tt_old[e];
     }
@@ -900,7 +789,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     LinkNow me;
     me.num = 0; me.dens = 0; me.avg_tt = 0;
     if (flw) {
-        if (!slv) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
+        if (!upd) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
         snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
         const int lag_i = tau + 1 - p.swtau;
         if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
@@ -923,18 +812,13 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     const Area ar = link_area(c, p, e, gate);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
 
-    if (slv) {
-        // node pass of step t for this link: its inflow/outflow and cumulative counts (node.py:146-162)
-        if (valid) {
-            link_solve<true>(c, l, 0, &dout, &din);
-            cin_tau = cin_prev + din;
-            cou_tau = cou_prev + dout;
-            c.n_outflow[e] = dout; c.n_cout[e] = cou_tau;
-            c.n_inflow[e] = din;   c.n_cin[e] = cin_tau;
-        }
-    }
     if (upd) {
         const int t = c.t;
+        cin_tau = cin_prev + din;                                           // link.py:19-25
+        cou_tau = cou_prev + dout;
+        if (valid) {
+            c.n_inflow[e] = din; c.n_outflow[e] = dout; c.n_cin[e] = cin_tau; c.n_cout[e] = cou_tau;
+        }
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
         me.dens = div_by_area(me.num, ar);                                  // link.py:136
         const float dens_rev = __shfl_xor_sync(FULL, me.dens, 1);
@@ -993,100 +877,15 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     }
     const double s_rev = __shfl_xor_sync(FULL, s.flow, 1);
     if (valid) {
-        c.f_snd[e] = s.flow;
         // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
-        c.f_rcv[e] = pymax(is_sep(p) ? r : r - s_rev, 0.0);
+        const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
+        c.f_snd[e] = s.flow;
+        c.f_rcv[e] = rcv;
+        c.s.nm_s[slots.x] = s.flow;        // node-major hand-over to the node pass
+        c.s.nm_r[slots.y] = rcv;
     }
 }
 
-// Single-replica node pass with one thread per (node, slot): the GS lanes of a node each own one
-// incoming/outgoing link pair, gather the sending flows of the whole node with shuffles, solve
-// their own *column* of the classic node model (all turns into their outgoing link) and reduce the
-// row sums (outflow of each incoming link) across the group.  Sums of floor()ed flows are integers,
-// so the reduction order does not matter; the demand sums D[j] keep the reference's order.
-template <int GS>
-__global__ void __launch_bounds__(kBlock, 8) k_node_slot(const __grid_constant__ Ctx c) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned node_u = gid / GS;
-    const int k = (int)(gid % GS);                        // my slot
-    const bool in_range = node_u < (unsigned)c.n.n_nodes;
-    const int node = in_range ? (int)node_u : 0;
-    const int lane = threadIdx.x & 31;
-    const int g0 = lane & ~(GS - 1);                      // first lane of my group
-    const int4* rec = reinterpret_cast<const int4*>(c.n.nd_meta) + 2 * (size_t)node;
-    const int4 meta = __ldg(rec);
-    const int m = in_range ? (meta.y & 0xff) : 0;
-    const int kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
-    const bool mine = k < m;                              // this lane owns a slot
-    const int L = c.n.n_links;
-    int icol = 0;
-    if (mine) icol = k < 4 ? reinterpret_cast<const int*>(rec + 1)[k] : __ldg(c.n.nd_in_col + meta.x + k);
-    const size_t ei = (size_t)icol, eo = (size_t)(icol ^ 1);
-    double s = 0.0, r = 0.0, co = 0.0, ci = 0.0;
-    if (mine) {
-        if (icol >= L) { s = c.n_demand[meta.z]; r = 1e6; }                 // node.py:176, 186
-        else { s = c.n_snd[ei]; r = c.n_rcv[eo]; }
-        co = c.n_coutp[ei];
-        ci = c.n_cinp[eo];
-        if ((s < 0.0) | (r < 0.0)) atomicOr(c.s.err, PNS_ERR_NEG_NODE_FLOW);
-    }
-    // routed nodes: lane i evaluates row i of the turning fractions, the group then reads columns
-    const double* tf = nullptr;
-    if (tf_mode == 2) {
-        if (k == 0 && m > 0) routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, 0, c.s.tf_routed + meta.w);
-        tf = c.s.tf_routed + meta.w;
-    } else if (tf_mode == 1) {
-        tf = c.s.tf_static + meta.w;
-    }
-    __syncwarp();
-    double s_all[GS];
-#pragma unroll
-    for (int i = 0; i < GS; ++i) s_all[i] = __shfl_sync(FULL, s, g0 + i);
-    double q_in = 0.0;
-    double f[GS];
-#pragma unroll
-    for (int i = 0; i < GS; ++i) f[i] = 0.0;
-    if (kind == 0) {
-        // OneToOneNode.solve (node.py:230-242): q_out[0] = q_in[1] = min(s0, r1), q_out[1] = q_in[0] = min(s1, r0)
-        if (mine) { f[1 - k] = fmin(s_all[1 - k], r); q_in = f[1 - k]; }
-    } else if (mine) {
-        // my column j = k of RegularNode.solve 'classic' (node.py:272-300)
-        const double phi = 1.0 / (double)(m - 1);
-        double w[GS];
-        double D = 0.0;
-#pragma unroll
-        for (int i = 0; i < GS; ++i) {
-            w[i] = 0.0;
-            if (i < m && i != k) {
-                const double pij = tf ? tf[i * (m - 1) + (k < i ? k : k - 1)] : phi;
-                w[i] = pij * s_all[i];
-                D = D + w[i];                          // np.sum(axis=0): rows added in order
-            }
-        }
-        D = D != 0.0 ? D : 1e-5;
-#pragma unroll
-        for (int i = 0; i < GS; ++i)
-            if (i < m && i != k) { f[i] = turn_flow(w[i], r, D); q_in += f[i]; }
-        q_in = fmax(0.0, q_in);
-    }
-    // outflow of incoming link i = sum over columns of f[i][.]
-    double q_out = 0.0;
-#pragma unroll
-    for (int i = 0; i < GS; ++i) {
-        double v = f[i];
-#pragma unroll
-        for (int d = 1; d < GS; d <<= 1) v += __shfl_xor_sync(FULL, v, d);
-        if (i == k) q_out = v;
-    }
-    if (kind != 0) q_out = fmax(0.0, q_out);
-    if (mine) {                                            // Node.update_links (node.py:146-162)
-        c.n_outflow[ei] = q_out;
-        c.n_cout[ei] = co + q_out;
-        c.n_inflow[eo] = q_in;
-        c.n_cin[eo] = ci + q_in;
-    }
-}
 #endif  // !PNS_HOST_EMULATION
 
 // =================================================================================================
@@ -1335,9 +1134,7 @@ void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
-        if (c.phase == (PH_SOLVE | PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_SOLVE | PH_UPDATE | PH_FLOWS>(2 * n, s, c);
-        else if (c.phase == (PH_SOLVE | PH_UPDATE)) launch_lane_mode<PH_SOLVE | PH_UPDATE>(2 * n, s, c);
-        else if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
+        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
         else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
         else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, c);
         return;
@@ -1346,46 +1143,7 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     if (net->replicas == 1) launch_pair_phase<true>(n, s, c);
     else launch_pair_phase<false>(n, s, c);
 }
-bool use_fused_solve(const pns_net* net) {
-#ifdef PNS_HOST_EMULATION
-    (void)net;
-    return false;
-#else
-    // Measured on B200 (profiles/r1_e_*): recomputing the turns per link triples the scattered 8-byte
-    // loads of sending/receiving flows and loses to the node kernel (118 vs 71 us per 512x512 step), so
-    // the fused SOLVE phase is an opt-in experiment, not the default.
-    static const bool on = getenv("PNS_FUSE_SOLVE") != nullptr && getenv("PNS_PAIR_THREADS") == nullptr;
-    return on && net->replicas == 1 && net->lk_solve && net->dem_node && net->max_degree <= 4;
-#endif
-}
-bool use_link_solve(const pns_net* net) {
-    static const bool want = getenv("PNS_LINK_SOLVE") != nullptr;
-    return want && net->lk_solve && net->dem_node && net->max_degree <= 4;
-}
-// node pass evaluated per link (+ the few nodes that own virtual links, + routed fractions first)
-void launch_link_solve(const pns_net* net, cudaStream_t s, const Ctx& c) {
-    const size_t R = net->replicas;
-    const size_t n_rt = (size_t)net->n_routed * R, n_lk = (size_t)net->n_links * R, n_v = (size_t)net->n_demand_rows * R;
-    if (net->replicas == 1) {
-        if (n_rt) PNS_LAUNCH(k_route_tf<true>, blocks_for(n_rt), kBlock, s, c);
-        if (n_lk) PNS_LAUNCH(k_link_solve<true>, blocks_for(n_lk), kBlock, s, c);
-        if (n_v) PNS_LAUNCH(k_virtual_flows<true>, blocks_for(n_v), kBlock, s, c);
-    } else {
-        if (n_rt) PNS_LAUNCH(k_route_tf<false>, blocks_for(n_rt), kBlock, s, c);
-        if (n_lk) PNS_LAUNCH(k_link_solve<false>, blocks_for(n_lk), kBlock, s, c);
-        if (n_v) PNS_LAUNCH(k_virtual_flows<false>, blocks_for(n_v), kBlock, s, c);
-    }
-}
-
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
-    if (use_link_solve(net)) { launch_link_solve(net, s, c); return; }
-#ifndef PNS_HOST_EMULATION
-    if (net->replicas == 1 && getenv("PNS_NODE_SLOT")) {          // experimental: one thread per (node, slot)
-        if (c.max_degree <= 4) k_node_slot<4><<<blocks_for(4 * n), kBlock, 0, s>>>(c);
-        else k_node_slot<8><<<blocks_for(8 * n), kBlock, 0, s>>>(c);
-        return;
-    }
-#endif
     if (net->replicas == 1) PNS_LAUNCH(k_node_flows<true>, blocks_for(n), kBlock, s, c);
     else PNS_LAUNCH(k_node_flows<false>, blocks_for(n), kBlock, s, c);
 }
@@ -1417,29 +1175,6 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     (void)ms; (void)launches;
 #define PNS_MARK(k, j) do { } while (0)
 #endif
-    if (use_fused_solve(net)) {
-        // single replica, nodes of degree <= 4: the node model is evaluated inside the link kernel
-        //   FLOWS(t0) | [route(t) | virtual(t) | SOLVE+UPDATE(t)+FLOWS(t+1)] ... | SOLVE+UPDATE(t_last)
-        for (int k = 0; k <= n_steps; ++k) {
-            const int t = t0 + k - 1;
-            if (k > 0) {
-                const Ctx cn = make_ctx(net, st, io, 0, t, t, rng_mode, k - 1, k - 1);
-                PNS_MARK(k - 1, 1);
-                if (z.n_grp) {
-                    PNS_LAUNCH(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
-                    PNS_LAUNCH(k_route_tf<true>, blocks_for((size_t)net->n_routed), kBlock, s, cn);
-                }
-                PNS_MARK(k - 1, 2);
-                if (net->n_demand_rows) PNS_LAUNCH(k_virtual_flows<true>, blocks_for((size_t)net->n_demand_rows), kBlock, s, cn);
-                PNS_MARK(k - 1, 3);
-            }
-            const int phase = (k > 0 ? (PH_SOLVE | PH_UPDATE) : 0) | (k < n_steps ? PH_FLOWS : 0);
-            const Ctx cp = make_ctx(net, st, io, phase, t, t0 + k, rng_mode, k - 1, k);
-            PNS_MARK(k, 0);
-            if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
-            if (k == n_steps) PNS_MARK(k, 1);
-        }
-    } else {
     // launch k (0..n_steps): pair kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
     for (int k = 0; k <= n_steps; ++k) {
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
@@ -1453,7 +1188,6 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
-    }
     }
 #undef PNS_MARK
 #ifndef PNS_HOST_EMULATION

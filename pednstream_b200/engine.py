@@ -21,7 +21,7 @@ import torch
 from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
-_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_in_col", "nd_routed", "lk_solve", "dem_node",
+_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
                "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
@@ -76,7 +76,8 @@ class Engine:
         net.n_rows = len(p["rt_row_ptr"]) - 1
         net.n_terms = len(p["rt_term_opt"])
         net.n_classes = len(p["classes"])
-        net.max_degree = int((np.asarray(p["nd_meta"])[:, 1] & 0xff).max()) if len(p["nd_meta"]) else 0
+        net.max_degree = int(p["max_degree"])
+        net.nd_stride = int(p["nd_stride"])
         net.unit_time = p["unit_time"]
         for k in _NET_ARRAYS + ("classes",):
             setattr(net, k, _ptr(self._net_t[k]))
@@ -93,8 +94,14 @@ class Engine:
         self.tf_routed = torch.zeros((max(1, p["n_edges"]) * R,), dtype=torch.float64, device=dev)
         self.probs = torch.zeros((max(1, net.n_opts) * R,), dtype=torch.float64, device=dev)
         self.err = torch.zeros((R,), dtype=torch.int32, device=dev)
+        nm = max(1, self.N * int(p["nd_stride"]) * R)       # node-major exchange arrays (link <-> node passes)
+        self.nm_s = torch.zeros((nm,), dtype=torch.float64, device=dev)
+        self.nm_r = torch.zeros((nm,), dtype=torch.float64, device=dev)
+        self.nm_qo = torch.zeros((nm,), dtype=torch.float64, device=dev)
+        self.nm_qi = torch.zeros((nm,), dtype=torch.float64, device=dev)
         st = _native.PnsState()
-        for k in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static", "tf_routed", "probs", "err"):
+        for k in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static", "tf_routed", "probs",
+                  "nm_s", "nm_r", "nm_qo", "nm_qi", "err"):
             setattr(st, k, _ptr(getattr(self, k)))
         st.n_f64 = self.n_f64
         self.state = st

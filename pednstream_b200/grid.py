@@ -122,17 +122,15 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     edges = (m_o * (m_o - 1)).astype(np.int64)
     tf_ptr = np.concatenate([[0], np.cumsum(edges)]).astype(np.int32)
     assert (out_col == (in_col ^ 1)).all()
-    meta = np.zeros((N, 8), dtype=np.int32)
+    meta = np.zeros((N, 4), dtype=np.int32)
     meta[:, 0] = nd_ptr[:-1]
     meta[:, 1] = (m_o | (kind[order].astype(np.int64) << 8)).astype(np.int32)
     meta[:, 2] = dem_row
     meta[:, 3] = tf_ptr[:-1]
-    for k in range(4):                       # in-columns of the first four slots, inline
-        has = m_o > k
-        meta[has, 4 + k] = in_col[nd_ptr[:-1][has] + k]
-
-    from .plan import link_solve_records
-    lk_solve = link_solve_records(meta, in_col, L)
+    from .plan import link_slots, node_stride
+    max_degree = int(m_o.max())
+    stride = node_stride(max_degree)
+    lk_slots = link_slots(meta, in_col, L, stride)
 
     from .plan import class_record, CLASS_DTYPE
     rec = class_record(lk["length"], lk["width"], lk["free_flow_speed"], lk["k_critical"], lk["k_jam"],
@@ -143,7 +141,8 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         window=int(round(100 / unit_time)),
         classes=np.array([rec], dtype=CLASS_DTYPE).reshape(1), lk_class=np.zeros(L, dtype=np.int32),
         lk_width=np.full(L, float(lk["width"])), has_separators=False,
-        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_solve=lk_solve, dem_node=np.nonzero(virtual[order])[0].astype(np.int32),
+        nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_slots=lk_slots,
+        max_degree=max_degree, nd_stride=stride,
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,
     )

@@ -79,26 +79,29 @@ def link_classes(links, unit_time):
     return np.array(rows, dtype=CLASS_DTYPE).reshape(len(rows)), _i32(idx)
 
 
-def link_solve_records(nd_meta, nd_in_col, n_links):
-    """[n_links, 12] int32: what a link needs to evaluate its own row/column of the node model at
-    its two ends without a separate node pass (`link_solve` in csrc/pns_kernels.cu):
-      [0] m | kind<<8 | tf_mode<<16 | slot<<24 of the END node (slot = position of the link in the
-          node's incoming list), [1] that node's tf offset, [2..5] in-columns of its slots 0..3;
-      [6..11] the same for the START node (slot = position in the outgoing list, which is the slot of
-          the link's reverse in the incoming list).
-    Only meaningful when no node has more than four slots."""
+def node_stride(max_degree: int) -> int:
+    """Slots reserved per node in the node-major exchange arrays (4 or 8)."""
+    return 4 if max_degree <= 4 else 8
+
+
+def link_slots(nd_meta, nd_in_col, n_links, stride):
+    """[n_links, 2] int32 exchange slots of every physical link (see `pns_net.lk_slots`):
+    column 0: node-major slot that receives the link's sending flow / returns its outflow
+              (END node * stride + position of the link in that node's incoming list);
+    column 1: slot that receives its receiving flow / returns its inflow
+              (START node * stride + position in the outgoing list = slot of its reverse)."""
     nd_meta = np.asarray(nd_meta)
     m = nd_meta[:, 1] & 0xff
     node_of_slot = np.repeat(np.arange(len(nd_meta)), m)
     slot = np.arange(len(nd_in_col)) - np.repeat(nd_meta[:, 0], m)
-    phys = np.asarray(nd_in_col) < n_links
-    cols, node, k = np.asarray(nd_in_col)[phys], node_of_slot[phys], slot[phys]
-    rec = np.zeros((n_links, 12), dtype=np.int32)
-    for off, target in ((0, cols), (6, cols ^ 1)):      # incoming link ends here; its reverse starts here
-        rec[target, off] = nd_meta[node, 1] | (k << 24)
-        rec[target, off + 1] = nd_meta[node, 3]
-        rec[target, off + 2: off + 6] = nd_meta[node, 4:8]
-    return rec
+    cols = np.asarray(nd_in_col)
+    phys = cols < n_links
+    out = np.full((n_links, 2), -1, dtype=np.int32)
+    where = (node_of_slot * stride + slot).astype(np.int32)
+    out[cols[phys], 0] = where[phys]
+    out[cols[phys] ^ 1, 1] = where[phys]
+    assert (out >= 0).all(), "every link must end and start at a node slot"
+    return out
 
 
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
@@ -149,17 +152,19 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
             demand_nodes.append(n)
             n_virtual_nodes += 1
         tf_mode = 2 if n.node_id in routed_ids else 0
-        first4 = [l._col for l in n.incoming_links[:4]] + [0] * (4 - min(m, 4))
-        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr, *first4))
+        if dem_row >= 0:
+            assert n.incoming_links[0]._col == L + 2 * dem_row, "virtual columns follow the demand rows"
+        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr))
         slot0 += m
         tf_ptr += m * (m - 1)
-    p["nd_meta"] = _i32(meta).reshape(-1, 8)
-    p["nd_in_col"] = _i32(in_col)
-    p["lk_solve"] = link_solve_records(p["nd_meta"], p["nd_in_col"], L)
+    p["nd_meta"] = _i32(meta).reshape(-1, 4)
+    p["nd_in_col"] = _i32(in_col)                       # host-side only (used to derive lk_slots)
+    p["max_degree"] = int(max((n.source_num for n in nodes), default=0))
+    p["nd_stride"] = node_stride(p["max_degree"])
+    p["lk_slots"] = link_slots(p["nd_meta"], p["nd_in_col"], L, p["nd_stride"])
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
-    p["dem_node"] = _i32([n.index for n in demand_nodes])
     p["n_edges"] = tf_ptr
 
     # ---- route plan -------------------------------------------------------------------

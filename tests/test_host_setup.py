@@ -33,7 +33,8 @@ def test_build_and_plan(name):
             else:
                 assert lin.reverse_link is lout
     meta = p["nd_meta"]
-    assert meta.shape == (len(net.nodes), 8)
+    assert meta.shape == (len(net.nodes), 4)
+    assert p["lk_slots"].shape == (L, 2) and p["nd_stride"] in (4, 8)
     assert int((meta[:, 1] & 0xff).sum()) == len(p["nd_in_col"])
     assert len(p["classes"]) >= 1 and p["lk_class"].max() < len(p["classes"])
     assert p["rt_opt_ptr"][-1] == len(p["rt_opt_link"])
