@@ -27,6 +27,29 @@
 #else
 #include <cuda_runtime.h>
 #define PNS_LAUNCH(kern, nblk, nthr, stream, ...) kern<<<(nblk), (nthr), 0, (stream)>>>(__VA_ARGS__)
+// Programmatic dependent launch (sm_90+): the kernels of a step form a strict chain on one stream.
+// Each kernel lets its successor start launching at once (TRIGGER) and waits for its predecessor's
+// memory only after its own index arithmetic and static-table loads (WAIT), so launch latency and
+// the ramp-up of one kernel overlap the tail of the previous one.
+#define PNS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define PNS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <typename K>
+static inline void pns_launch_chain(K kern, unsigned nblk, unsigned nthr, cudaStream_t stream, const void* ctx_arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(nthr); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    void* args[1] = {const_cast<void*>(ctx_arg)};
+    cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+}
+#define PNS_LAUNCH_CHAIN(kern, nblk, nthr, stream, ctx) pns_launch_chain(kern, (nblk), (nthr), (stream), &(ctx))
+#endif
+#ifdef PNS_HOST_EMULATION
+#define PNS_PDL_TRIGGER() do { } while (0)
+#define PNS_PDL_WAIT() do { } while (0)
+#define PNS_LAUNCH_CHAIN(kern, nblk, nthr, stream, ctx) PNS_LAUNCH(kern, nblk, nthr, stream, ctx)
 #endif
 #include <math.h>
 #include <stdint.h>
@@ -345,6 +368,8 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     const int rep = R1 ? 0 : (int)(gid % R);
     const int l0 = 2 * pair;
     const size_t e[2] = {(size_t)l0 * R + rep, (size_t)(l0 + 1) * R + rep};
+    PNS_PDL_TRIGGER();
+    PNS_PDL_WAIT();
     typedef Lanes<R1> V;
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     const int tau = c.t_flows - 1;
@@ -515,6 +540,8 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
     if (gid >= (size_t)c.n.n_groups * R) return;
     const int g = (int)(gid / R);
     const int rep = (int)(gid % R);
+    PNS_PDL_TRIGGER();
+    PNS_PDL_WAIT();
     const int o0 = c.n.rt_opt_ptr[g], o1 = c.n.rt_opt_ptr[g + 1];
     const int n = o1 - o0;
     const bool wide = c.n.rt_grp_has_virtual[g] != 0;   // np.array([... float32 ..., 0]) is float64
@@ -742,8 +769,10 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
     if (gid >= (size_t)c.n.n_nodes * R) return;
     const int node = R1 ? (int)gid : (int)(gid / R);
     const int rep = R1 ? 0 : (int)(gid % R);
+    PNS_PDL_TRIGGER();
     const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
+    PNS_PDL_WAIT();
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
         case 2: node_body<2, R1>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w); break;
@@ -769,15 +798,18 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     const int l = valid ? (int)gid : 0;
     const size_t e = (size_t)l;
     const int tau = c.t_flows - 1;
+    PNS_PDL_TRIGGER();
     const bool one_class = c.n.n_classes == 1;
     const LinkP& p = c.n.classes[one_class ? 0 : __ldg(c.n.lk_class + l)];
+    const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
+    const int fftau = p.fftau, swtau = p.swtau;
+    PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
     const double gate = c.s.gate[e];
     // ---- batch of independent loads --------------------------------------------------------
     double din = 0, dout = 0;
     float np_ = 0, rs = 0, tt_old = 0;
     const bool windowed = c.u_tt_old != nullptr;
     double cin_prev = 0, cou_prev = 0;
-    const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
     if (upd) {
         // Node.update_links for this link (node.py:146-162): flows come from the node-major exchange arrays
         dout = c.s.nm_qo[slots.x]; din = c.s.nm_qi[slots.y];
@@ -791,7 +823,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     if (flw) {
         if (!upd) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
         snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
-        const int lag_i = tau + 1 - p.swtau;
+        const int lag_i = tau + 1 - swtau;
         if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
         if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
     }
@@ -800,11 +832,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     // fall back to a dependent load only when the link is congested.
     int pre_i0 = -1, pre_i1 = -1;
     double pre_v0 = 0.0, pre_v1 = 0.0;
-    if (flw && tau >= p.fftau) {
-        pre_i0 = max(0, tau + 1 - p.fftau);
+    if (flw && tau >= fftau) {
+        pre_i0 = max(0, tau + 1 - fftau);
         pre_v0 = H64(c, PNS_F64_CUM_INFLOW, pre_i0)[e];
-        if (p.fftau > 1) {
-            pre_i1 = max(0, tau + 2 - p.fftau);
+        if (fftau > 1) {
+            pre_i1 = max(0, tau + 2 - fftau);
             pre_v1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1)[e];
         }
     }
@@ -1112,9 +1144,9 @@ int check_step_io(const pns_net* net, const pns_step_io* io, int rng_mode) {
 
 template <bool R1, int PHASE>
 void launch_pair_mode(size_t n, cudaStream_t s, const Ctx& c) {
-    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_PHILOX>), blocks_for(n), kBlock, s, c);
-    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_TABLE>), blocks_for(n), kBlock, s, c);
-    else PNS_LAUNCH((k_link_pair<R1, PHASE, PNS_RNG_REQUEST>), blocks_for(n), kBlock, s, c);
+    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_pair<R1, PHASE, PNS_RNG_PHILOX>), blocks_for(n), kBlock, s, c);
+    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_pair<R1, PHASE, PNS_RNG_TABLE>), blocks_for(n), kBlock, s, c);
+    else PNS_LAUNCH_CHAIN((k_link_pair<R1, PHASE, PNS_RNG_REQUEST>), blocks_for(n), kBlock, s, c);
 }
 template <bool R1>
 void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
@@ -1126,9 +1158,9 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
 template <int PHASE>
 void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
     const unsigned nb = blocks_for(n_links);
-    if (c.mode == PNS_RNG_PHILOX) k_link_lane<PHASE, PNS_RNG_PHILOX><<<nb, kBlock, 0, s>>>(c);
-    else if (c.mode == PNS_RNG_TABLE) k_link_lane<PHASE, PNS_RNG_TABLE><<<nb, kBlock, 0, s>>>(c);
-    else k_link_lane<PHASE, PNS_RNG_REQUEST><<<nb, kBlock, 0, s>>>(c);
+    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX>), nb, kBlock, s, c);
+    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE>), nb, kBlock, s, c);
+    else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST>), nb, kBlock, s, c);
 }
 #endif
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
@@ -1144,8 +1176,8 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     else launch_pair_phase<false>(n, s, c);
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
-    if (net->replicas == 1) PNS_LAUNCH(k_node_flows<true>, blocks_for(n), kBlock, s, c);
-    else PNS_LAUNCH(k_node_flows<false>, blocks_for(n), kBlock, s, c);
+    if (net->replicas == 1) PNS_LAUNCH_CHAIN(k_node_flows<true>, blocks_for(n), kBlock, s, c);
+    else PNS_LAUNCH_CHAIN(k_node_flows<false>, blocks_for(n), kBlock, s, c);
 }
 
 struct StepSizes { size_t n_pair, n_grp, n_node; };
@@ -1184,7 +1216,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         PNS_MARK(k, 1);
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
-        if (z.n_grp) PNS_LAUNCH(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
+        if (z.n_grp) PNS_LAUNCH_CHAIN(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
