@@ -277,21 +277,17 @@ def run_ours(args):
 
     # ---- end to end through the public call, host buffers: every step copies its demand row from
     # pinned host memory, launches the step, and reads the network-wide pedestrian count back ----
-    pinned = torch.from_numpy(np.ascontiguousarray(demand)).pin_memory()
-    result_host = torch.zeros(Ke, dtype=torch.float32).pin_memory()
-    result_dev = torch.zeros(Ke, dtype=torch.float32, device=dev)
-    num_hist = eng.history("num_pedestrians")
+    pinned = torch.zeros((eng.demand.shape[0], eng.demand.shape[1]), dtype=torch.float64).pin_memory()
+    pinned[: demand.shape[0], : demand.shape[1]] = torch.from_numpy(np.ascontiguousarray(demand))
+    result_host = torch.zeros(Ke, dtype=torch.float64).pin_memory()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for k, t in enumerate(range(t_next, t_next + Ke)):
-        eng.demand[t - 1, : pinned.shape[1]].copy_(pinned[t - 1], non_blocking=True)     # H2D, this step's input
-        eng.run(t, 1)                                                                    # the public step call
-        result_dev[k: k + 1].copy_(num_hist[t].sum().reshape(1))                         # the step's metric
-        result_host[k: k + 1].copy_(result_dev[k: k + 1], non_blocking=True)             # D2H, every step
+    eng.run_streamed(t_next, Ke, pinned, result_host)      # public API: per-step H2D demand row + D2H step metric
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    num_hist = None
     eng.check_errors()
     total_peds = float(result_host[-1])
 
@@ -301,7 +297,7 @@ def run_ours(args):
     ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
 
     # free the lattice history before the batched environment allocates its own
-    h2d_bytes = int(pinned.shape[1] * 8)
+    h2d_bytes = int(plan["n_demand_rows"] * 8)
     del num_hist, pinned
     eng = None
     torch.cuda.empty_cache()
@@ -331,10 +327,10 @@ def run_ours(args):
                                     f"{B_ALG * L / 1e6:.0f} MB of history",
                        "multi_gpu": "replicas only: one independent grid per rank, no data-path collective"},
             "e2e": {"value": e2e, "unit": "link-timesteps/s", "steps": Ke,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "note": "per step: H2D of the demand row from pinned memory, one native step call through the "
-                            "torch custom op, a reduction to the network-wide pedestrian count and its D2H copy "
-                            "into pinned memory (copies are stream-ordered; the host waits once at the end)"},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                    "note": "Engine.run_streamed (C-ABI pns_step_streamed): every step copies its demand row from "
+                            "pinned host memory, runs the step, reduces the network-wide pedestrian count on the "
+                            "device and copies it to pinned host memory; stream-ordered, one host wait at the end"},
             "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak,

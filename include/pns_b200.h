@@ -222,6 +222,15 @@ int pns_step(const pns_net *net, const pns_state *st, const pns_step_io *io, int
 int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
                       int rng_mode, void *stream, double *ms, int64_t *launches);
 
+/* pns_step with the host traffic of a driving loop folded in (reference callers:
+ * `for t in range(1, steps): net.network_loading(t)` with demand edited between steps, examples/long_corridor.py:65-66,
+ * 126-134): before the node pass of every step its demand row is copied from pinned host memory
+ * (`host_demand`, same layout as pns_step_io.demand) into the device table, and after every step the network-wide
+ * pedestrian count of that step is reduced on the device and copied to `host_metric[k]` (pinned).  Everything is
+ * stream-ordered; the caller synchronises once at the end. */
+int pns_step_streamed(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
+                      int rng_mode, const double *host_demand, double *dev_metric, double *host_metric, void *stream);
+
 /* ActionApplier.apply_all_actions (rl/builders.py:264-352): rate-limit, clip, write the gate table. */
 int pns_env_apply_actions(const pns_net *net, const pns_state *st, const pns_env *env, const float *actions,
                           void *stream);

@@ -60,7 +60,7 @@ OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens"
 
 
 EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
-           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_env_apply_actions", "pns_env_observe", "pns_rng_selftest")
+           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_rng_selftest")
 
 _LIB = None
 
@@ -76,6 +76,7 @@ def _declare(lib):
     lib.pns_link_update.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
     lib.pns_step.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p]
     lib.pns_step_profiled.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p, _p, _p]
+    lib.pns_step_streamed.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p]
     env_p = C.POINTER(PnsEnv)
     lib.pns_env_apply_actions.argtypes = [net_p, st_p, env_p, _p, _p]
     lib.pns_env_observe.argtypes = [net_p, st_p, env_p, C.c_int, _p, _p, _p]

@@ -1052,6 +1052,20 @@ __global__ void k_state_init(const __grid_constant__ Ctx c) {
     }
 }
 
+// Network-wide pedestrian count of row t (sum over links and replicas), accumulated in double.
+__global__ void __launch_bounds__(256) k_metric_pedestrians(const __grid_constant__ Ctx c, double* out) {
+    const float* row = c.u_num;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.row32; i += (size_t)gridDim.x * blockDim.x)
+        acc += (double)row[i];
+#ifndef PNS_HOST_EMULATION
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+#else
+    *out += acc;
+#endif
+}
+
 __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t,
                                int site, int32_t* out_i, double* out_d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,8 +1203,14 @@ StepSizes sizes_of(const pns_net* net) {
     return z;
 }
 
+struct Streamed {           // per-step host traffic of pns_step_streamed
+    const double* host_demand;   // pinned [rows][n_demand_rows*R]
+    double* dev_metric;          // [n_steps]
+    double* host_metric;         // pinned [n_steps]
+};
+
 int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps, int rng_mode,
-              cudaStream_t s, double* ms, int64_t* launches) {
+              cudaStream_t s, double* ms, int64_t* launches, const Streamed* sx = nullptr) {
     if (n_steps <= 0) return 0;
     if (check_common(net, st, t0) || check_common(net, st, t0 + n_steps - 1)) return 1;
     if (check_step_io(net, io, rng_mode)) return 1;
@@ -1214,6 +1234,18 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         PNS_MARK(k, 0);
         if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
+#ifndef PNS_HOST_EMULATION
+        if (sx && k > 0) {          // result of step t0+k-1: reduce on the device, copy to the host, every step
+            cudaMemsetAsync(sx->dev_metric + (k - 1), 0, sizeof(double), s);
+            k_metric_pedestrians<<<148 * 4, 256, 0, s>>>(cp, sx->dev_metric + (k - 1));
+            cudaMemcpyAsync(sx->host_metric + (k - 1), sx->dev_metric + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, s);
+        }
+        if (sx && k < n_steps && net->n_demand_rows) {   // input of step t0+k: its demand row, from pinned host memory
+            const size_t row = (size_t)net->n_demand_rows * net->replicas, off = (size_t)(t0 + k - 1) * row;
+            cudaMemcpyAsync(const_cast<double*>(io->demand) + off, sx->host_demand + off, row * sizeof(double),
+                            cudaMemcpyHostToDevice, s);
+        }
+#endif
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
         if (z.n_grp) PNS_LAUNCH_CHAIN(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
@@ -1339,6 +1371,19 @@ int pns_env_observe(const pns_net* net, const pns_state* st, const pns_env* env,
     x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward;
     PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_observe");
+}
+
+int pns_step_streamed(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps,
+                      int rng_mode, const double* host_demand, double* dev_metric, double* host_metric, void* stream) {
+#ifdef PNS_HOST_EMULATION
+    (void)host_demand; (void)dev_metric; (void)host_metric;
+    return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, nullptr, nullptr);
+#else
+    if (!host_demand || !dev_metric || !host_metric) return fail("pns_step_streamed: null buffer");
+    Streamed sx;
+    sx.host_demand = host_demand; sx.dev_metric = dev_metric; sx.host_metric = host_metric;
+    return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, nullptr, nullptr, &sx);
+#endif
 }
 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,
