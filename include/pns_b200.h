@@ -96,6 +96,8 @@ typedef struct pns_net {
     int32_t n_routed, n_groups, n_opts, n_rows, n_terms, n_classes, max_degree, nd_stride; /* nd_stride: 4 or 8 */
     double unit_time;
     const pns_link_class *classes; /* [n_classes] */
+    pns_link_class class0;         /* host copy of classes[0]: single-class networks read parameters from the
+                                      kernel-parameter (constant) bank instead of loading the table */
     const int32_t *lk_class;       /* [n_links] */
     const double *lk_width;        /* [n_links] corridor width `_width` (link.py:53): initial gate / lane widths */
     /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id).

@@ -22,13 +22,21 @@ _p = C.c_void_p
 _i32 = C.c_int32
 
 
+class PnsLinkClass(C.Structure):
+    _fields_ = ([(k, C.c_double) for k in ("length", "area", "space", "kc", "vf", "kj", "act", "sigma")]
+                + [(k, C.c_float) for k in ("kc32", "kj32", "kj_minus_kc32", "gamma32", "bi32", "area32", "length32",
+                                            "yp_coef32", "neg_vf32", "vf32", "sm_gamma32", "inv_kj32", "max_tt32", "tt0")]
+                + [(k, _i32) for k in ("fftau", "swtau", "flags", "pad_")])
+
+
 class PnsNet(C.Structure):
     _fields_ = (
         [(n, _i32) for n in ("abi_version", "n_links", "n_nodes", "n_cols64", "sim_steps", "replicas",
                              "window", "n_edges", "n_od", "n_demand_rows",
                              "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes", "max_degree", "nd_stride")]
         + [("unit_time", C.c_double)]
-        + [(n, _p) for n in ("classes", "lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
+        + [("classes", _p), ("class0", PnsLinkClass)]
+        + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
                              "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",

@@ -76,6 +76,9 @@ constexpr int kBlock = 128;
 #ifndef PNS_MIN_BLOCKS
 #define PNS_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (tuning knob)
 #endif
+#ifndef PNS_LANE_MIN_BLOCKS
+#define PNS_LANE_MIN_BLOCKS 8
+#endif
 #ifndef PNS_NODE_MIN_BLOCKS
 #define PNS_NODE_MIN_BLOCKS 4
 #endif
@@ -789,8 +792,8 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
 // sending flow) with warp shuffles.  Same arithmetic as link_pair_body, half the critical path
 // per thread and no cross-direction state to keep in registers.  (The host-emulation test build
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
-template <int PHASE, int MODE>
-__global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__ Ctx c) {
+template <int PHASE, int MODE, bool ONECLASS>
+__global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -799,8 +802,8 @@ __global__ void __launch_bounds__(kBlock, 8) k_link_lane(const __grid_constant__
     const size_t e = (size_t)l;
     const int tau = c.t_flows - 1;
     PNS_PDL_TRIGGER();
-    const bool one_class = c.n.n_classes == 1;
-    const LinkP& p = c.n.classes[one_class ? 0 : __ldg(c.n.lk_class + l)];
+    // single-class networks: parameters are kernel-parameter constants, no table loads at all
+    const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[__ldg(c.n.lk_class + l)];
     const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
     const int fftau = p.fftau, swtau = p.swtau;
     PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
@@ -1172,9 +1175,15 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
 template <int PHASE>
 void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
     const unsigned nb = blocks_for(n_links);
-    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX>), nb, kBlock, s, c);
-    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE>), nb, kBlock, s, c);
-    else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST>), nb, kBlock, s, c);
+    if (c.n.n_classes == 1) {
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, true>), nb, kBlock, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, true>), nb, kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, true>), nb, kBlock, s, c);
+    } else {
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, false>), nb, kBlock, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, false>), nb, kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, false>), nb, kBlock, s, c);
+    }
 }
 #endif
 void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {

@@ -81,6 +81,7 @@ class Engine:
         net.unit_time = p["unit_time"]
         for k in _NET_ARRAYS + ("classes",):
             setattr(net, k, _ptr(self._net_t[k]))
+        C.memmove(C.byref(net.class0), np.ascontiguousarray(p["classes"][:1]).ctypes.data, C.sizeof(net.class0))
         net.rt_temp, net.rt_alpha, net.rt_beta, net.rt_omega, net.rt_eps = [float(x) for x in p["rt_scalars"]]
         self.net = net
 
