@@ -2,13 +2,18 @@
 //
 // One simulation step t (reference Network.network_loading, src/LTM/network.py:266-287) is
 //
-//   k_link_pair    one thread per (link pair, replica)   FLOWS : sending + receiving flow at tau = t-1
-//                                                         UPDATE: pedestrians, density, speed, travel time at t
-//   k_route_probs  one thread per (route group, replica) logit P(down | up, od)           (routed nets only)
-//   k_node_flows   one thread per (node, replica)        turning fractions, node model, cumulative counts
+//   link kernel    FLOWS : sending + receiving flow at tau = t-1, handed to the node pass in node-major order
+//                  UPDATE: the link's inflow/outflow of step t picked up from the node pass, cumulative
+//                          counts, pedestrians, density, speed, travel time at t
+//       k_link_pair<R1,PHASE,MODE>      one thread per (link pair, replica)      any replica count
+//       k_link_lane<PHASE,MODE,ONECLASS> one thread per directed link            single replica (GPU only)
+//   k_route_probs  one thread per (route group, replica)  logit P(down | up, od)  (routed nets only)
+//   k_node_flows   one thread per (node, replica)         turning fractions + node model on contiguous
+//                                                          node-major records
 //
 // and inside a multi-step call the UPDATE of step t and the FLOWS of step t+1 run in the same
-// thread (the link state stays in registers), so a step costs two launches:
+// thread (the link state stays in registers), so a step costs two launches, chained with
+// programmatic dependent launch:
 //
 //   FLOWS(t0) | node(t0) | UPDATE(t0)+FLOWS(t0+1) | node(t0+1) | ... | UPDATE(t0+n-1)
 //
@@ -16,8 +21,9 @@
 // pass produced for the same link pair), which is what makes the step
 // data-parallel.  All state is time-major structure-of-arrays history in HBM (include/pns_b200.h);
 // the replica index is the fastest-varying one, so for batched replicas a warp touches 32
-// consecutive elements of every row; for a single replica a thread owns the two adjacent columns of
-// a link pair.  Per-link parameters come from a small class table that stays in L1.
+// consecutive elements of every row; for a single replica adjacent lanes are the two directions of
+// a corridor.  Per-link parameters come from a small class table (L1) or, for single-class
+// networks, from the kernel-parameter constant bank.
 //
 // Numerics: the reference mixes float32 history with float64 counters under numpy-2 scalar
 // promotion; every expression below states its precision explicitly and the file is compiled
@@ -92,21 +98,19 @@ struct Ctx {
     int t_flows;  // FLOWS computes the flows of step t_flows (time index t_flows-1)
     int phase;    // PH_* mask
     int mode;     // PNS_RNG_*
-    int max_degree;   // largest slot count of any node (selects the node kernel's group size)
     const int32_t* draw_b;  // TABLE: R1..R3 outcomes for step t_flows
     const double* draw_n;   // TABLE: R4 noise for step t
     size_t row64, row32;    // elements per history row
     size_t fld64, fld32;    // elements per history field
     // rows known at launch time, resolved on the host (saves 64-bit index arithmetic per access)
-    const double *u_inflow, *u_outflow;                 // UPDATE inputs, row t
     const float *u_num_prev, *u_tt_old;                 // row t-1; row t-window (null while t < window)
     float *u_num, *u_dens, *u_speed, *u_tt, *u_flow, *u_avg;   // UPDATE outputs, row t
     double *u_bgw, *u_sepw;
     const float *f_num, *f_dens, *f_avg;                // FLOWS inputs, row tau = t_flows-1
     const double *f_cin, *f_cou, *f_sndp, *f_rcvp;      // rows tau, tau, tau-1 (wrapped), tau-1
     double *f_snd, *f_rcv;                              // FLOWS outputs, row tau
-    const double *n_snd, *n_rcv, *n_coutp, *n_cinp, *n_demand;   // node inputs, row t-1
-    double *n_outflow, *n_inflow, *n_cout, *n_cin;      // node outputs, row t
+    const double *n_coutp, *n_cinp, *n_demand;          // cumulative counts of row t-1; demand row of step t
+    double *n_outflow, *n_inflow, *n_cout, *n_cin;      // flows and cumulative counts of row t
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -1098,7 +1102,6 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
     c.t_flows = t_flows;
     c.phase = phase;
     c.mode = mode;
-    c.max_degree = net->max_degree;
     c.row64 = (size_t)net->n_cols64 * net->replicas;
     c.row32 = (size_t)net->n_links * net->replicas;
     c.fld64 = c.row64 * (size_t)(net->sim_steps + 1);
@@ -1108,7 +1111,6 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
         auto h64 = [&](int f, int row) { return st->hist64 + (size_t)f * c.fld64 + (size_t)row * c.row64; };
         auto h32 = [&](int f, int row) { return st->hist32 + (size_t)f * c.fld32 + (size_t)row * c.row32; };
         const int tu = t >= 1 && t < S1 ? t : 1;                 // UPDATE / node row (clamped when unused)
-        c.u_inflow = h64(PNS_F64_INFLOW, tu); c.u_outflow = h64(PNS_F64_OUTFLOW, tu);
         c.u_num_prev = h32(PNS_F32_NUM_PED, tu - 1);
         c.u_tt_old = tu >= net->window ? h32(PNS_F32_TRAVEL_TIME, tu - net->window) : nullptr;
         c.u_num = h32(PNS_F32_NUM_PED, tu); c.u_dens = h32(PNS_F32_DENSITY, tu); c.u_speed = h32(PNS_F32_SPEED, tu);
@@ -1124,7 +1126,6 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
         c.f_cin = h64(PNS_F64_CUM_INFLOW, tau); c.f_cou = h64(PNS_F64_CUM_OUTFLOW, tau);
         c.f_sndp = h64(PNS_F64_SENDING, prev); c.f_rcvp = h64(PNS_F64_RECEIVING, prev);
         c.f_snd = h64(PNS_F64_SENDING, tau); c.f_rcv = h64(PNS_F64_RECEIVING, tau);
-        c.n_snd = h64(PNS_F64_SENDING, tu - 1); c.n_rcv = h64(PNS_F64_RECEIVING, tu - 1);
         c.n_coutp = h64(PNS_F64_CUM_OUTFLOW, tu - 1); c.n_cinp = h64(PNS_F64_CUM_INFLOW, tu - 1);
         c.n_outflow = h64(PNS_F64_OUTFLOW, tu); c.n_inflow = h64(PNS_F64_INFLOW, tu);
         c.n_cout = h64(PNS_F64_CUM_OUTFLOW, tu); c.n_cin = h64(PNS_F64_CUM_INFLOW, tu);

@@ -65,3 +65,58 @@ def test_gate_width_edits_between_steps(emu_lib):
     for f in F64_FIELDS[:7] + F32_FIELDS:
         assert np.array_equal(o.h[f], b._store.field(f)), f
     assert b.links[(4, 5)].back_gate_width_data[45] == 0.5
+
+
+def _lattice(size, origins, steps=200):
+    from pednstream_b200 import Network
+    from pednstream_b200.grid import DEFAULT_LINK, grid_adjacency
+    params = {"unit_time": 10, "simulation_steps": steps, "default_link": dict(DEFAULT_LINK),
+              "demand": {f"origin_{o}": {"peak_lambda": 40, "base_lambda": 25} for o in origins}}
+    np.random.seed(3)
+    return Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
+
+
+def test_user_supplied_turning_fractions(emu_lib):
+    """Network.update_turning_fractions_per_node (reference network.py:250-255, usage
+    examples/long_corridor.py:111-113): host-owned fractions reach the node kernel (tf_mode 1)."""
+    rng = np.random.RandomState(0)
+
+    def fractions(node):
+        m = node.source_num
+        f = rng.uniform(0.1, 1.0, size=(m, m - 1))
+        return (f / f.sum(axis=1, keepdims=True)).reshape(-1)
+
+    a, b = _lattice(3, [0, 8]), _lattice(3, [0, 8])
+    for net in (a, b):
+        rng = np.random.RandomState(0)
+        net.update_turning_fractions_per_node([4, 1], [fractions(net.nodes[4]), fractions(net.nodes[1])])
+    o = LtmOracle(a)
+    attach(b, emu_lib)
+    state = np.random.get_state()
+    for t in range(1, 150):
+        if t == 70:                                   # change them mid-run as well
+            rng = np.random.RandomState(9)
+            o.tf[4] = fractions(a.nodes[4])
+        o.network_loading(t)
+    np.random.set_state(state)
+    for t in range(1, 150):
+        if t == 70:
+            rng = np.random.RandomState(9)
+            b.update_turning_fractions_per_node([4], [fractions(b.nodes[4])])
+        b.network_loading(t)
+    for f in F64_FIELDS[:7] + F32_FIELDS:
+        assert np.array_equal(o.h[f], b._store.field(f)), f
+    assert float(o.h["cumulative_inflow"][149].sum()) > 1000
+
+
+def test_device_fault_is_raised_like_the_reference(emu_lib):
+    """Negative flows make the reference raise (node.py:219 Warning, link.py:346 ValueError); the
+    kernels flag them and the facade raises at the next synchronisation point."""
+    net = _lattice(3, [0, 8])
+    attach(net, emu_lib)
+    net.nodes[0].demand = np.asarray(net.nodes[0].demand, dtype=np.float64)
+    net.nodes[0].demand[5:] = -3.0
+    with pytest.raises(ValueError, match="negative node flow"):
+        for t in range(1, 12):
+            net.network_loading(t)
+        net.links[(0, 1)].inflow
