@@ -113,10 +113,6 @@ typedef struct pns_net {
                                    (end node * nd_stride + its slot there) and where its receiving flow goes
                                    (start node * nd_stride + its slot there); the node pass answers in the same
                                    slots with the link's outflow (nm_qo) and inflow (nm_qi) */
-    /* block tables of the fused single-replica kernel (may be null): block b of 128 link threads solves the
-     * nodes bn_node[bn_ptr[b] .. bn_ptr[b+1]) in shared memory (sign bit: this block owns the node's virtual
-     * links); lk_local[l] = {local node*4 + slot of the link's outflow, ... of its inflow} */
-    const int32_t *bn_ptr, *bn_node, *lk_local;
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
@@ -139,8 +135,7 @@ typedef struct pns_state {
     double *tf_static;   /* [n_edges] host-owned turning fractions (uniform default / user supplied) */
     double *tf_routed;   /* [n_edges*R] fractions computed this step for routed nodes */
     double *probs;       /* [n_opts*R] scratch: P(down | up, od) of this step */
-    double *nm_s, *nm_r;   /* [2][n_nodes*nd_stride*R] node-major sending / receiving flows (link -> node), double
-                              buffered by the parity of the step they belong to */
+    double *nm_s, *nm_r;   /* [n_nodes*nd_stride*R] node-major sending / receiving flows of the step (link -> node) */
     double *nm_qo, *nm_qi; /* [n_nodes*nd_stride*R] node-major outflow / inflow of the step (node -> link) */
     int32_t *err;        /* [R] error bits */
     int32_t n_f64;       /* 7, or 8 when the network has separators */

@@ -36,7 +36,7 @@ class PnsNet(C.Structure):
                              "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes", "max_degree", "nd_stride")]
         + [("unit_time", C.c_double)]
         + [("classes", _p), ("class0", PnsLinkClass)]
-        + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "bn_ptr", "bn_node", "lk_local",
+        + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
                              "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",

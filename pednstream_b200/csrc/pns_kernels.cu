@@ -111,10 +111,6 @@ struct Ctx {
     double *f_snd, *f_rcv;                              // FLOWS outputs, row tau
     const double *n_coutp, *n_cinp, *n_demand;          // cumulative counts of row t-1; demand row of step t
     double *n_outflow, *n_inflow, *n_cout, *n_cin;      // flows and cumulative counts of row t
-    // node-major hand-over buffers are double buffered by step parity: FLOWS of step t_flows fills one
-    // half while node solves of step t may still be reading the other
-    double *nm_s_w, *nm_r_w;                            // written by FLOWS (parity of t_flows)
-    const double *nm_s_rd, *nm_r_rd;                    // read by the node solve (parity of t)
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -534,8 +530,8 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     V::st(c.f_snd, e[0], e[1], s[0].flow, s[1].flow);
     V::st(c.f_rcv, e[0], e[1], q0, q1);
     // hand the flows to the node pass in node-major order (slot of each link at its end / start node)
-    c.nm_s_w[(size_t)slots.x * R + rep] = s[0].flow; c.nm_r_w[(size_t)slots.y * R + rep] = q0;
-    c.nm_s_w[(size_t)slots.z * R + rep] = s[1].flow; c.nm_r_w[(size_t)slots.w * R + rep] = q1;
+    c.s.nm_s[(size_t)slots.x * R + rep] = s[0].flow; c.s.nm_r[(size_t)slots.y * R + rep] = q0;
+    c.s.nm_s[(size_t)slots.z * R + rep] = s[1].flow; c.s.nm_r[(size_t)slots.w * R + rep] = q1;
 }
 
 template <bool R1, int PHASE, int MODE>
@@ -653,61 +649,12 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
     return floor(pymin(w, r * (w / D)));
 }
 
-// The node model on values held in registers: s[i] sending flow of slot i, r[j] receiving flow of
-// slot j -> q_out[i] outflow of incoming link i, q_in[j] inflow of outgoing link j.
-// OneToOneNode.solve (node.py:230-242) / RegularNode.solve 'classic' (node.py:272-300), one column
-// (outgoing slot j) at a time: W[i][j] = P[i][j]*s[i], D[j] = sum_i W[i][j] in slot order,
-// f = floor(min(W, r[j]*(W/D[j]))).  tf == nullptr: P = 1/(m-1) (network.py:269-271); otherwise
-// P[i][j] = tf[(i*(m-1) + (j<i ? j : j-1)) * ts].  s[] is clobbered.
-template <int CAP>
-__device__ __forceinline__ void node_solve(int m, int kind, const double* tf, size_t ts, double* s, const double* r,
-                                           double* q_out, double* q_in) {
-    if (kind == 0) {
-        const double a = fmin(s[0], r[CAP > 1 ? 1 : 0]), b = fmin(s[CAP > 1 ? 1 : 0], r[0]);
-        q_out[0] = a; q_out[CAP > 1 ? 1 : 0] = b;
-        q_in[0] = b;  q_in[CAP > 1 ? 1 : 0] = a;
-        return;
-    }
-    const double phi = 1.0 / (double)(m - 1);
-    if (tf == nullptr) {
-#pragma unroll
-        for (int i = 0; i < CAP; ++i)
-            if (i < m) s[i] = phi * s[i];             // from here on s[] holds W[i][*]
-    }
-#pragma unroll
-    for (int i = 0; i < CAP; ++i) q_out[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < CAP; ++j) {
-        if (j >= m) continue;
-        double w[CAP];
-        double D = 0.0;               // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
-#pragma unroll
-        for (int i = 0; i < CAP; ++i) {
-            w[i] = 0.0;
-            if (i >= m || i == j) continue;
-            w[i] = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i] : s[i];
-            D = D + w[i];
-        }
-        D = D != 0.0 ? D : 1e-5;
-        double in_j = 0.0;
-#pragma unroll
-        for (int i = 0; i < CAP; ++i) {
-            if (i >= m || i == j) continue;
-            const double f = turn_flow(w[i], r[j], D);
-            q_out[i] += f;
-            in_j += f;
-        }
-        q_in[j] = fmax(0.0, in_j);
-    }
-#pragma unroll
-    for (int i = 0; i < CAP; ++i) q_out[i] = fmax(0.0, q_out[i]);
-}
-
-// One node of the stand-alone node pass.  The link kernels hand over sending/receiving flows in
-// *node-major* order (slot k of node n at index n*stride + k, replica fastest) and pick the
-// resulting flows up from nm_qo / nm_qi, so this pass reads and writes contiguous, coalesced
-// records and all scatter/gather over the link<->node incidence happens once per link in the
-// link kernels.  M > 0: slot count known at compile time (registers); M == 0: generic (<= 8 slots).
+// One node.  The link kernels hand over sending/receiving flows in *node-major* order
+// (nm_s / nm_r: slot k of node n at index n*stride + k, replica fastest) and pick the resulting
+// flows up from nm_qo / nm_qi, so this pass reads and writes contiguous, coalesced records and
+// all scatter/gather over the link<->node incidence happens once per link in the link kernels.
+// M > 0: slot count known at compile time (loops unrolled, everything in registers);
+// M == 0: generic path for rare high-degree nodes (arrays in local memory).
 template <int M, bool R1>
 __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int kind, int tf_mode,
                                           int dem_row, int tf_ptr) {
@@ -717,19 +664,16 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     const size_t base = (size_t)node * c.n.nd_stride;
     double s[CAP], r[CAP];
     if (R1 && M == 4) {
-        const double2* ps = reinterpret_cast<const double2*>(c.nm_s_rd + base);
-        const double2* pr = reinterpret_cast<const double2*>(c.nm_r_rd + base);
+        const double2* ps = reinterpret_cast<const double2*>(c.s.nm_s + base);
+        const double2* pr = reinterpret_cast<const double2*>(c.s.nm_r + base);
         const double2 a0 = ps[0], a1 = ps[1], b0 = pr[0], b1 = pr[1];
         s[0] = a0.x; s[1 % CAP] = a0.y; s[2 % CAP] = a1.x; s[3 % CAP] = a1.y;
         r[0] = b0.x; r[1 % CAP] = b0.y; r[2 % CAP] = b1.x; r[3 % CAP] = b1.y;
     } else {
 #pragma unroll
-        for (int i = 0; i < CAP; ++i) {
-            s[i] = 0.0; r[i] = 0.0;
-            if (i < m) {
-                s[i] = c.nm_s_rd[(base + i) * R + rep];
-                r[i] = c.nm_r_rd[(base + i) * R + rep];
-            }
+        for (int i = 0; i < m; ++i) {
+            s[i] = c.s.nm_s[(base + i) * R + rep];
+            r[i] = c.s.nm_r[(base + i) * R + rep];
         }
     }
     if (dem_row >= 0) {                                                     // slot 0 is the virtual O/D link pair
@@ -738,22 +682,61 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     }
     bool negative = false;
 #pragma unroll
-    for (int i = 0; i < CAP; ++i) negative |= (i < m) & ((s[i] < 0.0) | (r[i] < 0.0));
+    for (int i = 0; i < m; ++i) negative |= (s[i] < 0.0) | (r[i] < 0.0);
     if (negative) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
 
-    const double* tf = nullptr;
-    size_t ts = 1;
-    if (kind != 0 && tf_mode == 2) {
-        double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
-        routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
-        tf = out;
-        ts = (size_t)R;
-    } else if (kind != 0 && tf_mode == 1) {
-        tf = c.s.tf_static + tf_ptr;
-    }
     double q_out[CAP], q_in[CAP];
-    node_solve<CAP>(m, kind, tf, ts, s, r, q_out, q_in);
-
+    if (kind == 0) {
+        // OneToOneNode.solve (node.py:230-242): exactly two slots
+        const double a = fmin(s[0], r[CAP > 1 ? 1 : 0]), b = fmin(s[CAP > 1 ? 1 : 0], r[0]);
+        q_out[0] = a; q_out[CAP > 1 ? 1 : 0] = b;
+        q_in[0] = b;  q_in[CAP > 1 ? 1 : 0] = a;
+    } else {
+        // RegularNode.solve, 'classic' (node.py:272-300), one column (outgoing slot j) at a time:
+        // W[i][j] = P[i][j]*s[i], D[j] = sum_i W[i][j] in slot order, f = floor(min(W, r[j]*(W/D[j]))).
+        // tf_mode 0: P = phi = 1/(m-1) (network.py:269-271); otherwise P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)].
+        const double* tf = nullptr;
+        size_t ts = 1;
+        if (tf_mode == 2) {
+            double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
+            routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
+            tf = out;
+            ts = (size_t)R;
+        } else if (tf_mode == 1) {
+            tf = c.s.tf_static + tf_ptr;
+        }
+        const double phi = 1.0 / (double)(m - 1);
+        if (tf == nullptr) {
+#pragma unroll
+            for (int i = 0; i < m; ++i) s[i] = phi * s[i];        // from here on s[] holds W[i][*]
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) q_out[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            double w[CAP];
+            double D = 0.0;               // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                w[i] = 0.0;
+                if (i == j) continue;
+                w[i] = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i] : s[i];
+                D = D + w[i];
+            }
+            D = D != 0.0 ? D : 1e-5;
+            double in_j = 0.0;
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                if (i == j) continue;
+                const double f = turn_flow(w[i], r[j], D);
+                q_out[i] += f;
+                in_j += f;
+            }
+            q_in[j] = fmax(0.0, in_j);
+        }
+#pragma unroll
+        for (int i = 0; i < m; ++i) q_out[i] = fmax(0.0, q_out[i]);
+    }
     if (R1 && M == 4) {
         double2* po = reinterpret_cast<double2*>(c.s.nm_qo + base);
         double2* pi = reinterpret_cast<double2*>(c.s.nm_qi + base);
@@ -764,11 +747,10 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         v.x = q_in[2 % CAP]; v.y = q_in[3 % CAP]; pi[1] = v;
     } else {
 #pragma unroll
-        for (int i = 0; i < CAP; ++i)
-            if (i < m) {
-                c.s.nm_qo[(base + i) * R + rep] = q_out[i];
-                c.s.nm_qi[(base + i) * R + rep] = q_in[i];
-            }
+        for (int i = 0; i < m; ++i) {
+            c.s.nm_qo[(base + i) * R + rep] = q_out[i];
+            c.s.nm_qi[(base + i) * R + rep] = q_in[i];
+        }
     }
     if (dem_row >= 0) {
         // the virtual links have no link thread: keep their counters here (node.py:154-161, link.py:19-25)
@@ -814,15 +796,9 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
 // sending flow) with warp shuffles.  Same arithmetic as link_pair_body, half the critical path
 // per thread and no cross-direction state to keep in registers.  (The host-emulation test build
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
-// SOLVE (with UPDATE): the block first evaluates the node model of every node its 128 links start or
-// end at -- contiguous node-major records in, results into shared memory -- so the step needs no
-// separate node kernel and no global round trip for the flows.  A node is solved by each block that
-// touches it (about two on a lattice); the lowest such block keeps the counters of its virtual links.
-template <int PHASE, int MODE, bool ONECLASS, bool SOLVE>
+template <int PHASE, int MODE, bool ONECLASS>
 __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
-    static_assert(!SOLVE || upd, "the block-local node solve feeds UPDATE");
-    __shared__ double sm_qo[SOLVE ? 2 * kBlock * 4 : 1], sm_qi[SOLVE ? 2 * kBlock * 4 : 1];
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
@@ -834,12 +810,6 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[__ldg(c.n.lk_class + l)];
     const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
     const int fftau = p.fftau, swtau = p.swtau;
-    int2 local = {0, 0};
-    int bn0 = 0, bn1 = 0;
-    if (SOLVE) {
-        local = __ldg(reinterpret_cast<const int2*>(c.n.lk_local) + l);            // my flows in shared memory
-        bn0 = __ldg(c.n.bn_ptr + blockIdx.x); bn1 = __ldg(c.n.bn_ptr + blockIdx.x + 1);
-    }
     PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
     const double gate = c.s.gate[e];
     // ---- batch of independent loads --------------------------------------------------------
@@ -849,7 +819,7 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     double cin_prev = 0, cou_prev = 0;
     if (upd) {
         // Node.update_links for this link (node.py:146-162): flows come from the node-major exchange arrays
-        if (!SOLVE) { dout = c.s.nm_qo[slots.x]; din = c.s.nm_qi[slots.y]; }
+        dout = c.s.nm_qo[slots.x]; din = c.s.nm_qi[slots.y];
         cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e];
         np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
         if (windowed) tt_old = c.u_tt_old[e];
@@ -881,37 +851,6 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     const Area ar = link_area(c, p, e, gate);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
 
-    if (SOLVE) {
-        for (int j = threadIdx.x; j < bn1 - bn0; j += kBlock) {
-            const int entry = __ldg(c.n.bn_node + bn0 + j);
-            const int node = entry & 0x7fffffff;
-            const bool owner = entry < 0;
-            const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);
-            const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
-            const size_t base = (size_t)node * 4;
-            const double2* ps = reinterpret_cast<const double2*>(c.nm_s_rd + base);
-            const double2* pr = reinterpret_cast<const double2*>(c.nm_r_rd + base);
-            const double2 a0 = ps[0], a1 = ps[1], b0 = pr[0], b1 = pr[1];
-            double sv[4] = {a0.x, a0.y, a1.x, a1.y}, rv[4] = {b0.x, b0.y, b1.x, b1.y};
-            if (meta.z >= 0) { sv[0] = c.n_demand[meta.z]; rv[0] = 1e6; }   // node.py:176, 186
-            bool negative = false;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) negative |= (i < m) & ((sv[i] < 0.0) | (rv[i] < 0.0));
-            if (negative) atomicOr(c.s.err, PNS_ERR_NEG_NODE_FLOW);
-            double qo[4], qi[4];
-            node_solve<4>(m, kind, tf_mode == 1 ? c.s.tf_static + meta.w : nullptr, 1, sv, rv, qo, qi);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { sm_qo[j * 4 + i] = qo[i]; sm_qi[j * 4 + i] = qi[i]; }
-            if (owner) {                                                     // virtual links' counters
-                const size_t vin = (size_t)(c.n.n_links + 2 * meta.z), vout = vin + 1;
-                c.n_outflow[vin] = qo[0]; c.n_cout[vin] = c.n_coutp[vin] + qo[0];
-                c.n_inflow[vout] = qi[0]; c.n_cin[vout] = c.n_cinp[vout] + qi[0];
-            }
-        }
-        __syncthreads();
-        dout = sm_qo[local.x];
-        din = sm_qi[local.y];
-    }
     if (upd) {
         const int t = c.t;
         cin_tau = cin_prev + din;                                           // link.py:19-25
@@ -981,8 +920,8 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
         const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
         c.f_snd[e] = s.flow;
         c.f_rcv[e] = rcv;
-        c.nm_s_w[slots.x] = s.flow;        // node-major hand-over to the node pass
-        c.nm_r_w[slots.y] = rcv;
+        c.s.nm_s[slots.x] = s.flow;        // node-major hand-over to the node pass
+        c.s.nm_r[slots.y] = rcv;
     }
 }
 
@@ -1190,9 +1129,6 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
         c.n_coutp = h64(PNS_F64_CUM_OUTFLOW, tu - 1); c.n_cinp = h64(PNS_F64_CUM_INFLOW, tu - 1);
         c.n_outflow = h64(PNS_F64_OUTFLOW, tu); c.n_inflow = h64(PNS_F64_INFLOW, tu);
         c.n_cout = h64(PNS_F64_CUM_OUTFLOW, tu); c.n_cin = h64(PNS_F64_CUM_INFLOW, tu);
-        const size_t nm = (size_t)net->n_nodes * net->nd_stride * net->replicas;
-        c.nm_s_w = st->nm_s + (size_t)(tf_ & 1) * nm; c.nm_r_w = st->nm_r + (size_t)(tf_ & 1) * nm;
-        c.nm_s_rd = st->nm_s + (size_t)(tu & 1) * nm; c.nm_r_rd = st->nm_r + (size_t)(tu & 1) * nm;
         c.n_demand = (io && io->demand) ? io->demand + (size_t)(tu - 1) * net->n_demand_rows * net->replicas : nullptr;
     }
     const int64_t stride = io ? io->draw_row_stride : 0;
@@ -1237,46 +1173,29 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
     else if (c.phase == PH_FLOWS) launch_pair_mode<R1, PH_FLOWS>(n, s, c);
 }
 #ifndef PNS_HOST_EMULATION
-template <int PHASE, bool ONECLASS, bool SOLVE>
+template <int PHASE>
 void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
     const unsigned nb = blocks_for(n_links);
-    if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, ONECLASS, SOLVE>), nb, kBlock, s, c);
-    else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, ONECLASS, SOLVE>), nb, kBlock, s, c);
-    else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, ONECLASS, SOLVE>), nb, kBlock, s, c);
-}
-template <bool ONECLASS>
-void launch_lane(size_t n_links, cudaStream_t s, const Ctx& c, bool solve) {
-    if (solve) {
-        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS, ONECLASS, true>(n_links, s, c);
-        else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE, ONECLASS, true>(n_links, s, c);
-        return;
+    if (c.n.n_classes == 1) {
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, true>), nb, kBlock, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, true>), nb, kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, true>), nb, kBlock, s, c);
+    } else {
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, false>), nb, kBlock, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, false>), nb, kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, false>), nb, kBlock, s, c);
     }
-    if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS, ONECLASS, false>(n_links, s, c);
-    else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE, ONECLASS, false>(n_links, s, c);
-    else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS, ONECLASS, false>(n_links, s, c);
 }
 #endif
-// The node model can run inside the lane kernel (block-local solve in shared memory) when there is a
-// single replica, no node has more than four slots and no node is routed.
-bool fused_node_solve(const pns_net* net) {
-#ifdef PNS_HOST_EMULATION
-    (void)net;
-    return false;
-#else
-    static const bool off = getenv("PNS_NO_FUSE") != nullptr || getenv("PNS_PAIR_THREADS") != nullptr;
-    return !off && net->replicas == 1 && net->nd_stride == 4 && net->n_routed == 0 && net->bn_ptr && net->bn_node &&
-           net->lk_local;
-#endif
-}
-void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, bool solve = false) {
+void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
-        if (net->n_classes == 1) launch_lane<true>(2 * n, s, c, solve);
-        else launch_lane<false>(2 * n, s, c, solve);
+        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
+        else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
+        else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, c);
         return;
     }
 #endif
-    (void)solve;
     if (net->replicas == 1) launch_pair_phase<true>(n, s, c);
     else launch_pair_phase<false>(n, s, c);
 }
@@ -1318,14 +1237,12 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     (void)ms; (void)launches;
 #define PNS_MARK(k, j) do { } while (0)
 #endif
-    // launch k (0..n_steps): link kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
-    // (fused: the node model of step t0+k-1 runs inside the link kernel of launch k, no node kernel)
-    const bool fused = fused_node_solve(net);
+    // launch k (0..n_steps): pair kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
     for (int k = 0; k <= n_steps; ++k) {
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
         const Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
         PNS_MARK(k, 0);
-        if (z.n_pair) launch_pair(net, z.n_pair, s, cp, fused && k > 0);
+        if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
 #ifndef PNS_HOST_EMULATION
         if (sx && k > 0) {          // result of step t0+k-1: reduce on the device, copy to the host, every step
@@ -1343,7 +1260,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
         if (z.n_grp) PNS_LAUNCH_CHAIN(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
         PNS_MARK(k, 2);
-        if (z.n_node && !fused) launch_node(net, z.n_node, s, cn);
+        if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
     }
 #undef PNS_MARK

@@ -104,42 +104,6 @@ def link_slots(nd_meta, nd_in_col, n_links, stride):
     return out
 
 
-LANE_BLOCK = 128      # threads per block of the single-replica lane kernel (one thread per directed link)
-
-
-def lane_blocks(lk_slots, n_nodes, stride, has_virtual):
-    """Per-block node lists for the fused single-replica kernel: block b of the lane kernel owns the
-    links [128b, 128b+128) and solves, in shared memory, every node one of those links starts or ends
-    at.  Returns (bn_ptr[n_blocks+1], bn_node[...], lk_local[n_links, 2]):
-      bn_node   node index, sign bit set on the block that *owns* the node (the lowest block touching
-                it writes the counters of the node's virtual links);
-      lk_local  for every link the shared-memory slots (local node * 4 + slot) holding its outflow
-                (end node) and its inflow (start node)."""
-    lk_slots = np.asarray(lk_slots, dtype=np.int64)
-    L = lk_slots.shape[0]
-    n_blocks = (L + LANE_BLOCK - 1) // LANE_BLOCK
-    blk = np.arange(L, dtype=np.int64) // LANE_BLOCK
-    node_e, slot_e = lk_slots[:, 0] // stride, lk_slots[:, 0] % stride
-    node_s, slot_s = lk_slots[:, 1] // stride, lk_slots[:, 1] % stride
-    key_e, key_s = blk * n_nodes + node_e, blk * n_nodes + node_s
-    uniq = np.unique(np.concatenate([key_e, key_s]))
-    bn_blk, bn_node = uniq // n_nodes, uniq % n_nodes
-    bn_ptr = np.searchsorted(bn_blk, np.arange(n_blocks + 1)).astype(np.int32)
-    loc_e = np.searchsorted(uniq, key_e) - bn_ptr[blk]
-    loc_s = np.searchsorted(uniq, key_s) - bn_ptr[blk]
-    lk_local = np.stack([loc_e * 4 + slot_e, loc_s * 4 + slot_s], axis=1).astype(np.int32)
-    # owner = first (lowest-block) entry of each node
-    order = np.lexsort((bn_blk, bn_node))
-    first = np.ones(len(order), dtype=bool)
-    first[1:] = bn_node[order][1:] != bn_node[order][:-1]
-    owner = np.zeros(len(uniq), dtype=bool)
-    owner[order[first]] = True
-    entry = bn_node.astype(np.int64)
-    entry = np.where(owner & np.asarray(has_virtual, dtype=bool)[bn_node], entry | (1 << 31), entry)
-    assert int((bn_ptr[1:] - bn_ptr[:-1]).max(initial=0)) <= 2 * LANE_BLOCK
-    return bn_ptr, entry.astype(np.uint32).view(np.int32), lk_local
-
-
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -198,8 +162,6 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     p["max_degree"] = int(max((n.source_num for n in nodes), default=0))
     p["nd_stride"] = node_stride(p["max_degree"])
     p["lk_slots"] = link_slots(p["nd_meta"], p["nd_in_col"], L, p["nd_stride"])
-    p["bn_ptr"], p["bn_node"], p["lk_local"] = lane_blocks(p["lk_slots"], len(nodes), p["nd_stride"],
-                                                           p["nd_meta"][:, 2] >= 0)
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
