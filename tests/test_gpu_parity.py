@@ -204,3 +204,67 @@ def test_streamed_run_equals_resident_run():
         assert torch.equal(a.history(f)[: steps + 1], b.history(f)[: steps + 1]), f
     want = a.history("num_pedestrians")[1: steps + 1, :, 0].double().sum(dim=1).cpu()
     assert torch.allclose(metric, want, rtol=0, atol=1e-6) and float(metric[-1]) > 0
+
+
+def _lattice(size, origins, steps=200, **kw):
+    from pednstream_b200 import Network
+    from pednstream_b200.grid import DEFAULT_LINK, grid_adjacency
+    params = {"unit_time": 10, "simulation_steps": steps, "default_link": dict(DEFAULT_LINK),
+              "demand": {f"origin_{o}": {"peak_lambda": 40, "base_lambda": 25} for o in origins}}
+    np.random.seed(3)
+    return Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False, **kw)
+
+
+@pytest.mark.parametrize("mode", ["numpy", "philox"])
+def test_cuda_unrouted_lattice_matches_oracle(mode):
+    """Single-replica lattice through the lane-per-link kernels vs the oracle, with default and with
+    user-supplied turning fractions (network.py:250-255), including a mid-run change."""
+    steps = 160
+    rng = np.random.RandomState(0)
+
+    def fractions(node):
+        m = node.source_num
+        f = rng.uniform(0.1, 1.0, size=(m, m - 1))
+        return (f / f.sum(axis=1, keepdims=True)).reshape(-1)
+
+    a = _lattice(6, [0, 35, 5])
+    b = _lattice(6, [0, 35, 5], rng=mode, seed=4, device="cuda:0")
+    for net in (a, b):
+        rng = np.random.RandomState(0)
+        net.update_turning_fractions_per_node([14, 21], [fractions(net.nodes[14]), fractions(net.nodes[21])])
+    o = LtmOracle(a, draws=PhiloxDraws(seed=4) if mode == "philox" else None)
+    state = np.random.get_state()
+    for t in range(1, steps):
+        if t == 80:
+            rng = np.random.RandomState(9)
+            o.tf[14] = fractions(a.nodes[14])
+        o.network_loading(t)
+    np.random.set_state(state)
+    for t in range(1, steps):
+        if t == 80:
+            rng = np.random.RandomState(9)
+            b.update_turning_fractions_per_node([14], [fractions(b.nodes[14])])
+        b.network_loading(t)
+    for f in FIELDS:
+        assert np.array_equal(o.h[f], b._store.field(f)), f
+    # counters of the virtual origin/destination links
+    for node in b.nodes.values():
+        if node.virtual_incoming_link is not None:
+            col = node.virtual_incoming_link._col
+            assert np.array_equal(o.h["cumulative_outflow"][:, col], node.virtual_incoming_link.cumulative_outflow)
+            assert np.array_equal(o.h["cumulative_inflow"][:, col + 1], node.virtual_outgoing_link.cumulative_inflow)
+    assert float(o.h["cumulative_inflow"][steps - 1].sum()) > 1000
+
+
+def test_fused_multi_step_equals_single_steps():
+    """run(t0, n) (UPDATE+FLOWS fused across steps, chained launches) vs n calls of run(t, 1)."""
+    plan, gate, tf, demand = build_grid_plan(48, 101, locality_order=True)
+    a = Engine(plan, replicas=1, rng="philox", seed=9, device="cuda:0")
+    a.initialise(gate, None, tf, demand, None)
+    a.run(1, 100)
+    b = Engine(plan, replicas=1, rng="philox", seed=9, device="cuda:0")
+    b.initialise(gate, None, tf, demand, None)
+    for t in range(1, 101):
+        b.run(t, 1)
+    for f in FIELDS:
+        assert torch.equal(a.history(f), b.history(f)), f
