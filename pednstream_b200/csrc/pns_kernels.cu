@@ -82,11 +82,17 @@ constexpr int kBlock = 128;
 #ifndef PNS_MIN_BLOCKS
 #define PNS_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (tuning knob)
 #endif
+#ifndef PNS_LANE_BLOCK
+#define PNS_LANE_BLOCK 128     // threads per CTA of k_link_lane
+#endif
+#ifndef PNS_PF_AHEAD_CTAS
+#define PNS_PF_AHEAD_CTAS 592  // k_link_lane: each CTA pulls the rows of the CTA this far ahead into L2 (0 = off)
+#endif
 #ifndef PNS_LANE_MIN_BLOCKS
-#define PNS_LANE_MIN_BLOCKS 8
+#define PNS_LANE_MIN_BLOCKS (1024 / PNS_LANE_BLOCK)
 #endif
 #ifndef PNS_NODE_MIN_BLOCKS
-#define PNS_NODE_MIN_BLOCKS 4
+#define PNS_NODE_MIN_BLOCKS 8
 #endif
 constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
@@ -152,6 +158,55 @@ __device__ __forceinline__ int wrap_index(const Ctx& c, int i, int replica) {
     }
     return i;
 }
+
+#ifndef PNS_HOST_EMULATION
+// ---- L2 residency hints (sm_80+ cache policies) -------------------------------------------------
+// One step of a large network streams ~190 MB through a 126 MB L2, so with plain LRU little of what
+// one kernel writes survives until the next kernel (or the next step) reads it.  Accesses can carry
+// an evict_last policy (hand-over data: exchange arrays, static incidence tables, gate array, the
+// rows the next step reads back) or evict_first (rows written or read once).  PNS_L2_STAGE selects
+// how much is marked: 0 nothing, 1 exchange arrays + static tables, 2 + gate and running sums,
+// 3 + the rows the next step reads back (with evict_first on their final read).
+// Measured on the 512x512 lattice (profiles/r1_h_l2_*.md): stage 1 shortens the link kernel by 4 us
+// (the index load at the head of its only dependent load chain now hits L2); stages 2 and 3 lower
+// DRAM traffic a little but not the time, and a persisting-L2 set-aside
+// (cudaLimitPersistingL2CacheSize) cuts traffic by 15% while making the step 25% slower -- the
+// step is latency-bound, not bandwidth-bound.  Stage 1 is the default.
+#ifndef PNS_L2_STAGE
+#define PNS_L2_STAGE 1
+#endif
+struct L2Pol { uint64_t keep, once; };
+__device__ __forceinline__ L2Pol l2_policies() {
+    L2Pol p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.once));
+    return p;
+}
+__device__ __forceinline__ double ldh(const double* a, uint64_t pol) {
+    double v; asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ float ldh(const float* a, uint64_t pol) {
+    float v; asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ double2 ldh(const double2* a, uint64_t pol) {
+    double2 v; asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ int2 ldh_nc(const int2* a, uint64_t pol) {
+    int2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(pol)); return v;
+}
+__device__ __forceinline__ void sth(double* a, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(a), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void sth(float* a, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(a), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" :: "l"(a)); }
+// stage-gated forms: S = the stage from which the hint applies
+template <int S, typename T> __device__ __forceinline__ T ld_keep(const T* a, const L2Pol p) { if (PNS_L2_STAGE >= S) return ldh(a, p.keep); return *a; }
+template <int S, typename T> __device__ __forceinline__ T ld_once(const T* a, const L2Pol p) { if (PNS_L2_STAGE >= S) return ldh(a, p.once); return *a; }
+template <int S, typename T> __device__ __forceinline__ void st_keep(T* a, T v, const L2Pol p) { if (PNS_L2_STAGE >= S) sth(a, v, p.keep); else *a = v; }
+template <int S, typename T> __device__ __forceinline__ void st_once(T* a, T v, const L2Pol p) { if (PNS_L2_STAGE >= S) sth(a, v, p.once); else *a = v; }
+#endif
 
 typedef pns_link_class LinkP;
 __device__ __forceinline__ bool is_sep(const LinkP& p) { return p.flags & 1; }
@@ -655,7 +710,7 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
 // all scatter/gather over the link<->node incidence happens once per link in the link kernels.
 // M > 0: slot count known at compile time (loops unrolled, everything in registers);
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
-template <int M, bool R1>
+template <int M, bool R1, bool ROUTED>
 __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int kind, int tf_mode,
                                           int dem_row, int tf_ptr) {
     constexpr int CAP = M ? M : PNS_MAX_DEGREE;
@@ -697,7 +752,7 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         // tf_mode 0: P = phi = 1/(m-1) (network.py:269-271); otherwise P[i][j] = tf[i*(m-1) + (j<i ? j : j-1)].
         const double* tf = nullptr;
         size_t ts = 1;
-        if (tf_mode == 2) {
+        if (ROUTED && tf_mode == 2) {
             double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
             routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
             tf = out;
@@ -762,14 +817,16 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     }
 }
 
-template <bool R1>
+template <bool R1, bool ROUTED>
 __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int kind, int tf_mode,
                                                int dem_row, int tf_ptr) {
-    node_body<0, R1>(c, node, rep, m, kind, tf_mode, dem_row, tf_ptr);
+    node_body<0, R1, ROUTED>(c, node, rep, m, kind, tf_mode, dem_row, tf_ptr);
 }
 
 // Node.assign_flows / solve (node.py:164-300) + turning fractions (path_finder.py:591-715)
-template <bool R1>
+// ROUTED: some node takes its fractions from the route-choice model (the callee's registers would
+// otherwise be charged to every launch)
+template <bool R1, bool ROUTED>
 __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -782,10 +839,10 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
     PNS_PDL_WAIT();
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
-        case 2: node_body<2, R1>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w); break;
-        case 3: node_body<3, R1>(c, node, rep, 3, kind, tf_mode, meta.z, meta.w); break;
-        case 4: node_body<4, R1>(c, node, rep, 4, kind, tf_mode, meta.z, meta.w); break;
-        default: node_body_generic<R1>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
+        case 2: node_body<2, R1, ROUTED>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w); break;
+        case 3: node_body<3, R1, ROUTED>(c, node, rep, 3, kind, tf_mode, meta.z, meta.w); break;
+        case 4: node_body<4, R1, ROUTED>(c, node, rep, 4, kind, tf_mode, meta.z, meta.w); break;
+        default: node_body_generic<R1, ROUTED>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
     }
 }
 
@@ -797,7 +854,7 @@ __global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(cons
 // per thread and no cross-direction state to keep in registers.  (The host-emulation test build
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
 template <int PHASE, int MODE, bool ONECLASS>
-__global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
+__global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -808,10 +865,12 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     PNS_PDL_TRIGGER();
     // single-class networks: parameters are kernel-parameter constants, no table loads at all
     const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[__ldg(c.n.lk_class + l)];
-    const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);      // {sending slot, receiving slot}
+    const L2Pol pol = l2_policies();
+    const int2 slots = PNS_L2_STAGE >= 1 ? ldh_nc(reinterpret_cast<const int2*>(c.n.lk_slots) + l, pol.keep)
+                                         : __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);   // {sending slot, receiving slot}
     const int fftau = p.fftau, swtau = p.swtau;
     PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
-    const double gate = c.s.gate[e];
+    const double gate = ld_keep<2>(c.s.gate + e, pol);
     // ---- batch of independent loads --------------------------------------------------------
     double din = 0, dout = 0;
     float np_ = 0, rs = 0, tt_old = 0;
@@ -819,19 +878,19 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     double cin_prev = 0, cou_prev = 0;
     if (upd) {
         // Node.update_links for this link (node.py:146-162): flows come from the node-major exchange arrays
-        dout = c.s.nm_qo[slots.x]; din = c.s.nm_qi[slots.y];
-        cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e];
-        np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
-        if (windowed) tt_old = c.u_tt_old[e];
+        cin_prev = ld_once<3>(c.n_cinp + e, pol); cou_prev = ld_once<3>(c.n_coutp + e, pol);
+        np_ = ld_once<3>(c.u_num_prev + e, pol); rs = ld_keep<2>(c.s.runsum + e, pol);
+        if (windowed) tt_old = ld_once<3>(c.u_tt_old + e, pol);
+        dout = ld_keep<1>(c.s.nm_qo + slots.x, pol); din = ld_keep<1>(c.s.nm_qi + slots.y, pol);   // last: the only loads behind an index load
     }
     double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
     LinkNow me;
     me.num = 0; me.dens = 0; me.avg_tt = 0;
     if (flw) {
         if (!upd) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
-        snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
+        snd_prev = ld_once<3>(c.f_sndp + e, pol); rcv_prev = ld_once<3>(c.f_rcvp + e, pol);
         const int lag_i = tau + 1 - swtau;
-        if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
+        if (lag_i >= 0) cou_lag = ld_once<3>(H64(c, PNS_F64_CUM_OUTFLOW, lag_i) + e, pol);
         if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
     }
     // The arrival row cumulative_inflow[tau+1-lag] depends on the travel-time lag computed below; in
@@ -841,10 +900,36 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     double pre_v0 = 0.0, pre_v1 = 0.0;
     if (flw && tau >= fftau) {
         pre_i0 = max(0, tau + 1 - fftau);
-        pre_v0 = H64(c, PNS_F64_CUM_INFLOW, pre_i0)[e];
+        pre_v0 = ld_once<3>(H64(c, PNS_F64_CUM_INFLOW, pre_i0) + e, pol);
         if (fftau > 1) {
             pre_i1 = max(0, tau + 2 - fftau);
-            pre_v1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1)[e];
+            pre_v1 = ld_keep<3>(H64(c, PNS_F64_CUM_INFLOW, pre_i1) + e, pol);   // next step's pre_v0
+        }
+    }
+    // ---- software prefetch for a later CTA ---------------------------------------------------
+    // A thread spends most of its memory time waiting for the batch above to come back from DRAM.
+    // CTAs are dispatched in index order, so while this CTA's loads are in flight it asks L2 to
+    // fetch the same columns for the CTA PNS_PF_AHEAD_CTAS further on (half a resident wave, a few
+    // microseconds ahead); that CTA's batch then hits in L2.  No registers are held across it.
+    if (PNS_PF_AHEAD_CTAS > 0) {
+        constexpr unsigned ahead = (unsigned)PNS_PF_AHEAD_CTAS * (unsigned)PNS_LANE_BLOCK;
+        if (gid + ahead < (unsigned)c.n.n_links) {
+            const size_t ea = e + ahead;
+            const int2 sl = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
+            prefetch_l2(c.s.gate + ea);
+            if (upd) {
+                prefetch_l2(c.n_cinp + ea); prefetch_l2(c.n_coutp + ea);
+                prefetch_l2(c.u_num_prev + ea); prefetch_l2(c.s.runsum + ea);
+                if (windowed) prefetch_l2(c.u_tt_old + ea);
+            }
+            if (flw) {
+                if (!upd) { prefetch_l2(c.f_cin + ea); prefetch_l2(c.f_cou + ea); }
+                prefetch_l2(c.f_sndp + ea); prefetch_l2(c.f_rcvp + ea);
+                if (tau + 1 - swtau >= 0) prefetch_l2(H64(c, PNS_F64_CUM_OUTFLOW, tau + 1 - swtau) + ea);
+                if (pre_i0 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i0) + ea);
+                if (pre_i1 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i1) + ea);
+            }
+            if (upd) { prefetch_l2(c.s.nm_qo + sl.x); prefetch_l2(c.s.nm_qi + sl.y); }
         }
     }
     const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
@@ -856,7 +941,8 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
         cin_tau = cin_prev + din;                                           // link.py:19-25
         cou_tau = cou_prev + dout;
         if (valid) {
-            c.n_inflow[e] = din; c.n_outflow[e] = dout; c.n_cin[e] = cin_tau; c.n_cout[e] = cou_tau;
+            st_once<3>(c.n_inflow + e, din, pol); st_once<3>(c.n_outflow + e, dout, pol);
+            st_keep<3>(c.n_cin + e, cin_tau, pol); st_keep<3>(c.n_cout + e, cou_tau, pol);     // read back by the next step
         }
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
         me.dens = div_by_area(me.num, ar);                                  // link.py:136
@@ -884,11 +970,12 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
             me.avg_tt = p.tt0;
         }
         if (valid) {
-            c.u_num[e] = me.num; c.u_dens[e] = me.dens; c.u_speed[e] = v; c.u_tt[e] = tt;
-            c.u_flow[e] = v * me.dens;                                      // functions.py:97-101
-            if (windowed) c.u_avg[e] = me.avg_tt;
-            c.s.runsum[e] = sum;
-            c.u_bgw[e] = gate;                                              // link.py:188, 451-452
+            st_keep<3>(c.u_num + e, me.num, pol); st_once<3>(c.u_dens + e, me.dens, pol);
+            st_once<3>(c.u_speed + e, v, pol); st_once<3>(c.u_tt + e, tt, pol);
+            st_once<3>(c.u_flow + e, v * me.dens, pol);                     // functions.py:97-101
+            if (windowed) st_once<3>(c.u_avg + e, me.avg_tt, pol);
+            st_keep<2>(c.s.runsum + e, sum, pol);
+            st_once<3>(c.u_bgw + e, gate, pol);                             // link.py:188, 451-452
             if (is_sep(p)) c.u_sepw[e] = gate;
         }
     }
@@ -918,10 +1005,10 @@ __global__ void __launch_bounds__(kBlock, PNS_LANE_MIN_BLOCKS) k_link_lane(const
     if (valid) {
         // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
         const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
-        c.f_snd[e] = s.flow;
-        c.f_rcv[e] = rcv;
-        c.s.nm_s[slots.x] = s.flow;        // node-major hand-over to the node pass
-        c.s.nm_r[slots.y] = rcv;
+        st_keep<3>(c.f_snd + e, s.flow, pol);      // read back by the next step's smoothing (link.py:363, 400)
+        st_keep<3>(c.f_rcv + e, rcv, pol);
+        st_keep<1>(c.s.nm_s + slots.x, s.flow, pol);   // node-major hand-over to the node pass
+        st_keep<1>(c.s.nm_r + slots.y, rcv, pol);
     }
 }
 
@@ -1175,15 +1262,15 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
 template <int PHASE>
 void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
-    const unsigned nb = blocks_for(n_links);
+    const unsigned nb = (unsigned)((n_links + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK);
     if (c.n.n_classes == 1) {
-        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, true>), nb, kBlock, s, c);
-        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, true>), nb, kBlock, s, c);
-        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, true>), nb, kBlock, s, c);
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, true>), nb, PNS_LANE_BLOCK, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, true>), nb, PNS_LANE_BLOCK, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, true>), nb, PNS_LANE_BLOCK, s, c);
     } else {
-        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, false>), nb, kBlock, s, c);
-        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, false>), nb, kBlock, s, c);
-        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, false>), nb, kBlock, s, c);
+        if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, false>), nb, PNS_LANE_BLOCK, s, c);
+        else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, false>), nb, PNS_LANE_BLOCK, s, c);
+        else PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_REQUEST, false>), nb, PNS_LANE_BLOCK, s, c);
     }
 }
 #endif
@@ -1200,8 +1287,14 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     else launch_pair_phase<false>(n, s, c);
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
-    if (net->replicas == 1) PNS_LAUNCH_CHAIN(k_node_flows<true>, blocks_for(n), kBlock, s, c);
-    else PNS_LAUNCH_CHAIN(k_node_flows<false>, blocks_for(n), kBlock, s, c);
+    const bool routed = net->n_routed > 0;
+    if (net->replicas == 1) {
+        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<true, true>), blocks_for(n), kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_node_flows<true, false>), blocks_for(n), kBlock, s, c);
+    } else {
+        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<false, true>), blocks_for(n), kBlock, s, c);
+        else PNS_LAUNCH_CHAIN((k_node_flows<false, false>), blocks_for(n), kBlock, s, c);
+    }
 }
 
 struct StepSizes { size_t n_pair, n_grp, n_node; };
