@@ -83,10 +83,11 @@ constexpr int kBlock = 128;
 #define PNS_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (tuning knob)
 #endif
 #ifndef PNS_LANE_BLOCK
-#define PNS_LANE_BLOCK 128     // threads per CTA of k_link_lane
+#define PNS_LANE_BLOCK 64      // threads per CTA of k_link_lane (measured: 64 < 128 < 256 < 512 in step time)
 #endif
 #ifndef PNS_PF_AHEAD_CTAS
-#define PNS_PF_AHEAD_CTAS 592  // k_link_lane: each CTA pulls the rows of the CTA this far ahead into L2 (0 = off)
+#define PNS_PF_AHEAD_CTAS (75776 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
+                                                     // into L2: half a resident wave of 148 SMs x 1024 threads (0 = off)
 #endif
 #ifndef PNS_LANE_MIN_BLOCKS
 #define PNS_LANE_MIN_BLOCKS (1024 / PNS_LANE_BLOCK)
@@ -191,6 +192,12 @@ __device__ __forceinline__ float ldh(const float* a, uint64_t pol) {
 __device__ __forceinline__ double2 ldh(const double2* a, uint64_t pol) {
     double2 v; asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol) : "memory"); return v;
 }
+__device__ __forceinline__ int4 ldh_nc(const int4* a, uint64_t pol) {
+    int4 v; asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol)); return v;
+}
+__device__ __forceinline__ void sth(double2* a, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ int2 ldh_nc(const int2* a, uint64_t pol) {
     int2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(pol)); return v;
 }
@@ -206,6 +213,14 @@ template <int S, typename T> __device__ __forceinline__ T ld_keep(const T* a, co
 template <int S, typename T> __device__ __forceinline__ T ld_once(const T* a, const L2Pol p) { if (PNS_L2_STAGE >= S) return ldh(a, p.once); return *a; }
 template <int S, typename T> __device__ __forceinline__ void st_keep(T* a, T v, const L2Pol p) { if (PNS_L2_STAGE >= S) sth(a, v, p.keep); else *a = v; }
 template <int S, typename T> __device__ __forceinline__ void st_once(T* a, T v, const L2Pol p) { if (PNS_L2_STAGE >= S) sth(a, v, p.once); else *a = v; }
+__device__ __forceinline__ int4 ld_meta(const int4* a, const L2Pol p) { if (PNS_L2_STAGE >= 1) return ldh_nc(a, p.keep); return __ldg(a); }
+#else   // host-emulation test build: plain accesses
+struct L2Pol { };
+static inline L2Pol l2_policies() { return L2Pol(); }
+static inline void prefetch_l2(const void*) { }
+template <int S, typename T> static inline T ld_keep(const T* a, const L2Pol) { return *a; }
+template <int S, typename T> static inline void st_keep(T* a, T v, const L2Pol) { *a = v; }
+static inline int4 ld_meta(const int4* a, const L2Pol) { return *a; }
 #endif
 
 typedef pns_link_class LinkP;
@@ -712,7 +727,7 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
 template <int M, bool R1, bool ROUTED>
 __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m_dyn, int kind, int tf_mode,
-                                          int dem_row, int tf_ptr) {
+                                          int dem_row, int tf_ptr, const L2Pol pol) {
     constexpr int CAP = M ? M : PNS_MAX_DEGREE;
     const int m = M ? M : m_dyn;
     const int R = R1 ? 1 : c.n.replicas;
@@ -721,14 +736,15 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     if (R1 && M == 4) {
         const double2* ps = reinterpret_cast<const double2*>(c.s.nm_s + base);
         const double2* pr = reinterpret_cast<const double2*>(c.s.nm_r + base);
-        const double2 a0 = ps[0], a1 = ps[1], b0 = pr[0], b1 = pr[1];
+        const double2 a0 = ld_keep<1>(ps, pol), a1 = ld_keep<1>(ps + 1, pol);
+        const double2 b0 = ld_keep<1>(pr, pol), b1 = ld_keep<1>(pr + 1, pol);
         s[0] = a0.x; s[1 % CAP] = a0.y; s[2 % CAP] = a1.x; s[3 % CAP] = a1.y;
         r[0] = b0.x; r[1 % CAP] = b0.y; r[2 % CAP] = b1.x; r[3 % CAP] = b1.y;
     } else {
 #pragma unroll
         for (int i = 0; i < m; ++i) {
-            s[i] = c.s.nm_s[(base + i) * R + rep];
-            r[i] = c.s.nm_r[(base + i) * R + rep];
+            s[i] = R1 ? ld_keep<1>(c.s.nm_s + base + i, pol) : c.s.nm_s[(base + i) * R + rep];
+            r[i] = R1 ? ld_keep<1>(c.s.nm_r + base + i, pol) : c.s.nm_r[(base + i) * R + rep];
         }
     }
     if (dem_row >= 0) {                                                     // slot 0 is the virtual O/D link pair
@@ -796,15 +812,20 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         double2* po = reinterpret_cast<double2*>(c.s.nm_qo + base);
         double2* pi = reinterpret_cast<double2*>(c.s.nm_qi + base);
         double2 v;
-        v.x = q_out[0]; v.y = q_out[1 % CAP]; po[0] = v;
-        v.x = q_out[2 % CAP]; v.y = q_out[3 % CAP]; po[1] = v;
-        v.x = q_in[0]; v.y = q_in[1 % CAP]; pi[0] = v;
-        v.x = q_in[2 % CAP]; v.y = q_in[3 % CAP]; pi[1] = v;
+        v.x = q_out[0]; v.y = q_out[1 % CAP]; st_keep<1>(po, v, pol);
+        v.x = q_out[2 % CAP]; v.y = q_out[3 % CAP]; st_keep<1>(po + 1, v, pol);
+        v.x = q_in[0]; v.y = q_in[1 % CAP]; st_keep<1>(pi, v, pol);
+        v.x = q_in[2 % CAP]; v.y = q_in[3 % CAP]; st_keep<1>(pi + 1, v, pol);
     } else {
 #pragma unroll
         for (int i = 0; i < m; ++i) {
-            c.s.nm_qo[(base + i) * R + rep] = q_out[i];
-            c.s.nm_qi[(base + i) * R + rep] = q_in[i];
+            if (R1) {
+                st_keep<1>(c.s.nm_qo + base + i, q_out[i], pol);
+                st_keep<1>(c.s.nm_qi + base + i, q_in[i], pol);
+            } else {
+                c.s.nm_qo[(base + i) * R + rep] = q_out[i];
+                c.s.nm_qi[(base + i) * R + rep] = q_in[i];
+            }
         }
     }
     if (dem_row >= 0) {
@@ -820,28 +841,42 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
 template <bool R1, bool ROUTED>
 __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, int m, int kind, int tf_mode,
                                                int dem_row, int tf_ptr) {
-    node_body<0, R1, ROUTED>(c, node, rep, m, kind, tf_mode, dem_row, tf_ptr);
+    node_body<0, R1, ROUTED>(c, node, rep, m, kind, tf_mode, dem_row, tf_ptr, l2_policies());
 }
 
 // Node.assign_flows / solve (node.py:164-300) + turning fractions (path_finder.py:591-715)
 // ROUTED: some node takes its fractions from the route-choice model (the callee's registers would
 // otherwise be charged to every launch)
 template <bool R1, bool ROUTED>
-__global__ void __launch_bounds__(kBlock, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
+__global__ void __launch_bounds__(kBlock, ROUTED ? 4 : PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)c.n.n_nodes * R) return;
     const int node = R1 ? (int)gid : (int)(gid / R);
     const int rep = R1 ? 0 : (int)(gid % R);
     PNS_PDL_TRIGGER();
-    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
+    const L2Pol pol = l2_policies();
+    const int4 meta = R1 ? ld_meta(reinterpret_cast<const int4*>(c.n.nd_meta) + node, pol)
+                         : __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     PNS_PDL_WAIT();
+#ifndef PNS_NODE_PF_AHEAD_CTAS
+#define PNS_NODE_PF_AHEAD_CTAS 888
+#endif
+    if (R1 && PNS_NODE_PF_AHEAD_CTAS > 0) {
+        // fewer than two resident waves: the first wave pulls the records of the second into L2
+        const size_t na = gid + (size_t)PNS_NODE_PF_AHEAD_CTAS * kBlock;
+        if (na < (size_t)c.n.n_nodes) {
+            prefetch_l2(reinterpret_cast<const int4*>(c.n.nd_meta) + na);
+            prefetch_l2(c.s.nm_s + na * c.n.nd_stride);
+            prefetch_l2(c.s.nm_r + na * c.n.nd_stride);
+        }
+    }
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
-        case 2: node_body<2, R1, ROUTED>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w); break;
-        case 3: node_body<3, R1, ROUTED>(c, node, rep, 3, kind, tf_mode, meta.z, meta.w); break;
-        case 4: node_body<4, R1, ROUTED>(c, node, rep, 4, kind, tf_mode, meta.z, meta.w); break;
+        case 2: node_body<2, R1, ROUTED>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w, pol); break;
+        case 3: node_body<3, R1, ROUTED>(c, node, rep, 3, kind, tf_mode, meta.z, meta.w, pol); break;
+        case 4: node_body<4, R1, ROUTED>(c, node, rep, 4, kind, tf_mode, meta.z, meta.w, pol); break;
         default: node_body_generic<R1, ROUTED>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
     }
 }
