@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 3
+#define PNS_ABI_VERSION 4
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -111,8 +111,10 @@ typedef struct pns_net {
     const int32_t *nd_routed;   /* [n_nodes] index into the routed-node arrays, -1 = none */
     const int32_t *lk_slots;    /* [n_links][2] node-major exchange slots of each link: where its sending flow goes
                                    (end node * nd_stride + its slot there) and where its receiving flow goes
-                                   (start node * nd_stride + its slot there); the node pass answers in the same
-                                   slots with the link's outflow (nm_qo) and inflow (nm_qi) */
+                                   (start node * nd_stride + its slot there) */
+    const int32_t *nd_in_link;  /* [n_nodes*nd_stride] the inverse map: history column of the incoming link of each
+                                   slot (virtual O/D link: n_links + 2*demand row), -1 = unused slot.  The node pass
+                                   stores outflow[t] of that column and inflow[t] of column ^ 1 (node.py:146-162) */
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
@@ -136,7 +138,6 @@ typedef struct pns_state {
     double *tf_routed;   /* [n_edges*R] fractions computed this step for routed nodes */
     double *probs;       /* [n_opts*R] scratch: P(down | up, od) of this step */
     double *nm_s, *nm_r;   /* [n_nodes*nd_stride*R] node-major sending / receiving flows of the step (link -> node) */
-    double *nm_qo, *nm_qi; /* [n_nodes*nd_stride*R] node-major outflow / inflow of the step (node -> link) */
     int32_t *err;        /* [R] error bits */
     int32_t n_f64;       /* 7, or 8 when the network has separators */
 } pns_state;

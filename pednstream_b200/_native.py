@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 RNG_TABLE, RNG_PHILOX, RNG_REQUEST = 0, 1, 2
 ERR_BITS = {1: "negative sending flow (reference link.py:346,366 ValueError)",
@@ -36,7 +36,7 @@ class PnsNet(C.Structure):
                              "n_routed", "n_groups", "n_opts", "n_rows", "n_terms", "n_classes", "max_degree", "nd_stride")]
         + [("unit_time", C.c_double)]
         + [("classes", _p), ("class0", PnsLinkClass)]
-        + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
+        + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
                              "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
@@ -47,7 +47,7 @@ class PnsNet(C.Structure):
 
 class PnsState(C.Structure):
     _fields_ = [(n, _p) for n in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static",
-                                  "tf_routed", "probs", "nm_s", "nm_r", "nm_qo", "nm_qi", "err")] + [("n_f64", _i32)]
+                                  "tf_routed", "probs", "nm_s", "nm_r", "err")] + [("n_f64", _i32)]
 
 
 class PnsStepIO(C.Structure):

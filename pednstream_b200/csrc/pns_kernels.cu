@@ -195,9 +195,6 @@ __device__ __forceinline__ double2 ldh(const double2* a, uint64_t pol) {
 __device__ __forceinline__ int4 ldh_nc(const int4* a, uint64_t pol) {
     int4 v; asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol)); return v;
 }
-__device__ __forceinline__ void sth(double2* a, double2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
-}
 __device__ __forceinline__ int2 ldh_nc(const int2* a, uint64_t pol) {
     int2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(pol)); return v;
 }
@@ -464,10 +461,10 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
     // where this pair's flows live in the node-major exchange arrays (see k_node_flows)
     const int4 slots = __ldg(reinterpret_cast<const int4*>(c.n.lk_slots) + pair);   // {s0, r0, s1, r1}
     if (upd) {
-        // Node.update_links for this pair (node.py:146-162): the node pass left the flows in node-major
-        // order; fetch ours and extend the cumulative counts
-        dout[0] = c.s.nm_qo[(size_t)slots.x * R + rep]; din[0] = c.s.nm_qi[(size_t)slots.y * R + rep];
-        dout[1] = c.s.nm_qo[(size_t)slots.z * R + rep]; din[1] = c.s.nm_qi[(size_t)slots.w * R + rep];
+        // Node.update_links for this pair (node.py:146-162): the node pass wrote inflow[t] / outflow[t]
+        // of every link; fetch ours and extend the cumulative counts
+        V::ld(c.n_inflow, e[0], e[1], din);
+        V::ld(c.n_outflow, e[0], e[1], dout);
         V::ld(c.n_cinp, e[0], e[1], cin_p);
         V::ld(c.n_coutp, e[0], e[1], cou_p);
         V::ld(c.u_num_prev, e[0], e[1], np_);
@@ -507,8 +504,6 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
             cin_tau[a] = cin_p[a] + din[a];
             cou_tau[a] = cou_p[a] + dout[a];
         }
-        V::st(c.n_inflow, e[0], e[1], din[0], din[1]);
-        V::st(c.n_outflow, e[0], e[1], dout[0], dout[1]);
         V::st(c.n_cin, e[0], e[1], cin_tau[0], cin_tau[1]);
         V::st(c.n_cout, e[0], e[1], cou_tau[0], cou_tau[1]);
 #pragma unroll
@@ -720,9 +715,10 @@ __device__ __forceinline__ double turn_flow(double w, double r, double D) {
 }
 
 // One node.  The link kernels hand over sending/receiving flows in *node-major* order
-// (nm_s / nm_r: slot k of node n at index n*stride + k, replica fastest) and pick the resulting
-// flows up from nm_qo / nm_qi, so this pass reads and writes contiguous, coalesced records and
-// all scatter/gather over the link<->node incidence happens once per link in the link kernels.
+// (nm_s / nm_r: slot k of node n at index n*stride + k, replica fastest), so this pass reads
+// contiguous, coalesced records; it answers by storing every link's inflow[t] / outflow[t] straight
+// into the history rows (link-major).  Both directions of the link<->node incidence are therefore
+// crossed by *stores* (scattered 8-byte writes nobody waits for) and all loads are coalesced.
 // M > 0: slot count known at compile time (loops unrolled, everything in registers);
 // M == 0: generic path for rare high-degree nodes (arrays in local memory).
 template <int M, bool R1, bool ROUTED>
@@ -733,6 +729,14 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     const int R = R1 ? 1 : c.n.replicas;
     const size_t base = (size_t)node * c.n.nd_stride;
     double s[CAP], r[CAP];
+    int in_link[CAP];                                                       // incoming link column of each slot
+    if (M == 4) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(c.n.nd_in_link + base));
+        in_link[0] = v.x; in_link[1 % CAP] = v.y; in_link[2 % CAP] = v.z; in_link[3 % CAP] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < m; ++i) in_link[i] = __ldg(c.n.nd_in_link + base + i);
+    }
     if (R1 && M == 4) {
         const double2* ps = reinterpret_cast<const double2*>(c.s.nm_s + base);
         const double2* pr = reinterpret_cast<const double2*>(c.s.nm_r + base);
@@ -808,32 +812,19 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
 #pragma unroll
         for (int i = 0; i < m; ++i) q_out[i] = fmax(0.0, q_out[i]);
     }
-    if (R1 && M == 4) {
-        double2* po = reinterpret_cast<double2*>(c.s.nm_qo + base);
-        double2* pi = reinterpret_cast<double2*>(c.s.nm_qi + base);
-        double2 v;
-        v.x = q_out[0]; v.y = q_out[1 % CAP]; st_keep<1>(po, v, pol);
-        v.x = q_out[2 % CAP]; v.y = q_out[3 % CAP]; st_keep<1>(po + 1, v, pol);
-        v.x = q_in[0]; v.y = q_in[1 % CAP]; st_keep<1>(pi, v, pol);
-        v.x = q_in[2 % CAP]; v.y = q_in[3 % CAP]; st_keep<1>(pi + 1, v, pol);
-    } else {
+    // Node.update_links (node.py:146-162): slot i's incoming link gets outflow[t] = q_out[i], its reverse
+    // (the slot's outgoing link) gets inflow[t] = q_in[i].  Scattered 8-byte stores straight into the
+    // history rows: nothing waits on them, and the link pass reads its own column back coalesced.
 #pragma unroll
-        for (int i = 0; i < m; ++i) {
-            if (R1) {
-                st_keep<1>(c.s.nm_qo + base + i, q_out[i], pol);
-                st_keep<1>(c.s.nm_qi + base + i, q_in[i], pol);
-            } else {
-                c.s.nm_qo[(base + i) * R + rep] = q_out[i];
-                c.s.nm_qi[(base + i) * R + rep] = q_in[i];
-            }
-        }
+    for (int i = 0; i < m; ++i) {
+        const int col = in_link[i];
+        c.n_outflow[(size_t)col * R + rep] = q_out[i];
+        c.n_inflow[(size_t)(col ^ 1) * R + rep] = q_in[i];
     }
     if (dem_row >= 0) {
-        // the virtual links have no link thread: keep their counters here (node.py:154-161, link.py:19-25)
+        // the virtual links have no link thread: keep their counters here (link.py:19-25)
         const size_t vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep, vout = vin + R;
-        c.n_outflow[vin] = q_out[0];
         c.n_cout[vin] = c.n_coutp[vin] + q_out[0];
-        c.n_inflow[vout] = q_in[0];
         c.n_cin[vout] = c.n_cinp[vout] + q_in[0];
     }
 }
@@ -912,11 +903,11 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     const bool windowed = c.u_tt_old != nullptr;
     double cin_prev = 0, cou_prev = 0;
     if (upd) {
-        // Node.update_links for this link (node.py:146-162): flows come from the node-major exchange arrays
+        // Node.update_links for this link (node.py:146-162): the node pass wrote inflow[t] / outflow[t]
         cin_prev = ld_once<3>(c.n_cinp + e, pol); cou_prev = ld_once<3>(c.n_coutp + e, pol);
         np_ = ld_once<3>(c.u_num_prev + e, pol); rs = ld_keep<2>(c.s.runsum + e, pol);
         if (windowed) tt_old = ld_once<3>(c.u_tt_old + e, pol);
-        dout = ld_keep<1>(c.s.nm_qo + slots.x, pol); din = ld_keep<1>(c.s.nm_qi + slots.y, pol);   // last: the only loads behind an index load
+        dout = c.n_outflow[e]; din = c.n_inflow[e];
     }
     double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
     LinkNow me;
@@ -950,7 +941,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         constexpr unsigned ahead = (unsigned)PNS_PF_AHEAD_CTAS * (unsigned)PNS_LANE_BLOCK;
         if (gid + ahead < (unsigned)c.n.n_links) {
             const size_t ea = e + ahead;
-            const int2 sl = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
+            prefetch_l2(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
             prefetch_l2(c.s.gate + ea);
             if (upd) {
                 prefetch_l2(c.n_cinp + ea); prefetch_l2(c.n_coutp + ea);
@@ -964,7 +955,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
                 if (pre_i0 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i0) + ea);
                 if (pre_i1 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i1) + ea);
             }
-            if (upd) { prefetch_l2(c.s.nm_qo + sl.x); prefetch_l2(c.s.nm_qi + sl.y); }
+            if (upd) { prefetch_l2(c.n_outflow + ea); prefetch_l2(c.n_inflow + ea); }
         }
     }
     const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
@@ -976,7 +967,6 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         cin_tau = cin_prev + din;                                           // link.py:19-25
         cou_tau = cou_prev + dout;
         if (valid) {
-            st_once<3>(c.n_inflow + e, din, pol); st_once<3>(c.n_outflow + e, dout, pol);
             st_keep<3>(c.n_cin + e, cin_tau, pol); st_keep<3>(c.n_cout + e, cou_tau, pol);     // read back by the next step
         }
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135

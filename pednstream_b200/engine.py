@@ -21,7 +21,7 @@ import torch
 from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
-_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots",
+_NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
                "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
@@ -95,14 +95,12 @@ class Engine:
         self.tf_routed = torch.zeros((max(1, p["n_edges"]) * R,), dtype=torch.float64, device=dev)
         self.probs = torch.zeros((max(1, net.n_opts) * R,), dtype=torch.float64, device=dev)
         self.err = torch.zeros((R,), dtype=torch.int32, device=dev)
-        nm = max(1, self.N * int(p["nd_stride"]) * R)       # node-major exchange arrays (link <-> node passes)
+        nm = max(1, self.N * int(p["nd_stride"]) * R)       # node-major exchange arrays (link pass -> node pass)
         self.nm_s = torch.zeros((nm,), dtype=torch.float64, device=dev)
         self.nm_r = torch.zeros((nm,), dtype=torch.float64, device=dev)
-        self.nm_qo = torch.zeros((nm,), dtype=torch.float64, device=dev)
-        self.nm_qi = torch.zeros((nm,), dtype=torch.float64, device=dev)
         st = _native.PnsState()
         for k in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static", "tf_routed", "probs",
-                  "nm_s", "nm_r", "nm_qo", "nm_qi", "err"):
+                  "nm_s", "nm_r", "err"):
             setattr(st, k, _ptr(getattr(self, k)))
         st.n_f64 = self.n_f64
         self.state = st

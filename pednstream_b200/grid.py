@@ -127,7 +127,7 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     meta[:, 1] = (m_o | (kind[order].astype(np.int64) << 8)).astype(np.int32)
     meta[:, 2] = dem_row
     meta[:, 3] = tf_ptr[:-1]
-    from .plan import link_slots, node_stride
+    from .plan import link_slots, node_stride, slot_links
     max_degree = int(m_o.max())
     stride = node_stride(max_degree)
     lk_slots = link_slots(meta, in_col, L, stride)
@@ -142,6 +142,7 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         classes=np.array([rec], dtype=CLASS_DTYPE).reshape(1), lk_class=np.zeros(L, dtype=np.int32),
         lk_width=np.full(L, float(lk["width"])), has_separators=False,
         nd_meta=meta, nd_in_col=in_col, nd_routed=np.full(N, -1, dtype=np.int32), lk_slots=lk_slots,
+        nd_in_link=slot_links(meta, in_col, stride),
         max_degree=max_degree, nd_stride=stride,
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,

@@ -104,6 +104,18 @@ def link_slots(nd_meta, nd_in_col, n_links, stride):
     return out
 
 
+def slot_links(nd_meta, nd_in_col, stride):
+    """[n_nodes * stride] int32: history column of the incoming link of every node-major slot
+    (`pns_net.nd_in_link`), -1 for unused slots; the slot's outgoing link is that column ^ 1."""
+    nd_meta = np.asarray(nd_meta)
+    m = nd_meta[:, 1] & 0xff
+    node_of_slot = np.repeat(np.arange(len(nd_meta)), m)
+    slot = np.arange(len(nd_in_col)) - np.repeat(nd_meta[:, 0], m)
+    out = np.full((len(nd_meta) * stride,), -1, dtype=np.int32)
+    out[node_of_slot * stride + slot] = np.asarray(nd_in_col)
+    return out
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -162,6 +174,7 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     p["max_degree"] = int(max((n.source_num for n in nodes), default=0))
     p["nd_stride"] = node_stride(p["max_degree"])
     p["lk_slots"] = link_slots(p["nd_meta"], p["nd_in_col"], L, p["nd_stride"])
+    p["nd_in_link"] = slot_links(p["nd_meta"], p["nd_in_col"], p["nd_stride"])
     p["n_virtual"] = 2 * n_virtual_nodes
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
