@@ -118,6 +118,10 @@ struct Ctx {
     double *f_snd, *f_rcv;                              // FLOWS outputs, row tau
     const double *n_coutp, *n_cinp, *n_demand;          // cumulative counts of row t-1; demand row of step t
     double *n_outflow, *n_inflow, *n_cout, *n_cin;      // flows and cumulative counts of row t
+    // single-class networks: every link has the same lags, so the lagged rows of FLOWS are launch constants too
+    const double *c0_coulag;                            // cumulative_outflow[tau+1-swtau] (null while negative)
+    const double *c0_pre0, *c0_pre1;                    // cumulative_inflow rows of the two likeliest arrival lags
+    int c0_pre_i0, c0_pre_i1;                           // their indices (-1: not applicable)
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -915,8 +919,12 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     if (flw) {
         if (!upd) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
         snd_prev = ld_once<3>(c.f_sndp + e, pol); rcv_prev = ld_once<3>(c.f_rcvp + e, pol);
-        const int lag_i = tau + 1 - swtau;
-        if (lag_i >= 0) cou_lag = ld_once<3>(H64(c, PNS_F64_CUM_OUTFLOW, lag_i) + e, pol);
+        if (ONECLASS) {
+            if (c.c0_coulag) cou_lag = ld_once<3>(c.c0_coulag + e, pol);
+        } else {
+            const int lag_i = tau + 1 - swtau;
+            if (lag_i >= 0) cou_lag = ld_once<3>(H64(c, PNS_F64_CUM_OUTFLOW, lag_i) + e, pol);
+        }
         if (!upd) { me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e]; }
     }
     // The arrival row cumulative_inflow[tau+1-lag] depends on the travel-time lag computed below; in
@@ -924,38 +932,51 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // fall back to a dependent load only when the link is congested.
     int pre_i0 = -1, pre_i1 = -1;
     double pre_v0 = 0.0, pre_v1 = 0.0;
-    if (flw && tau >= fftau) {
-        pre_i0 = max(0, tau + 1 - fftau);
-        pre_v0 = ld_once<3>(H64(c, PNS_F64_CUM_INFLOW, pre_i0) + e, pol);
-        if (fftau > 1) {
-            pre_i1 = max(0, tau + 2 - fftau);
-            pre_v1 = ld_keep<3>(H64(c, PNS_F64_CUM_INFLOW, pre_i1) + e, pol);   // next step's pre_v0
+    const double *pre_row0 = nullptr, *pre_row1 = nullptr;
+    if (flw) {
+        if (ONECLASS) {
+            pre_i0 = c.c0_pre_i0; pre_i1 = c.c0_pre_i1; pre_row0 = c.c0_pre0; pre_row1 = c.c0_pre1;
+        } else if (tau >= fftau) {
+            pre_i0 = max(0, tau + 1 - fftau);
+            pre_row0 = H64(c, PNS_F64_CUM_INFLOW, pre_i0);
+            if (fftau > 1) {
+                pre_i1 = max(0, tau + 2 - fftau);
+                pre_row1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1);
+            }
         }
+        if (pre_row0) pre_v0 = ld_once<3>(pre_row0 + e, pol);
+        if (pre_row1) pre_v1 = ld_keep<3>(pre_row1 + e, pol);   // next step's pre_v0
     }
-    // ---- software prefetch for a later CTA ---------------------------------------------------
+    // ---- software prefetch for later CTAs ----------------------------------------------------
     // A thread spends most of its memory time waiting for the batch above to come back from DRAM.
-    // CTAs are dispatched in index order, so while this CTA's loads are in flight it asks L2 to
-    // fetch the same columns for the CTA PNS_PF_AHEAD_CTAS further on (half a resident wave, a few
-    // microseconds ahead); that CTA's batch then hits in L2.  No registers are held across it.
-    if (PNS_PF_AHEAD_CTAS > 0) {
+    // CTAs are dispatched in index order, so while these loads are in flight the kernel asks L2 to
+    // fetch the same columns for the links PNS_PF_AHEAD_CTAS CTAs further on (half a resident wave,
+    // a few microseconds ahead); their batch then hits in L2.  One warp in four does it for all
+    // four: its 32 lanes touch one 32-byte sector each, 128 consecutive links per array.
+    if (PNS_PF_AHEAD_CTAS > 0 && ((gid >> 5) & 3u) == 0) {
         constexpr unsigned ahead = (unsigned)PNS_PF_AHEAD_CTAS * (unsigned)PNS_LANE_BLOCK;
-        if (gid + ahead < (unsigned)c.n.n_links) {
-            const size_t ea = e + ahead;
+        const unsigned ga = (gid & ~31u) + ahead + 4u * (gid & 31u);
+        if (ga < (unsigned)c.n.n_links) {
+            const size_t ea = ga;
             prefetch_l2(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
             prefetch_l2(c.s.gate + ea);
             if (upd) {
                 prefetch_l2(c.n_cinp + ea); prefetch_l2(c.n_coutp + ea);
                 prefetch_l2(c.u_num_prev + ea); prefetch_l2(c.s.runsum + ea);
                 if (windowed) prefetch_l2(c.u_tt_old + ea);
+                prefetch_l2(c.n_outflow + ea); prefetch_l2(c.n_inflow + ea);
             }
             if (flw) {
                 if (!upd) { prefetch_l2(c.f_cin + ea); prefetch_l2(c.f_cou + ea); }
                 prefetch_l2(c.f_sndp + ea); prefetch_l2(c.f_rcvp + ea);
-                if (tau + 1 - swtau >= 0) prefetch_l2(H64(c, PNS_F64_CUM_OUTFLOW, tau + 1 - swtau) + ea);
-                if (pre_i0 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i0) + ea);
-                if (pre_i1 >= 0) prefetch_l2(H64(c, PNS_F64_CUM_INFLOW, pre_i1) + ea);
+                if (ONECLASS) {
+                    if (c.c0_coulag) prefetch_l2(c.c0_coulag + ea);
+                } else if (tau + 1 - swtau >= 0) {
+                    prefetch_l2(H64(c, PNS_F64_CUM_OUTFLOW, tau + 1 - swtau) + ea);
+                }
+                if (pre_row0) prefetch_l2(pre_row0 + ea);
+                if (pre_row1) prefetch_l2(pre_row1 + ea);
             }
-            if (upd) { prefetch_l2(c.n_outflow + ea); prefetch_l2(c.n_inflow + ea); }
         }
     }
     const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
@@ -1242,6 +1263,19 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
         c.n_outflow = h64(PNS_F64_OUTFLOW, tu); c.n_inflow = h64(PNS_F64_INFLOW, tu);
         c.n_cout = h64(PNS_F64_CUM_OUTFLOW, tu); c.n_cin = h64(PNS_F64_CUM_INFLOW, tu);
         c.n_demand = (io && io->demand) ? io->demand + (size_t)(tu - 1) * net->n_demand_rows * net->replicas : nullptr;
+        // lagged rows of a single-class network (same expressions as k_link_lane evaluates per link otherwise)
+        const int fftau = net->class0.fftau, swtau = net->class0.swtau;
+        c.c0_coulag = tau + 1 - swtau >= 0 ? h64(PNS_F64_CUM_OUTFLOW, tau + 1 - swtau) : nullptr;
+        c.c0_pre_i0 = c.c0_pre_i1 = -1;
+        c.c0_pre0 = c.c0_pre1 = nullptr;
+        if (tau >= fftau) {
+            c.c0_pre_i0 = tau + 1 - fftau > 0 ? tau + 1 - fftau : 0;
+            c.c0_pre0 = h64(PNS_F64_CUM_INFLOW, c.c0_pre_i0);
+            if (fftau > 1) {
+                c.c0_pre_i1 = tau + 2 - fftau > 0 ? tau + 2 - fftau : 0;
+                c.c0_pre1 = h64(PNS_F64_CUM_INFLOW, c.c0_pre_i1);
+            }
+        }
     }
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
