@@ -279,7 +279,8 @@ def run_ours(args):
     # pinned host memory, launches the step, and reads the network-wide pedestrian count back ----
     pinned = torch.zeros((eng.demand.shape[0], eng.demand.shape[1]), dtype=torch.float64).pin_memory()
     pinned[: demand.shape[0], : demand.shape[1]] = torch.from_numpy(np.ascontiguousarray(demand))
-    result_host = torch.zeros(Ke, dtype=torch.float64).pin_memory()
+    from pednstream_b200 import _native as _nat
+    result_host = torch.zeros((Ke, _nat.METRIC_ROW), dtype=torch.float64).pin_memory()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -289,7 +290,7 @@ def run_ours(args):
     ms_e2e = e2.elapsed_time(e3)
     num_hist = None
     eng.check_errors()
-    total_peds = float(result_host[-1])
+    total_peds = float(eng.streamed_metric(result_host, Ke)[-1])
 
     t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -327,13 +328,14 @@ def run_ours(args):
                                     f"{B_ALG * L / 1e6:.0f} MB of history",
                        "multi_gpu": "replicas only: one independent grid per rank, no data-path collective"},
             "e2e": {"value": e2e, "unit": "link-timesteps/s", "steps": Ke,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8 * _nat.METRIC_ROW,
                     "note": "Engine.run_streamed (C-ABI pns_step_streamed): every step copies its demand row from "
-                            "pinned host memory, runs the step, reduces the network-wide pedestrian count on the "
-                            "device and copies it to pinned host memory; stream-ordered, one host wait at the end"},
+                            "pinned host memory, runs the step (whose link kernel also reduces the network-wide "
+                            "pedestrian count to 64 partial sums) and copies those to pinned host memory; "
+                            "stream-ordered, one host wait at the end"},
             "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": dom_gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_link_lane" if dom == "link_pair" else "k_" + dom, "achieved": dom_gbs, "peak": peak,
                          "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_link_step": B_ALG_PASS[dom],
                          "kernel_ms": {k: v for k, v in per_kernel.items() if v},

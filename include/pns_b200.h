@@ -229,8 +229,13 @@ int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io
  * `for t in range(1, steps): net.network_loading(t)` with demand edited between steps, examples/long_corridor.py:65-66,
  * 126-134): before the node pass of every step its demand row is copied from pinned host memory
  * (`host_demand`, same layout as pns_step_io.demand) into the device table, and after every step the network-wide
- * pedestrian count of that step is reduced on the device and copied to `host_metric[k]` (pinned).  Everything is
- * stream-ordered; the caller synchronises once at the end. */
+ * pedestrian count of that step is reduced on the device to PNS_METRIC_SLOTS partial sums and copied to the host.
+ * `dev_metric` (device scratch) and `host_metric` (pinned) hold [n_steps][PNS_METRIC_SLOTS * PNS_METRIC_STRIDE]
+ * doubles; the count of step t0+k is the sum over j of host_metric[k][j * PNS_METRIC_STRIDE] (counts are
+ * integer-valued, so the sum is exact in any order).  Everything is stream-ordered; the caller synchronises once at
+ * the end. */
+#define PNS_METRIC_SLOTS 64   /* partial sums per step (a power of two) */
+#define PNS_METRIC_STRIDE 4   /* doubles between slots: one 32-byte sector each */
 int pns_step_streamed(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
                       int rng_mode, const double *host_demand, double *dev_metric, double *host_metric, void *stream);
 

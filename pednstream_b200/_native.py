@@ -11,6 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
 ABI_VERSION = 4
+METRIC_SLOTS, METRIC_STRIDE = 64, 4          # PNS_METRIC_SLOTS / PNS_METRIC_STRIDE of pns_step_streamed
+METRIC_ROW = METRIC_SLOTS * METRIC_STRIDE
 
 RNG_TABLE, RNG_PHILOX, RNG_REQUEST = 0, 1, 2
 ERR_BITS = {1: "negative sending flow (reference link.py:346,366 ValueError)",

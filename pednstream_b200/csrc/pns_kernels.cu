@@ -92,8 +92,11 @@ constexpr int kBlock = 128;
 #ifndef PNS_LANE_MIN_BLOCKS
 #define PNS_LANE_MIN_BLOCKS (1024 / PNS_LANE_BLOCK)
 #endif
+#ifndef PNS_NODE_BLOCK
+#define PNS_NODE_BLOCK 128     // threads per CTA of k_node_flows
+#endif
 #ifndef PNS_NODE_MIN_BLOCKS
-#define PNS_NODE_MIN_BLOCKS 8
+#define PNS_NODE_MIN_BLOCKS 4  // 72 registers, no spills; 4..8 measured within 1%
 #endif
 constexpr int PH_UPDATE = 1, PH_FLOWS = 2;
 
@@ -122,6 +125,7 @@ struct Ctx {
     const double *c0_coulag;                            // cumulative_outflow[tau+1-swtau] (null while negative)
     const double *c0_pre0, *c0_pre1;                    // cumulative_inflow rows of the two likeliest arrival lags
     int c0_pre_i0, c0_pre_i1;                           // their indices (-1: not applicable)
+    double* metric;                                     // streamed runs: PNS_METRIC_SLOTS partial sums of num_pedestrians[t]
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -755,9 +759,12 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
             r[i] = R1 ? ld_keep<1>(c.s.nm_r + base + i, pol) : c.s.nm_r[(base + i) * R + rep];
         }
     }
+    double v_cout = 0.0, v_cin = 0.0;                                       // counters of the virtual links
     if (dem_row >= 0) {                                                     // slot 0 is the virtual O/D link pair
         s[0] = c.n_demand[(size_t)dem_row * R + rep];                       // node.py:176
         r[0] = 1e6;                                                         // node.py:186
+        const size_t vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep;
+        v_cout = c.n_coutp[vin]; v_cin = c.n_cinp[vin + R];                 // fetched with the rest of the batch
     }
     bool negative = false;
 #pragma unroll
@@ -828,8 +835,8 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     if (dem_row >= 0) {
         // the virtual links have no link thread: keep their counters here (link.py:19-25)
         const size_t vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep, vout = vin + R;
-        c.n_cout[vin] = c.n_coutp[vin] + q_out[0];
-        c.n_cin[vout] = c.n_cinp[vout] + q_in[0];
+        c.n_cout[vin] = v_cout + q_out[0];
+        c.n_cin[vout] = v_cin + q_in[0];
     }
 }
 
@@ -843,7 +850,7 @@ __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, 
 // ROUTED: some node takes its fractions from the route-choice model (the callee's registers would
 // otherwise be charged to every launch)
 template <bool R1, bool ROUTED>
-__global__ void __launch_bounds__(kBlock, ROUTED ? 4 : PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
+__global__ void __launch_bounds__(PNS_NODE_BLOCK, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)c.n.n_nodes * R) return;
@@ -855,12 +862,12 @@ __global__ void __launch_bounds__(kBlock, ROUTED ? 4 : PNS_NODE_MIN_BLOCKS) k_no
                          : __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     PNS_PDL_WAIT();
-#ifndef PNS_NODE_PF_AHEAD_CTAS
-#define PNS_NODE_PF_AHEAD_CTAS 888
+#ifndef PNS_NODE_PF_AHEAD
+#define PNS_NODE_PF_AHEAD 113664   // nodes: three quarters of a resident wave of 148 SMs x 1024 threads
 #endif
-    if (R1 && PNS_NODE_PF_AHEAD_CTAS > 0) {
+    if (R1 && PNS_NODE_PF_AHEAD > 0) {
         // fewer than two resident waves: the first wave pulls the records of the second into L2
-        const size_t na = gid + (size_t)PNS_NODE_PF_AHEAD_CTAS * kBlock;
+        const size_t na = gid + (size_t)PNS_NODE_PF_AHEAD;
         if (na < (size_t)c.n.n_nodes) {
             prefetch_l2(reinterpret_cast<const int4*>(c.n.nd_meta) + na);
             prefetch_l2(c.s.nm_s + na * c.n.nd_stride);
@@ -992,6 +999,15 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         }
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
         me.dens = div_by_area(me.num, ar);                                  // link.py:136
+        if (c.metric) {
+            // streamed runs report the network-wide pedestrian count of every step: counts are
+            // integer-valued, so the sum is exact in any order; one atomic per warp, spread over slots
+            double v = valid ? (double)me.num : 0.0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            if ((threadIdx.x & 31u) == 0 && v != 0.0)
+                atomicAdd(c.metric + (size_t)PNS_METRIC_STRIDE * ((gid >> 5) & (PNS_METRIC_SLOTS - 1)), v);
+        }
         const float dens_rev = __shfl_xor_sync(FULL, me.dens, 1);
         const bool noisy = p.sigma > 0.0;
         double z = 0.0;
@@ -1277,6 +1293,7 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
             }
         }
     }
+    c.metric = nullptr;
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
     c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
@@ -1347,12 +1364,13 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     const bool routed = net->n_routed > 0;
+    const unsigned nb = (unsigned)((n + PNS_NODE_BLOCK - 1) / PNS_NODE_BLOCK);
     if (net->replicas == 1) {
-        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<true, true>), blocks_for(n), kBlock, s, c);
-        else PNS_LAUNCH_CHAIN((k_node_flows<true, false>), blocks_for(n), kBlock, s, c);
+        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<true, true>), nb, PNS_NODE_BLOCK, s, c);
+        else PNS_LAUNCH_CHAIN((k_node_flows<true, false>), nb, PNS_NODE_BLOCK, s, c);
     } else {
-        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<false, true>), blocks_for(n), kBlock, s, c);
-        else PNS_LAUNCH_CHAIN((k_node_flows<false, false>), blocks_for(n), kBlock, s, c);
+        if (routed) PNS_LAUNCH_CHAIN((k_node_flows<false, true>), nb, PNS_NODE_BLOCK, s, c);
+        else PNS_LAUNCH_CHAIN((k_node_flows<false, false>), nb, PNS_NODE_BLOCK, s, c);
     }
 }
 
@@ -1365,10 +1383,11 @@ StepSizes sizes_of(const pns_net* net) {
     return z;
 }
 
+constexpr size_t kMetricRow = (size_t)PNS_METRIC_SLOTS * PNS_METRIC_STRIDE;   // doubles per step in the metric buffers
 struct Streamed {           // per-step host traffic of pns_step_streamed
     const double* host_demand;   // pinned [rows][n_demand_rows*R]
-    double* dev_metric;          // [n_steps]
-    double* host_metric;         // pinned [n_steps]
+    double* dev_metric;          // [n_steps][PNS_METRIC_SLOTS * PNS_METRIC_STRIDE]
+    double* host_metric;         // pinned, same shape
 };
 
 int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps, int rng_mode,
@@ -1378,6 +1397,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     if (check_step_io(net, io, rng_mode)) return 1;
     const StepSizes z = sizes_of(net);
 #ifndef PNS_HOST_EMULATION
+    if (sx) cudaMemsetAsync(sx->dev_metric, 0, (size_t)n_steps * kMetricRow * sizeof(double), s);
     cudaEvent_t* ev = nullptr;
     const int per_step = 4;   // before pair | after pair | after route | after node
     if (ms) {
@@ -1392,15 +1412,21 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     // launch k (0..n_steps): pair kernel = UPDATE(t0+k-1) [k>0] + FLOWS(t0+k) [k<n_steps]; then route+node(t0+k)
     for (int k = 0; k <= n_steps; ++k) {
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
-        const Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
+        Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
+#ifndef PNS_HOST_EMULATION
+        // streamed runs: the single-replica link kernel accumulates the step's pedestrian count itself
+        const bool lane_metric = sx && k > 0 && net->replicas == 1 && !getenv("PNS_PAIR_THREADS");
+        if (lane_metric) cp.metric = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
+#endif
         PNS_MARK(k, 0);
         if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
 #ifndef PNS_HOST_EMULATION
-        if (sx && k > 0) {          // result of step t0+k-1: reduce on the device, copy to the host, every step
-            cudaMemsetAsync(sx->dev_metric + (k - 1), 0, sizeof(double), s);
-            k_metric_pedestrians<<<148 * 4, 256, 0, s>>>(cp, sx->dev_metric + (k - 1));
-            cudaMemcpyAsync(sx->host_metric + (k - 1), sx->dev_metric + (k - 1), sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (sx && k > 0) {          // result of step t0+k-1: partial sums reduced on the device, copied to the host every step
+            double* row = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
+            if (!lane_metric) k_metric_pedestrians<<<148 * 4, 256, 0, s>>>(cp, row);
+            cudaMemcpyAsync(sx->host_metric + (size_t)(k - 1) * kMetricRow, row, kMetricRow * sizeof(double),
+                            cudaMemcpyDeviceToHost, s);
         }
         if (sx && k < n_steps && net->n_demand_rows) {   // input of step t0+k: its demand row, from pinned host memory
             const size_t row = (size_t)net->n_demand_rows * net->replicas, off = (size_t)(t0 + k - 1) * row;

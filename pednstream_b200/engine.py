@@ -335,22 +335,30 @@ class Engine:
     def run_streamed(self, t0: int, n_steps: int, host_demand: torch.Tensor, host_metric: torch.Tensor,
                      rng_mode: int = _native.RNG_PHILOX):
         """Advance n_steps with the per-step host traffic enqueued natively: every step copies its demand
-        row from `host_demand` (pinned float64, same layout as the device demand table) and writes the
-        network-wide pedestrian count of the step to `host_metric[k]` (pinned float64 [n_steps]).
+        row from `host_demand` (pinned float64, same layout as the device demand table) and copies the
+        partial sums of the step's network-wide pedestrian count to `host_metric[k]` (pinned float64
+        [n_steps, METRIC_ROW]; `streamed_metric(host_metric)` adds them up).
         Stream-ordered; synchronise before reading `host_metric`."""
         if not (host_demand.is_pinned() and host_metric.is_pinned()):
             raise ValueError("run_streamed needs pinned host tensors")
-        if host_demand.dtype != torch.float64 or host_metric.dtype != torch.float64 or host_metric.numel() < n_steps:
-            raise ValueError("host_demand / host_metric must be float64 and host_metric at least n_steps long")
+        if (host_demand.dtype != torch.float64 or host_metric.dtype != torch.float64
+                or host_metric.numel() < n_steps * _native.METRIC_ROW or not host_metric.is_contiguous()):
+            raise ValueError("host_demand / host_metric must be float64 and host_metric [n_steps, METRIC_ROW]")
         if host_demand.shape[0] < t0 + n_steps - 1 or host_demand.shape[1] != self.demand.shape[1]:
             raise ValueError("host_demand must cover rows [0, t0+n_steps-1) with the device table's width")
-        if not hasattr(self, "_dev_metric") or self._dev_metric.numel() < n_steps:
-            self._dev_metric = torch.zeros(n_steps, dtype=torch.float64, device=self.device)
+        if not hasattr(self, "_dev_metric") or self._dev_metric.numel() < n_steps * _native.METRIC_ROW:
+            self._dev_metric = torch.zeros(n_steps * _native.METRIC_ROW, dtype=torch.float64, device=self.device)
         with self._guard():
             _native.check(self.lib, self.lib.pns_step_streamed(
                 C.byref(self.net), C.byref(self.state), C.byref(self.io), t0, n_steps, rng_mode,
                 _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")
         self.t_done = t0 + n_steps - 1
+
+    @staticmethod
+    def streamed_metric(host_metric: torch.Tensor, n_steps: int) -> np.ndarray:
+        """Pedestrian count of every streamed step: the sum of its partial sums (exact, integer-valued)."""
+        m = host_metric.reshape(-1)[: n_steps * _native.METRIC_ROW].numpy()
+        return m.reshape(n_steps, _native.METRIC_SLOTS, _native.METRIC_STRIDE)[:, :, 0].sum(axis=1)
 
     def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor):
         """draw_b [rows, 3, L*R] int32, draw_n [rows, L*R] float64; row k serves step t0+k of `run`."""

@@ -196,14 +196,16 @@ def test_streamed_run_equals_resident_run():
     b.initialise(gate, None, tf, np.zeros_like(demand), None)          # device table starts empty
     host_demand = torch.zeros(tuple(b.demand.shape), dtype=torch.float64).pin_memory()
     host_demand[: demand.shape[0], : demand.shape[1]] = torch.from_numpy(demand)
-    metric = torch.zeros(steps, dtype=torch.float64).pin_memory()
-    b.run_streamed(1, steps, host_demand, metric)
+    from pednstream_b200 import _native
+    metric_raw = torch.zeros((steps, _native.METRIC_ROW), dtype=torch.float64).pin_memory()
+    b.run_streamed(1, steps, host_demand, metric_raw)
     torch.cuda.synchronize()
     b.check_errors()
     for f in FIELDS:
         assert torch.equal(a.history(f)[: steps + 1], b.history(f)[: steps + 1]), f
+    metric = torch.from_numpy(b.streamed_metric(metric_raw, steps))
     want = a.history("num_pedestrians")[1: steps + 1, :, 0].double().sum(dim=1).cpu()
-    assert torch.allclose(metric, want, rtol=0, atol=1e-6) and float(metric[-1]) > 0
+    assert torch.equal(metric, want) and float(metric[-1]) > 0
 
 
 def _lattice(size, origins, steps=200, **kw):
