@@ -249,7 +249,8 @@ int pns_env_observe(const pns_net *net, const pns_state *st, const pns_env *env,
                     float *reward, void *stream);
 
 /* Draw `n` samples with the on-device Philox samplers (test hook for oracle/philox.py):
- * kind 0: binomial(n_trials[i], p[i]) -> out_i; kind 1: standard normal -> out_d. */
+ * kind 0: binomial(n_trials[i], p[i]) -> out_i; kind 1: the four normals of quad key i -> out_d[4i..4i+3];
+ * kind 2: det_pow08(p[i]) -> out_d[i]. */
 int pns_rng_selftest(int kind, int n, const int32_t *n_trials, const double *p, uint64_t seed, int t,
                      int site, int32_t *out_i, double *out_d, void *stream);
 

@@ -144,7 +144,7 @@ def binomial_inversion(m, pp, u):
     while u > pk and k < m:
         u = u - pk
         k += 1
-        pk = ((pk * ratio) * float(m - k + 1)) / float(k)
+        pk = ((pk * ratio) * float(m - k + 1)) * (1.0 / float(k))
     return k
 
 
@@ -244,14 +244,26 @@ def det_sincos2pif(u):
     return ((c, s), (-s, c), (-c, -s), (s, -c))[q]
 
 
-def normal_pair_philox(seed, t, link, replica, site):
-    """Two independent standard normals from one block: (cosine branch, sine branch), float32 math."""
-    w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
-    u1 = F32((w[0] >> 8) + 1) * F32(5.9604644775390625e-8)
-    u2 = F32(w[1] >> 8) * F32(5.9604644775390625e-8)
+def box_muller_f32(wa, wb):
+    """Box-Muller on two 32-bit words in float32: (cosine branch, sine branch)."""
+    u1 = F32((wa >> 8) + 1) * F32(5.9604644775390625e-8)
+    u2 = F32(wb >> 8) * F32(5.9604644775390625e-8)
     rad = np.sqrt(F32(-2.0) * det_logf(u1))
     cs, sn = det_sincos2pif(u2)
     return float(rad * cs), float(rad * sn)
+
+
+def normal_quad_philox(seed, t, quad_link, replica, site):
+    """Four standard normals from the block keyed by `quad_link`: words 0,1 -> first corridor of the
+    quad (cosine, sine branch), words 2,3 -> second corridor (pns_rng.cuh normal_quad_philox)."""
+    w = philox4x32_10(t, quad_link, site, replica, seed & M32, (seed >> 32) & M32)
+    return box_muller_f32(w[0], w[1]) + box_muller_f32(w[2], w[3])
+
+
+def normal_pair_philox(seed, t, link, replica, site):
+    """The two normals of the corridor whose even link is `link`: its half of the quad's block."""
+    g = normal_quad_philox(seed, t, link & ~3, replica, site)
+    return (g[2], g[3]) if link & 2 else (g[0], g[1])
 
 
 class PhiloxDraws:

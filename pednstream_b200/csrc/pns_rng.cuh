@@ -169,7 +169,17 @@ struct DrawKey {
     uint32_t t, link, replica, k0, k1;
 };
 
-// Binomial(m, pp) by CDF inversion, m <= 512, 0 < pp <= 0.5, u in [0, 1)
+// correctly rounded 1/x (one rounding, like the host's 1.0 / x): a third of the cost of a division
+__host__ __device__ inline double pns_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// Binomial(m, pp) by CDF inversion, m <= 512, 0 < pp <= 0.5, u in [0, 1).  The pmf recurrence
+// multiplies by the rounded reciprocal of k instead of dividing by k (restated in oracle/philox.py).
 __host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
     const double q = 1.0 - pp;
     const double ratio = pp / q;
@@ -182,14 +192,17 @@ __host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
     while (u > pk && k < m) {
         u = u - pk;
         k += 1;
-        pk = ((pk * ratio) * (double)(m - k + 1)) / (double)k;
+        pk = ((pk * ratio) * (double)(m - k + 1)) * pns_rcp((double)k);
     }
     return k;
 }
 
 // Exact Binomial(n, p), 0 < p < 1, n > 0; chunks of 512 trials keep q^m representable (binomial
 // additivity).  Out of line and with scalar arguments: it is called on a minority of the links and
-// must not bloat the callers' register footprint.
+// must not bloat the callers' register footprint.  (A rejection sampler for large means -- BTRS,
+// 1.2 rounds instead of n*min(p,1-p) inversion steps -- was tried: its register needs made ptxas
+// spill 170 bytes per thread on the link kernels' main path, and behind a separately compiled ABI
+// boundary the call overhead cost as much as it saved; see DESIGN.md.)
 #ifdef __CUDACC__
 __device__ __noinline__
 #else
@@ -305,17 +318,35 @@ __host__ __device__ inline void det_sincos2pif(float u, float* cos_out, float* s
     else { *cos_out = s; *sin_out = -c; }
 }
 
-// Two independent standard normals from one Philox block (Box-Muller, both branches): the two
-// directions of a link pair share the block, the even link takes the cosine branch.
-__host__ __device__ inline void normal_pair_philox(const DrawKey& key, uint32_t site, double* g0, double* g1) {
-    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
-    const float u1 = (float)((w.v[0] >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1], 24 bits
-    const float u2 = (float)(w.v[1] >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+// Box-Muller on two 32-bit words: (cosine branch, sine branch)
+__host__ __device__ inline void box_muller_f32(uint32_t wa, uint32_t wb, float* g_cos, float* g_sin) {
+    const float u1 = (float)((wa >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1], 24 bits
+    const float u2 = (float)(wb >> 8) * 5.9604644775390625e-8f;          // [0, 1)
     const float rad = pns_sqrtf(-2.0f * det_logf(u1));
     float cs, sn;
     det_sincos2pif(u2, &cs, &sn);
-    *g0 = (double)(rad * cs);
-    *g1 = (double)(rad * sn);
+    *g_cos = rad * cs;
+    *g_sin = rad * sn;
+}
+
+// Speed noise is drawn per *quad* of links (two adjacent corridors, links 4q .. 4q+3): one Philox
+// block keyed by the quad's first link gives four independent standard normals -- words 0,1 serve
+// links 4q (cosine branch) and 4q+1 (sine branch), words 2,3 serve links 4q+2 and 4q+3.  Nothing of
+// the block is wasted, and a warp of the single-replica link kernel can draw for four warps.
+__host__ __device__ inline void normal_quad_philox(const DrawKey& key, uint32_t site, float g[4]) {
+    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
+    box_muller_f32(w.v[0], w.v[1], &g[0], &g[1]);
+    box_muller_f32(w.v[2], w.v[3], &g[2], &g[3]);
+}
+
+// The two normals of one corridor (key.link = its even link): the half of the quad's block it owns.
+__host__ __device__ inline void normal_pair_philox(const DrawKey& key, uint32_t site, double* g0, double* g1) {
+    const Philox4 w = philox4x32_10(key.t, key.link & ~3u, site, key.replica, key.k0, key.k1);
+    const bool second = (key.link & 2u) != 0;
+    float a, b;
+    box_muller_f32(second ? w.v[2] : w.v[0], second ? w.v[3] : w.v[1], &a, &b);
+    *g0 = (double)a;
+    *g1 = (double)b;
 }
 
 }  // namespace pns

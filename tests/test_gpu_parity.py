@@ -80,7 +80,7 @@ def test_philox_samplers_match_python_restatement():
     dt = torch.from_numpy(trials).cuda()
     dp = torch.from_numpy(p).cuda()
     oi = torch.zeros(n, dtype=torch.int32, device="cuda")
-    od = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    od = torch.zeros(4 * n, dtype=torch.float64, device="cuda")
     seed, t = 0x1234567890ABCDEF, 77
     for kind, site in ((0, 1), (0, 3), (1, 4), (2, 0)):
         rc = lib.pns_rng_selftest(kind, n, C.c_void_p(dt.data_ptr()), C.c_void_p(dp.data_ptr()), seed, t, site,
@@ -91,7 +91,7 @@ def test_philox_samplers_match_python_restatement():
             want = [ph.binomial_philox(seed, t, i, 0, site, int(trials[i]), float(p[i])) for i in range(n)]
             assert oi.cpu().numpy().tolist() == want
         elif kind == 1:
-            want = np.array([ph.normal_pair_philox(seed, t, i, 0, site) for i in range(n)]).reshape(-1)
+            want = np.array([ph.normal_quad_philox(seed, t, i, 0, site) for i in range(n)]).reshape(-1)
             assert np.array_equal(od.cpu().numpy(), want)
         else:
             want = np.array([float(ph.det_pow08(np.float32(p[i]))) for i in range(n)])

@@ -1,0 +1,85 @@
+"""Counter-based samplers of the on-device draw mode: the Python restatement (oracle/philox.py) is
+checked against the exact distributions, and the kernel source (host-emulation build) against the
+restatement.  The GPU build is checked against the same restatement in test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import philox as ph
+
+
+def _selftest(lib, kind, site, trials, p, seed, t):
+    n = len(trials)
+    tr = np.ascontiguousarray(trials, dtype=np.int32)
+    pp = np.ascontiguousarray(p, dtype=np.float64)
+    oi = np.zeros(n, dtype=np.int32)
+    od = np.zeros(4 * n, dtype=np.float64)
+    rc = lib.pns_rng_selftest(kind, n, tr.ctypes.data_as(C.c_void_p), pp.ctypes.data_as(C.c_void_p),
+                              C.c_uint64(seed), t, site, oi.ctypes.data_as(C.c_void_p),
+                              od.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0
+    return oi, od
+
+
+def test_emulated_samplers_match_python_restatement(emu_lib):
+    n = 600
+    rng = np.random.default_rng(11)
+    trials = rng.integers(0, 1400, n).astype(np.int32)
+    trials[:40] = rng.integers(0, 12, 40)
+    p = rng.uniform(0.01, 0.99, n)
+    p[100:160] = 0.9                                  # R3 blockers (link.py:382)
+    trials[100:130] = 1200                            # a jammed link: three chunks of inversion
+    seed, t = 0xFEEDFACE12345678, 41
+    for site in (1, 3):
+        oi, _ = _selftest(emu_lib, 0, site, trials, p, seed, t)
+        want = [ph.binomial_philox(seed, t, i, 0, site, int(trials[i]), float(p[i])) for i in range(n)]
+        assert oi.tolist() == want
+    _, od = _selftest(emu_lib, 1, 4, trials, p, seed, t)
+    want = np.array([ph.normal_quad_philox(seed, t, i, 0, 4) for i in range(n)]).reshape(-1)
+    assert np.array_equal(od, want)
+    # a corridor's normals are its half of the quad's block: links 4q, 4q+1 | 4q+2, 4q+3
+    for link in (0, 2, 4, 6, 10):
+        quad = ph.normal_quad_philox(seed, t, link & ~3, 0, 4)
+        assert ph.normal_pair_philox(seed, t, link, 0, 4) == (quad[2:] if link & 2 else quad[:2])
+
+
+@pytest.mark.parametrize("n,p", [(1200, 0.9), (88, 0.775), (40, 0.25), (300, 0.5), (2000, 0.02), (9, 0.3)])
+def test_binomial_sampler_follows_the_binomial_law(n, p):
+    """Chunked CDF inversion (with the p > 0.5 flip) against scipy's pmf: moments within 5 standard
+    errors and a chi-square test over pooled cells."""
+    from scipy import stats
+    N = 6000
+    x = np.array([ph.binomial_philox(1234, 7, i, 0, 3, n, p) for i in range(N)])
+    assert x.min() >= 0 and x.max() <= n
+    mean, var = n * p, n * p * (1 - p)
+    assert abs(x.mean() - mean) < 5 * np.sqrt(var / N)
+    assert abs(x.var() - var) < 5 * var * np.sqrt(2.0 / N) + 0.05 * var
+    lo, hi = int(stats.binom.ppf(0.001, n, p)), int(stats.binom.ppf(0.999, n, p))
+    edges = np.arange(lo, hi + 2)
+    obs = np.histogram(np.clip(x, lo, hi), bins=edges)[0].astype(float)
+    exp = stats.binom.pmf(np.arange(lo, hi + 1), n, p)
+    exp[0] += stats.binom.cdf(lo - 1, n, p)
+    exp[-1] += stats.binom.sf(hi, n, p)
+    exp *= N
+    # pool cells with small expectation
+    o2, e2, ao, ae = [], [], 0.0, 0.0
+    for o, e in zip(obs, exp):
+        ao += o; ae += e
+        if ae >= 8:
+            o2.append(ao); e2.append(ae); ao = ae = 0.0
+    if ae > 0:
+        o2[-1] += ao; e2[-1] += ae
+    chi2 = float(((np.array(o2) - np.array(e2)) ** 2 / np.array(e2)).sum())
+    assert chi2 < stats.chi2.ppf(1 - 1e-4, len(o2) - 1), (chi2, len(o2))
+
+
+def test_speed_noise_sampler_is_standard_normal():
+    from scipy import stats
+    g = np.array([ph.normal_quad_philox(99, 3, 4 * i, 0, 4) for i in range(3000)])
+    assert g.shape == (3000, 4)
+    flat = g.reshape(-1)
+    assert abs(flat.mean()) < 5 / np.sqrt(flat.size) and abs(flat.var() - 1) < 0.06
+    assert stats.kstest(flat, "norm").pvalue > 1e-4
+    c = np.corrcoef(g.T)
+    assert np.abs(c - np.eye(4)).max() < 0.08
