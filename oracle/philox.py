@@ -144,7 +144,7 @@ def binomial_inversion(m, pp, u):
     while u > pk and k < m:
         u = u - pk
         k += 1
-        pk = ((pk * ratio) * float(m - k + 1)) * (1.0 / float(k))
+        pk = pk * ((ratio * float(m - k + 1)) * (1.0 / float(k)))
     return k
 
 

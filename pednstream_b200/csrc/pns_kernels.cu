@@ -89,6 +89,9 @@ constexpr int kBlock = 128;
 #define PNS_PF_AHEAD_CTAS (75776 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
                                                      // into L2: half a resident wave of 148 SMs x 1024 threads (0 = off)
 #endif
+#ifndef PNS_PF_TAPS
+#define PNS_PF_TAPS 1          // k_link_lane: early fetch of the diffusion taps of occupied links
+#endif
 #ifndef PNS_LANE_MIN_BLOCKS
 #define PNS_LANE_MIN_BLOCKS (1024 / PNS_LANE_BLOCK)
 #endif
@@ -213,6 +216,7 @@ __device__ __forceinline__ void sth(float* a, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(a), "f"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" :: "l"(a)); }
+__device__ __forceinline__ void prefetch_l1(const void* a) { asm volatile("prefetch.global.L1 [%0];" :: "l"(a)); }
 // stage-gated forms: S = the stage from which the hint applies
 template <int S, typename T> __device__ __forceinline__ T ld_keep(const T* a, const L2Pol p) { if (PNS_L2_STAGE >= S) return ldh(a, p.keep); return *a; }
 template <int S, typename T> __device__ __forceinline__ T ld_once(const T* a, const L2Pol p) { if (PNS_L2_STAGE >= S) return ldh(a, p.once); return *a; }
@@ -1044,6 +1048,16 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         }
     }
     if (!flw) return;
+    // Links that hold pedestrians will probably smooth their outflow over four lagged inflow rows
+    // (get_outflow, link.py:199-214): rows tau-lag-k of a lag that is only known deep inside the
+    // sending-flow computation.  In free flow the lag is the free-flow lag or one less, so ask for the
+    // five candidate rows now; by the time they are needed the dependent DRAM round trip is over.
+    if (PNS_PF_TAPS && me.num > 0.0f && tau >= fftau) {
+        const double* row = H64(c, PNS_F64_INFLOW, tau - fftau + 1) + e;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (tau - fftau + 1 - k >= 0) prefetch_l1(row - (size_t)k * c.row64);
+    }
     const float num_rev = __shfl_xor_sync(FULL, me.num, 1);
     pns::DrawKey key;
     key.t = (uint32_t)c.t_flows; key.link = (uint32_t)l; key.replica = c.io.replica_base; key.k0 = k0; key.k1 = k1;
