@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 4
+#define PNS_ABI_VERSION 5
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -122,6 +122,14 @@ typedef struct pns_net {
     const double *rt_opt_dist;
     const int32_t *rt_row_ptr, *rt_row_od, *rt_term_ptr, *rt_term_opt, *rt_term_row_entry;
     double rt_temp, rt_alpha, rt_beta, rt_omega, rt_eps; /* path_finder.py:158-163 */
+    /* optional launch order of the single-replica link kernel: CTA i processes the block of
+     * lane_order_block consecutive links number lane_order[i] (a permutation of the blocks; NULL = index
+     * order).  A schedule, not a result: blocks whose links sit next to demand origins -- where queues form and
+     * the blockers draw of a jammed link is a long serial walk -- go first, so that their latency is covered by
+     * the rest of the grid instead of extending its tail.  Ignored unless lane_order_block equals
+     * pns_lane_block_size(). */
+    const int32_t *lane_order;
+    int32_t lane_order_block, n_lane_blocks;
 } pns_net;
 
 /* Mutable simulation state; all device pointers, caller-owned. */
@@ -247,6 +255,9 @@ int pns_env_apply_actions(const pns_net *net, const pns_state *st, const pns_env
  * PedNetParallelEnv._compute_rewards (rl/pz_pednet_env.py:548-581) at simulation row t. */
 int pns_env_observe(const pns_net *net, const pns_state *st, const pns_env *env, int t, float *obs,
                     float *reward, void *stream);
+
+/* Links per CTA of the single-replica link kernel (the granularity of pns_net.lane_order). */
+int pns_lane_block_size(void);
 
 /* Draw `n` samples with the on-device Philox samplers (test hook for oracle/philox.py):
  * kind 0: binomial(n_trials[i], p[i]) -> out_i; kind 1: the four normals of quad key i -> out_d[4i..4i+3];

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 METRIC_SLOTS, METRIC_STRIDE = 64, 4          # PNS_METRIC_SLOTS / PNS_METRIC_STRIDE of pns_step_streamed
 METRIC_ROW = METRIC_SLOTS * METRIC_STRIDE
 
@@ -44,6 +44,7 @@ class PnsNet(C.Structure):
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
                              "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
         + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
+        + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32)]
     )
 
 
@@ -69,7 +70,7 @@ OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens"
            "speed": 6, "gate": 7}
 
 
-EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
+EXPORTS = ("pns_abi_version", "pns_lane_block_size", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
            "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_rng_selftest")
 
 _LIB = None

@@ -898,7 +898,11 @@ template <int PHASE, int MODE, bool ONECLASS>
 __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     constexpr unsigned FULL = 0xffffffffu;
-    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // launch order (pns_net.lane_order): CTA i works on link block order[i]; blocks likely to hold long
+    // sampler walks come first so that they overlap the rest of the grid
+    const bool ordered = c.n.lane_order != nullptr && c.n.lane_order_block == PNS_LANE_BLOCK;
+    const unsigned blk = ordered ? (unsigned)__ldg(c.n.lane_order + blockIdx.x) : blockIdx.x;
+    const unsigned gid = blk * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
     const int l = valid ? (int)gid : 0;
     const size_t e = (size_t)l;
@@ -962,12 +966,13 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // A thread spends most of its memory time waiting for the batch above to come back from DRAM.
     // CTAs are dispatched in index order, so while these loads are in flight the kernel asks L2 to
     // fetch the same columns for the links PNS_PF_AHEAD_CTAS CTAs further on (half a resident wave,
-    // a few microseconds ahead); their batch then hits in L2.  One warp in four does it for all
-    // four: its 32 lanes touch one 32-byte sector each, 128 consecutive links per array.
-    if (PNS_PF_AHEAD_CTAS > 0 && ((gid >> 5) & 3u) == 0) {
-        constexpr unsigned ahead = (unsigned)PNS_PF_AHEAD_CTAS * (unsigned)PNS_LANE_BLOCK;
-        const unsigned ga = (gid & ~31u) + ahead + 4u * (gid & 31u);
-        if (ga < (unsigned)c.n.n_links) {
+    // a few microseconds ahead); their batch then hits in L2.
+    if (PNS_PF_AHEAD_CTAS > 0 && threadIdx.x < 32u) {
+        // the CTA's first warp covers the PNS_LANE_BLOCK links of the target CTA, 16 bytes apart
+        const unsigned tb = blockIdx.x + (unsigned)PNS_PF_AHEAD_CTAS;
+        const unsigned tgt = tb < gridDim.x ? (ordered ? (unsigned)__ldg(c.n.lane_order + tb) : tb) : 0xffffffu;
+        const unsigned ga = tgt * (unsigned)PNS_LANE_BLOCK + (unsigned)(PNS_LANE_BLOCK / 32) * threadIdx.x;
+        if (tb < gridDim.x && ga < (unsigned)c.n.n_links) {
             const size_t ea = ga;
             prefetch_l2(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
             prefetch_l2(c.s.gate + ea);
@@ -1483,6 +1488,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
 extern "C" {
 
 int pns_abi_version(void) { return PNS_ABI_VERSION; }
+int pns_lane_block_size(void) { return PNS_LANE_BLOCK; }
 const char* pns_last_error(void) { return g_err; }
 
 int pns_state_init(const pns_net* net, const pns_state* st, void* stream) {

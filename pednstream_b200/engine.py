@@ -83,6 +83,15 @@ class Engine:
             setattr(net, k, _ptr(self._net_t[k]))
         C.memmove(C.byref(net.class0), np.ascontiguousarray(p["classes"][:1]).ctypes.data, C.sizeof(net.class0))
         net.rt_temp, net.rt_alpha, net.rt_beta, net.rt_omega, net.rt_eps = [float(x) for x in p["rt_scalars"]]
+        # launch order of the single-replica link kernel (a schedule; results do not depend on it)
+        self._lane_order = None
+        if R == 1 and not emulation and L > 0:
+            from .plan import lane_block_order
+            block = int(self.lib.pns_lane_block_size())
+            order = lane_block_order(p["nd_meta"], p["nd_in_link"], L, int(p["nd_stride"]), block)
+            if order is not None:
+                self._lane_order = torch.from_numpy(order).to(dev)
+                net.lane_order, net.lane_order_block, net.n_lane_blocks = _ptr(self._lane_order), block, len(order)
         self.net = net
 
         # ---- mutable state ---------------------------------------------------------------------

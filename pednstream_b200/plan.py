@@ -116,6 +116,42 @@ def slot_links(nd_meta, nd_in_col, stride):
     return out
 
 
+def lane_block_order(nd_meta, nd_in_link, n_links, stride, block, hops=4):
+    """Launch order of the single-replica link kernel (`pns_net.lane_order`): a permutation of the
+    blocks of `block` consecutive links that puts first the blocks holding a link within `hops` nodes
+    of a demand origin (queues form there, and the blockers draw of a jammed link is the longest
+    serial piece of work in the step), index order otherwise.  Returns None when nothing moves."""
+    nd_meta = np.asarray(nd_meta)
+    n_nodes = len(nd_meta)
+    slots = np.asarray(nd_in_link).reshape(n_nodes, stride)
+    head = np.full(n_links, -1, dtype=np.int64)                 # end node of every physical link
+    nn, kk = np.nonzero((slots >= 0) & (slots < n_links))
+    head[slots[nn, kk]] = nn
+    tail = head[np.arange(n_links) ^ 1]                         # start node = end node of the reverse link
+    dist = np.full(n_nodes, hops + 1, dtype=np.int64)
+    frontier = np.nonzero(nd_meta[:, 2] >= 0)[0]                # nodes with a demand row
+    if frontier.size == 0:
+        return None
+    dist[frontier] = 0
+    for d in range(1, hops + 1):
+        reach = np.zeros(n_nodes, dtype=bool)
+        reach[frontier] = True
+        nxt = np.unique(head[reach[tail]])                      # nodes one link downstream of the frontier
+        nxt = nxt[dist[nxt] > d]
+        if nxt.size == 0:
+            break
+        dist[nxt] = d
+        frontier = nxt
+    near = (np.minimum(dist[head], dist[tail]) <= hops)
+    n_blocks = (n_links + block - 1) // block
+    pad = np.zeros(n_blocks * block, dtype=bool)
+    pad[:n_links] = near
+    first = pad.reshape(n_blocks, block).any(axis=1)
+    if not first.any() or first.all():
+        return None
+    return np.concatenate([np.nonzero(first)[0], np.nonzero(~first)[0]]).astype(np.int32)
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
