@@ -902,6 +902,8 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // sampler walks come first so that they overlap the rest of the grid
     const bool ordered = c.n.lane_order != nullptr && c.n.lane_order_block == PNS_LANE_BLOCK;
     const unsigned blk = ordered ? (unsigned)__ldg(c.n.lane_order + blockIdx.x) : blockIdx.x;
+    const unsigned pf_slot = blockIdx.x + (unsigned)PNS_PF_AHEAD_CTAS;       // the CTA this one prefetches for (below)
+    const unsigned pf_blk = pf_slot < gridDim.x ? (ordered ? (unsigned)__ldg(c.n.lane_order + pf_slot) : pf_slot) : 0xffffffu;
     const unsigned gid = blk * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
     const int l = valid ? (int)gid : 0;
@@ -969,10 +971,8 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // a few microseconds ahead); their batch then hits in L2.
     if (PNS_PF_AHEAD_CTAS > 0 && threadIdx.x < 32u) {
         // the CTA's first warp covers the PNS_LANE_BLOCK links of the target CTA, 16 bytes apart
-        const unsigned tb = blockIdx.x + (unsigned)PNS_PF_AHEAD_CTAS;
-        const unsigned tgt = tb < gridDim.x ? (ordered ? (unsigned)__ldg(c.n.lane_order + tb) : tb) : 0xffffffu;
-        const unsigned ga = tgt * (unsigned)PNS_LANE_BLOCK + (unsigned)(PNS_LANE_BLOCK / 32) * threadIdx.x;
-        if (tb < gridDim.x && ga < (unsigned)c.n.n_links) {
+        const unsigned ga = pf_blk * (unsigned)PNS_LANE_BLOCK + (unsigned)(PNS_LANE_BLOCK / 32) * threadIdx.x;
+        if (pf_slot < gridDim.x && ga < (unsigned)c.n.n_links) {
             const size_t ea = ga;
             prefetch_l2(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
             prefetch_l2(c.s.gate + ea);
