@@ -201,7 +201,8 @@ int pns_state_init(const pns_net *net, const pns_state *st, void *stream);
 /* Link demand/supply pass for step t (time index tau = t-1), one thread per link pair and replica:
  * Link.cal_sending_flow (link.py:216-370) incl. get_outflow (:199-214) and
  * Link/Separator.cal_receiving_flow_with_reverse (:372-416, :480-512).
- * Writes sending_flow[tau], receiving_flow[tau] (or the draw requests in REQUEST mode).
+ * Writes sending_flow[tau], receiving_flow[tau] and the node-major copies nm_s / nm_r the node pass reads
+ * (or only the draw requests in REQUEST mode).
  * Inside pns_step this pass for step t+1 is fused with pns_link_update of step t (same thread,
  * state kept in registers). */
 int pns_link_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
@@ -213,10 +214,12 @@ int pns_route_probs(const pns_net *net, const pns_state *st, const pns_step_io *
 
 /* Node pass for step t, one thread per node and replica: turning fractions
  * (path_finder.py:591-715), Node.assign_flows / solve / update_links (node.py:146-300).
- * Writes inflow/outflow/cumulative counts at row t. */
+ * Writes inflow[t] / outflow[t] of every link (physical and virtual) and the cumulative counts of the virtual
+ * O/D links at row t. */
 int pns_node_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, void *stream);
 
-/* Link state update for step t, one thread per link pair and replica:
+/* Link state update for step t, one thread per link pair and replica: cumulative counts from the
+ * inflow/outflow the node pass stored (link.py:19-25),
  * Link.update_link_density_flow + update_speeds (link.py:133-188, 430-452) and
  * BiDirectionalFd.__call__ (src/utils/functions.py:112-134). */
 int pns_link_update(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
@@ -228,7 +231,7 @@ int pns_step(const pns_net *net, const pns_state *st, const pns_step_io *io, int
              int rng_mode, void *stream);
 
 /* pns_step with CUDA-event timing of every launch on `stream` (bench/roofline instrumentation):
- * adds the elapsed milliseconds of each pass to ms[0..2] (link-pair kernel, route_probs, node_flows;
+ * adds the elapsed milliseconds of each pass to ms[0..2] (link kernel, route_probs, node_flows;
  * ms[3] is unused) and the launch counts to launches[0..2].  Synchronises the stream before returning. */
 int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,
                       int rng_mode, void *stream, double *ms, int64_t *launches);
