@@ -36,6 +36,11 @@ CASES = {
     "od_flow_example": dict(dataset="od_flow_example", run=499, seed=0),
     "delft": dict(dataset="delft", run=120, seed=0),
     "melbourne_2000": dict(dataset="melbourne", run=1999, steps_override=2000, seed=0),
+    # domain randomisation (reference env_loader.py:160-424): create the scenario, then
+    # NetworkEnvGenerator.randomize_network(dataset, seed=randomize) and run the perturbed network
+    "45_intersections_rand7": dict(dataset="45_intersections", run=400, seed=0, randomize=7),
+    "nine_intersections_rand3": dict(dataset="nine_intersections", run=300, seed=0, randomize=3),
+    "delft_rand11": dict(dataset="delft", run=80, seed=0, randomize=11),
 }
 
 # parameters of reference examples/long_corridor.py:25-63 (scenario 1), restated as data
@@ -67,7 +72,12 @@ def build_reference_network(case):
         import logging
         net.logger.setLevel(logging.ERROR)
         return net
-    net, _ = rh.create_network(case["dataset"], steps_override=case.get("steps_override"))
+    net, gen = rh.create_network(case["dataset"], steps_override=case.get("steps_override"))
+    if case.get("randomize") is not None:
+        import logging
+        net = gen.randomize_network(case["dataset"], seed=case["randomize"])
+        if net.logger is not None:
+            net.logger.setLevel(logging.ERROR)
     return net
 
 
@@ -84,7 +94,9 @@ def generate(name):
     out = {"steps_run": np.int64(case["run"]), "seed": np.int64(case["seed"]),
            "sim_steps": np.int64(net.simulation_steps), "n_links": np.int64(L),
            "link_keys": arrays["link_keys"], "sample_links": np.asarray(keep, dtype=np.int64),
-           "reference_seconds": np.float64(wall)}
+           "reference_seconds": np.float64(wall),
+           "origin_nodes": np.asarray(net.origin_nodes, dtype=np.int64),
+           "destination_nodes": np.asarray(net.destination_nodes, dtype=np.int64)}
     for f in rh.LINK_FIELDS:
         out["rows_" + f] = row_digests(arrays[f])
         out["sample_" + f] = arrays[f][:, keep]

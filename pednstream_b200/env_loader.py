@@ -94,6 +94,135 @@ class NetworkEnvGenerator:
             verbose=verbose, **engine_kw)
         return self.network
 
-    def randomize_network(self, *a, **k):
-        raise NotImplementedError("per-episode domain randomisation is not part of the accelerated "
-                                  "path (SURVEY.md section 8f.1)")
+    # ------------------------------------------------------------------ domain randomisation
+    # (reference env_loader.py:160-424).  The four generators consume the
+    # global numpy stream in the reference's order, each re-seeding it with `seed` when one is given,
+    # so the same seed yields the same scenario -- and, after it, the same trajectory.
+    def randomize_network(self, yaml_file_path: str, seed: int = None, randomize_params: dict = None,
+                          verbose: bool = True, **engine_kw):
+        """A perturbed copy of the scenario: OD nodes, link bottlenecks, OD weights, demand patterns
+        (env_loader.py:160-181).  Like the reference it needs a network created before (controller
+        nodes are read from it).  `verbose`/engine keywords are additions of this implementation."""
+        self.generate_random_od_nodes(seed)
+        link_params = self.generate_random_link_params(seed)
+        od_flows = self.generate_random_od_flows(seed)
+        demand_params = self.generate_random_demand_params(seed)
+        return self.create_network(yaml_file_path, od_flows=od_flows, link_params_overrides=link_params,
+                                   demand_params_overrides=demand_params, verbose=verbose, **engine_kw)
+
+    def generate_random_demand_params(self, seed: int = None) -> dict:
+        """Per origin: a pattern, a base rate in [2, 10) and a peak rate in [10, 30), at least 5 above
+        the base (env_loader.py:183-221).  The seed travels with the parameters."""
+        if seed is not None:
+            np.random.seed(seed)
+        patterns = ["gaussian_peaks", "constant", "sudden_demand"]
+        out = {}
+        for origin in self.config.get("origin_nodes", []):
+            pattern = np.random.choice(patterns)
+            base = np.random.uniform(2.0, 10.0)
+            peak = max(np.random.uniform(10.0, 30.0), base + 5)
+            out[f"origin_{origin}"] = {"pattern": pattern, "base_lambda": float(base),
+                                       "peak_lambda": float(peak), "seed": seed}
+        return out
+
+    def generate_random_od_flows(self, seed: int = None) -> dict:
+        """One weight in [1, 10) per (origin, destination) pair, constant over the episode
+        (env_loader.py:223-258)."""
+        if seed is not None:
+            np.random.seed(seed)
+        steps = self.config["params"]["simulation_steps"]
+        out = {}
+        for o in self.config.get("origin_nodes", []):
+            for d in self.config.get("destination_nodes", []):
+                if o != d:
+                    out[(o, d)] = np.full(steps + 1, np.random.uniform(1.0, 10.0))
+        return out
+
+    def _within_two_hops(self, nodes) -> list:
+        """Neighbours and neighbours of neighbours, in the iteration order of a Python set (the
+        candidate order matters: np.random.choice indexes into it; env_loader.py:283-298)."""
+        adj = self.network_data["adjacency_matrix"]
+        near = set()
+        for n in nodes:
+            near.update(np.where(adj[n, :] == 1)[0].tolist())
+        second = set()
+        for n in near:
+            second.update(np.where(adj[n, :] == 1)[0].tolist())
+        near.update(second)
+        return list(near)
+
+    def generate_random_od_nodes(self, seed: int = None) -> dict:
+        """Add / remove / swap origins and add / remove destinations near the configured ones; controller
+        nodes never become origins or destinations (env_loader.py:260-359).  Updates the configuration."""
+        if seed is not None:
+            np.random.seed(seed)
+        rnd = np.random
+        controllers = self.network.controller_nodes
+        origins = self.config.get("origin_nodes", []).copy()
+        dests = self.config.get("destination_nodes", []).copy()
+
+        if rnd.random() < 0.5:                                                   # add an origin
+            cand = [n for n in self._within_two_hops(origins) if n not in origins and n not in controllers]
+            if cand:
+                k = rnd.randint(1, min(2, len(cand) + 1))
+                origins.extend(int(x) for x in rnd.choice(cand, k, replace=False))
+        if len(origins) > 1 and rnd.random() < 0.5:                              # remove one, keep >= 1
+            k = rnd.randint(1, min(2, len(origins)))
+            drop = rnd.choice(len(origins), k, replace=False)
+            origins = [o for i, o in enumerate(origins) if i not in drop]
+        if rnd.random() < 0.5:                                                   # move one to a neighbour
+            victim = rnd.choice(origins)
+            cand = [n for n in self._within_two_hops([victim]) if n not in origins and n not in controllers]
+            if cand:
+                origins[origins.index(victim)] = int(rnd.choice(cand))
+
+        if rnd.random() < 0.5:                                                   # add destinations
+            cand = [n for n in self._within_two_hops(dests) if n not in dests and n not in controllers]
+            if cand:
+                k = rnd.randint(1, min(3, len(cand) + 1))
+                dests.extend(int(x) for x in rnd.choice(cand, k, replace=False))
+        if len(dests) > len(origins) and rnd.random() < 0.5:                     # remove destinations
+            removable = [d for d in dests if d not in origins]
+            if removable:
+                k = rnd.randint(1, min(2, len(removable) + 1))
+                gone = [int(x) for x in rnd.choice(removable, k, replace=False)]
+                dests = [d for d in dests if d not in gone]
+
+        origins, dests = [int(x) for x in origins], [int(x) for x in dests]
+        self.config["origin_nodes"], self.config["destination_nodes"] = origins, dests
+        return {"origin_nodes": origins, "destination_nodes": dests}
+
+    def generate_random_link_params(self, seed: int = None) -> dict:
+        """Local incidents on 20 % of the corridors: a capacity factor in [0.6, 1.2) on k_critical / k_jam
+        and/or a free-flow speed factor in [0.6, 0.9), each with probability 1/2
+        (env_loader.py:363-424).  Only the u < v direction of a corridor is listed."""
+        if seed is not None:
+            np.random.seed(seed)
+        rnd = np.random
+        fallback = self.data_dir.name if self.data_dir.name != "data" else "delft"
+        if not self.network_data:
+            self.network_data = self.load_network_data(fallback)
+        if not self.config:
+            self.config = load_config(os.path.join(self.data_dir, fallback, "sim_params.yaml"))
+        if self.network_data.get("edge_distances"):
+            corridors = [f"{u}_{v}" for (u, v) in self.network_data["edge_distances"].keys() if u < v]
+        else:
+            rows, cols = np.where(self.network_data["adjacency_matrix"] == 1)
+            corridors = [f"{u}_{v}" for u, v in zip(rows, cols) if u < v]
+        params = self.config["params"]
+        defaults = params["default_link"]
+        out = {}
+        n_change = int(len(corridors) * 0.2)
+        if n_change > 0:
+            for link_id in rnd.choice(corridors, n_change, replace=False):
+                have = params["links"].get(link_id, {})
+                over = {}
+                if rnd.random() < 0.5:
+                    f = rnd.uniform(0.6, 1.2)
+                    over["k_critical"] = max(0.5, have.get("k_critical", defaults["k_critical"]) * f)
+                    over["k_jam"] = max(over["k_critical"] * 2.0, have.get("k_jam", defaults["k_jam"]) * f)
+                if rnd.random() < 0.5:
+                    over["free_flow_speed"] = have.get("free_flow_speed", defaults["free_flow_speed"]) * rnd.uniform(0.6, 0.9)
+                if over:
+                    out[link_id] = over
+        return out

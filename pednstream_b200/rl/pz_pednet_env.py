@@ -93,8 +93,13 @@ class PedNetParallelEnv(_Base):
     # ------------------------------------------------------------------ episode control
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None) -> Tuple[Dict, Dict]:
         if options and options.get("randomize", False):
-            raise NotImplementedError("randomized resets are outside the accelerated path (SURVEY 8f.1)")
-        self.network = self.env_generator.create_network(self.dataset, verbose=self.verbose, **self._engine_kw)
+            # the reference passes `verbose=` to a randomize_network that does not take it and raises
+            # TypeError (pz_pednet_env.py:163-165); this is the evident intent of that branch
+            self.network = self.env_generator.randomize_network(self.dataset, seed=None, verbose=self.verbose,
+                                                                **self._engine_kw)
+        else:
+            self.network = self.env_generator.create_network(self.dataset, verbose=self.verbose,
+                                                             **self._engine_kw)
         self._bind_network()
         self.sim_step = 1
         self._cumulative_rewards = {a: 0.0 for a in self.possible_agents}

@@ -76,4 +76,7 @@ def make_network(case, **kw):
     if c.get("steps_override"):
         g.network_data = g.load_network_data(c["dataset"])
         g.config["params"]["simulation_steps"] = c["steps_override"]
-    return g.create_network(c["dataset"], verbose=False, **kw)
+    net = g.create_network(c["dataset"], verbose=False, **({} if c.get("randomize") is not None else kw))
+    if c.get("randomize") is not None:
+        net = g.randomize_network(c["dataset"], seed=c["randomize"], verbose=False, **kw)
+    return net

@@ -68,6 +68,29 @@ def test_env_api_surface(emu_lib):
         PedNetParallelEnv("nine_intersections", obs_mode="bogus", _lib=emu_lib, _emulation=True)
 
 
+def test_env_randomized_reset(emu_lib):
+    """reset(options={'randomize': True}) (pz_pednet_env.py:163-165) builds a perturbed scenario through
+    randomize_network; with the numpy stream seeded the same way it is reproducible, and it differs from
+    the plain scenario."""
+    def episode(randomize, steps=25):
+        env = PedNetParallelEnv("45_intersections", obs_mode="option3", seed=4, _lib=emu_lib, _emulation=True)
+        np.random.seed(77)
+        obs, _ = env.reset(options={"randomize": randomize})
+        agents = env.possible_agents
+        for _ in range(steps):
+            obs, rew, *_ = env.step({a: np.full(env.action_space(a).shape, 2.0, dtype=np.float32) for a in agents})
+        return env, np.concatenate([obs[a] for a in agents])
+    a, oa = episode(True)
+    b, ob = episode(True)
+    c, oc = episode(False)
+    assert np.array_equal(oa, ob)
+    assert a.network.origin_nodes == b.network.origin_nodes
+    changed = [k for k in a.network.links if a.network.links[k].k_jam != c.network.links[k].k_jam
+               or a.network.links[k].free_flow_speed != c.network.links[k].free_flow_speed]
+    assert changed, "randomisation must perturb some links"
+    assert not np.array_equal(oa, oc)
+
+
 # ---------------------------------------------------------------------------------- batched
 def _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, lib=None, emulation=False, device=None):
     """Replica r of the batched environment must equal a single-network facade run that uses the

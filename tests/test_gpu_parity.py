@@ -30,7 +30,10 @@ def run_numpy_mode(case, steps):
                                          ("nine_intersections", 499), ("45_intersections", 699),
                                          ("butterfly_scA", 599), ("small_network", 499),
                                          ("one_intersection_v0", 599), ("od_flow_example", 499),
-                                         ("delft", 120), ("melbourne_2000", 1999)])
+                                         ("delft", 120), ("melbourne_2000", 1999),
+                                         # randomised scenarios (randomize_network, env_loader.py:160-424)
+                                         ("45_intersections_rand7", 400), ("nine_intersections_rand3", 300),
+                                         ("delft_rand11", 80)])
 def test_cuda_numpy_mode_matches_reference_fixture(case, steps):
     gold = load_golden(case)
     net = run_numpy_mode(case, steps)
