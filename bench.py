@@ -46,6 +46,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this build
+    (profiles/r1_final_traffic.json; measured offline -- never under this run), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        return rec[{"link_pair": "k_link_lane", "node_flows": "k_node_flows"}[kernel]]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -339,7 +349,8 @@ def run_ours(args):
             "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_link_lane" if dom == "link_pair" else "k_" + dom, "achieved": dom_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": dom_gbs / peak, "traffic": measured_traffic(dom),
+                         "peak_source": peak_src,
                          "alg_bytes_per_link_step": B_ALG_PASS[dom],
                          "kernel_ms": {k: v for k, v in per_kernel.items() if v},
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak, "alg_bytes_per_link_step": B_ALG}},
