@@ -1404,6 +1404,24 @@ StepSizes sizes_of(const pns_net* net) {
 }
 
 constexpr size_t kMetricRow = (size_t)PNS_METRIC_SLOTS * PNS_METRIC_STRIDE;   // doubles per step in the metric buffers
+#ifndef PNS_HOST_EMULATION
+// copy stream + event ring of pns_step_streamed (per device; a re-recorded event does not disturb
+// waits that were enqueued on its earlier record)
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ring[256];
+    int dev = -1, next = 0;
+    void ensure() {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (stream && d == dev) return;
+        dev = d;
+        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        for (auto& e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    cudaEvent_t event() { next = (next + 1) & 255; return ring[next]; }
+};
+#endif
 struct Streamed {           // per-step host traffic of pns_step_streamed
     const double* host_demand;   // pinned [rows][n_demand_rows*R]
     double* dev_metric;          // [n_steps][PNS_METRIC_SLOTS * PNS_METRIC_STRIDE]
@@ -1417,7 +1435,14 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     if (check_step_io(net, io, rng_mode)) return 1;
     const StepSizes z = sizes_of(net);
 #ifndef PNS_HOST_EMULATION
-    if (sx) cudaMemsetAsync(sx->dev_metric, 0, (size_t)n_steps * kMetricRow * sizeof(double), s);
+    static SideStream side;
+    if (sx) {
+        cudaMemsetAsync(sx->dev_metric, 0, (size_t)n_steps * kMetricRow * sizeof(double), s);
+        side.ensure();
+        cudaEvent_t e = side.event();                  // the side stream starts after everything queued so far
+        cudaEventRecord(e, s);
+        cudaStreamWaitEvent(side.stream, e, 0);
+    }
     cudaEvent_t* ev = nullptr;
     const int per_step = 4;   // before pair | after pair | after route | after node
     if (ms) {
@@ -1438,6 +1463,19 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         const bool lane_metric = sx && k > 0 && net->replicas == 1 && !getenv("PNS_PAIR_THREADS");
         if (lane_metric) cp.metric = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
 #endif
+#ifndef PNS_HOST_EMULATION
+        // Host traffic of streamed runs rides on a second stream, tied to the kernel chain by events, so
+        // that no copy sits between two kernels of the chain (a copy there costs its own latency and the
+        // programmatic overlap of the launches around it).
+        cudaEvent_t demand_ready = nullptr;
+        if (sx && k < n_steps && net->n_demand_rows) {   // input of step t0+k: its demand row, from pinned host memory
+            const size_t row = (size_t)net->n_demand_rows * net->replicas, off = (size_t)(t0 + k - 1) * row;
+            cudaMemcpyAsync(const_cast<double*>(io->demand) + off, sx->host_demand + off, row * sizeof(double),
+                            cudaMemcpyHostToDevice, side.stream);      // queued ahead of the link pass: not behind the
+            demand_ready = side.event();                               // result copy that waits for it
+            cudaEventRecord(demand_ready, side.stream);
+        }
+#endif
         PNS_MARK(k, 0);
         if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
@@ -1445,14 +1483,13 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         if (sx && k > 0) {          // result of step t0+k-1: partial sums reduced on the device, copied to the host every step
             double* row = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
             if (!lane_metric) k_metric_pedestrians<<<148 * 4, 256, 0, s>>>(cp, row);
+            cudaEvent_t e = side.event();
+            cudaEventRecord(e, s);
+            cudaStreamWaitEvent(side.stream, e, 0);
             cudaMemcpyAsync(sx->host_metric + (size_t)(k - 1) * kMetricRow, row, kMetricRow * sizeof(double),
-                            cudaMemcpyDeviceToHost, s);
+                            cudaMemcpyDeviceToHost, side.stream);
         }
-        if (sx && k < n_steps && net->n_demand_rows) {   // input of step t0+k: its demand row, from pinned host memory
-            const size_t row = (size_t)net->n_demand_rows * net->replicas, off = (size_t)(t0 + k - 1) * row;
-            cudaMemcpyAsync(const_cast<double*>(io->demand) + off, sx->host_demand + off, row * sizeof(double),
-                            cudaMemcpyHostToDevice, s);
-        }
+        if (demand_ready) cudaStreamWaitEvent(s, demand_ready, 0);     // the node pass of this step reads the row
 #endif
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
@@ -1463,6 +1500,11 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     }
 #undef PNS_MARK
 #ifndef PNS_HOST_EMULATION
+    if (sx) {                                          // the caller synchronises `s` only
+        cudaEvent_t e = side.event();
+        cudaEventRecord(e, side.stream);
+        cudaStreamWaitEvent(s, e, 0);
+    }
     if (ev) {
         const cudaError_t err = cudaStreamSynchronize(s);
         for (int k = 0; k <= n_steps && err == cudaSuccess; ++k) {
