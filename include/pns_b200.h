@@ -259,6 +259,13 @@ int pns_env_apply_actions(const pns_net *net, const pns_state *st, const pns_env
 int pns_env_observe(const pns_net *net, const pns_state *st, const pns_env *env, int t, float *obs,
                     float *reward, void *stream);
 
+/* One environment step (rl/pz_pednet_env.py:194-254 with action_gap 1) in one call: apply the actions (skipped when
+ * `actions` is NULL), Network.network_loading(t), build observations and the reward; `cum_reward` (optional, [R])
+ * accumulates the rewards.  Same launches as pns_env_apply_actions + pns_step + pns_env_observe. */
+int pns_env_step(const pns_net *net, const pns_state *st, const pns_step_io *io, const pns_env *env,
+                 const float *actions, int t, int rng_mode, float *obs, float *reward, float *cum_reward,
+                 void *stream);
+
 /* Links per CTA of the single-replica link kernel (the granularity of pns_net.lane_order). */
 int pns_lane_block_size(void);
 

@@ -70,8 +70,9 @@ OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens"
            "speed": 6, "gate": 7}
 
 
-EXPORTS = ("pns_abi_version", "pns_lane_block_size", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
-           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_rng_selftest")
+EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
+           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_env_step",
+           "pns_lane_block_size", "pns_rng_selftest")
 
 _LIB = None
 
@@ -90,6 +91,7 @@ def _declare(lib):
     lib.pns_step_streamed.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p]
     env_p = C.POINTER(PnsEnv)
     lib.pns_env_apply_actions.argtypes = [net_p, st_p, env_p, _p, _p]
+    lib.pns_env_step.argtypes = [net_p, st_p, io_p, env_p, _p, C.c_int, C.c_int, _p, _p, _p, _p]
     lib.pns_env_observe.argtypes = [net_p, st_p, env_p, C.c_int, _p, _p, _p]
     lib.pns_rng_selftest.argtypes = [C.c_int, C.c_int, _p, _p, C.c_uint64, C.c_int, C.c_int, _p, _p, _p]
     for name in EXPORTS[2:]:

@@ -1105,6 +1105,7 @@ struct EnvCtx {
     const float* actions;
     float* obs;
     float* reward;
+    float* cum_reward;      // optional running sum of the rewards (null: not kept)
 };
 
 // ActionApplier.clip_gater_action_value / clip_separator_action_value + setters
@@ -1193,6 +1194,7 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
         total = total - 10.0f * (d / (float)n);
     }
     x.reward[rep] = total;
+    if (x.cum_reward) x.cum_reward[rep] = x.cum_reward[rep] + total;
 }
 
 // =================================================================================================
@@ -1605,7 +1607,7 @@ int pns_env_apply_actions(const pns_net* net, const pns_state* st, const pns_env
     if (n == 0) return 0;
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
-    x.env = *env; x.actions = actions; x.obs = nullptr; x.reward = nullptr;
+    x.env = *env; x.actions = actions; x.obs = nullptr; x.reward = nullptr; x.cum_reward = nullptr;
     PNS_LAUNCH(k_env_actions, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_actions");
 }
@@ -1619,7 +1621,22 @@ int pns_env_observe(const pns_net* net, const pns_state* st, const pns_env* env,
     const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
-    x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward;
+    x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward; x.cum_reward = nullptr;
+    PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    return launched("k_env_observe");
+}
+
+int pns_env_step(const pns_net* net, const pns_state* st, const pns_step_io* io, const pns_env* env,
+                 const float* actions, int t, int rng_mode, float* obs, float* reward, float* cum_reward,
+                 void* stream) {
+    if (!net || !st || !env || !obs || !reward) return fail("pns_env_step: null argument");
+    if (actions && env->n_act > 0 && pns_env_apply_actions(net, st, env, actions, stream)) return 1;
+    if (step_impl(net, st, io, t, 1, rng_mode, (cudaStream_t)stream, nullptr, nullptr)) return 1;
+    if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_step: too many reward links");
+    const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
+    EnvCtx x;
+    x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
+    x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward; x.cum_reward = cum_reward;
     PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_observe");
 }

@@ -187,17 +187,18 @@ class BatchedPedNetEnv:
         eng = self.engine
         if self.sim_step > self.simulation_steps:
             raise RuntimeError("episode finished: call reset()")
+        act_ptr = C.c_void_p(0)
         if actions is not None and self.n_act:
             if actions.shape != (self.R, self.n_act) or actions.dtype != torch.float32:
                 raise ValueError(f"actions must be float32 [{self.R}, {self.n_act}]")
             actions = actions.contiguous()
-            with eng._guard():
-                _native.check(eng.lib, eng.lib.pns_env_apply_actions(
-                    C.byref(eng.net), C.byref(eng.state), C.byref(self._env), _ptr(actions), self._stream()),
-                    "pns_env_apply_actions")
-        eng.run(self.sim_step, 1, _native.RNG_PHILOX)
-        self._observe(self.sim_step)
-        self.cumulative_reward += self.reward
+            act_ptr = _ptr(actions)
+        with eng._guard():      # actions, the LTM step, observations + reward: one native call
+            _native.check(eng.lib, eng.lib.pns_env_step(
+                C.byref(eng.net), C.byref(eng.state), C.byref(eng.io), C.byref(self._env), act_ptr,
+                int(self.sim_step), _native.RNG_PHILOX, _ptr(self.obs), _ptr(self.reward),
+                _ptr(self.cumulative_reward), self._stream()), "pns_env_step")
+        eng.t_done = self.sim_step
         done = self.sim_step >= self.simulation_steps           # tested before the increment (quirk Q8)
         self.sim_step += 1
         return self.obs, self.reward, done, {"step": self.sim_step - 1}
