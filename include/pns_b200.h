@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 5
+#define PNS_ABI_VERSION 6
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -98,7 +98,7 @@ typedef struct pns_net {
     const pns_link_class *classes; /* [n_classes] */
     pns_link_class class0;         /* host copy of classes[0]: single-class networks read parameters from the
                                       kernel-parameter (constant) bank instead of loading the table */
-    const int32_t *lk_class;       /* [n_links] */
+    const int32_t *lk_class;       /* [n_links], or [n_links*replicas] with per_replica_scenario */
     const double *lk_width;        /* [n_links] corridor width `_width` (link.py:53): initial gate / lane widths */
     /* node table -- CSR over link slots (virtual link first, then neighbours by ascending id).
      * The outgoing link of a slot is the reverse of its incoming link: out column = in column ^ 1
@@ -130,6 +130,11 @@ typedef struct pns_net {
      * pns_lane_block_size(). */
     const int32_t *lane_order;
     int32_t lane_order_block, n_lane_blocks;
+    /* per-replica scenarios (domain randomisation, env_loader.py:160-424): when set, lk_class is
+     * [n_links*replicas] (replica fastest) -- every replica has its own parameter class per link -- and
+     * pns_step_io.od_w is [sim_steps+1][n_od*replicas] (replica fastest).  Topology, widths, OD nodes and the
+     * route plan are shared by all replicas. */
+    int32_t per_replica_scenario, pad2_;
 } pns_net;
 
 /* Mutable simulation state; all device pointers, caller-owned. */
@@ -153,7 +158,8 @@ typedef struct pns_state {
 /* Per-call inputs of one or more consecutive steps. */
 typedef struct pns_step_io {
     const double *demand;   /* [>= t][n_demand_rows*R]: row t-1 is node.demand[t-1] (node.py:176) */
-    const double *od_w;     /* [sim_steps+1][n_od]: od_flows[(o,d)][t] (od_manager.py:52-54) */
+    const double *od_w;     /* [sim_steps+1][n_od]: od_flows[(o,d)][t] (od_manager.py:52-54); [..][n_od*replicas] with
+                               pns_net.per_replica_scenario */
     const int32_t *draw_b;  /* TABLE: [rows][3][n_links*R] outcomes of sites R1, R2, R3 */
     const double *draw_n;   /* TABLE: [rows][n_links*R] speed noise (site R4) */
     int64_t draw_row_stride;/* rows advance by one per step when != 0 (0: one row reused) */

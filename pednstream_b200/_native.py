@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 METRIC_SLOTS, METRIC_STRIDE = 64, 4          # PNS_METRIC_SLOTS / PNS_METRIC_STRIDE of pns_step_streamed
 METRIC_ROW = METRIC_SLOTS * METRIC_STRIDE
 
@@ -44,7 +44,8 @@ class PnsNet(C.Structure):
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
                              "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
         + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
-        + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32)]
+        + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32),
+           ("per_replica_scenario", _i32), ("pad2_", _i32)]
     )
 
 

@@ -234,6 +234,10 @@ static inline int4 ld_meta(const int4* a, const L2Pol) { return *a; }
 
 typedef pns_link_class LinkP;
 __device__ __forceinline__ bool is_sep(const LinkP& p) { return p.flags & 1; }
+// parameter class of link l in replica rep (per-replica tables under domain randomisation)
+__device__ __forceinline__ int class_of(const Ctx& c, int l, int rep) {
+    return c.n.per_replica_scenario ? __ldg(c.n.lk_class + (size_t)l * c.n.replicas + rep) : __ldg(c.n.lk_class + l);
+}
 
 // Walkable area (link.py:128-131, 454-456).  For a separator it follows the lane width; `f64`
 // tells whether the reference holds that width as a numpy float64 (assigned from np.clip), in
@@ -462,8 +466,8 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
 
     // networks with a single parameter class (lattices, the shipped 45_intersections) skip the index load
     const bool one_class = c.n.n_classes == 1;
-    const LinkP* const pp[2] = {c.n.classes + (one_class ? 0 : __ldg(c.n.lk_class + l0)),
-                                c.n.classes + (one_class ? 0 : __ldg(c.n.lk_class + l0 + 1))};
+    const LinkP* const pp[2] = {c.n.classes + (one_class ? 0 : class_of(c, l0, rep)),
+                                c.n.classes + (one_class ? 0 : class_of(c, l0 + 1, rep))};
     double gate[2];
     V::ld(c.s.gate, e[0], e[1], gate);
     // ---- batch of independent loads --------------------------------------------------------
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
         const int l = c.n.rt_opt_link[o0 + k];
         sum_d = k == 0 ? c.n.rt_opt_dist[o0] : sum_d + c.n.rt_opt_dist[o0 + k];
         if (l >= 0) {
-            const LinkP& p = c.n.classes[c.n.lk_class[l]];
+            const LinkP& p = c.n.classes[class_of(c, l, rep)];
             const size_t e = (size_t)l * R + rep;
             const double gate = c.s.gate[e];
             if (is_sep(p)) {
@@ -687,19 +691,21 @@ __device__ __noinline__ void routed_fractions(const Ctx& c, int routed, int m, i
     const int R = c.n.replicas;
     const int row0 = c.n.rt_routed_row0[routed];
     const int edge0 = c.n.rt_routed_edge0[routed];
-    const double* w = c.io.od_w + (size_t)t * c.n.n_od;
+    // od weights of this step; one set per replica under domain randomisation
+    const size_t ws = c.n.per_replica_scenario ? (size_t)R : 1;
+    const double* w = c.io.od_w + (size_t)t * c.n.n_od * ws + (c.n.per_replica_scenario ? rep : 0);
     int k = 0;
     for (int i = 0; i < m; ++i) {
         const int ra = c.n.rt_row_ptr[row0 + i], rb = c.n.rt_row_ptr[row0 + i + 1];
         double total = 0.0;
-        for (int x = ra; x < rb; ++x) total = total + w[c.n.rt_row_od[x]];
+        for (int x = ra; x < rb; ++x) total = total + w[(size_t)c.n.rt_row_od[x] * ws];
         const double uniform = rb > ra ? 1.0 / (double)(rb - ra) : 0.0;
         double row_sum = 0.0;
         for (int j = 0; j < m - 1; ++j, ++k) {
             const int ta = c.n.rt_term_ptr[edge0 + k], tb = c.n.rt_term_ptr[edge0 + k + 1];
             double acc = 0.0;
             for (int x = ta; x < tb; ++x) {
-                const double od_p = total > 0.0 ? w[c.n.rt_row_od[c.n.rt_term_row_entry[x]]] / total : uniform;
+                const double od_p = total > 0.0 ? w[(size_t)c.n.rt_row_od[c.n.rt_term_row_entry[x]] * ws] / total : uniform;
                 acc = acc + c.s.probs[(size_t)c.n.rt_term_opt[x] * R + rep] * od_p;
             }
             out[(size_t)k * R] = acc;
@@ -911,7 +917,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     const int tau = c.t_flows - 1;
     PNS_PDL_TRIGGER();
     // single-class networks: parameters are kernel-parameter constants, no table loads at all
-    const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[__ldg(c.n.lk_class + l)];
+    const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[class_of(c, l, 0)];
     const L2Pol pol = l2_policies();
     const int2 slots = PNS_L2_STAGE >= 1 ? ldh_nc(reinterpret_cast<const int2*>(c.n.lk_slots) + l, pol.keep)
                                          : __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);   // {sending slot, receiving slot}
@@ -1137,7 +1143,7 @@ __global__ void __launch_bounds__(kBlock) k_env_actions(const __grid_constant__ 
 
 __device__ __forceinline__ float shared_density(const Ctx& c, int l, int rep, int t) {
     const int R = c.n.replicas;
-    const LinkP& p = c.n.classes[c.n.lk_class[l]];
+    const LinkP& p = c.n.classes[class_of(c, l, rep)];
     const size_t e = (size_t)l * R + rep;
     if (is_sep(p)) return H32(c, PNS_F32_DENSITY, t)[e];
     const float* num = H32(c, PNS_F32_NUM_PED, t);
@@ -1162,7 +1168,7 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
             case PNS_OBS_REV_INFLOW: v = (float)H64(c, PNS_F64_INFLOW, t)[er]; break;
             case PNS_OBS_REV_OUTFLOW: v = (float)H64(c, PNS_F64_OUTFLOW, t)[er]; break;
             case PNS_OBS_SHARED_DENSITY: v = shared_density(c, l, rep, t); break;
-            case PNS_OBS_SHARED_DENSITY_OVER_KJ: v = shared_density(c, l, rep, t) / c.n.classes[c.n.lk_class[l]].kj32; break;
+            case PNS_OBS_SHARED_DENSITY_OVER_KJ: v = shared_density(c, l, rep, t) / c.n.classes[class_of(c, l, rep)].kj32; break;
             case PNS_OBS_SPEED: v = H32(c, PNS_F32_SPEED, t)[e]; break;
             default: v = (float)c.s.gate[e]; break;
         }
@@ -1183,7 +1189,7 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
         rho[i] = shared_density(c, l, rep, t);
         const float* tt = H32(c, PNS_F32_TRAVEL_TIME, t);
         total = total - (tt[e] + tt[er]);
-        if (rho[i] > 4.0f) total = total - 10.0f * (rho[i] - c.n.classes[c.n.lk_class[l]].kc32);
+        if (rho[i] > 4.0f) total = total - 10.0f * (rho[i] - c.n.classes[class_of(c, l, rep)].kc32);
     }
     if (n > 1) {
         float s = rho[0];
@@ -1210,7 +1216,7 @@ __global__ void k_state_init(const __grid_constant__ Ctx c) {
         const size_t e = i % n64;
         const bool physical = e < n32;
         const int l = physical ? (int)(e / R) : 0;
-        const LinkP* p = physical ? c.n.classes + c.n.lk_class[l] : nullptr;
+        const LinkP* p = physical ? c.n.classes + class_of(c, l, (int)(e % R)) : nullptr;
         for (int f = 0; f < c.s.n_f64; ++f) {
             double v = 0.0;
             if (f == PNS_F64_SENDING || f == PNS_F64_RECEIVING) v = -1.0;

@@ -136,6 +136,7 @@ class Engine:
         io.seed = self.seed
         self.io = io
         self._table_io = None
+        self._od_per_replica = False
 
         self.handle = ops.register_engine(self)
         self.t_done = 0
@@ -178,11 +179,43 @@ class Engine:
             self.set_static_fractions(tf_static, tf_supplied)
             if demand is not None:
                 self.set_demand(demand)
-            if od_w is not None and od_w.size:
+            if od_w is not None and od_w.size and not self._od_per_replica:
                 self.od_w[: od_w.shape[0], : od_w.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(od_w)))
             ops.ltm_state_init(self.hist64, self.hist32, self.runsum, self.err, self.handle)
         self.t_done = 0
         self._initialised = True
+
+    def set_replica_scenarios(self, classes: np.ndarray, lk_class: np.ndarray, od_w: np.ndarray = None):
+        """Per-replica scenarios (domain randomisation): `classes` a table of pns_link_class records
+        (plan.CLASS_DTYPE), `lk_class` [L, R] the class of every link in every replica, `od_w`
+        [S+1, n_od, R] the OD weights of every replica (None: shared weights stay).  Call before
+        `initialise` (initial travel times come from the classes)."""
+        lk_class = np.ascontiguousarray(lk_class, dtype=np.int32)
+        if lk_class.shape != (self.L, self.R):
+            raise ValueError(f"lk_class must be [{self.L}, {self.R}]")
+        if lk_class.min() < 0 or lk_class.max() >= len(classes):
+            raise ValueError("lk_class refers to a class outside the table")
+        dev = self.device
+        cls_bytes = np.ascontiguousarray(classes).view(np.uint8).reshape(-1)
+        self._net_t["classes"] = torch.from_numpy(cls_bytes.copy()).to(dev)
+        self._net_t["lk_class"] = torch.from_numpy(lk_class.reshape(-1)).to(dev)
+        net = self.net
+        net.classes, net.lk_class = _ptr(self._net_t["classes"]), _ptr(self._net_t["lk_class"])
+        net.n_classes = len(classes)
+        C.memmove(C.byref(net.class0), np.ascontiguousarray(classes[:1]).ctypes.data, C.sizeof(net.class0))
+        net.per_replica_scenario = 1
+        n_od = int(self.plan["n_od"])
+        if od_w is not None and n_od:
+            od_w = np.ascontiguousarray(od_w, dtype=np.float64)
+            if od_w.shape != (self.S + 1, n_od, self.R):
+                raise ValueError(f"od_w must be [{self.S + 1}, {n_od}, {self.R}]")
+            self.od_w = torch.from_numpy(od_w.reshape(self.S + 1, -1)).to(dev)
+        elif n_od and not self._od_per_replica:
+            self.od_w = self.od_w.repeat_interleave(self.R, dim=1).contiguous()   # shared weights, per-replica layout
+        self._od_per_replica = True
+        self.io.od_w = _ptr(self.od_w)
+        if self._table_io is not None:
+            self._table_io.od_w = _ptr(self.od_w)
 
     def set_gate(self, gate, sep_np64=None):
         g = torch.from_numpy(np.ascontiguousarray(gate, dtype=np.float64).reshape(-1))

@@ -66,22 +66,12 @@ class NetworkEnvGenerator:
         defaults = params["default_link"]
 
         links_cfg = params.setdefault("links", {})
-        for link_id, over in (link_params_overrides or {}).items():
-            links_cfg.setdefault(link_id, {}).update(over)
+        self._merge_link_config(links_cfg, defaults, link_params_overrides)
         if od_flows:
             self.config["od_flows"] = od_flows
         demand_cfg = params.setdefault("demand", {}) if demand_params_overrides else params.get("demand")
         for key, over in (demand_params_overrides or {}).items():
             demand_cfg.setdefault(key, {}).update(over)
-
-        # measured edge lengths: the (u, v) entry fixes the length of u_v, and of v_u unless that
-        # direction already has its own block (env_loader.py:126-144)
-        for (u, v), dist in (self.network_data["edge_distances"] or {}).items():
-            merged = dict(defaults)
-            merged.update(links_cfg.get(f"{u}_{v}", {}))
-            merged["length"] = dist
-            links_cfg[f"{u}_{v}"] = merged
-            links_cfg.setdefault(f"{v}_{u}", merged)
 
         self.network = Network(
             adjacency_matrix=self.network_data["adjacency_matrix"],
@@ -93,6 +83,38 @@ class NetworkEnvGenerator:
             pos=self.network_data.get("node_positions"),
             verbose=verbose, **engine_kw)
         return self.network
+
+    def _merge_link_config(self, links_cfg: dict, defaults: dict, overrides: dict = None):
+        """Per-link blocks as create_network leaves them (env_loader.py:93-144), in place: overrides are
+        merged into the blocks, then every measured edge (u, v) fixes the length of u_v, and of v_u
+        unless that direction already has a block of its own.  Note that u_v and v_u may be the same
+        dict object after this (and stay so across calls), exactly as in the reference."""
+        for link_id, over in (overrides or {}).items():
+            links_cfg.setdefault(link_id, {}).update(over)
+        for (u, v), dist in (self.network_data["edge_distances"] or {}).items():
+            merged = dict(defaults)
+            merged.update(links_cfg.get(f"{u}_{v}", {}))
+            merged["length"] = dist
+            links_cfg[f"{u}_{v}"] = merged
+            links_cfg.setdefault(f"{v}_{u}", merged)
+        return links_cfg
+
+    def scenario_link_params(self, link_params_overrides: dict = None) -> dict:
+        """Parameters every corridor would get from `create_network(..., link_params_overrides=...)`,
+        without building a network and without touching the configuration: {(i, j): kwargs} for i < j
+        (both directions of a corridor share them, network.py link construction).  Used to build
+        per-replica parameter tables for the batched environment."""
+        import copy
+        params = self.config["params"]
+        defaults = params["default_link"]
+        cfg = self._merge_link_config(copy.deepcopy(params.get("links", {})), defaults, link_params_overrides)
+        adj = np.asarray(self.network_data["adjacency_matrix"])
+        out = {}
+        for i, j in zip(*np.nonzero(np.triu(adj == 1, 1))):
+            i, j = int(i), int(j)
+            block = cfg.get(f"{i}_{j}", cfg.get(f"{j}_{i}"))
+            out[(i, j)] = {**defaults, **block} if block is not None else dict(defaults)
+        return out
 
     # ------------------------------------------------------------------ domain randomisation
     # (reference env_loader.py:160-424; SURVEY.md section 8f.1).  The four generators consume the

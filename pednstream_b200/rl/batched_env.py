@@ -13,6 +13,14 @@ Tensors: `actions [R, n_act] float32` (agents concatenated in `possible_agents` 
 GPUs by the caller (`replica_base` is the global index of local replica 0); no collective is
 needed inside a step.  Demand is pre-drawn on the host per replica (`np.random.RandomState(seed +
 replica)`), Poisson around the scenario's gaussian peaks (od_manager.py:145-155).
+
+`randomize=True`: every replica and episode gets its own perturbed scenario from the
+reference's generators (env_loader.py:183-258, 363-424) -- link bottlenecks (k_critical / k_jam /
+free-flow speed of 20 % of the corridors), OD weights and demand patterns -- as per-replica parameter
+classes, OD weights and demand on the device.  OD *nodes* are not perturbed (they would need one route
+plan per replica).  Replica r equals a single-network facade built with
+`create_network(dataset, od_flows=, link_params_overrides=, demand_params_overrides=)` from
+`scenario(r)`.
 """
 from __future__ import annotations
 
@@ -43,7 +51,7 @@ def _gater_divisors(obs_mode, k):
 
 class BatchedPedNetEnv:
     def __init__(self, dataset: str, replicas: int, obs_mode: str = "option3", normalize_obs: bool = False,
-                 seed: int = 0, replica_base: int = 0, device=None, data_dir="data",
+                 seed: int = 0, replica_base: int = 0, device=None, data_dir="data", randomize: bool = False,
                  _lib=None, _emulation: bool = False):
         if obs_mode not in OBS_LAYOUT:
             raise ValueError(f"obs_mode must be one of {list(OBS_LAYOUT)}, got: {obs_mode}")
@@ -51,8 +59,11 @@ class BatchedPedNetEnv:
         self.replica_base = int(replica_base)
         state = np.random.get_state()                 # building the template must not disturb the caller's stream
         np.random.seed(self.seed)
-        self.network = NetworkEnvGenerator(data_dir).create_network(dataset, verbose=False)
+        self.generator = NetworkEnvGenerator(data_dir)
+        self.network = self.generator.create_network(dataset, verbose=False)
         np.random.set_state(state)
+        self.randomize = bool(randomize)
+        self._scenarios = None
         net = self.network
         self.simulation_steps = S = net.simulation_steps
         self.agent_manager = am = AgentManager(net)
@@ -124,6 +135,59 @@ class BatchedPedNetEnv:
         self.sim_step = 1
         self.reset()
 
+    # ------------------------------------------------------------------ per-replica scenarios
+    def scenario_seed(self, replica: int, episode: int) -> int:
+        return (self.seed + 7919 * (self.replica_base + replica) + 104729 * episode + 1) % (2 ** 32)
+
+    def scenario(self, replica: int, episode: int = None) -> dict:
+        """The overrides of local replica `replica` in `episode` (default: the current one), as the
+        reference's generators produce them for `scenario_seed(replica, episode)`."""
+        episode = self.episode - 1 if episode is None else episode
+        gen, s = self.generator, self.scenario_seed(replica, episode)
+        state = np.random.get_state()
+        try:
+            out = {"link_params_overrides": gen.generate_random_link_params(s),
+                   "od_flows": gen.generate_random_od_flows(s),
+                   "demand_params_overrides": gen.generate_random_demand_params(s)}
+        finally:
+            np.random.set_state(state)
+        return out
+
+    def _apply_scenarios(self, episode: int):
+        """Builds the class table, the per-replica class indices and OD weights of this episode and hands
+        them to the engine; keeps the per-replica demand parameters for `_draw_demand`."""
+        from ..plan import CLASS_DTYPE, class_record
+        net, gen, R = self.network, self.generator, self.R
+        links = list(net.links.values())
+        L = len(links)
+        od_keys = list(net.plan["od_keys"])
+        table, rows = {}, []
+        lk_class = np.zeros((L, R), dtype=np.int32)
+        od_w = np.zeros((self.simulation_steps + 1, len(od_keys), R)) if od_keys else None
+        self._scenarios = []
+        unit_time = net.params["unit_time"]
+        for r in range(R):
+            sc = self.scenario(r, episode)
+            self._scenarios.append(sc["demand_params_overrides"])
+            per_corridor = gen.scenario_link_params(sc["link_params_overrides"])
+            for l in links:
+                u, v = l.start_node.node_id, l.end_node.node_id
+                kw = per_corridor[(min(u, v), max(u, v))]
+                key = (l.length, l._width, kw["free_flow_speed"], kw["k_critical"], kw["k_jam"], l.gamma,
+                       l.activity_probability, l.bi_factor, l.speed_noise_std, l.fd_type, bool(l.is_separator))
+                k = table.get(key)
+                if k is None:
+                    k = table[key] = len(rows)
+                    rows.append(class_record(*key, unit_time))
+                lk_class[l.index, r] = k
+            if od_keys:
+                if set(sc["od_flows"]) != set(od_keys):
+                    raise NotImplementedError("randomised OD weights need the scenario's full origin x destination set")
+                for j, key in enumerate(od_keys):
+                    od_w[:, j, r] = sc["od_flows"][key]
+        classes = np.array(rows, dtype=CLASS_DTYPE).reshape(len(rows))
+        self.engine.set_replica_scenarios(classes, lk_class, od_w)
+
     # ------------------------------------------------------------------ demand
     def _draw_demand(self, episode: int) -> np.ndarray:
         """[S+1, rows * R] demand, replica fastest; replica r uses RandomState(seed + global r) and
@@ -147,7 +211,18 @@ class BatchedPedNetEnv:
             specs[k] = (pattern, lam, cfg.base_lambda)
         for r in range(R):
             rs = np.random.RandomState((self.seed + self.replica_base + r + 1_000_003 * episode) % (2 ** 32))
-            for k, (pattern, lam, base) in specs.items():
+            if self._scenarios is not None:                  # this replica's own demand parameters
+                own = {}
+                for k, node in enumerate(rows):
+                    p = self._scenarios[r].get(f"origin_{node.node_id}")
+                    if k in specs and p is not None:
+                        lam = (p["base_lambda"] + p["peak_lambda"] * np.exp(-(t - S / 4) ** 2 / width)
+                               + p["peak_lambda"] * np.exp(-(t - 3 * S / 4) ** 2 / width))
+                        own[k] = (str(p["pattern"]), lam, p["base_lambda"])
+                replica_specs = {**specs, **own}
+            else:
+                replica_specs = specs
+            for k, (pattern, lam, base) in replica_specs.items():
                 if pattern == "constant":                                  # od_manager.py:106-109
                     out[:, k, r] = base
                     continue
@@ -164,6 +239,8 @@ class BatchedPedNetEnv:
         """Start a new episode in every replica; returns obs [R, n_obs] at step 1 (all zeros + widths)."""
         eng, net = self.engine, self.network
         eng.io.seed = (self.seed + 0x9E3779B97F4A7C15 * self.episode) % (2 ** 64)
+        if self.randomize:
+            self._apply_scenarios(self.episode)
         eng.initialise(net._store.gate, net._store.sep_np64, self._tf, self._draw_demand(self.episode),
                        self._od_w, self._supplied)
         self.sim_step = 1

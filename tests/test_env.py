@@ -134,6 +134,61 @@ def _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, lib=None, emula
             assert np.array_equal(want[: steps + 1], got[: steps + 1]), (f, rep)
 
 
+def _randomized_batched_vs_facade(dataset, steps, R, picks, lib=None, emulation=False, device=None):
+    """randomize=True: replica r must equal the facade network built from `scenario(r)` through
+    create_network's override arguments (what randomize_network does, minus the OD-node perturbation)."""
+    kw = dict(_lib=lib, _emulation=emulation) if emulation else dict(device=device)
+    benv = BatchedPedNetEnv(dataset, replicas=R, obs_mode="option3", seed=5, randomize=True, **kw)
+    dev = benv.device
+    rs = np.random.RandomState(9)
+    acts = rs.uniform(0.0, 4.0, size=(steps, R, benv.n_act)).astype(np.float32)
+    demand = benv.engine.demand.cpu().numpy().reshape(benv.simulation_steps + 1, -1, R)
+    obs_b, rew_b = [benv.obs.cpu().numpy().copy()], []
+    for k in range(steps):
+        o, r, _, _ = benv.step(torch.from_numpy(acts[k]).to(dev))
+        obs_b.append(o.cpu().numpy().copy())
+        rew_b.append(r.cpu().numpy().copy())
+    benv.engine.check_errors()
+    assert benv.engine.net.n_classes > 1 and benv.engine.net.per_replica_scenario == 1
+    for rep in picks:
+        sc = benv.scenario(rep)
+        assert sc["link_params_overrides"], "the scenario must perturb some corridor"
+        fkw = dict(_lib=lib, _emulation=True) if emulation else dict(device=device)
+        env = PedNetParallelEnv(dataset, obs_mode="option3", seed=5, rng="philox", **fkw)
+        env.network = env.env_generator.create_network(dataset, verbose=False, rng="philox", **sc, **fkw)
+        env._bind_network()
+        for row, node in enumerate(env.network.plan["demand_nodes"]):
+            node.demand = demand[:, row, rep].copy()
+        eng = env.network.engine
+        eng.io.seed = benv.engine.io.seed
+        eng.io.replica_base = rep
+        agents = env.possible_agents
+        assert np.array_equal(np.concatenate([env._get_observations()[a] for a in agents]), obs_b[0][rep])
+        for k in range(steps):
+            obs, rew, *_ = env.step({a: acts[k, rep, benv.action_slices[a]] for a in agents})
+            assert np.array_equal(np.concatenate([obs[a] for a in agents]), obs_b[k + 1][rep]), (rep, k)
+            assert np.float32(rew.get(agents[0], 0.0)) == rew_b[k][rep], (rep, k)
+        for f in F64_FIELDS[:7] + F32_FIELDS:
+            want = env.network._store.field(f)
+            got = benv.engine.history(f)[:, :, rep].cpu().numpy()
+            assert np.array_equal(want[: steps + 1], got[: steps + 1]), (f, rep)
+    # replicas differ from each other, and a new episode draws new scenarios
+    a0, a1 = benv.scenario(0), benv.scenario(1)
+    assert a0["link_params_overrides"] != a1["link_params_overrides"]
+    before = benv.scenario(0)
+    benv.reset()
+    assert benv.scenario(0)["link_params_overrides"] != before["link_params_overrides"]
+
+
+def test_batched_env_randomized_scenarios_emulated(emu_lib):
+    _randomized_batched_vs_facade("45_intersections", 60, 3, (0, 2), lib=emu_lib, emulation=True)
+
+
+@pytest.mark.gpu
+def test_batched_env_randomized_scenarios_cuda():
+    _randomized_batched_vs_facade("45_intersections", 150, 48, (0, 17, 47), device="cuda:0")
+
+
 def test_batched_env_matches_facade_emulated(emu_lib):
     _batched_vs_facade("nine_intersections", "option3", False, 40, 3, (0, 2), lib=emu_lib, emulation=True)
 
