@@ -272,6 +272,25 @@ int pns_env_step(const pns_net *net, const pns_state *st, const pns_step_io *io,
                  const float *actions, int t, int rng_mode, float *obs, float *reward, float *cum_reward,
                  void *stream);
 
+/* Episode KPIs of every replica from the history rows 0..t_last (reference rl/rl_utils.py, which computes them
+ * from the JSON that handlers/output_handler.py saves): out[replica][PNS_KPI_COUNT].
+ *   TOTAL_DEMAND     sum of the origin demand                                  (compute_network_throughput :827-835)
+ *   TOTAL_OUTFLOW    sum of cumulative_outflow[t_last] over links ending at a destination   (:840-858, :1243-1262)
+ *   TOTAL_INFLOW     sum of cumulative_inflow[t_last] over links starting at an origin      (:1136-1156, :1225-1241)
+ *   PERSON_TIME      sum_t sum_l N * dt                                        (compute_average_travel_time_spent :1124-1133)
+ *   PERSON_TIME_MOVING, TOTAL_DELAY   the same sum and N * max(0, 1 - T_ff/T) * dt over entries with T > 0
+ *                                                                              (compute_total_network_delay :1010-1052)
+ *   CONGESTION_TIME, AREA_TIME, STEPS, CONGESTED_STEPS                         (compute_network_congestion_metric :1462-1486)
+ *   AVG_TRAVEL_TIME  mean over OD-path links of the time-mean travel time      (compute_network_travel_time :915-948)
+ * The ratios the reference returns (throughput, served-trips rate, delay intensity, ...) are quotients of these.
+ * lk_role[l]: bit0 link starts at an origin, bit1 ends at a destination, bit2 lies on an OD path (any_od_path = 0:
+ * no paths known, every link counts).  scratch: [n_links*replicas*8] doubles. */
+enum { PNS_KPI_TOTAL_DEMAND = 0, PNS_KPI_TOTAL_OUTFLOW, PNS_KPI_TOTAL_INFLOW, PNS_KPI_PERSON_TIME,
+       PNS_KPI_PERSON_TIME_MOVING, PNS_KPI_TOTAL_DELAY, PNS_KPI_CONGESTION_TIME, PNS_KPI_AREA_TIME, PNS_KPI_STEPS,
+       PNS_KPI_CONGESTED_STEPS, PNS_KPI_AVG_TRAVEL_TIME, PNS_KPI_COUNT };
+int pns_kpi(const pns_net *net, const pns_state *st, const pns_step_io *io, int t_last, const int32_t *lk_role,
+            int any_od_path, double *scratch, double *out, void *stream);
+
 /* Links per CTA of the single-replica link kernel (the granularity of pns_net.lane_order). */
 int pns_lane_block_size(void);
 

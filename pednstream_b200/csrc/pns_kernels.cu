@@ -1251,6 +1251,74 @@ __global__ void __launch_bounds__(256) k_metric_pedestrians(const __grid_constan
 #endif
 }
 
+// =================================================================================================
+// Episode KPIs per replica (reference rl/rl_utils.py:770-1512, which reads them from the JSON that
+// OutputHandler saves): reductions over the whole history, rows 0..t_last.
+// Pass 1: one thread per (link, replica) walks its column through time (coalesced over replicas).
+__global__ void __launch_bounds__(kBlock) k_kpi_links(const __grid_constant__ Ctx c, int t_last, double* part) {
+    const int R = c.n.replicas;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)c.n.n_links * R) return;
+    const int l = (int)(gid / R), rep = (int)(gid % R);
+    const LinkP& p = c.n.classes[class_of(c, l, rep)];
+    const double dt = c.n.unit_time;
+    const double t_free = p.length / p.vf;                       // rl_utils.py:1023
+    const double area_time = (p.length * c.n.lk_width[l]) * dt;   // rl_utils.py:1469-1477
+    double spent = 0.0, ptime = 0.0, delay = 0.0, cong = 0.0, n_dens = 0.0, n_cong = 0.0, sum_tt = 0.0, n_tt = 0.0;
+    for (int t = 0; t <= t_last; ++t) {
+        const double num = (double)H32(c, PNS_F32_NUM_PED, t)[gid];
+        const double tt = (double)H32(c, PNS_F32_TRAVEL_TIME, t)[gid];
+        const double dens = (double)H32(c, PNS_F32_DENSITY, t)[gid];
+        if (num >= 0.0) spent = spent + num * dt;                 // rl_utils.py:1131-1133
+        if (tt > 0.0) {                                           // rl_utils.py:1041-1050
+            const double frac = fmax(0.0, 1.0 - t_free / tt);
+            delay = delay + (num * frac) * dt;
+            ptime = ptime + num * dt;
+        }
+        if (dens >= 0.0) {                                        // rl_utils.py:1472-1484
+            n_dens += 1.0;
+            if (dens > p.kc) { n_cong += 1.0; cong = cong + (dens - p.kc) * area_time; }
+        }
+        if (tt >= 0.0) { sum_tt = sum_tt + tt; n_tt += 1.0; }     // rl_utils.py:935-941
+    }
+    double* o = part + gid * 8;
+    o[0] = spent; o[1] = ptime; o[2] = delay; o[3] = cong; o[4] = n_dens; o[5] = n_cong; o[6] = sum_tt; o[7] = n_tt;
+}
+
+// Pass 2: one thread per replica adds the links up in network.links order.
+// out[rep][PNS_KPI_COUNT]; lk_role bit0: starts at an origin, bit1: ends at a destination, bit2: on an OD path.
+__global__ void __launch_bounds__(kBlock) k_kpi_reduce(const __grid_constant__ Ctx c, int t_last, const double* part,
+                                                       const int32_t* lk_role, int any_od_path, double* out) {
+    const int R = c.n.replicas;
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= R) return;
+    double k[PNS_KPI_COUNT];
+    for (int i = 0; i < PNS_KPI_COUNT; ++i) k[i] = 0.0;
+    const double* cin = H64(c, PNS_F64_CUM_INFLOW, t_last);
+    const double* cou = H64(c, PNS_F64_CUM_OUTFLOW, t_last);
+    double tt_links = 0.0, n_links_tt = 0.0;
+    for (int l = 0; l < c.n.n_links; ++l) {
+        const size_t e = (size_t)l * R + rep;
+        const double* p = part + e * 8;
+        const int role = lk_role[l];
+        if (role & 1) k[PNS_KPI_TOTAL_INFLOW] += cin[e];
+        if (role & 2) k[PNS_KPI_TOTAL_OUTFLOW] += cou[e];
+        k[PNS_KPI_PERSON_TIME] += p[0];
+        k[PNS_KPI_PERSON_TIME_MOVING] += p[1];
+        k[PNS_KPI_TOTAL_DELAY] += p[2];
+        k[PNS_KPI_CONGESTION_TIME] += p[3];
+        k[PNS_KPI_AREA_TIME] += p[4] * ((c.n.classes[class_of(c, l, rep)].length * c.n.lk_width[l]) * c.n.unit_time);
+        k[PNS_KPI_STEPS] += p[4];
+        k[PNS_KPI_CONGESTED_STEPS] += p[5];
+        if ((!any_od_path || (role & 4)) && p[7] > 0.0) { tt_links += p[6] / p[7]; n_links_tt += 1.0; }
+    }
+    k[PNS_KPI_AVG_TRAVEL_TIME] = n_links_tt > 0.0 ? tt_links / n_links_tt : 0.0;
+    const int rows = c.n.n_demand_rows;
+    for (int t = 0; t < c.n.sim_steps; ++t)
+        for (int r0 = 0; r0 < rows; ++r0) k[PNS_KPI_TOTAL_DEMAND] += c.io.demand[((size_t)t * rows + r0) * R + rep];
+    for (int i = 0; i < PNS_KPI_COUNT; ++i) out[(size_t)rep * PNS_KPI_COUNT + i] = k[i];
+}
+
 __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t,
                                int site, int32_t* out_i, double* out_d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1658,6 +1726,20 @@ int pns_step_streamed(const pns_net* net, const pns_state* st, const pns_step_io
     sx.host_demand = host_demand; sx.dev_metric = dev_metric; sx.host_metric = host_metric;
     return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, nullptr, nullptr, &sx);
 #endif
+}
+
+int pns_kpi(const pns_net* net, const pns_state* st, const pns_step_io* io, int t_last, const int32_t* lk_role,
+            int any_od_path, double* scratch, double* out, void* stream) {
+    if (!net || !st || !lk_role || !scratch || !out) return fail("pns_kpi: null argument");
+    if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
+    if (t_last < 0 || t_last > net->sim_steps) return fail("pns_kpi: row out of range");
+    if (net->n_demand_rows > 0 && !(io && io->demand)) return fail("pns_kpi: demand table missing");
+    const Ctx c = make_ctx(net, st, io, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
+    const size_t n = (size_t)net->n_links * net->replicas;
+    if (n) PNS_LAUNCH(k_kpi_links, blocks_for(n), kBlock, (cudaStream_t)stream, c, t_last, scratch);
+    PNS_LAUNCH(k_kpi_reduce, blocks_for((size_t)net->replicas), kBlock, (cudaStream_t)stream, c, t_last,
+               (const double*)scratch, lk_role, any_od_path, out);
+    return launched("k_kpi");
 }
 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,

@@ -402,6 +402,19 @@ class Engine:
         m = host_metric.reshape(-1)[: n_steps * _native.METRIC_ROW].numpy()
         return m.reshape(n_steps, _native.METRIC_SLOTS, _native.METRIC_STRIDE)[:, :, 0].sum(axis=1)
 
+    def kpis(self, t_last: int, lk_role: np.ndarray, any_od_path: bool) -> torch.Tensor:
+        """Episode KPIs of every replica from history rows 0..t_last (C-ABI pns_kpi; reference
+        rl/rl_utils.py:770-1512): tensor [R, len(_native.KPI_NAMES)] on the engine's device.
+        lk_role[l]: bit0 starts at an origin, bit1 ends at a destination, bit2 on an OD path."""
+        role = torch.from_numpy(np.ascontiguousarray(lk_role, dtype=np.int32)).to(self.device)
+        scratch = torch.empty((max(1, self.L * self.R) * 8,), dtype=torch.float64, device=self.device)
+        out = torch.zeros((self.R, len(_native.KPI_NAMES)), dtype=torch.float64, device=self.device)
+        with self._guard():
+            _native.check(self.lib, self.lib.pns_kpi(C.byref(self.net), C.byref(self.state), C.byref(self.io),
+                                                     int(t_last), _ptr(role), int(bool(any_od_path)), _ptr(scratch),
+                                                     _ptr(out), self._stream()), "pns_kpi")
+        return out
+
     def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor):
         """draw_b [rows, 3, L*R] int32, draw_n [rows, L*R] float64; row k serves step t0+k of `run`."""
         self._table = (draw_b, draw_n)

@@ -196,6 +196,38 @@ class Network:
                            window=round(100 / self.unit_time),
                            bgw0=[l._width for l in links])
 
+    # ------------------------------------------------------------------ KPIs
+    def link_roles(self):
+        """(lk_role[L] int32, any_od_path): bit0 link starts at an origin, bit1 ends at a destination,
+        bit2 lies on one of the OD paths (the inputs of the reference's KPI readers,
+        rl/rl_utils.py:770-1512)."""
+        origins, dests = set(self.origin_nodes), set(self.destination_nodes)
+        on_path = set()
+        if self.path_finder is not None:
+            for paths in self.path_finder.od_paths.values():
+                for path in paths:
+                    on_path.update(zip(path[:-1], path[1:]))
+        role = np.zeros(len(self.links), dtype=np.int32)
+        for (u, v), link in self.links.items():
+            role[link.index] = (1 if u in origins else 0) | (2 if v in dests else 0) | (4 if (u, v) in on_path else 0)
+        return role, bool(on_path)
+
+    def kpis(self, t_last: int = None) -> dict:
+        """Episode KPIs computed on the device from the history up to row t_last (default: the last row):
+        the quantities and ratios of the reference's rl_utils.compute_* readers."""
+        t_last = self.simulation_steps if t_last is None else int(t_last)
+        from .kpi import kpi_dict
+        role, any_path = self.link_roles()
+        eng = self.engine
+        rows = self.plan["demand_nodes"]
+        if rows:                  # the readers sum each origin's whole demand series, also of a partial episode
+            table = np.zeros((self.simulation_steps + 1, len(rows)))
+            for k, node in enumerate(rows):
+                table[: len(node.demand), k] = node.demand
+            eng.set_demand(table)
+        raw = eng.kpis(t_last, role, any_path).cpu().numpy()
+        return kpi_dict(raw)[0]
+
     # ------------------------------------------------------------------ fractions
     def update_turning_fractions_per_node(self, node_ids: List[int], new_turning_fractions):
         for i, n in enumerate(node_ids):

@@ -280,6 +280,15 @@ class BatchedPedNetEnv:
         self.sim_step += 1
         return self.obs, self.reward, done, {"step": self.sim_step - 1}
 
+    def kpis(self, t_last: int = None) -> torch.Tensor:
+        """Per-replica episode KPIs from the device history up to row t_last (default: the last simulated
+        step): tensor [R, len(_native.KPI_NAMES)]; `pednstream_b200.kpi.kpi_dict` turns rows into the
+        reference's result dictionaries (rl/rl_utils.py:770-1512), `parallel.gather_replica_values`
+        collects them across GPUs."""
+        t_last = self.sim_step - 1 if t_last is None else int(t_last)
+        role, any_path = self.network.link_roles()
+        return self.engine.kpis(t_last, role, any_path)
+
     def split_obs(self, obs=None):
         obs = self.obs if obs is None else obs
         return {a: obs[:, s] for a, s in self.obs_slices.items()}
