@@ -13,34 +13,46 @@ import numpy as np
 import yaml
 
 
+_MISSING = object()
+# where every entry of `params` comes from: (params key, yaml section or None for top level, key, default)
+_PARAMS_SCHEMA = (
+    ("simulation_steps", "simulation", "simulation_steps", _MISSING),
+    ("unit_time", "simulation", "unit_time", _MISSING),
+    ("assign_flows_type", "simulation", "assign_flows_type", "classic"),
+    ("seed", "simulation", "seed", None),
+    ("path_finder", "simulation", "path_finder", dict),
+    ("default_link", None, "default_link", _MISSING),
+    ("links", None, "links", dict),
+    ("demand", None, "demand", dict),
+    ("controllers", None, "controllers", dict),
+)
+
+
+def _lookup(doc: dict, section, key, default):
+    scope = doc if section is None else doc[section]
+    if key in scope:
+        return scope[key]
+    if default is _MISSING:
+        raise KeyError(key)
+    return default() if default is dict else default
+
+
 def load_config(config_path: str) -> dict:
     """Returns {'params', 'origin_nodes', 'destination_nodes'[, 'adjacency_matrix'][, 'od_flows']}."""
     with open(config_path, "r") as fh:
-        raw = yaml.safe_load(fh)
-
-    sim = raw["simulation"]
-    net = raw["network"]
-    out = {
-        "params": {
-            "simulation_steps": sim["simulation_steps"],
-            "unit_time": sim["unit_time"],
-            "assign_flows_type": sim.get("assign_flows_type", "classic"),
-            "seed": sim.get("seed", None),
-            "path_finder": sim.get("path_finder", {}),
-            "default_link": raw["default_link"],
-            "links": raw.get("links", {}),
-            "demand": raw.get("demand", {}),
-            "controllers": raw.get("controllers", {}),
-        },
-        "origin_nodes": net["origin_nodes"],
-        "destination_nodes": net.get("destination_nodes", []),
-    }
-    if "adjacency_matrix" in net:
-        out["adjacency_matrix"] = np.array(net["adjacency_matrix"])
-    if "od_flows" in raw:
-        out["od_flows"] = {tuple(int(x) for x in key.split("_")): w
-                           for key, w in raw["od_flows"].items()}
-    return out
+        doc = yaml.safe_load(fh)
+    network = doc["network"]
+    loaded = {"params": {name: _lookup(doc, section, key, default)
+                         for name, section, key, default in _PARAMS_SCHEMA},
+              "origin_nodes": network["origin_nodes"],
+              "destination_nodes": network.get("destination_nodes", [])}
+    adjacency = network.get("adjacency_matrix")
+    if adjacency is not None:
+        loaded["adjacency_matrix"] = np.array(adjacency)
+    weights = doc.get("od_flows")
+    if weights is not None:                               # keys "o_d" -> (o, d)
+        loaded["od_flows"] = {tuple(map(int, name.split("_"))): w for name, w in weights.items()}
+    return loaded
 
 
 _REQUIRED = {

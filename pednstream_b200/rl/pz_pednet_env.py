@@ -103,69 +103,68 @@ class PedNetParallelEnv(_Base):
         self._bind_network()
         self.sim_step = 1
         self._cumulative_rewards = {a: 0.0 for a in self.possible_agents}
-        return self._get_observations(), self._get_infos()
+        return self._observe(), self._info()
 
     def step(self, actions: Dict[str, Any]):
+        unknown = [a for a in actions if a not in self.possible_agents]
+        if unknown:
+            raise ValueError(f"Unknown agent: {unknown[0]}")
         self.current_actions = actions
         if self.last_actions is None:
             self.last_actions = actions
-        for agent_id in actions:
-            if agent_id not in self.possible_agents:
-                raise ValueError(f"Unknown agent: {agent_id}")
-        if len(actions) > 0:
+        if actions:
             self.action_applier.apply_all_actions(actions)
         elif self.sim_step == 1:
             print("No actions provided, skipping action application.")
 
-        gap_rewards = {a: 0.0 for a in self.possible_agents}
-        observations = terminations = truncations = infos = None
-        for _ in range(self._action_gap):
+        earned = dict.fromkeys(self.possible_agents, 0.0)
+        result = None
+        for _ in range(self._action_gap):                 # `action_gap` simulation steps per decision
             self.network.network_loading(self.sim_step)
-            observations = self._get_observations()
-            for agent_id, r in self._compute_rewards().items():
-                gap_rewards[agent_id] += r
-            terminations = self._check_terminations()
-            truncations = {a: False for a in self.possible_agents}
-            infos = self._get_infos()
+            for agent_id, r in self._reward_now().items():
+                earned[agent_id] += r
+            finished = self.sim_step >= self.simulation_steps      # before the increment: S env steps (Q8)
+            result = (self._observe(), dict.fromkeys(self.possible_agents, finished),
+                      dict.fromkeys(self.possible_agents, False), self._info())
             self.sim_step += 1
-        for agent_id, r in gap_rewards.items():
+        for agent_id, r in earned.items():
             self._cumulative_rewards[agent_id] += r
-        return observations, gap_rewards, terminations, truncations, infos
+        obs, terminations, truncations, infos = result
+        return obs, earned, terminations, truncations, infos
 
     # ------------------------------------------------------------------ per-step quantities
-    def _get_observations(self) -> Dict[str, Any]:
-        return {a: self.obs_builder.build_observation(a, self.sim_step) for a in self.possible_agents}
+    def _observe(self) -> Dict[str, Any]:
+        build = self.obs_builder.build_observation
+        return {a: build(a, self.sim_step) for a in self.possible_agents}
 
-    def _compute_rewards(self) -> Dict[str, float]:
-        """Gate agent: -sum(T + T_rev) - sum 10 (rho - k_c)[rho > 4] - 10 mean|rho - mean rho|
-        over its controlled links at the step just simulated (pz_pednet_env.py:548-581)."""
-        rewards = {}
-        t = self.sim_step
-        for agent_id in self.possible_agents:
-            if self.agent_manager.get_agent_type(agent_id) == "gate":
-                total = 0.0
-                densities = []
-                for link in self.agent_manager.get_gater_outgoing_links(agent_id):
-                    rho = link.get_density(t)
-                    densities.append(rho)
-                    rev = link.reverse_link
-                    T = link.travel_time[t] if t < len(link.travel_time) else link.travel_time[0]
-                    T_rev = rev.travel_time[t] if t < len(rev.travel_time) else rev.travel_time[0]
-                    total -= T + T_rev
-                    if rho > 4:
-                        total -= 10 * (rho - link.k_critical)
-                if len(densities) > 1:
-                    mean = np.mean(densities)
-                    total -= 10.0 * np.mean(np.abs(np.array(densities) - mean))
-                rewards[agent_id] = total
-            return rewards          # reference quirk Q2: only the first agent is considered
-        return rewards
+    def _gate_reward(self, agent_id: str, t: int) -> float:
+        """-sum(T + T_rev) - sum 10 (rho - k_c)[rho > 4] - 10 mean|rho - mean rho| over the agent's links at
+        the step just simulated (pz_pednet_env.py:548-581)."""
+        total, rho_all = 0.0, []
+        for link in self.agent_manager.get_gater_outgoing_links(agent_id):
+            back = link.reverse_link
+            rho = link.get_density(t)
+            rho_all.append(rho)
+            t_fwd = link.travel_time[t] if t < len(link.travel_time) else link.travel_time[0]
+            t_back = back.travel_time[t] if t < len(back.travel_time) else back.travel_time[0]
+            total -= t_fwd + t_back
+            if rho > 4:
+                total -= 10 * (rho - link.k_critical)
+        if len(rho_all) > 1:
+            total -= 10.0 * np.mean(np.abs(np.array(rho_all) - np.mean(rho_all)))
+        return total
 
-    def _check_terminations(self) -> Dict[str, bool]:
-        done = self.sim_step >= self.simulation_steps
-        return {a: done for a in self.possible_agents}
+    def _reward_now(self) -> Dict[str, float]:
+        """Reference quirk Q2: its loop returns after the first agent, so only that agent can be
+        rewarded, and only if it is a gate agent."""
+        if not self.possible_agents:
+            return {}
+        first = self.possible_agents[0]
+        if self.agent_manager.get_agent_type(first) != "gate":
+            return {}
+        return {first: self._gate_reward(first, self.sim_step)}
 
-    def _get_infos(self) -> Dict[str, Dict]:
+    def _info(self) -> Dict[str, Dict]:
         return {a: {"step": self.sim_step, "cumulative_reward": self._cumulative_rewards.get(a, 0.0)}
                 for a in self.possible_agents}
 

@@ -121,7 +121,7 @@ def _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, lib=None, emula
         eng.io.seed = benv.engine.io.seed
         eng.io.replica_base = rep
         agents = env.possible_agents
-        first = np.concatenate([env._get_observations()[a] for a in agents])
+        first = np.concatenate([env._observe()[a] for a in agents])
         assert np.array_equal(first, obs_b[0][rep])
         for k in range(steps):
             act = {a: acts[k, rep, benv.action_slices[a]] for a in agents}
@@ -163,7 +163,7 @@ def _randomized_batched_vs_facade(dataset, steps, R, picks, lib=None, emulation=
         eng.io.seed = benv.engine.io.seed
         eng.io.replica_base = rep
         agents = env.possible_agents
-        assert np.array_equal(np.concatenate([env._get_observations()[a] for a in agents]), obs_b[0][rep])
+        assert np.array_equal(np.concatenate([env._observe()[a] for a in agents]), obs_b[0][rep])
         for k in range(steps):
             obs, rew, *_ = env.step({a: acts[k, rep, benv.action_slices[a]] for a in agents})
             assert np.array_equal(np.concatenate([obs[a] for a in agents]), obs_b[k + 1][rep]), (rep, k)
