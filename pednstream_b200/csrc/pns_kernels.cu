@@ -89,6 +89,9 @@ constexpr int kBlock = 128;
 #define PNS_PF_AHEAD_CTAS (75776 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
                                                      // into L2: half a resident wave of 148 SMs x 1024 threads (0 = off)
 #endif
+#ifndef PNS_QUIET_FAST_PATH
+#define PNS_QUIET_FAST_PATH 1  // k_link_lane: exact shortcut for the sending flow of empty links
+#endif
 #ifndef PNS_PF_TAPS
 #define PNS_PF_TAPS 1          // k_link_lane: early fetch of the diffusion taps of occupied links
 #endif
@@ -1077,6 +1080,16 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     double r = 0.0;
     int n3 = -1;
     if (valid) {
+        // A link with nobody on it and nobody in transit (everything that entered has left) sends nothing:
+        // arrived <= cin[tau] - cout[tau] = 0, so boundary = 0 and only the smoothing with the previous
+        // sending flow remains (link.py:363-364).  Same result as the general path, a seventh of its
+        // instructions; whole warps of such links take it on sparsely occupied networks.
+        if (PNS_QUIET_FAST_PATH && me.num == 0.0f && cin_tau == cou_tau && front >= 0.0 && tau >= fftau) {
+            s.kind = 0; s.n1 = 0; s.rf = 0.0f; s.sval = 0.0;
+            const double f = pymin(floor(0.8 * 0.0 + 0.2 * snd_prev), 0.0);
+            if (MODE != PNS_RNG_REQUEST && f < 0.0) atomicOr(c.s.err, PNS_ERR_NEG_SENDING);
+            s.flow = MODE == PNS_RNG_REQUEST ? 0.0 : f;
+        } else
         s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, pre_i0, pre_v0, pre_i1,
                                pre_v1);
         r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
