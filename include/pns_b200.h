@@ -249,8 +249,10 @@ int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io
  * pedestrian count of that step is reduced on the device to PNS_METRIC_SLOTS partial sums and copied to the host.
  * `dev_metric` (device scratch) and `host_metric` (pinned) hold [n_steps][PNS_METRIC_SLOTS * PNS_METRIC_STRIDE]
  * doubles; the count of step t0+k is the sum over j of host_metric[k][j * PNS_METRIC_STRIDE] (counts are
- * integer-valued, so the sum is exact in any order).  Everything is stream-ordered; the caller synchronises once at
- * the end. */
+ * integer-valued, so the sum is exact in any order).  The copies (one H2D and one D2H per step) run on an internal
+ * second stream that meets `stream` once per group of 8 steps: demand rows are copied one group ahead of their step,
+ * results up to one group after it.  The call returns with everything enqueued; after synchronising `stream` all
+ * results are on the host. */
 #define PNS_METRIC_SLOTS 64   /* partial sums per step (a power of two) */
 #define PNS_METRIC_STRIDE 4   /* doubles between slots: one 32-byte sector each */
 int pns_step_streamed(const pns_net *net, const pns_state *st, const pns_step_io *io, int t0, int n_steps,

@@ -1525,6 +1525,9 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     const StepSizes z = sizes_of(net);
 #ifndef PNS_HOST_EMULATION
     static SideStream side;
+    constexpr int kSyncGroup = 8;
+    cudaEvent_t demand_next = nullptr;
+    int results_copied = 0;
     if (sx) {
         cudaMemsetAsync(sx->dev_metric, 0, (size_t)n_steps * kMetricRow * sizeof(double), s);
         side.ensure();
@@ -1553,32 +1556,44 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         if (lane_metric) cp.metric = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
 #endif
 #ifndef PNS_HOST_EMULATION
-        // Host traffic of streamed runs rides on a second stream, tied to the kernel chain by events, so
-        // that no copy sits between two kernels of the chain (a copy there costs its own latency and the
-        // programmatic overlap of the launches around it).
-        cudaEvent_t demand_ready = nullptr;
-        if (sx && k < n_steps && net->n_demand_rows) {   // input of step t0+k: its demand row, from pinned host memory
-            const size_t row = (size_t)net->n_demand_rows * net->replicas, off = (size_t)(t0 + k - 1) * row;
-            cudaMemcpyAsync(const_cast<double*>(io->demand) + off, sx->host_demand + off, row * sizeof(double),
-                            cudaMemcpyHostToDevice, side.stream);      // queued ahead of the link pass: not behind the
-            demand_ready = side.event();                               // result copy that waits for it
-            cudaEventRecord(demand_ready, side.stream);
+        // Host traffic of streamed runs rides on a second stream: every step still has its own H2D copy (its
+        // demand row) and its own D2H copy (its result), but the two streams meet only once per group of
+        // kSyncGroup steps -- an event between two kernels of the chain costs the programmatic overlap of that
+        // launch pair, a copy there additionally its own latency.  Demand rows are copied one group ahead.
+        if (sx && k < n_steps && k % kSyncGroup == 0 && net->n_demand_rows) {
+            const size_t row = (size_t)net->n_demand_rows * net->replicas;
+            auto copy_group = [&](int first) {          // demand rows of steps t0+first .. t0+first+kSyncGroup-1
+                for (int j = first; j < first + kSyncGroup && j < n_steps; ++j) {
+                    const size_t off = (size_t)(t0 + j - 1) * row;
+                    cudaMemcpyAsync(const_cast<double*>(io->demand) + off, sx->host_demand + off, row * sizeof(double),
+                                    cudaMemcpyHostToDevice, side.stream);
+                }
+                cudaEvent_t e = side.event();
+                cudaEventRecord(e, side.stream);
+                return e;
+            };
+            if (k == 0) demand_next = copy_group(0);
+            cudaStreamWaitEvent(s, demand_next, 0);     // this group's rows are on the device
+            if (k + kSyncGroup < n_steps) demand_next = copy_group(k + kSyncGroup);
         }
 #endif
         PNS_MARK(k, 0);
         if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
         PNS_MARK(k, 1);
 #ifndef PNS_HOST_EMULATION
-        if (sx && k > 0) {          // result of step t0+k-1: partial sums reduced on the device, copied to the host every step
+        if (sx && k > 0) {          // result of step t0+k-1: partial sums reduced on the device
             double* row = sx->dev_metric + (size_t)(k - 1) * kMetricRow;
             if (!lane_metric) k_metric_pedestrians<<<148 * 4, 256, 0, s>>>(cp, row);
-            cudaEvent_t e = side.event();
-            cudaEventRecord(e, s);
-            cudaStreamWaitEvent(side.stream, e, 0);
-            cudaMemcpyAsync(sx->host_metric + (size_t)(k - 1) * kMetricRow, row, kMetricRow * sizeof(double),
-                            cudaMemcpyDeviceToHost, side.stream);
+            if (k % kSyncGroup == 0 || k == n_steps) {   // ... and copied to the host, one copy per step
+                cudaEvent_t e = side.event();
+                cudaEventRecord(e, s);
+                cudaStreamWaitEvent(side.stream, e, 0);
+                for (int j = results_copied; j < k; ++j)
+                    cudaMemcpyAsync(sx->host_metric + (size_t)j * kMetricRow, sx->dev_metric + (size_t)j * kMetricRow,
+                                    kMetricRow * sizeof(double), cudaMemcpyDeviceToHost, side.stream);
+                results_copied = k;
+            }
         }
-        if (demand_ready) cudaStreamWaitEvent(s, demand_ready, 0);     // the node pass of this step reads the row
 #endif
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
