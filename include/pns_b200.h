@@ -221,7 +221,11 @@ int pns_route_probs(const pns_net *net, const pns_state *st, const pns_step_io *
 /* Node pass for step t, one thread per node and replica: turning fractions
  * (path_finder.py:591-715), Node.assign_flows / solve / update_links (node.py:146-300).
  * Writes inflow[t] / outflow[t] of every link (physical and virtual) and the cumulative counts of the virtual
- * O/D links at row t. */
+ * O/D links at row t.
+ * Row contract: a node that receives no sending flow stores nothing, so rows inflow[t] and outflow[t] must be zero
+ * when the step starts.  pns_state_init leaves every row zero and each step writes only its own row, so a run that
+ * moves forward in time satisfies this by construction; a caller that repeats a step clears those two rows first
+ * (the Python engine does so whenever it is asked to go back in time). */
 int pns_node_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, void *stream);
 
 /* Link state update for step t, one thread per link pair and replica: cumulative counts from the

@@ -784,6 +784,20 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     for (int i = 0; i < m; ++i) negative |= (s[i] < 0.0) | (r[i] < 0.0);
     if (negative) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
 
+    // Nothing is sent into this node: every flow through it is zero, and the rows of step t already hold
+    // zeros (pns_state_init; see the row contract at pns_node_flows in the header), so neither the solve
+    // nor the eight scattered stores are needed.  Most nodes of a sparsely occupied network end here.
+    bool any_flow = false;
+#pragma unroll
+    for (int i = 0; i < m; ++i) any_flow |= s[i] != 0.0;
+    if (!any_flow) {
+        if (dem_row >= 0) {               // the cumulative counts of the virtual links still carry forward
+            const size_t vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep, vout = vin + R;
+            c.n_cout[vin] = v_cout;
+            c.n_cin[vout] = v_cin;
+        }
+        return;
+    }
     double q_out[CAP], q_in[CAP];
     if (kind == 0) {
         // OneToOneNode.solve (node.py:230-242): exactly two slots

@@ -183,7 +183,19 @@ class Engine:
                 self.od_w[: od_w.shape[0], : od_w.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(od_w)))
             ops.ltm_state_init(self.hist64, self.hist32, self.runsum, self.err, self.handle)
         self.t_done = 0
+        self._last_row = 0
         self._initialised = True
+
+    def _begin_steps(self, t0: int, n_steps: int):
+        """Row contract of the node pass (pns_b200.h, pns_node_flows): inflow/outflow rows of a step must be
+        zero before it runs.  Moving forward in time that holds by construction; when asked to repeat steps,
+        clear the rows from t0 up to the last row ever written."""
+        last = getattr(self, "_last_row", 0)
+        if t0 <= last:
+            lo, hi = max(int(t0), 0), min(last, self.S)
+            self.hist64[F64_INDEX["inflow"], lo:hi + 1].zero_()
+            self.hist64[F64_INDEX["outflow"], lo:hi + 1].zero_()
+        self._last_row = max(last, int(t0) + int(n_steps) - 1)
 
     def set_replica_scenarios(self, classes: np.ndarray, lk_class: np.ndarray, od_w: np.ndarray = None):
         """Per-replica scenarios (domain randomisation): `classes` a table of pns_link_class records
@@ -295,6 +307,7 @@ class Engine:
         if not (1 <= t <= self.S):
             raise IndexError(f"time step {t} outside [1, {self.S}]")
         with self._guard():
+            self._begin_steps(t, 1)
             self._push_host_edits(net, t)
             if self.rng == "philox":
                 ops.ltm_step(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
@@ -357,6 +370,7 @@ class Engine:
     def run(self, t0: int, n_steps: int, rng_mode: int = _native.RNG_PHILOX):
         """Advance n_steps without host involvement (PHILOX, or TABLE after `set_draw_table`)."""
         with self._guard():
+            self._begin_steps(t0, n_steps)
             ops.ltm_step(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
                          self.handle, t0, n_steps, rng_mode)
         self.t_done = t0 + n_steps - 1
@@ -368,6 +382,7 @@ class Engine:
         cnt = (C.c_int64 * 4)(0, 0, 0, 0)
         io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
         with self._guard():
+            self._begin_steps(t0, n_steps)
             _native.check(self.lib, self.lib.pns_step_profiled(
                 C.byref(self.net), C.byref(self.state), C.byref(io), t0, n_steps, rng_mode, self._stream(),
                 ms, cnt), "pns_step_profiled")
@@ -391,6 +406,7 @@ class Engine:
         if not hasattr(self, "_dev_metric") or self._dev_metric.numel() < n_steps * _native.METRIC_ROW:
             self._dev_metric = torch.zeros(n_steps * _native.METRIC_ROW, dtype=torch.float64, device=self.device)
         with self._guard():
+            self._begin_steps(t0, n_steps)
             _native.check(self.lib, self.lib.pns_step_streamed(
                 C.byref(self.net), C.byref(self.state), C.byref(self.io), t0, n_steps, rng_mode,
                 _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")

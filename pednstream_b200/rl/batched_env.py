@@ -271,6 +271,7 @@ class BatchedPedNetEnv:
             actions = actions.contiguous()
             act_ptr = _ptr(actions)
         with eng._guard():      # actions, the LTM step, observations + reward: one native call
+            eng._begin_steps(self.sim_step, 1)
             _native.check(eng.lib, eng.lib.pns_env_step(
                 C.byref(eng.net), C.byref(eng.state), C.byref(eng.io), C.byref(self._env), act_ptr,
                 int(self.sim_step), _native.RNG_PHILOX, _ptr(self.obs), _ptr(self.reward),

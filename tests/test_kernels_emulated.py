@@ -2,6 +2,7 @@
 reproduce the oracle bit for bit.  This is a test build only -- the product never loads it."""
 import numpy as np
 import pytest
+import torch
 
 from conftest import assert_matches_golden, load_golden, make_network
 from oracle.ltm_oracle import F32_FIELDS, F64_FIELDS, LtmOracle
@@ -120,3 +121,30 @@ def test_device_fault_is_raised_like_the_reference(emu_lib):
         for t in range(1, 12):
             net.network_loading(t)
         net.links[(0, 1)].inflow
+
+
+def test_going_back_in_time_clears_the_flow_rows(emu_lib):
+    """The node pass stores nothing for nodes without sending flow and relies on zeroed inflow/outflow
+    rows (pns_b200.h row contract).  Moving forward that holds by construction; when a caller repeats
+    steps the engine clears the rows first, so values of the earlier pass cannot leak into the new one.
+    (A rewind is not a replay -- the running travel-time sum is carried state in the reference too,
+    link.py:84,183-186 -- so the check is on the rows themselves.)"""
+    steps = 90
+    net = make_network("nine_intersections", rng="philox", seed=4)
+    eng = attach(net, emu_lib, rng="philox", seed=4)
+    for t in range(1, steps + 1):
+        net.network_loading(t)
+    inflow = eng.history("inflow").clone()
+    assert float(inflow[41:steps + 1].abs().sum()) > 0
+    # repeat from step 40 with the network emptied of demand: nothing may survive from the first pass
+    for n in net.nodes.values():
+        if n.demand is not None:
+            n.demand[:] = 0
+    net.network_loading(40)
+    for f in ("inflow", "outflow"):
+        h = eng.history(f)
+        assert float(h[41:steps + 1].abs().sum()) == 0.0, f          # rows above the repeated step: cleared
+        assert torch.equal(h[:40], (inflow if f == "inflow" else h)[:40])
+    # row 40 itself holds exactly what the repeated step stored: links next to idle nodes read zeros
+    cin = eng.history("cumulative_inflow")
+    assert torch.equal(cin[40] - cin[39], eng.history("inflow")[40])
