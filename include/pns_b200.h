@@ -208,7 +208,8 @@ int pns_state_init(const pns_net *net, const pns_state *st, void *stream);
  * Link.cal_sending_flow (link.py:216-370) incl. get_outflow (:199-214) and
  * Link/Separator.cal_receiving_flow_with_reverse (:372-416, :480-512).
  * Writes sending_flow[tau], receiving_flow[tau] and the node-major copies nm_s / nm_r the node pass reads
- * (or only the draw requests in REQUEST mode).
+ * (or only the draw requests in REQUEST mode).  The single-replica kernel does not rewrite an nm_s slot whose
+ * previous and new sending flow are both 0: a caller that repeats steps clears nm_s first (see pns_node_flows).
  * Inside pns_step this pass for step t+1 is fused with pns_link_update of step t (same thread,
  * state kept in registers). */
 int pns_link_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,

@@ -89,6 +89,9 @@ constexpr int kBlock = 128;
 #define PNS_PF_AHEAD_CTAS (75776 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
                                                      // into L2: half a resident wave of 148 SMs x 1024 threads (0 = off)
 #endif
+#ifndef PNS_SKIP_ZERO_HANDOVER
+#define PNS_SKIP_ZERO_HANDOVER 1
+#endif
 #ifndef PNS_QUIET_FAST_PATH
 #define PNS_QUIET_FAST_PATH 1  // k_link_lane: exact shortcut for the sending flow of empty links
 #endif
@@ -1123,7 +1126,9 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
         st_keep<3>(c.f_snd + e, s.flow, pol);      // read back by the next step's smoothing (link.py:363, 400)
         st_keep<3>(c.f_rcv + e, rcv, pol);
-        st_keep<1>(c.s.nm_s + slots.x, s.flow, pol);   // node-major hand-over to the node pass
+        // node-major hand-over to the node pass; a slot that held 0 (the previous sending flow) and gets 0 again
+        // needs no store (scattered 8-byte stores are the expensive kind)
+        if (!PNS_SKIP_ZERO_HANDOVER || s.flow != 0.0 || snd_prev != 0.0) st_keep<1>(c.s.nm_s + slots.x, s.flow, pol);
         st_keep<1>(c.s.nm_r + slots.y, rcv, pol);
     }
 }

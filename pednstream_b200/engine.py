@@ -195,6 +195,7 @@ class Engine:
             lo, hi = max(int(t0), 0), min(last, self.S)
             self.hist64[F64_INDEX["inflow"], lo:hi + 1].zero_()
             self.hist64[F64_INDEX["outflow"], lo:hi + 1].zero_()
+            self.nm_s.zero_()        # the link pass skips a hand-over store when the slot already holds its 0
         self._last_row = max(last, int(t0) + int(n_steps) - 1)
 
     def set_replica_scenarios(self, classes: np.ndarray, lk_class: np.ndarray, od_w: np.ndarray = None):
