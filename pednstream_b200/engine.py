@@ -137,6 +137,7 @@ class Engine:
         self.io = io
         self._table_io = None
         self._od_per_replica = False
+        self._last_row = 0
 
         self.handle = ops.register_engine(self)
         self.t_done = 0
@@ -190,12 +191,14 @@ class Engine:
         """Row contract of the node pass (pns_b200.h, pns_node_flows): inflow/outflow rows of a step must be
         zero before it runs.  Moving forward in time that holds by construction; when asked to repeat steps,
         clear the rows from t0 up to the last row ever written."""
-        last = getattr(self, "_last_row", 0)
-        if t0 <= last:
-            lo, hi = max(int(t0), 0), min(last, self.S)
-            self.hist64[F64_INDEX["inflow"], lo:hi + 1].zero_()
-            self.hist64[F64_INDEX["outflow"], lo:hi + 1].zero_()
-            self.nm_s.zero_()        # the link pass skips a hand-over store when the slot already holds its 0
+        last = self._last_row
+        if t0 > last:                         # the normal case: forward in time
+            self._last_row = t0 + n_steps - 1
+            return
+        lo, hi = max(int(t0), 0), min(last, self.S)
+        self.hist64[F64_INDEX["inflow"], lo:hi + 1].zero_()
+        self.hist64[F64_INDEX["outflow"], lo:hi + 1].zero_()
+        self.nm_s.zero_()        # the link pass skips a hand-over store when the slot already holds its 0
         self._last_row = max(last, int(t0) + int(n_steps) - 1)
 
     def set_replica_scenarios(self, classes: np.ndarray, lk_class: np.ndarray, od_w: np.ndarray = None):
