@@ -183,6 +183,8 @@ class Engine:
             if od_w is not None and od_w.size and not self._od_per_replica:
                 self.od_w[: od_w.shape[0], : od_w.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(od_w)))
             ops.ltm_state_init(self.hist64, self.hist32, self.runsum, self.err, self.handle)
+            self.nm_s.zero_()
+            self.nm_r.zero_()
         self.t_done = 0
         self._last_row = 0
         self._initialised = True
