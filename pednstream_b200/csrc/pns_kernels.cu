@@ -1153,8 +1153,10 @@ __global__ void __launch_bounds__(kBlock) k_env_actions(const __grid_constant__ 
     const int R = c.n.replicas;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)x.env.n_act * R) return;
+    PNS_PDL_TRIGGER();
     const int a = (int)(gid / R), rep = (int)(gid % R);
     const int l = x.env.act_link[a];
+    PNS_PDL_WAIT();                      // actions and gate table may come from the previous kernel
     const size_t e = (size_t)l * R + rep;
     double v = (double)x.actions[(size_t)rep * x.env.n_act + a];       // float(action[i])
     const double cur = c.s.gate[e];
@@ -1189,6 +1191,8 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
     const int t = c.t;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_obs_threads = (size_t)x.env.n_obs * R;
+    PNS_PDL_TRIGGER();
+    PNS_PDL_WAIT();                      // reads the rows the link pass has just written
     if (gid < n_obs_threads) {
         const int k = (int)(gid / R), rep = (int)(gid % R);
         const int l = x.env.obs_link[k];
@@ -1729,7 +1733,7 @@ int pns_env_apply_actions(const pns_net* net, const pns_state* st, const pns_env
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
     x.env = *env; x.actions = actions; x.obs = nullptr; x.reward = nullptr; x.cum_reward = nullptr;
-    PNS_LAUNCH(k_env_actions, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    PNS_LAUNCH_CHAIN(k_env_actions, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_actions");
 }
 
@@ -1743,7 +1747,7 @@ int pns_env_observe(const pns_net* net, const pns_state* st, const pns_env* env,
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
     x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward; x.cum_reward = nullptr;
-    PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    PNS_LAUNCH_CHAIN(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_observe");
 }
 
@@ -1758,7 +1762,7 @@ int pns_env_step(const pns_net* net, const pns_state* st, const pns_step_io* io,
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
     x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward; x.cum_reward = cum_reward;
-    PNS_LAUNCH(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
+    PNS_LAUNCH_CHAIN(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
     return launched("k_env_observe");
 }
 
