@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the LTM timestep (BASELINE.json metric: link-timesteps/sec, fp64 state).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload grid512|env45]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid SIZE] [--no-env] [--no-cpu-baseline]
 
 Workload at N=1 (`config.workload`): BASELINE config 4, the synthetic 512x512-node lattice of
 data/create_grid.py's rule (1 046 528 directed links, default_link of data/45_intersections, 35
