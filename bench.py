@@ -361,7 +361,7 @@ def run_ours(args):
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": "link-timesteps/s", "cores": 1, "kind": "port",
                                     "sample": f"Python oracle, {REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({cpu_L} links), "
-                                              f"40 steps, {cpu_dt:.1f} s; host has {os.cpu_count()} cores, the "
+                                              f"{cpu_steps} steps, {cpu_dt:.1f} s; host has {os.cpu_count()} cores, the "
                                               f"reference algorithm is single-threaded"}
         print(json.dumps(line), flush=True)
     if world > 1:
