@@ -187,6 +187,28 @@ def test_large_grid_invariants():
     assert float(eng.history("speed")[steps].max()) <= 1.1 + 0.5
 
 
+def test_lane_kernel_equals_pair_kernel_on_large_lattice(monkeypatch):
+    """The single-replica link kernel (lane per link: shuffles, L2 prefetch, launch order, shortcuts for
+    empty links, skipped hand-over stores) against the plain pair-per-thread kernel that the batched and the
+    host-emulation paths use, on a lattice with demand high enough to jam the origin links: all 13 series
+    bit-equal over 400 steps."""
+    size, steps = 192, 400
+    plan, gate, tf, demand = build_grid_plan(size, steps + 1, locality_order=True, peak_lambda=90, base_lambda=60)
+    a = Engine(plan, replicas=1, rng="philox", seed=9, device="cuda:0")
+    a.initialise(gate, None, tf, demand, None)
+    a.run(1, steps)
+    a.check_errors()
+    monkeypatch.setenv("PNS_PAIR_THREADS", "1")
+    b = Engine(plan, replicas=1, rng="philox", seed=9, device="cuda:0")
+    b.initialise(gate, None, tf, demand, None)
+    b.run(1, steps)
+    b.check_errors()
+    monkeypatch.delenv("PNS_PAIR_THREADS")
+    assert float(a.history("num_pedestrians")[steps].max()) > 800          # jammed links exist
+    for f in FIELDS:
+        assert torch.equal(a.history(f)[: steps + 1], b.history(f)[: steps + 1]), f
+
+
 def test_streamed_run_equals_resident_run():
     """Engine.run_streamed (per-step H2D demand row + D2H metric inside the native loop) must produce
     the same trajectory as a device-resident run, and the metric must be the pedestrian count."""
