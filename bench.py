@@ -5,7 +5,7 @@
 
 Workload at N=1 (`config.workload`): BASELINE config 4, the synthetic 512x512-node lattice of
 data/create_grid.py's rule (1 046 528 directed links, default_link of data/45_intersections, 35
-origins = 4 corners + every 64th boundary node, gaussian-peak Poisson demand pre-drawn on the host,
+origins = 4 corners + every 64th boundary node, gaussian-peak Poisson demand pre-drawn on the host (lattice),
 uniform turning fractions), single replica, on-device Philox draws.  configs[1] (nine_intersections,
 24 links) is a parity-test case: at 24 links a step is pure launch latency and says nothing about the
 HBM roofline the metric is quoted against; the 512x512 grid is the largest single-GPU configuration.
@@ -215,19 +215,30 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     env.engine.check_errors()
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # episode turnover: reset = state init + demand of the next episode drawn on the device (wall clock, it
+    # has host work in it)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    env.reset()
+    torch.cuda.synchronize()
+    reset_ms = (time.perf_counter() - w0) * 1e3
+    t = torch.tensor([ms, ms_e2e, reset_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, reset_ms = float(t[0]), float(t[1]), float(t[2])
+    S_ep = env.simulation_steps
+    episode_ms = S_ep * ms / steps + reset_ms
     links = env.engine.L
     return {"env_steps_per_s": world * R * steps / (ms * 1e-3),
             "env_steps_per_s_e2e": world * R * steps / (ms_e2e * 1e-3),
+            "env_steps_per_s_with_resets": world * R * S_ep / (episode_ms * 1e-3),
+            "reset_ms": reset_ms, "steps_per_episode": S_ep,
             "link_timesteps_per_s": world * R * links * steps / (ms * 1e-3),
             "replicas_per_gpu": R, "replicas_total": world * R, "env_steps": steps, "ms_per_env_step": ms / steps,
             "launches_per_env_step": env.launches_per_step(), "links": links,
             "h2d_bytes_per_step": R * A * 4, "d2h_bytes_per_step": R * (env.n_obs + 1) * 4,
             "workload": "config 5: data/45_intersections, obs option3, uniform random gate actions, philox draws, "
-                        "per-replica pre-drawn demand",
+                        "per-replica demand drawn on the device at reset",
             "mean_reward_last_step": float(host_rew.mean())}
 
 

@@ -279,6 +279,15 @@ int pns_env_step(const pns_net *net, const pns_state *st, const pns_step_io *io,
                  const float *actions, int t, int rng_mode, float *obs, float *reward, float *cum_reward,
                  void *stream);
 
+/* Origin demand of a batch of replicas, drawn on the device (reference od_manager.py:100-155): demand[t][row*R + r]
+ * for t = 0..sim_steps.  pattern[row*R + r]: 0 gaussian_peaks = Poisson(base + peak*bump1[t] + peak*bump2[t]),
+ * 1 constant = base, 2 sudden_demand = gaussian_peaks plus a burst of 10..19 steps at a random start with height
+ * 20..49, -1 none.  Every value is a pure function of (seed, replica_base + r; t, row): independent of the sharding
+ * of replicas over GPUs.  bump1/bump2: [sim_steps] (host-evaluated gaussian bumps); base/peak/pattern: [rows*R]. */
+int pns_env_draw_demand(int sim_steps, int rows, int replicas, uint32_t replica_base, uint64_t seed,
+                        const double *bump1, const double *bump2, const double *base, const double *peak,
+                        const int32_t *pattern, double *demand, void *stream);
+
 /* Episode KPIs of every replica from the history rows 0..t_last (reference rl/rl_utils.py, which computes them
  * from the JSON that handlers/output_handler.py saves): out[replica][PNS_KPI_COUNT].
  *   TOTAL_DEMAND     sum of the origin demand                                  (compute_network_throughput :827-835)

@@ -171,6 +171,29 @@ def binomial_philox(seed, t, link, replica, site, n, p):
     return n - total if flip else total
 
 
+def poisson_philox(seed, t, row, replica, lam):
+    """Demand draw of the batched environment (pns_kernels.cu k_demand_draw): Poisson(lam) by inversion from 0,
+    uniform from words 0,1 of the block keyed (t, row, site 8, replica)."""
+    w = philox4x32_10(t, row, 8, replica, seed & M32, (seed >> 32) & M32)
+    u = u53(w[0], w[1])
+    if not lam > 0.0:
+        return 0
+    pk, k = det_exp(-lam), 0
+    while u > pk and k < 4096:
+        u = u - pk
+        k += 1
+        pk = (pk * lam) / float(k)
+    return k
+
+
+def sudden_burst_philox(seed, row, replica, steps):
+    """(start, period, height) of a sudden-demand burst (k_demand_draw, site 9)."""
+    b = philox4x32_10(0, row, 9, replica, seed & M32, (seed >> 32) & M32)
+    period = 10 + b[0] % 10
+    span = max(1, steps - period)
+    return b[1] % span, period, 20 + b[2] % 30
+
+
 def normal_philox(seed, t, link, replica, site):
     w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
     u1 = 1.0 - u53(w[0], w[1])

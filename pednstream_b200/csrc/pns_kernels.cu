@@ -1288,6 +1288,49 @@ __global__ void __launch_bounds__(256) k_metric_pedestrians(const __grid_constan
 }
 
 // =================================================================================================
+// Origin demand of the batched environment, drawn on the device (reference od_manager.py:100-155:
+// Poisson around base + peak * (bump(S/4) + bump(3S/4)); 'constant'; 'sudden_demand' adds a burst of
+// random length, start and height).  One thread per (step, demand row, replica); every value is a pure
+// function of (seed, global replica; step, row), so it does not depend on how replicas are sharded.
+struct DemandCtx {
+    int S, rows, R;
+    uint32_t replica_base;
+    uint64_t seed;
+    const double *bump1, *bump2;     // [S] the two gaussian bumps, evaluated on the host like the reference does
+    const double *base, *peak;       // [rows*R]
+    const int32_t* pattern;          // [rows*R] 0 gaussian_peaks, 1 constant, 2 sudden_demand, -1 no demand
+    double* out;                     // [S+1][rows*R]
+};
+__global__ void __launch_bounds__(kBlock) k_demand_draw(const DemandCtx d) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per_row = (size_t)d.rows * d.R;
+    if (gid >= (size_t)(d.S + 1) * per_row) return;
+    const int t = (int)(gid / per_row);
+    const size_t col = gid % per_row;
+    const int row = (int)(col / d.R), rep = (int)(col % d.R);
+    const int pat = d.pattern[col];
+    double v = 0.0;
+    if (pat == 1) {
+        v = d.base[col];                                              // od_manager.py:106-109, all S+1 entries
+    } else if (pat >= 0 && t < d.S) {
+        pns::DrawKey key;
+        key.t = (uint32_t)t; key.link = (uint32_t)row; key.replica = d.replica_base + (uint32_t)rep;
+        key.k0 = (uint32_t)d.seed; key.k1 = (uint32_t)(d.seed >> 32);
+        const double lam = (d.base[col] + d.peak[col] * d.bump1[t]) + d.peak[col] * d.bump2[t];
+        const pns::Philox4 w = pns::philox4x32_10(key.t, key.link, 8u, key.replica, key.k0, key.k1);
+        v = (double)pns::poisson_inversion(lam, pns::u53(w.v[0], w.v[1]));
+        if (pat == 2) {                                               // od_manager.py:111-123
+            const pns::Philox4 b = pns::philox4x32_10(0u, key.link, 9u, key.replica, key.k0, key.k1);
+            const int period = 10 + (int)(b.v[0] % 10u);
+            const int span = d.S - period > 1 ? d.S - period : 1;
+            const int start = (int)(b.v[1] % (uint32_t)span);
+            if (t >= start && t < start + period) v += (double)(20 + (int)(b.v[2] % 30u));
+        }
+    }
+    d.out[gid] = v;
+}
+
+// =================================================================================================
 // Episode KPIs per replica (reference rl/rl_utils.py:770-1512, which reads them from the JSON that
 // OutputHandler saves): reductions over the whole history, rows 0..t_last.
 // Pass 1: one thread per (link, replica) walks its column through time (coalesced over replicas).
@@ -1777,6 +1820,19 @@ int pns_step_streamed(const pns_net* net, const pns_state* st, const pns_step_io
     sx.host_demand = host_demand; sx.dev_metric = dev_metric; sx.host_metric = host_metric;
     return step_impl(net, st, io, t0, n_steps, rng_mode, (cudaStream_t)stream, nullptr, nullptr, &sx);
 #endif
+}
+
+int pns_env_draw_demand(int sim_steps, int rows, int replicas, uint32_t replica_base, uint64_t seed,
+                        const double* bump1, const double* bump2, const double* base, const double* peak,
+                        const int32_t* pattern, double* demand, void* stream) {
+    if (sim_steps <= 0 || rows <= 0 || replicas <= 0) return 0;
+    if (!bump1 || !bump2 || !base || !peak || !pattern || !demand) return fail("pns_env_draw_demand: null argument");
+    DemandCtx d;
+    d.S = sim_steps; d.rows = rows; d.R = replicas; d.replica_base = replica_base; d.seed = seed;
+    d.bump1 = bump1; d.bump2 = bump2; d.base = base; d.peak = peak; d.pattern = pattern; d.out = demand;
+    const size_t n = (size_t)(sim_steps + 1) * rows * replicas;
+    PNS_LAUNCH(k_demand_draw, blocks_for(n), kBlock, (cudaStream_t)stream, d);
+    return launched("k_demand_draw");
 }
 
 int pns_kpi(const pns_net* net, const pns_state* st, const pns_step_io* io, int t_last, const int32_t* lk_role,

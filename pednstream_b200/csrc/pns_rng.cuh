@@ -343,6 +343,20 @@ int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
     return binomial_philox_core(key.t, key.link, key.replica, key.k0, key.k1, site, n, p);
 }
 
+// Poisson(lam), 0 <= lam <= 700, by CDF inversion from 0 (demand draws of the batched environment:
+// lam is a pedestrian arrival rate per step, a few tens): pmf(0) = exp(-lam), pmf(k) = pmf(k-1)*lam/k.
+__host__ __device__ inline int poisson_inversion(double lam, double u) {
+    if (!(lam > 0.0)) return 0;
+    double pk = det_exp(-lam);
+    int k = 0;
+    while (u > pk && k < 4096) {
+        u = u - pk;
+        k += 1;
+        pk = (pk * lam) / (double)k;
+    }
+    return k;
+}
+
 // Standard normal by Box-Muller on one Philox block.
 __host__ __device__ inline double normal_philox(const DrawKey& key, uint32_t site) {
     const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);

@@ -11,8 +11,8 @@ over the replica-fastest state, so a warp is 32 replicas of the same link or nod
 Tensors: `actions [R, n_act] float32` (agents concatenated in `possible_agents` order),
 `obs [R, n_obs] float32`, `reward [R] float32`, `done [R] bool`.  Replicas are sharded over
 GPUs by the caller (`replica_base` is the global index of local replica 0); no collective is
-needed inside a step.  Demand is pre-drawn on the host per replica (`np.random.RandomState(seed +
-replica)`), Poisson around the scenario's gaussian peaks (od_manager.py:145-155).
+needed inside a step.  Demand is drawn on the device at reset (`pns_env_draw_demand`): Poisson around the
+scenario's gaussian peaks (od_manager.py:145-155), keyed by the global replica index.
 
 `randomize=True`: every replica and episode gets its own perturbed scenario from the
 reference's generators (env_loader.py:183-258, 363-424) -- link bottlenecks (k_critical / k_jam /
@@ -189,50 +189,49 @@ class BatchedPedNetEnv:
         self.engine.set_replica_scenarios(classes, lk_class, od_w)
 
     # ------------------------------------------------------------------ demand
-    def _draw_demand(self, episode: int) -> np.ndarray:
-        """[S+1, rows * R] demand, replica fastest; replica r uses RandomState(seed + global r) and
-        draws its origins in node creation order, like the reference's setup does."""
-        net, S, R = self.network, self.simulation_steps, self.R
+    _PATTERN_CODE = {"gaussian_peaks": 0, "constant": 1, "sudden_demand": 2}
+
+    def demand_seed(self, episode: int) -> int:
+        return (self.seed * 0x9E3779B1 + 0x7F4A7C15 * (episode + 1)) % (2 ** 64)
+
+    def _draw_demand(self, episode: int):
+        """Fills the engine's demand table [S+1, rows * R] on the device (C-ABI pns_env_draw_demand): every
+        origin of every replica draws Poisson demand around its two-peak rate (od_manager.py:145-155), or
+        its constant / sudden-demand variant, keyed by (demand_seed(episode), global replica; step, row) --
+        no host loop over replicas, and independent of how the replicas are sharded."""
+        net, S, R, eng = self.network, self.simulation_steps, self.R, self.engine
         rows = net.plan["demand_nodes"]
-        out = np.zeros((S + 1, max(1, len(rows)), R), dtype=np.float64)
+        if not rows:
+            return
+        n = len(rows)
+        base = np.zeros((n, R)); peak = np.zeros((n, R)); pattern = np.full((n, R), -1, dtype=np.int32)
         gen = net.demand_generator
-        t = np.arange(S)
-        width = 2 * (S / 20) ** 2
-        specs = {}
         for k, node in enumerate(rows):
             if node.node_id not in net.origin_nodes:
                 continue
             cfg = gen._get_demand_config(node.node_id)
-            pattern = net.params.get("demand", {}).get(f"origin_{node.node_id}", {}).get("pattern", "gaussian_peaks")
-            if pattern not in ("gaussian_peaks", "sudden_demand", "constant"):
-                raise NotImplementedError(f"batched demand does not support the custom pattern {pattern!r}")
-            lam = (cfg.base_lambda + cfg.peak_lambda * np.exp(-(t - S / 4) ** 2 / width)
-                   + cfg.peak_lambda * np.exp(-(t - 3 * S / 4) ** 2 / width))
-            specs[k] = (pattern, lam, cfg.base_lambda)
-        for r in range(R):
-            rs = np.random.RandomState((self.seed + self.replica_base + r + 1_000_003 * episode) % (2 ** 32))
-            if self._scenarios is not None:                  # this replica's own demand parameters
-                own = {}
-                for k, node in enumerate(rows):
-                    p = self._scenarios[r].get(f"origin_{node.node_id}")
-                    if k in specs and p is not None:
-                        lam = (p["base_lambda"] + p["peak_lambda"] * np.exp(-(t - S / 4) ** 2 / width)
-                               + p["peak_lambda"] * np.exp(-(t - 3 * S / 4) ** 2 / width))
-                        own[k] = (str(p["pattern"]), lam, p["base_lambda"])
-                replica_specs = {**specs, **own}
-            else:
-                replica_specs = specs
-            for k, (pattern, lam, base) in replica_specs.items():
-                if pattern == "constant":                                  # od_manager.py:106-109
-                    out[:, k, r] = base
-                    continue
-                d = rs.poisson(lam).astype(np.float64)
-                if pattern == "sudden_demand":                             # od_manager.py:111-123
-                    period = rs.randint(10, 20)
-                    start = rs.randint(0, max(1, S - period))
-                    d[start:start + period] += rs.randint(20, 50)
-                out[:S, k, r] = d
-        return out.reshape(S + 1, -1)
+            name = net.params.get("demand", {}).get(f"origin_{node.node_id}", {}).get("pattern", "gaussian_peaks")
+            if name not in self._PATTERN_CODE:
+                raise NotImplementedError(f"batched demand does not support the custom pattern {name!r}")
+            base[k], peak[k], pattern[k] = cfg.base_lambda, cfg.peak_lambda, self._PATTERN_CODE[name]
+            if self._scenarios is not None:                  # per-replica demand parameters (randomize=True)
+                key = f"origin_{node.node_id}"
+                for r, sc in enumerate(self._scenarios):
+                    p = sc.get(key)
+                    if p is not None:
+                        base[k, r], peak[k, r] = p["base_lambda"], p["peak_lambda"]
+                        pattern[k, r] = self._PATTERN_CODE[str(p["pattern"])]
+        t = np.arange(S)
+        spread = 2 * (S / 20) ** 2
+        bump1 = np.exp(-(t - S / 4) ** 2 / spread)
+        bump2 = np.exp(-(t - 3 * S / 4) ** 2 / spread)
+        dev = eng.device
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self._demand_args = (to(bump1), to(bump2), to(base.reshape(-1)), to(peak.reshape(-1)), to(pattern.reshape(-1)))
+        with eng._guard():
+            _native.check(eng.lib, eng.lib.pns_env_draw_demand(
+                S, n, R, self.replica_base, C.c_uint64(self.demand_seed(episode)),
+                *[_ptr(x) for x in self._demand_args], _ptr(eng.demand), self._stream()), "pns_env_draw_demand")
 
     # ------------------------------------------------------------------ API
     def reset(self):
@@ -241,8 +240,8 @@ class BatchedPedNetEnv:
         eng.io.seed = (self.seed + 0x9E3779B97F4A7C15 * self.episode) % (2 ** 64)
         if self.randomize:
             self._apply_scenarios(self.episode)
-        eng.initialise(net._store.gate, net._store.sep_np64, self._tf, self._draw_demand(self.episode),
-                       self._od_w, self._supplied)
+        eng.initialise(net._store.gate, net._store.sep_np64, self._tf, None, self._od_w, self._supplied)
+        self._draw_demand(self.episode)
         self.sim_step = 1
         self.cumulative_reward.zero_()
         self.episode += 1

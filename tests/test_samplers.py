@@ -83,3 +83,60 @@ def test_speed_noise_sampler_is_standard_normal():
     assert stats.kstest(flat, "norm").pvalue > 1e-4
     c = np.corrcoef(g.T)
     assert np.abs(c - np.eye(4)).max() < 0.08
+
+
+def _draw_demand(lib, S, rows, R, replica_base, seed, base, peak, pattern):
+    t = np.arange(S)
+    spread = 2 * (S / 20) ** 2
+    b1 = np.ascontiguousarray(np.exp(-(t - S / 4) ** 2 / spread))
+    b2 = np.ascontiguousarray(np.exp(-(t - 3 * S / 4) ** 2 / spread))
+    base = np.ascontiguousarray(base, dtype=np.float64).reshape(-1)
+    peak = np.ascontiguousarray(peak, dtype=np.float64).reshape(-1)
+    pattern = np.ascontiguousarray(pattern, dtype=np.int32).reshape(-1)
+    out = np.zeros((S + 1, rows * R))
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.pns_env_draw_demand(S, rows, R, replica_base, C.c_uint64(seed), ptr(b1), ptr(b2), ptr(base), ptr(peak),
+                                 ptr(pattern), ptr(out), None)
+    assert rc == 0
+    return out.reshape(S + 1, rows, R), b1, b2
+
+
+def test_device_demand_draws(emu_lib):
+    """pns_env_draw_demand (kernel source, host build): equal to the Python restatement, Poisson around the
+    two-peak rate, constant and sudden-demand variants, and independent of the sharding of replicas."""
+    from scipy import stats
+    S, rows, R, seed = 120, 3, 16, 0xABCDEF0123
+    base = np.tile(np.array([[5.0], [8.0], [3.0]]), (1, R))
+    peak = np.tile(np.array([[20.0], [12.0], [30.0]]), (1, R))
+    pattern = np.tile(np.array([[0], [1], [2]], dtype=np.int32), (1, R))
+    pattern[0, 5] = -1
+    d, b1, b2 = _draw_demand(emu_lib, S, rows, R, 0, seed, base, peak, pattern)
+    # restatement, value by value
+    for r in (0, 7, 15):
+        for t in (0, 30, 31, 90, 119):
+            lam = (base[0, r] + peak[0, r] * b1[t]) + peak[0, r] * b2[t]
+            assert d[t, 0, r] == ph.poisson_philox(seed, t, 0, r, lam)
+        start, period, height = ph.sudden_burst_philox(seed, 2, r, S)
+        for t in range(S):
+            lam = (base[2, r] + peak[2, r] * b1[t]) + peak[2, r] * b2[t]
+            want = ph.poisson_philox(seed, t, 2, r, lam) + (height if start <= t < start + period else 0)
+            assert d[t, 2, r] == want
+    assert (d[:, 1, :] == 8.0).all()                       # constant: all S+1 entries (od_manager.py:106-109)
+    assert (d[:, 0, 5] == 0).all() and (d[S, 0, :] == 0).all() and (d[S, 2, :] == 0).all()
+    # sharding: replicas 8..15 drawn as a second shard are the same numbers
+    d2, _, _ = _draw_demand(emu_lib, S, rows, 8, 8, seed, base[:, 8:], peak[:, 8:], pattern[:, 8:])
+    assert np.array_equal(d2, d[:, :, 8:])
+    # Poisson law at a fixed rate: many replicas, constant lam (peak 0)
+    Rn = 4000
+    flat, _, _ = _draw_demand(emu_lib, 4, 1, Rn, 0, 99, np.full((1, Rn), 37.5), np.zeros((1, Rn)),
+                              np.zeros((1, Rn), dtype=np.int32))
+    x = flat[:4].reshape(-1)
+    assert abs(x.mean() - 37.5) < 5 * np.sqrt(37.5 / x.size) and abs(x.var() - 37.5) < 0.1 * 37.5
+    lo, hi = int(stats.poisson.ppf(0.001, 37.5)), int(stats.poisson.ppf(0.999, 37.5))
+    obs = np.histogram(np.clip(x, lo, hi), bins=np.arange(lo, hi + 2))[0].astype(float)
+    exp = stats.poisson.pmf(np.arange(lo, hi + 1), 37.5)
+    exp[0] += stats.poisson.cdf(lo - 1, 37.5); exp[-1] += stats.poisson.sf(hi, 37.5)
+    exp *= x.size
+    keep = exp >= 8
+    chi2 = float(((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+    assert chi2 < stats.chi2.ppf(1 - 1e-4, int(keep.sum()) - 1), chi2
