@@ -253,8 +253,8 @@ int pns_step_profiled(const pns_net *net, const pns_state *st, const pns_step_io
  * (`host_demand`, same layout as pns_step_io.demand) into the device table, and after every step the network-wide
  * pedestrian count of that step is reduced on the device to PNS_METRIC_SLOTS partial sums and copied to the host.
  * `dev_metric` (device scratch) and `host_metric` (pinned) hold [n_steps][PNS_METRIC_SLOTS * PNS_METRIC_STRIDE]
- * doubles; the count of step t0+k is the sum over j of host_metric[k][j * PNS_METRIC_STRIDE] (counts are
- * integer-valued, so the sum is exact in any order).  The copies (one H2D and one D2H per step) run on an internal
+ * doubles; the count of step t0+k is the sum over j of host_metric[k][j * PNS_METRIC_STRIDE] (exact in any
+ * order whenever the counts are integer-valued, i.e. unless a gate capacity makes a sending flow fractional).  The copies (one H2D and one D2H per step) run on an internal
  * second stream that meets `stream` once per group of 8 steps: demand rows are copied one group ahead of their step,
  * results up to one group after it.  The call returns with everything enqueued; after synchronising `stream` all
  * results are on the host. */
