@@ -318,7 +318,6 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
     if (tau < p.fftau) return o;                                          // link.py:267-269
     const float dens = is_sep(p) ? me.dens : div_by_area(me.num + num_rev, ar);
     const int lag = __float2int_rn(me.avg_tt / (float)c.n.unit_time);     // round(), half to even (link.py:260)
-    if (lag == 0) atomicOr(c.s.err + replica, PNS_ERR_ZERO_LAG);
     const int idx = max(0, tau + 1 - lag);
     const float cong = clip01((me.dens - p.kc32) / p.kj_minus_kc32);
     // cumulative_inflow[idx]: the caller may have fetched the rows of the two most likely lags early
@@ -329,6 +328,8 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
     const double gate_cap = ((front_gate * p.kc) * p.vf) * c.n.unit_time;
     double flow = pymin(boundary, gate_cap);
     const double original = flow;
+    // a zero lag makes the reference's result depend on its node visiting order; it only matters when the link sends
+    if (lag == 0 && flow > 0.0) atomicOr(c.s.err + replica, PNS_ERR_ZERO_LAG);
     if (flow > 0.0) {
         const float rf = dens == 0.0f ? 0.0f : clip01(dens / p.kj32);
         o.rf = rf;
