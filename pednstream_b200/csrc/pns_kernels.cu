@@ -86,8 +86,9 @@ constexpr int kBlock = 128;
 #define PNS_LANE_BLOCK 64      // threads per CTA of k_link_lane (measured: 64 < 128 < 256 < 512 in step time)
 #endif
 #ifndef PNS_PF_AHEAD_CTAS
-#define PNS_PF_AHEAD_CTAS (75776 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
-                                                     // into L2: half a resident wave of 148 SMs x 1024 threads (0 = off)
+#define PNS_PF_AHEAD_CTAS (113664 / PNS_LANE_BLOCK)  // k_link_lane: each CTA pulls the rows of the CTA this far ahead
+                                                     // into L2: three quarters of a resident wave of 148 SMs x 1024
+                                                     // threads (measured 1/4 .. 1 wave: 43.0 42.3 41.4 41.0 41.6 us; 0 = off)
 #endif
 #ifndef PNS_SKIP_ZERO_HANDOVER
 #define PNS_SKIP_ZERO_HANDOVER 1
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // ---- software prefetch for later CTAs ----------------------------------------------------
     // A thread spends most of its memory time waiting for the batch above to come back from DRAM.
     // CTAs are dispatched in index order, so while these loads are in flight the kernel asks L2 to
-    // fetch the same columns for the links PNS_PF_AHEAD_CTAS CTAs further on (half a resident wave,
+    // fetch the same columns for the links PNS_PF_AHEAD_CTAS CTAs further on (most of a resident wave,
     // a few microseconds ahead); their batch then hits in L2.
     if (PNS_PF_AHEAD_CTAS > 0 && threadIdx.x < 32u) {
         // the CTA's first warp covers the PNS_LANE_BLOCK links of the target CTA, 16 bytes apart
