@@ -27,3 +27,29 @@ def test_grid_plan_equals_generic_plan(size, origins):
     assert not net._static_fractions()[1].any()
     for row, node in enumerate(want["demand_nodes"]):
         assert np.array_equal(np.asarray(node.demand, dtype=np.float64)[:S], demand[:, row]), node.node_id
+
+
+def test_lane_block_order_is_a_permutation_that_starts_next_to_the_origins():
+    """The launch schedule of the single-replica link kernel (plan.lane_block_order, pns_net.lane_order)."""
+    from pednstream_b200.grid import build_grid_plan
+    from pednstream_b200.plan import lane_block_order
+    plan, _, _, _ = build_grid_plan(48, 20, locality_order=True)
+    L, stride, block = plan["n_links"], plan["nd_stride"], 64
+    order = lane_block_order(plan["nd_meta"], plan["nd_in_link"], L, stride, block, hops=4)
+    n_blocks = (L + block - 1) // block
+    assert order.dtype == np.int32 and sorted(order.tolist()) == list(range(n_blocks))
+    # links that leave an origin node sit in the leading group
+    meta = np.asarray(plan["nd_meta"])
+    slots = np.asarray(plan["nd_in_link"]).reshape(len(meta), stride)
+    origin_nodes = np.nonzero(meta[:, 2] >= 0)[0]
+    first_len = int(np.nonzero(np.diff(order) < 0)[0][0]) + 1
+    leading = set(order[:first_len].tolist())
+    for n in origin_nodes:
+        for col in slots[n]:
+            if 0 <= col < L:
+                assert col // block in leading and (col ^ 1) // block in leading
+    assert first_len < n_blocks                                  # and the rest follows in index order
+    assert np.all(np.diff(order[first_len:]) > 0)
+    # nothing to schedule without origins
+    meta2 = meta.copy(); meta2[:, 2] = -1
+    assert lane_block_order(meta2, plan["nd_in_link"], L, stride, block) is None
