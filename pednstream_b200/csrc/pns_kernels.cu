@@ -1036,11 +1036,20 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
         me.dens = div_by_area(me.num, ar);                                  // link.py:136
         if (c.metric) {
-            // streamed runs report the network-wide pedestrian count of every step: counts are
-            // integer-valued, so the sum is exact in any order; one atomic per warp, spread over slots
-            double v = valid ? (double)me.num : 0.0;
+            // streamed runs report the network-wide pedestrian count of every step: one atomic per warp, spread
+            // over slots.  Counts are whole numbers unless a gate capacity made a sending flow fractional, so the
+            // warp sum is normally one integer reduction (REDUX); otherwise five double-precision shuffles.
+            const float x = valid ? me.num : 0.0f;
+            const int xi = (int)x;
+            const bool whole = (float)xi == x && x < 6.0e7f;
+            double v;
+            if (__all_sync(FULL, whole)) {
+                v = (double)__reduce_add_sync(FULL, xi);
+            } else {
+                v = (double)x;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            }
             if ((threadIdx.x & 31u) == 0 && v != 0.0)
                 atomicAdd(c.metric + (size_t)PNS_METRIC_STRIDE * ((gid >> 5) & (PNS_METRIC_SLOTS - 1)), v);
         }
