@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 6
+#define PNS_ABI_VERSION 7
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -117,6 +117,9 @@ typedef struct pns_net {
                                    stores outflow[t] of that column and inflow[t] of column ^ 1 (node.py:146-162) */
     /* route plan (path_finder.py:510-546 structures, flattened by PathFinder.export_route_plan) */
     const int32_t *rt_routed_nodes, *rt_routed_edge0, *rt_routed_row0;
+    const int32_t *rt_row_routed;     /* [n_rows] routed node (index into rt_routed_*) of each upstream-slot row */
+    const int32_t *rt_row_grp_ptr, *rt_row_grp; /* [n_rows+1], [n_groups]: the (od, upstream) groups registered at each row */
+    const int32_t *rt_term_od;        /* [n_terms] OD column of each accumulation term (= rt_row_od[rt_term_row_entry]) */
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
     const int32_t *rt_opt_link, *rt_opt_slot;
     const double *rt_opt_dist;
@@ -169,6 +172,10 @@ typedef struct pns_step_io {
     float *req_rf;          /* releasing factor: p = 0.7 + 0.15*rf**0.8 is evaluated by the host in numpy */
     double *req_sval;       /* sending flow after the release stage when kind != 2 */
     int32_t *req_n3;        /* trials of R3 (-1: separator, no draw) */
+    double *req_exp;        /* REQUEST output [n_opts*R]: the arguments -temp*U of the route-choice exponentials of the
+                               step (path_finder.py:585) -- numpy-compatible stepping evaluates them with the host's
+                               numpy, whose exp differs from CUDA's in the last bit of a few percent of arguments */
+    const double *draw_exp; /* TABLE input [rows][n_opts*R]: exp of those arguments (NULL: evaluated on the device) */
     uint64_t seed;          /* PHILOX */
     uint32_t replica_base;  /* PHILOX: global index of local replica 0 (replicas sharded over GPUs) */
     uint32_t pad_;
@@ -194,6 +201,16 @@ typedef struct pns_env {
     const float *obs_div;      /* [n_obs] fixed normalisation divisor (1 = none, rl/builders.py:179-238) */
     const int32_t *reward_link;/* [n_reward_links] controlled links of the first agent when it is a gate agent
                                   (the reference rewards only that agent, pz_pednet_env.py:548-581) */
+    /* The same programs indexed by directed link, for the batched link kernel of pns_env_step, which applies the
+     * actions inside the link pass and emits observations and the reward from the state update (no separate
+     * environment launches).  Optional as a set: with lk_act == NULL pns_env_step runs the stand-alone kernels. */
+    const int32_t *lk_act;     /* [n_links] index of the action that sets this link's width, -1 = none */
+    const int32_t *lk_obs_ptr; /* [n_links+1] observation entries produced by each directed link ... */
+    const int32_t *lk_obs_col; /* ... their column in obs[r][.] ... */
+    const int32_t *lk_obs_src; /* ... PNS_OBS_* (REV_* entries are listed under the reverse link as INFLOW/OUTFLOW) ... */
+    const float *lk_obs_div;   /* ... and divisor */
+    const int32_t *lk_reward;  /* [n_links] 1 = the link or its reverse is a reward link */
+    int32_t *reward_count;     /* [R] scratch, zero before the first step (the kernel leaves it zero) */
 } pns_env;
 
 int pns_abi_version(void);
@@ -208,19 +225,27 @@ int pns_state_init(const pns_net *net, const pns_state *st, void *stream);
  * Link.cal_sending_flow (link.py:216-370) incl. get_outflow (:199-214) and
  * Link/Separator.cal_receiving_flow_with_reverse (:372-416, :480-512).
  * Writes sending_flow[tau], receiving_flow[tau] and the node-major copies nm_s / nm_r the node pass reads
- * (or only the draw requests in REQUEST mode).  The single-replica kernel does not rewrite an nm_s slot whose
+ * (or only the draw requests in REQUEST mode; with io->req_exp set and a routed network that call also runs
+ * pns_route_fractions in REQUEST mode, so one call collects everything the host must supply for the step).  The single-replica kernel does not rewrite an nm_s slot whose
  * previous and new sending flow are both 0: a caller that repeats steps clears nm_s first (see pns_node_flows).
  * Inside pns_step this pass for step t+1 is fused with pns_link_update of step t (same thread,
  * state kept in registers). */
 int pns_link_flows(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
                    void *stream);
 
-/* Logit route choice for step t, one thread per (od, upstream) group and replica:
- * PathFinder.update_node_turn_probs (path_finder.py:561-589). Writes st->probs. */
-int pns_route_probs(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, void *stream);
+/* Route choice for step t, one thread per (upstream slot of a routed node, replica): the logit P(down | up, od) of
+ * the (od, upstream) groups registered at the slot (PathFinder.update_node_turn_probs, path_finder.py:561-589; writes
+ * st->probs), then the OD mixing and row check of that row of turning fractions (update_turning_fractions + check_fractions,
+ * path_finder.py:591-715; writes st->tf_routed, which the node pass reads).  Runs for every routed node on every step,
+ * like the reference (network.py:273-278).  rng_mode REQUEST: writes only the exponentials' arguments to io->req_exp;
+ * TABLE with io->draw_exp: takes the exponentials from that table; otherwise they are evaluated on the device
+ * (libdevice exp, or the operation-exact det_exp in PHILOX mode). */
+int pns_route_fractions(const pns_net *net, const pns_state *st, const pns_step_io *io, int t, int rng_mode,
+                        void *stream);
 
-/* Node pass for step t, one thread per node and replica: turning fractions
- * (path_finder.py:591-715), Node.assign_flows / solve / update_links (node.py:146-300).
+/* Node pass for step t, one thread per node and replica: Node.assign_flows / solve / update_links
+ * (node.py:146-300) with the turning fractions pns_route_fractions left in st->tf_routed (routed nodes), the
+ * host-owned st->tf_static, or uniform 1/(m-1).
  * Writes inflow[t] / outflow[t] of every link (physical and virtual) and the cumulative counts of the virtual
  * O/D links at row t.
  * Row contract: a node that receives no sending flow stores nothing, so rows inflow[t] and outflow[t] must be zero

@@ -41,6 +41,12 @@ CASES = {
     "45_intersections_rand7": dict(dataset="45_intersections", run=400, seed=0, randomize=7),
     "nine_intersections_rand3": dict(dataset="nine_intersections", run=300, seed=0, randomize=3),
     "delft_rand11": dict(dataset="delft", run=80, seed=0, randomize=11),
+    # the third fundamental diagram (reference src/utils/functions.py:124-128): no shipped scenario selects it, so
+    # the scenario's default_link block is overridden before the network is built
+    "nine_intersections_smulders": dict(dataset="nine_intersections", run=499, seed=0,
+                                        default_link={"fd_type": "smulders"}),
+    "45_intersections_smulders": dict(dataset="45_intersections", run=400, seed=2,
+                                      default_link={"fd_type": "smulders", "speed_noise_std": 0.2}),
 }
 
 # parameters of reference examples/long_corridor.py:25-63 (scenario 1), restated as data
@@ -72,7 +78,8 @@ def build_reference_network(case):
         import logging
         net.logger.setLevel(logging.ERROR)
         return net
-    net, gen = rh.create_network(case["dataset"], steps_override=case.get("steps_override"))
+    net, gen = rh.create_network(case["dataset"], steps_override=case.get("steps_override"),
+                                 default_link=case.get("default_link"))
     if case.get("randomize") is not None:
         import logging
         net = gen.randomize_network(case["dataset"], seed=case["randomize"])
@@ -123,6 +130,11 @@ ENV_CASES = {
     "env_nine_intersections_opt2n": dict(dataset="nine_intersections", obs_mode="option2", normalize_obs=True,
                                          seed=9, steps=120),
     "env_butterfly_opt5": dict(dataset="butterfly_scA", obs_mode="option5", normalize_obs=False, seed=3, steps=200),
+    # option4 = [get_density / k_jam, back gate width] per controlled link (reference rl/builders.py:147-152)
+    "env_nine_intersections_opt4": dict(dataset="nine_intersections", obs_mode="option4", normalize_obs=False,
+                                        seed=21, steps=250),
+    "env_45_intersections_opt4": dict(dataset="45_intersections", obs_mode="option4", normalize_obs=False,
+                                      seed=4, steps=150),
 }
 
 

@@ -3,7 +3,7 @@
 Mirrors pednstream_b200/csrc/pns_rng.cuh operation for operation in IEEE doubles (Python floats
 never contract multiply-adds), so device samples can be checked bit for bit:
 Philox4x32-10 (Salmon et al., SC'11), 53-bit uniforms, fdlibm-style log/exp/sin/cos kernels,
-chunked CDF-inversion binomial, Box-Muller normal.  There is no reference-side counterpart: the
+CDF-inversion binomial (from zero for small means, outward from the mode for large ones), Box-Muller normal.  There is no reference-side counterpart: the
 reference draws from numpy's sequential global stream (SURVEY.md "RNG ledger"); this mode replaces
 the generator, not the distributions.
 """
@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import math
 import struct
+from fractions import Fraction
 
 import numpy as np
 
@@ -131,24 +132,133 @@ def det_pow08(x32):
     return np.float32(det_exp(float(np.float32(0.8)) * det_log(x)))   # numpy demotes the exponent to float32
 
 
-def binomial_inversion(m, pp, u):
+def fma(a, b, c):
+    """Correctly rounded a*b + c (what __fma_rn / fma() give): exact through rationals."""
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+INV_TABLE = 2048          # pns_rng.cuh kInvK: correctly rounded reciprocals of 1 .. 2048
+
+
+def inv_k(k):
+    return 1.0 / float(k)          # the table holds exactly these values; beyond it the kernel divides
+
+
+def binomial_from_zero(n, pp, u):
+    """CDF inversion from 0 (pns_rng.cuh binomial_from_zero): pmf(0) = q^n by squaring, then
+    pmf(k) = pmf(k-1) * (A/k - ratio) with A = ratio*(n+1), the factor formed by one fused multiply-add."""
     q = 1.0 - pp
     ratio = pp / q
-    pk, b, e = 1.0, q, m
+    A = ratio * float(n + 1)
+    pk, b, e = 1.0, q, n
     while e:
         if e & 1:
             pk = pk * b
         b = b * b
         e >>= 1
     k = 0
-    while u > pk and k < m:
+    while u > pk and k < n:
         u = u - pk
         k += 1
-        pk = pk * ((ratio * float(m - k + 1)) * (1.0 / float(k)))
+        pk = pk * fma(A, inv_k(k), -ratio)
     return k
 
 
-def binomial_philox(seed, t, link, replica, site, n, p):
+SFE = tuple(float.fromhex(h) for h in (
+    "0x0.0p+0", "0x1.4c071bcda0a5bp-4", "0x1.52a9b923ea649p-5", "0x1.c579a268d80b3p-6", "0x1.54a2662fd78a9p-6",
+    "0x1.10b4e513fcbedp-6", "0x1.c6b167bebdf36p-7", "0x1.85d4d612e4a86p-7", "0x1.552805e7b3076p-7",
+    "0x1.2f4871b12ab64p-7", "0x1.10f9d4c0743a7p-7", "0x1.f0593088014f8p-8", "0x1.c7018733aa9c6p-8",
+    "0x1.a40514700f36cp-8", "0x1.86076c002d4a7p-8", "0x1.6c08f6f194a10p-8"))
+
+
+def stirlerr(x):
+    """log(x!) - log(sqrt(2 pi x) (x/e)^x) for an integer-valued x >= 0 (Loader 2000): table below 16, the
+    asymptotic series above."""
+    if x < 16.0:
+        return SFE[int(x)]
+    r = 1.0 / x
+    rr = r * r
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0) * rr) * rr) * rr) * rr) * r
+
+
+def bd0(x, np_):
+    """Deviance term x*log(x/np) + np - x by its series in v = (x-np)/(x+np) (|x - np| << x + np at the mode)."""
+    d = x - np_
+    v = d / (x + np_)
+    s = d * v
+    if abs(s) < 2.2250738585072014e-308:
+        return s
+    ej = (2.0 * x) * v
+    v = v * v
+    for j in range(1, 64):
+        ej = ej * v
+        s1 = s + ej * (1.0 / float(2 * j + 1))
+        if s1 == s:
+            return s1
+        s = s1
+    return s
+
+
+def binomial_pmf_mode(n, m, pp, q):
+    """pmf of Binomial(n, pp) at m (its mode; 0 < m < n), saddle-point form (Loader 2000)."""
+    nd, md, kd = float(n), float(m), float(n - m)
+    lc = (((stirlerr(nd) - stirlerr(md)) - stirlerr(kd)) - bd0(md, nd * pp)) - bd0(kd, nd * q)
+    return det_exp(lc) * math.sqrt(nd / ((6.283185307179586 * md) * kd))
+
+
+PP09 = 1.0 - 0.9               # the flipped probability of the blockers draw (link.py:382)
+MODE_MEAN_TABULATED = 12.0     # mean from which the search starts at the mode: blockers draw (mode pmf tabulated)
+MODE_MEAN_GENERIC = 48.0       # ... any other probability (mode pmf evaluated per draw)
+MODE_TABLE_N = 4096
+
+
+def binomial_from_mode(n, pp, u):
+    """Search outward from the mode m = floor((n+1) pp): m, then the pairs {m+1, m-1}, {m+2, m-2}, ... subtracting the pmf values from u
+    (pns_rng.cuh binomial_from_mode).  Expected work ~ 1.6 standard deviations instead of the mean."""
+    q = 1.0 - pp
+    ratio = pp / q
+    iratio = q / pp
+    m = int(float(n + 1) * pp)
+    pm = binomial_pmf_mode(n, m, pp, q)
+    if not u > pm:
+        return m
+    u = u - pm
+    A = ratio * float(n + 1)
+    B = iratio * float(n + 1)
+    pu = pd = pm
+    paired = min(m, n - m)
+    for i in range(1, paired + 1):           # candidates m+i and m-i tested as a pair
+        pu = pu * fma(A, inv_k(m + i), -ratio)
+        pd = pd * fma(B, inv_k(n - m + i), -iratio)
+        both = pu + pd
+        if not u > both:
+            return m + i if not u > pu else m - i
+        u = u - both
+    ku, kd = m + paired, m - paired
+    while True:                              # far tail: one side is exhausted
+        if ku < n:
+            ku += 1
+            pu = pu * fma(A, inv_k(ku), -ratio)
+            if not u > pu:
+                return ku
+            u = u - pu
+        else:
+            pu = 0.0
+        if kd > 0:
+            pd = pd * fma(B, inv_k(n - kd + 1), -iratio)
+            kd -= 1
+            if not u > pd:
+                return kd
+            u = u - pd
+        else:
+            pd = 0.0
+        if not pu > 0.0 and not pd > 0.0:
+            return m               # u fell into the rounding leftover of the total mass
+
+
+def binomial_u(n, p, u):
+    """Exact Binomial(n, p) from one uniform (pns_rng.cuh binomial_u / binomial_core; binomial09_u is the same
+    algorithm with the constants of p = 0.9 folded and 0.9^n, the mode pmf tabulated)."""
     n = int(n)
     p = float(p)
     if n <= 0 or not p > 0.0:
@@ -157,18 +267,25 @@ def binomial_philox(seed, t, link, replica, site, n, p):
         return n
     flip = p > 0.5
     pp = 1.0 - p if flip else p
-    k0, k1 = seed & M32, (seed >> 32) & M32
-    total, left, chunk = 0, n, 0
-    while left > 0:
-        w = philox4x32_10(t, link, site | ((chunk >> 1) << 8), replica, k0, k1)
-        for h in range(2):
-            if left <= 0:
-                break
-            m = min(left, 512)
-            total += binomial_inversion(m, pp, u53(w[2 * h], w[2 * h + 1]))
-            left -= m
-            chunk += 1
-    return n - total if flip else total
+    mean = float(n) * pp
+    tabulated = pp == PP09 and n <= MODE_TABLE_N
+    if mean >= (MODE_MEAN_TABULATED if tabulated else MODE_MEAN_GENERIC):
+        k = binomial_from_mode(n, pp, u)
+    else:
+        k = binomial_from_zero(n, pp, u)
+    return n - k if flip else k
+
+
+def binomial_philox(seed, t, link, replica, site, n, p):
+    """A draw with a Philox block of its own (site in the counter): the activity draw R2, test hooks."""
+    w = philox4x32_10(t, link, site, replica, seed & M32, (seed >> 32) & M32)
+    return binomial_u(n, p, u53(w[0], w[1]))
+
+
+def link_draws(seed, t, link, replica):
+    """(u1, u3): the uniforms of a link's release (R1) and blockers (R3) draws of step t -- one block, site 1."""
+    w = philox4x32_10(t, link, 1, replica, seed & M32, (seed >> 32) & M32)
+    return u53(w[0], w[1]), u53(w[2], w[3])
 
 
 def poisson_philox(seed, t, row, replica, lam):
@@ -202,7 +319,6 @@ def normal_philox(seed, t, link, replica, site):
 
 
 # ---- float32 Box-Muller with exact fused multiply-adds (mirrors pns_rng.cuh) -----------------------
-from fractions import Fraction
 
 F32 = np.float32
 
@@ -305,8 +421,12 @@ class PhiloxDraws:
         return np.array([det_exp(float(v)) for v in values], dtype=np.float64)
 
     def binomial(self, site, link, t, n, p):
-        # the kernels key the draw by the step being computed (= time index + 1)
-        return binomial_philox(self.seed, t + 1, link.col, self.replica, self._SITE[site], int(n), float(p))
+        # the kernels key the draw by the step being computed (= time index + 1); the release and blockers draws of
+        # a link share one block, the activity draw has its own
+        if site == "R2":
+            return binomial_philox(self.seed, t + 1, link.col, self.replica, 2, int(n), float(p))
+        u1, u3 = link_draws(self.seed, t + 1, link.col, self.replica)
+        return binomial_u(int(n), float(p), u1 if site == "R1" else u3)
 
     def normal(self, link, t, sigma):
         # the two directions of a corridor share one block keyed by the even link of the pair

@@ -1,13 +1,15 @@
-"""TEST INFRASTRUCTURE ONLY -- live-reference harness (runs only where /root/reference exists).
+"""TEST / BASELINE INFRASTRUCTURE ONLY -- live-reference harness.
 
-Imports the *unmodified* reference (WaimenMak/PedNStream) from a writable temp copy of
-/root/reference with runtime shims only (matplotlib / pettingzoo / gymnasium stubs, a
-`verbose` kwarg for create_network -- SURVEY.md Appendix C).  Used by
-`oracle/gen_golden.py` to produce the committed fixtures under `tests/golden/` and by
-CPU-side tests (skipped when /root/reference is absent) to pin the oracle restatement.
+Imports the *unmodified* reference (WaimenMak/PedNStream) with runtime shims only (matplotlib /
+pettingzoo / gymnasium stubs, a `verbose` kwarg for create_network -- SURVEY.md Appendix C), from
+a writable temp copy of /root/reference where that tree exists (the build container), otherwise
+from `baseline/_ref/` -- the git-ignored install of the reference that `__graft_entry__.build()`
+makes in the build container and that travels to the GPU box with the repository snapshot.
+Used by `oracle/gen_golden.py` to produce the committed fixtures under `tests/golden/`, by
+CPU-side tests (skipped when no reference tree is present) to pin the oracle restatement, and by
+`bench.py --impl reference` (the reference arm times the reference's own code on the host cores).
 
-Nothing in the product package, the `-m gpu` tests, `bench.py` or `smoke()` imports this
-file: /root/reference does not exist on the GPU box.
+Nothing in the product package, the `-m gpu` tests or `smoke()` imports this file.
 """
 from __future__ import annotations
 
@@ -21,6 +23,26 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REFERENCE_SUBDIRS = ("src", "data", "handlers", "rl")
+_IGNORE = shutil.ignore_patterns("*.pt", "outputs", "*_agents_*", "ppo_agent_best", "*.gif", "__pycache__", "*.md")
+
+
+def install_reference(force: bool = False) -> str | None:
+    """Copy the reference's importable trees into baseline/_ref (git-ignored; ships with the snapshot).
+    Returns the path, or None when /root/reference is not present."""
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM")):
+        return INSTALLED_ROOT if os.path.isdir(os.path.join(INSTALLED_ROOT, "src", "LTM")) else None
+    stamp = os.path.join(INSTALLED_ROOT, ".installed")
+    if os.path.exists(stamp) and not force:
+        return INSTALLED_ROOT
+    if os.path.isdir(INSTALLED_ROOT):
+        shutil.rmtree(INSTALLED_ROOT)
+    os.makedirs(INSTALLED_ROOT)
+    for sub in REFERENCE_SUBDIRS:
+        shutil.copytree(os.path.join(REFERENCE_ROOT, sub), os.path.join(INSTALLED_ROOT, sub), ignore=_IGNORE)
+    open(stamp, "w").write("copied from /root/reference by oracle/ref_harness.install_reference\n")
+    return INSTALLED_ROOT
 
 LINK_FIELDS_F64 = ("inflow", "outflow", "cumulative_inflow", "cumulative_outflow",
                    "sending_flow", "receiving_flow", "back_gate_width_data")
@@ -32,7 +54,8 @@ _REF_COPY = None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM"))
+    return (os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM"))
+            or os.path.isdir(os.path.join(INSTALLED_ROOT, "src", "LTM")))
 
 
 class _Anything:
@@ -95,10 +118,12 @@ def reference_copy() -> str:
     """Writable copy of the reference tree (the reference mkdirs outputs/logs and data/)."""
     global _REF_COPY
     if _REF_COPY is None:
+        if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "LTM")):
+            _REF_COPY = INSTALLED_ROOT               # the installed copy is ours to write into
+            return _REF_COPY
         dst = tempfile.mkdtemp(prefix="pns_ref_")
-        for sub in ("src", "data", "handlers", "rl"):
-            shutil.copytree(os.path.join(REFERENCE_ROOT, sub), os.path.join(dst, sub),
-                            ignore=shutil.ignore_patterns("*.pt", "outputs", "*_agents_*", "*.gif"))
+        for sub in REFERENCE_SUBDIRS:
+            shutil.copytree(os.path.join(REFERENCE_ROOT, sub), os.path.join(dst, sub), ignore=_IGNORE)
         _REF_COPY = dst
     return _REF_COPY
 
@@ -138,15 +163,19 @@ def make_reference_env(dataset, **kw):
     return PedNetParallelEnv(dataset, **kw)
 
 
-def create_network(name: str, steps_override: int | None = None, verbose: bool = True, **kw):
+def create_network(name: str, steps_override: int | None = None, verbose: bool = True, default_link: dict = None,
+                   **kw):
     """reference NetworkEnvGenerator.create_network(name) (env_loader.py:81), optional
-    simulation_steps override."""
+    simulation_steps override and overrides of the scenario's default_link block."""
     import logging
     Network, Gen = import_reference()
     g = Gen()
-    if steps_override is not None:
+    if steps_override is not None or default_link:
         g.network_data = g.load_network_data(name)
-        g.config["params"]["simulation_steps"] = steps_override
+        if steps_override is not None:
+            g.config["params"]["simulation_steps"] = steps_override
+        if default_link:
+            g.config["params"]["default_link"].update(default_link)
     net = g.create_network(name, **kw)
     if net.logger is not None:
         net.logger.setLevel(logging.ERROR)

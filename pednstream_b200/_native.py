@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 METRIC_SLOTS, METRIC_STRIDE = 64, 4          # PNS_METRIC_SLOTS / PNS_METRIC_STRIDE of pns_step_streamed
 METRIC_ROW = METRIC_SLOTS * METRIC_STRIDE
 KPI_NAMES = ("total_demand", "total_outflow", "total_inflow", "person_time", "person_time_moving", "total_delay",
@@ -41,7 +41,7 @@ class PnsNet(C.Structure):
         + [("unit_time", C.c_double)]
         + [("classes", _p), ("class0", PnsLinkClass)]
         + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
-                             "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0",
+                             "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
                              "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
@@ -60,20 +60,23 @@ class PnsStepIO(C.Structure):
     _fields_ = [("demand", _p), ("od_w", _p), ("draw_b", _p), ("draw_n", _p),
                 ("draw_row_stride", C.c_int64),
                 ("req_kind", _p), ("req_n1", _p), ("req_rf", _p), ("req_sval", _p), ("req_n3", _p),
+                ("req_exp", _p), ("draw_exp", _p),
                 ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class PnsEnv(C.Structure):
     _fields_ = [("n_act", _i32), ("n_obs", _i32), ("n_reward_links", _i32), ("pad_", _i32)] + \
                [(k, _p) for k in ("act_link", "act_sep", "act_lo", "act_hi", "act_max_delta", "act_total_width",
-                                  "obs_link", "obs_src", "obs_div", "reward_link")]
+                                  "obs_link", "obs_src", "obs_div", "reward_link",
+                                  "lk_act", "lk_obs_ptr", "lk_obs_col", "lk_obs_src", "lk_obs_div", "lk_reward",
+                                  "reward_count")]
 
 
 OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens": 4, "gdens/kjam": 5,
            "speed": 6, "gate": 7}
 
 
-EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_probs",
+EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_fractions",
            "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_env_step", "pns_env_draw_demand", "pns_kpi",
            "pns_lane_block_size", "pns_rng_selftest")
 
@@ -86,7 +89,7 @@ def _declare(lib):
     lib.pns_last_error.restype = C.c_char_p
     lib.pns_state_init.argtypes = [net_p, st_p, _p]
     lib.pns_link_flows.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
-    lib.pns_route_probs.argtypes = [net_p, st_p, io_p, C.c_int, _p]
+    lib.pns_route_fractions.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
     lib.pns_node_flows.argtypes = [net_p, st_p, io_p, C.c_int, _p]
     lib.pns_link_update.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, _p]
     lib.pns_step.argtypes = [net_p, st_p, io_p, C.c_int, C.c_int, C.c_int, _p]

@@ -7,9 +7,10 @@
 //                          counts, pedestrians, density, speed, travel time at t
 //       k_link_pair<R1,PHASE,MODE>      one thread per (link pair, replica)      any replica count
 //       k_link_lane<PHASE,MODE,ONECLASS> one thread per directed link            single replica (GPU only)
-//   k_route_probs  one thread per (route group, replica)  logit P(down | up, od)  (routed nets only)
-//   k_node_flows   one thread per (node, replica)         turning fractions + node model on contiguous
-//                                                          node-major records
+//       k_link_rep<PHASE,MODE,ONECLASS,ENV> one thread per (directed link, replica)  batched replicas (GPU only)
+//   k_route_fractions one thread per (routed node, replica) logit P(down | up, od) of the node's groups + OD mixing
+//                                                          into its turning fractions (routed nets only)
+//   k_node_flows   one thread per (node, replica)         node model on contiguous node-major records
 //
 // and inside a multi-step call the UPDATE of step t and the FLOWS of step t+1 run in the same
 // thread (the link state stays in registers), so a step costs two launches, chained with
@@ -40,9 +41,9 @@
 #define PNS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define PNS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 template <typename K>
-static inline void pns_launch_chain(K kern, unsigned nblk, unsigned nthr, cudaStream_t stream, const void* ctx_arg) {
+static inline void pns_launch_chain(K kern, dim3 nblk, unsigned nthr, cudaStream_t stream, const void* ctx_arg) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(nthr); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.gridDim = nblk; cfg.blockDim = dim3(nthr); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -120,6 +121,7 @@ struct Ctx {
     int mode;     // PNS_RNG_*
     const int32_t* draw_b;  // TABLE: R1..R3 outcomes for step t_flows
     const double* draw_n;   // TABLE: R4 noise for step t
+    const double* draw_exp; // TABLE: route-choice exponentials of step t (null: evaluated on the device)
     size_t row64, row32;    // elements per history row
     size_t fld64, fld32;    // elements per history field
     // rows known at launch time, resolved on the host (saves 64-bit index arithmetic per access)
@@ -136,6 +138,20 @@ struct Ctx {
     const double *c0_pre0, *c0_pre1;                    // cumulative_inflow rows of the two likeliest arrival lags
     int c0_pre_i0, c0_pre_i1;                           // their indices (-1: not applicable)
     double* metric;                                     // streamed runs: PNS_METRIC_SLOTS partial sums of num_pedestrians[t]
+};
+
+// Control environment (reference rl/builders.py, rl/pz_pednet_env.py): the step context plus the action /
+// observation / reward programs
+struct EnvCtx {
+    Ctx c;
+    pns_env env;
+    const float* actions;
+    float* obs;
+    float* reward;
+    float* cum_reward;      // optional running sum of the rewards (null: not kept)
+    // route choice riding in a FLOWS-only launch of k_link_rep: route_blocks extra grid rows run route_thread for
+    // step route_t (independent of the link pass: it reads rows <= t-1 and writes probs / tf_routed)
+    int route_blocks, route_t;
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -254,13 +270,13 @@ struct Area {
     float area32;
     bool f64;
 };
-__device__ __forceinline__ Area link_area(const Ctx& c, const LinkP& p, size_t e, double gate) {
+__device__ __forceinline__ Area link_area(const Ctx& c, const LinkP& p, size_t e, double gate, bool np64_now = false) {
     Area a;
     if (is_sep(p)) {
         a.area = p.length * gate;
         a.space = p.kj * a.area;
         a.area32 = (float)a.area;
-        a.f64 = c.s.sep_np64[e] != 0;
+        a.f64 = np64_now || c.s.sep_np64[e] != 0;
     } else {
         a.area = p.area; a.space = p.space; a.area32 = p.area32; a.f64 = false;
     }
@@ -312,8 +328,8 @@ template <int MODE>
 __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, size_t e, int tau, const LinkNow& me,
                                                 float num_rev, const Area& ar, double front_gate, double cum_out_tau,
                                                 double snd_prev, int replica, const pns::DrawKey& key,
-                                                int pre_idx0 = -1, double pre_val0 = 0.0, int pre_idx1 = -1,
-                                                double pre_val1 = 0.0) {
+                                                const pns::LinkDraws& dr, int pre_idx0 = -1, double pre_val0 = 0.0,
+                                                int pre_idx1 = -1, double pre_val1 = 0.0) {
     SendOut o;
     o.kind = 0; o.n1 = 0; o.rf = 0.0f; o.sval = 0.0; o.flow = 0.0;
     if (tau < p.fftau) return o;                                          // link.py:267-269
@@ -351,7 +367,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
                 flow = (double)c.draw_b[e];
             } else if (MODE == PNS_RNG_PHILOX) {
                 const float p32 = 0.7f + 0.15f * pns::det_pow08(rf);
-                flow = (double)pns::binomial_philox(key, 1u, trials, (double)p32);
+                flow = (double)pns::binomial_u(trials, (double)p32, dr.u1);
             } else {
                 return o;   // REQUEST: the host draws R1 (and R2, which depends on it)
             }
@@ -378,7 +394,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
 template <int MODE>
 __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev,
                                                  const Area& ar, double back_gate, double cum_in_tau,
-                                                 double cum_out_lag, double rcv_prev, const pns::DrawKey& key,
+                                                 double cum_out_lag, double rcv_prev, const pns::LinkDraws& dr,
                                                  int* n3) {
     const int lag_i = tau + 1 - p.swtau;   // cum_out_lag = cumulative_outflow[lag_i] when lag_i >= 0
     double bound;
@@ -391,7 +407,7 @@ __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, s
         *n3 = trials;
         int blockers = 0;
         if (MODE == PNS_RNG_TABLE) blockers = c.draw_b[2 * c.row32 + e];
-        else if (MODE == PNS_RNG_PHILOX) blockers = pns::binomial_philox(key, 3u, trials, 0.9);
+        else if (MODE == PNS_RNG_PHILOX) blockers = pns::binomial09_u(trials, dr.u3);
         else return 0.0;
         if (lag_i < 0) {
             bound = ar.space - (double)blockers;
@@ -597,10 +613,16 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
         // front gate of a plain link is the back gate of its reverse (link.py:110-126); a separator's
         // gates both equal its lane width (link.py:462-478)
         const double front = is_sep(p) ? gate[a] : gate[1 - a];
+        // one Philox block per link and step serves its release (R1) and blockers (R3) draws; a link with nobody
+        // on it, in transit or opposite draws nothing
+        pns::LinkDraws dr;
+        dr.u1 = 0.0; dr.u3 = 0.0;
+        if (MODE == PNS_RNG_PHILOX && (now[a].num > 0.0f || now[1 - a].num >= 1.0f || cin_tau[a] != cou_tau[a]))
+            dr = pns::link_draws(key);
         s[a] = sending_flow<MODE>(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep,
-                                  key);
+                                  key, dr);
         r[a] = receiving_flow<MODE>(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], cou_lag[a],
-                                    rcv_prev[a], key, &n3[a]);
+                                    rcv_prev[a], dr, &n3[a]);
     }
     if (MODE == PNS_RNG_REQUEST) {
 #pragma unroll
@@ -629,20 +651,23 @@ __global__ void __launch_bounds__(kBlock, PNS_MIN_BLOCKS) k_link_pair(const __gr
 }
 
 // =================================================================================================
-// PathFinder.update_node_turn_probs (path_finder.py:561-589)
-__global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ Ctx c) {
+// PathFinder.update_node_turn_probs (path_finder.py:561-589) for one (od, upstream) group g: the logit
+// P(down | up, od) over the group's options, written to st->probs.  REQUEST mode writes the arguments of the
+// exponentials instead (numpy-compatible stepping evaluates them with the host's numpy: its exp differs from
+// CUDA's in the last bit of a few percent of arguments, and a last-bit change of a turning fraction can move
+// floor(P*s) across an integer); TABLE mode takes the exponentials from draw_exp when it is given.
+__device__ __forceinline__ void group_probs(const Ctx& c, int g, int rep, int t) {
     const int R = c.n.replicas;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)c.n.n_groups * R) return;
-    const int g = (int)(gid / R);
-    const int rep = (int)(gid % R);
-    PNS_PDL_TRIGGER();
-    PNS_PDL_WAIT();
-    const int o0 = c.n.rt_opt_ptr[g], o1 = c.n.rt_opt_ptr[g + 1];
+    const int o0 = __ldg(c.n.rt_opt_ptr + g), o1 = __ldg(c.n.rt_opt_ptr + g + 1);
     const int n = o1 - o0;
-    const bool wide = c.n.rt_grp_has_virtual[g] != 0;   // np.array([... float32 ..., 0]) is float64
-    const int tm1 = c.t - 1;
-    const int tm2 = wrap_index(c, c.t - 2, rep);
+    if (n == 1 && c.mode != PNS_RNG_REQUEST) {
+        // a single option: exp(x) / exp(x) = 1 exactly (x = -temp*U is far from the over/underflow range)
+        c.s.probs[(size_t)o0 * R + rep] = 1.0;
+        return;
+    }
+    const bool wide = __ldg(c.n.rt_grp_has_virtual + g) != 0;   // np.array([... float32 ..., 0]) is float64
+    const int tm1 = t - 1;
+    const int tm2 = wrap_index(c, t - 2, rep);
     const float* num = H32(c, PNS_F32_NUM_PED, tm1);
     const float* dens_row = H32(c, PNS_F32_DENSITY, tm1);
     const double* rcv = H64(c, PNS_F64_RECEIVING, tm2);
@@ -651,8 +676,8 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
     double cap[PNS_MAX_DEGREE];
     double sum_d = 0.0, sum_c = 0.0;
     for (int k = 0; k < n; ++k) {
-        const int l = c.n.rt_opt_link[o0 + k];
-        sum_d = k == 0 ? c.n.rt_opt_dist[o0] : sum_d + c.n.rt_opt_dist[o0 + k];
+        const int l = __ldg(c.n.rt_opt_link + o0 + k);
+        sum_d = k == 0 ? __ldg(c.n.rt_opt_dist + o0) : sum_d + __ldg(c.n.rt_opt_dist + o0 + k);
         if (l >= 0) {
             const LinkP& p = c.n.classes[class_of(c, l, rep)];
             const size_t e = (size_t)l * R + rep;
@@ -682,52 +707,84 @@ __global__ void __launch_bounds__(kBlock) k_route_probs(const __grid_constant__ 
             const float d = dens[k] - 2.0f;
             crowd_term = (double)((float)c.n.rt_beta * (fmaxf(d, 0.0f) / 8.0f));
         }
-        const double util = (((c.n.rt_alpha * c.n.rt_opt_dist[o0 + k]) / (sum_d + 1e-6) + crowd_term) -
+        const double util = (((c.n.rt_alpha * __ldg(c.n.rt_opt_dist + o0 + k)) / (sum_d + 1e-6) + crowd_term) -
                              (c.n.rt_omega * cap[k]) / (sum_c + 1e-6)) + c.n.rt_eps;
-        // numpy's exp in the reference-compatible modes; the operation-exact restatement when the
-        // whole step is counter-based (so oracle/philox.py can reproduce it bit for bit anywhere)
-        ex[k] = c.mode == PNS_RNG_PHILOX ? pns::det_exp(-c.n.rt_temp * util) : exp(-c.n.rt_temp * util);
+        const double arg = -c.n.rt_temp * util;
+        if (c.mode == PNS_RNG_REQUEST) {
+            c.io.req_exp[(size_t)(o0 + k) * R + rep] = arg;
+            continue;
+        }
+        // the operation-exact restatement when the whole step is counter-based (oracle/philox.py reproduces it
+        // bit for bit anywhere); the host's exponentials in numpy-compatible stepping; libdevice otherwise
+        ex[k] = c.mode == PNS_RNG_PHILOX ? pns::det_exp(arg)
+              : c.draw_exp ? c.draw_exp[(size_t)(o0 + k) * R + rep] : exp(arg);
         sum_e = k == 0 ? ex[0] : sum_e + ex[k];
     }
+    if (c.mode == PNS_RNG_REQUEST) return;
     for (int k = 0; k < n; ++k) c.s.probs[(size_t)(o0 + k) * R + rep] = ex[k] / sum_e;
 }
 
 // =================================================================================================
-// PathFinder.update_turning_fractions + check_fractions (path_finder.py:591-715) for one routed node;
-// writes the node's m(m-1) fractions to tf_routed (element k at out[k*R]).
-__device__ __noinline__ void routed_fractions(const Ctx& c, int routed, int m, int t, int rep, double* out) {
+// PathFinder.update_turning_fractions + check_fractions (path_finder.py:591-715) for one upstream slot i of a
+// routed node (row = the node's first row + i): P(od | up) from this step's OD weights, the m-1 fractions of
+// the row as sum over ODs of P(down | up, od) * P(od | up) in the reference's accumulation order, and the row
+// check.  Writes element j of the row to out[j*R].
+__device__ __forceinline__ void routed_row_fractions(const Ctx& c, int routed, int m, int i, int row, int t, int rep,
+                                                     double* out) {
     const int R = c.n.replicas;
-    const int row0 = c.n.rt_routed_row0[routed];
-    const int edge0 = c.n.rt_routed_edge0[routed];
+    const int edge0 = __ldg(c.n.rt_routed_edge0 + routed) + i * (m - 1);
     // od weights of this step; one set per replica under domain randomisation
     const size_t ws = c.n.per_replica_scenario ? (size_t)R : 1;
     const double* w = c.io.od_w + (size_t)t * c.n.n_od * ws + (c.n.per_replica_scenario ? rep : 0);
-    int k = 0;
-    for (int i = 0; i < m; ++i) {
-        const int ra = c.n.rt_row_ptr[row0 + i], rb = c.n.rt_row_ptr[row0 + i + 1];
-        double total = 0.0;
-        for (int x = ra; x < rb; ++x) total = total + w[(size_t)c.n.rt_row_od[x] * ws];
-        const double uniform = rb > ra ? 1.0 / (double)(rb - ra) : 0.0;
-        double row_sum = 0.0;
-        for (int j = 0; j < m - 1; ++j, ++k) {
-            const int ta = c.n.rt_term_ptr[edge0 + k], tb = c.n.rt_term_ptr[edge0 + k + 1];
-            double acc = 0.0;
-            for (int x = ta; x < tb; ++x) {
-                const double od_p = total > 0.0 ? w[(size_t)c.n.rt_row_od[c.n.rt_term_row_entry[x]] * ws] / total : uniform;
-                acc = acc + c.s.probs[(size_t)c.n.rt_term_opt[x] * R + rep] * od_p;
-            }
-            out[(size_t)k * R] = acc;
-            row_sum = j == 0 ? acc : row_sum + acc;
+    const int ra = __ldg(c.n.rt_row_ptr + row), rb = __ldg(c.n.rt_row_ptr + row + 1);
+    // a single registered OD: P(od | up) = w/w = 1, or the uniform 1/1 when w = 0 (weights are finite, >= 0)
+    const bool single = rb - ra == 1;
+    double total = 0.0;
+    if (!single)
+        for (int x = ra; x < rb; ++x) total = total + w[(size_t)__ldg(c.n.rt_row_od + x) * ws];
+    const double uniform = rb > ra ? 1.0 / (double)(rb - ra) : 0.0;
+    double row_sum = 0.0;
+    for (int j = 0; j < m - 1; ++j) {
+        const int ta = __ldg(c.n.rt_term_ptr + edge0 + j), tb = __ldg(c.n.rt_term_ptr + edge0 + j + 1);
+        double acc = 0.0;
+        for (int x = ta; x < tb; ++x) {
+            const double od_p = single ? 1.0 : total > 0.0 ? w[(size_t)__ldg(c.n.rt_term_od + x) * ws] / total : uniform;
+            acc = acc + c.s.probs[(size_t)__ldg(c.n.rt_term_opt + x) * R + rep] * od_p;
         }
-        if (fabs(row_sum - 1.0) > 1e-3) {                                  // check_fractions
-            double* rowp = out + (size_t)(k - (m - 1)) * R;
-            if (row_sum > 1e-6) {
-                for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = rowp[(size_t)j * R] / row_sum;
-            } else {
-                for (int j = 0; j < m - 1; ++j) rowp[(size_t)j * R] = 1.0 / (double)(m - 1);
-            }
+        out[(size_t)j * R] = acc;
+        row_sum = j == 0 ? acc : row_sum + acc;
+    }
+    if (fabs(row_sum - 1.0) > 1e-3) {                                      // check_fractions
+        if (row_sum > 1e-6) {
+            for (int j = 0; j < m - 1; ++j) out[(size_t)j * R] = out[(size_t)j * R] / row_sum;
+        } else {
+            for (int j = 0; j < m - 1; ++j) out[(size_t)j * R] = 1.0 / (double)(m - 1);
         }
     }
+}
+
+// Route choice, one thread per (upstream slot of a routed node, replica): the probabilities of the (od, upstream)
+// groups registered at that slot, then the slot's row of turning fractions (tf_routed; read by the node pass of
+// the same step).  Runs for every routed node on every step, as the reference does (network.py:273-278), so the
+// fractions a caller reads back are those of the last step.
+__device__ __forceinline__ void route_thread(const Ctx& c, int t, int row, int rep) {
+    const int R = c.n.replicas;
+    PNS_PDL_TRIGGER();
+    const int routed = __ldg(c.n.rt_row_routed + row);
+    const int ga = __ldg(c.n.rt_row_grp_ptr + row), gb = __ldg(c.n.rt_row_grp_ptr + row + 1);
+    const int i = row - __ldg(c.n.rt_routed_row0 + routed);
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + __ldg(c.n.rt_routed_nodes + routed));
+    const int m = meta.y & 0xff;
+    PNS_PDL_WAIT();
+    for (int x = ga; x < gb; ++x) group_probs(c, __ldg(c.n.rt_row_grp + x), rep, t);
+    if (c.mode == PNS_RNG_REQUEST) return;
+    routed_row_fractions(c, routed, m, i, row, t, rep, c.s.tf_routed + (size_t)(meta.w + i * (m - 1)) * R + rep);
+}
+__global__ void __launch_bounds__(kBlock) k_route_fractions(const __grid_constant__ Ctx c) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned R = (unsigned)c.n.replicas;
+    if (gid >= (size_t)c.n.n_rows * R) return;
+    route_thread(c, c.t, (int)((unsigned)gid / R), (int)((unsigned)gid % R));
 }
 
 // floor(min(w, r * (w / D))) of node.py:296-298 with two exact shortcuts that avoid the IEEE division:
@@ -816,9 +873,7 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
         const double* tf = nullptr;
         size_t ts = 1;
         if (ROUTED && tf_mode == 2) {
-            double* out = c.s.tf_routed + (size_t)tf_ptr * R + rep;
-            routed_fractions(c, __ldg(c.n.nd_routed + node), m, c.t, rep, out);
-            tf = out;
+            tf = c.s.tf_routed + (size_t)tf_ptr * R + rep;      // written by k_route_fractions for this step
             ts = (size_t)R;
         } else if (tf_mode == 1) {
             tf = c.s.tf_static + tf_ptr;
@@ -879,8 +934,7 @@ __device__ __noinline__ void node_body_generic(const Ctx& c, int node, int rep, 
 }
 
 // Node.assign_flows / solve (node.py:164-300) + turning fractions (path_finder.py:591-715)
-// ROUTED: some node takes its fractions from the route-choice model (the callee's registers would
-// otherwise be charged to every launch)
+// ROUTED: some node takes its fractions from the route-choice model (tf_routed)
 template <bool R1, bool ROUTED>
 __global__ void __launch_bounds__(PNS_NODE_BLOCK, PNS_NODE_MIN_BLOCKS) k_node_flows(const __grid_constant__ Ctx c) {
     const int R = R1 ? 1 : c.n.replicas;
@@ -1107,6 +1161,10 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     SendOut s;
     double r = 0.0;
     int n3 = -1;
+    pns::LinkDraws dr;          // one Philox block serves the link's release (R1) and blockers (R3) draws
+    dr.u1 = 0.0; dr.u3 = 0.0;
+    if (MODE == PNS_RNG_PHILOX && valid && (me.num > 0.0f || num_rev >= 1.0f || cin_tau != cou_tau))
+        dr = pns::link_draws(key);
     if (valid) {
         // A link with nobody on it and nobody in transit (everything that entered has left) sends nothing:
         // arrived <= cin[tau] - cout[tau] = 0, so boundary = 0 and only the smoothing with the previous
@@ -1118,9 +1176,9 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
             if (MODE != PNS_RNG_REQUEST && f < 0.0) atomicOr(c.s.err, PNS_ERR_NEG_SENDING);
             s.flow = MODE == PNS_RNG_REQUEST ? 0.0 : f;
         } else
-        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, pre_i0, pre_v0, pre_i1,
-                               pre_v1);
-        r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, dr, pre_i0, pre_v0,
+                               pre_i1, pre_v1);
+        r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, dr, &n3);
     } else {
         s.flow = 0; s.sval = 0; s.kind = 0; s.n1 = 0; s.rf = 0;
     }
@@ -1148,14 +1206,17 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
 
 // =================================================================================================
 // Control environment (reference rl/builders.py, rl/pz_pednet_env.py)
-struct EnvCtx {
-    Ctx c;
-    pns_env env;
-    const float* actions;
-    float* obs;
-    float* reward;
-    float* cum_reward;      // optional running sum of the rewards (null: not kept)
-};
+
+// ActionApplier.clip_gater_action_value / clip_separator_action_value (rl/builders.py:281-352): the width an
+// action asks for, rate-limited around the current width and clipped to the agent's bounds
+__device__ __forceinline__ double clipped_action(const pns_env& env, int a, double v /* float(action[i]) */, double cur) {
+    const double md = env.act_max_delta[a];
+    if (fabs(v - cur) > md) {
+        const double d = fmin(fmax(v - cur, -md), md);                   // np.clip
+        v = cur + d;
+    }
+    return fmin(fmax(v, env.act_lo[a]), env.act_hi[a]);
+}
 
 // ActionApplier.clip_gater_action_value / clip_separator_action_value + setters
 // (rl/builders.py:281-352; link.py:121-126, 462-478)
@@ -1169,14 +1230,7 @@ __global__ void __launch_bounds__(kBlock) k_env_actions(const __grid_constant__ 
     const int l = x.env.act_link[a];
     PNS_PDL_WAIT();                      // actions and gate table may come from the previous kernel
     const size_t e = (size_t)l * R + rep;
-    double v = (double)x.actions[(size_t)rep * x.env.n_act + a];       // float(action[i])
-    const double cur = c.s.gate[e];
-    const double md = x.env.act_max_delta[a];
-    if (fabs(v - cur) > md) {
-        const double d = fmin(fmax(v - cur, -md), md);                   // np.clip
-        v = cur + d;
-    }
-    v = fmin(fmax(v, x.env.act_lo[a]), x.env.act_hi[a]);
+    const double v = clipped_action(x.env, a, (double)x.actions[(size_t)rep * x.env.n_act + a], c.s.gate[e]);
     c.s.gate[e] = v;
     if (x.env.act_sep[a]) {
         const size_t er = (size_t)(l ^ 1) * R + rep;
@@ -1186,14 +1240,45 @@ __global__ void __launch_bounds__(kBlock) k_env_actions(const __grid_constant__ 
     }
 }
 
+// Link.get_density(t) (link.py:190-197, 427): both directions' pedestrians over the shared area; a separator
+// lane's own density.  CG: read around L1 (values another CTA of the same launch has just written).
+template <bool CG>
 __device__ __forceinline__ float shared_density(const Ctx& c, int l, int rep, int t) {
     const int R = c.n.replicas;
     const LinkP& p = c.n.classes[class_of(c, l, rep)];
     const size_t e = (size_t)l * R + rep;
-    if (is_sep(p)) return H32(c, PNS_F32_DENSITY, t)[e];
+    if (is_sep(p)) return CG ? __ldcg(H32(c, PNS_F32_DENSITY, t) + e) : H32(c, PNS_F32_DENSITY, t)[e];
     const float* num = H32(c, PNS_F32_NUM_PED, t);
+    const size_t er = (size_t)(l ^ 1) * R + rep;
     const Area ar = link_area(c, p, e, 0.0);
-    return div_by_area(num[e] + num[(size_t)(l ^ 1) * R + rep], ar);
+    return div_by_area((CG ? __ldcg(num + e) : num[e]) + (CG ? __ldcg(num + er) : num[er]), ar);
+}
+
+// PedNetParallelEnv._compute_rewards (pz_pednet_env.py:548-581) of one replica at row t, float32 arithmetic as numpy
+// evaluates it: the first agent's controlled links only (the reference returns inside its loop)
+template <bool CG>
+__device__ __forceinline__ float env_reward(const EnvCtx& x, int rep, int t) {
+    const Ctx& c = x.c;
+    const int R = c.n.replicas;
+    const int n = x.env.n_reward_links;
+    float total = 0.0f, rho[PNS_MAX_DEGREE];
+    const float* tt = H32(c, PNS_F32_TRAVEL_TIME, t);
+    for (int i = 0; i < n; ++i) {
+        const int l = x.env.reward_link[i];
+        const size_t e = (size_t)l * R + rep, er = (size_t)(l ^ 1) * R + rep;
+        rho[i] = shared_density<CG>(c, l, rep, t);
+        total = total - ((CG ? __ldcg(tt + e) : tt[e]) + (CG ? __ldcg(tt + er) : tt[er]));
+        if (rho[i] > 4.0f) total = total - 10.0f * (rho[i] - c.n.classes[class_of(c, l, rep)].kc32);
+    }
+    if (n > 1) {
+        float s = rho[0];
+        for (int i = 1; i < n; ++i) s = s + rho[i];
+        const float mean = s / (float)n;
+        float d = fabsf(rho[0] - mean);
+        for (int i = 1; i < n; ++i) d = d + fabsf(rho[i] - mean);
+        total = total - 10.0f * (d / (float)n);
+    }
+    return total;
 }
 
 __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ EnvCtx x) {
@@ -1214,8 +1299,8 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
             case PNS_OBS_OUTFLOW: v = (float)H64(c, PNS_F64_OUTFLOW, t)[e]; break;
             case PNS_OBS_REV_INFLOW: v = (float)H64(c, PNS_F64_INFLOW, t)[er]; break;
             case PNS_OBS_REV_OUTFLOW: v = (float)H64(c, PNS_F64_OUTFLOW, t)[er]; break;
-            case PNS_OBS_SHARED_DENSITY: v = shared_density(c, l, rep, t); break;
-            case PNS_OBS_SHARED_DENSITY_OVER_KJ: v = shared_density(c, l, rep, t) / c.n.classes[class_of(c, l, rep)].kj32; break;
+            case PNS_OBS_SHARED_DENSITY: v = shared_density<false>(c, l, rep, t); break;
+            case PNS_OBS_SHARED_DENSITY_OVER_KJ: v = shared_density<false>(c, l, rep, t) / c.n.classes[class_of(c, l, rep)].kj32; break;
             case PNS_OBS_SPEED: v = H32(c, PNS_F32_SPEED, t)[e]; break;
             default: v = (float)c.s.gate[e]; break;
         }
@@ -1228,27 +1313,258 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
     const size_t rid = gid - n_obs_threads;
     if (rid >= (size_t)R) return;
     const int rep = (int)rid;
-    const int n = x.env.n_reward_links;
-    float total = 0.0f, rho[PNS_MAX_DEGREE];
-    for (int i = 0; i < n; ++i) {
-        const int l = x.env.reward_link[i];
-        const size_t e = (size_t)l * R + rep, er = (size_t)(l ^ 1) * R + rep;
-        rho[i] = shared_density(c, l, rep, t);
-        const float* tt = H32(c, PNS_F32_TRAVEL_TIME, t);
-        total = total - (tt[e] + tt[er]);
-        if (rho[i] > 4.0f) total = total - 10.0f * (rho[i] - c.n.classes[class_of(c, l, rep)].kc32);
-    }
-    if (n > 1) {
-        float s = rho[0];
-        for (int i = 1; i < n; ++i) s = s + rho[i];
-        const float mean = s / (float)n;
-        float d = fabsf(rho[0] - mean);
-        for (int i = 1; i < n; ++i) d = d + fabsf(rho[i] - mean);
-        total = total - 10.0f * (d / (float)n);
-    }
+    const float total = env_reward<false>(x, rep, t);
     x.reward[rep] = total;
     if (x.cum_reward) x.cum_reward[rep] = x.cum_reward[rep] + total;
 }
+
+#ifndef PNS_HOST_EMULATION
+// =================================================================================================
+// Batched replicas: one thread per (directed link, replica).  A CTA is one warp pair: its two warps are the two
+// directions of one corridor for the same 32 replicas (every access of a warp is 32 consecutive elements of a
+// history row) and trade pedestrians, density, speed noise and sending flow through shared memory behind the
+// CTA barrier.  (One barrier per CTA: a dynamic named-barrier id makes ptxas reserve all 16 hardware barriers,
+// which caps an SM at 4 resident CTAs.)  Same device functions as k_link_pair, half the state per thread
+// (twice the resident warps), every load that does not depend on a computed lag issued up front, the arrival
+// row fetched for the two likeliest lags and the diffusion taps requested as soon as the link is known to be
+// occupied.  ENV: the control environment rides along -- the FLOWS phase applies the step's actions to the
+// widths it reads (ActionApplier, rl/builders.py:264-352), the UPDATE phase emits the observation entries of
+// its link and, as the last thread of a replica's reward links to finish, the reward (pz_pednet_env.py:548-581).
+// (The host-emulation test build runs k_link_pair and the stand-alone environment kernels instead; the GPU
+// parity tests compare the two paths.)
+#ifndef PNS_REP_MIN_BLOCKS
+#define PNS_REP_MIN_BLOCKS 12
+#endif
+constexpr int kRepBlock = 64;
+
+template <int PHASE, int MODE, bool ONECLASS, bool ENV>
+__global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(const __grid_constant__ EnvCtx x) {
+    constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
+    const Ctx& c = x.c;
+    __shared__ float sh_num[kRepBlock], sh_dens[kRepBlock];
+    __shared__ double sh_noise[kRepBlock], sh_send[kRepBlock];
+    const int R = c.n.replicas;
+    const unsigned dir = threadIdx.x >> 5;
+    const int rep_raw = (int)(blockIdx.x * 32u + (threadIdx.x & 31u));
+    const unsigned n_pairs = (unsigned)c.n.n_links >> 1;
+    if (PHASE == PH_FLOWS && blockIdx.y >= n_pairs) {       // route choice rides along: two rows per CTA
+        const unsigned row = 2u * (blockIdx.y - n_pairs) + dir;
+        if (row < (unsigned)c.n.n_rows && rep_raw < R) route_thread(c, x.route_t, (int)row, rep_raw);
+        return;
+    }
+    const unsigned pair = blockIdx.y;
+    const bool valid = rep_raw < R;
+    const int rep = valid ? rep_raw : R - 1;          // idle lanes shadow the last replica and store nothing
+    const int l = (int)(2u * pair + dir);
+    const size_t e = (size_t)l * R + rep, er = (size_t)(l ^ 1) * R + rep;
+    const unsigned mate = threadIdx.x ^ 32u;
+    const int tau = c.t_flows - 1;
+    PNS_PDL_TRIGGER();
+    const LinkP& p = ONECLASS ? c.n.class0 : c.n.classes[class_of(c, l, rep)];
+    const int2 slots = __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);   // {sending slot, receiving slot}
+    const int fftau = p.fftau, swtau = p.swtau;
+    int act_own = -1, act_mate = -1, obs0 = 0, obs1 = 0, rewarded = 0;
+    if (ENV && flw && x.actions) {
+        act_own = __ldg(x.env.lk_act + l);
+        act_mate = __ldg(x.env.lk_act + (l ^ 1));
+    }
+    if (ENV && upd && x.obs) {
+        obs0 = __ldg(x.env.lk_obs_ptr + l); obs1 = __ldg(x.env.lk_obs_ptr + l + 1);
+        rewarded = x.env.n_reward_links > 0 ? __ldg(x.env.lk_reward + l) : 0;
+    }
+    PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
+    double gate = c.s.gate[e];
+    double gate_rev = flw ? c.s.gate[er] : 0.0;
+    // ---- batch of independent loads --------------------------------------------------------
+    double din = 0, dout = 0, cin_prev = 0, cou_prev = 0;
+    float np_ = 0, rs = 0, tt_old = 0;
+    const bool windowed = c.u_tt_old != nullptr;
+    if (upd) {
+        cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e];
+        np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
+        if (windowed) tt_old = c.u_tt_old[e];
+        dout = c.n_outflow[e]; din = c.n_inflow[e];
+    }
+    double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
+    LinkNow me;
+    me.num = 0; me.dens = 0; me.avg_tt = 0;
+    float num_rev = 0.0f;
+    int pre_i0 = -1, pre_i1 = -1;
+    double pre_v0 = 0.0, pre_v1 = 0.0;
+    if (flw) {
+        if (!upd) {
+            cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e];
+            me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e];
+            num_rev = c.f_num[er];
+        }
+        snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
+        if (ONECLASS) {
+            if (c.c0_coulag) cou_lag = c.c0_coulag[e];
+        } else {
+            const int lag_i = tau + 1 - swtau;
+            if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
+        }
+        // the arrival row cumulative_inflow[tau+1-lag]: in free flow the lag is the free-flow lag or one less
+        // (speed noise), so both rows are fetched with the batch; a congested link falls back to a dependent load
+        const double *pre_row0 = nullptr, *pre_row1 = nullptr;
+        if (ONECLASS) {
+            pre_i0 = c.c0_pre_i0; pre_i1 = c.c0_pre_i1; pre_row0 = c.c0_pre0; pre_row1 = c.c0_pre1;
+        } else if (tau >= fftau) {
+            pre_i0 = max(0, tau + 1 - fftau);
+            pre_row0 = H64(c, PNS_F64_CUM_INFLOW, pre_i0);
+            if (fftau > 1) {
+                pre_i1 = max(0, tau + 2 - fftau);
+                pre_row1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1);
+            }
+        }
+        if (pre_row0) pre_v0 = pre_row0[e];
+        if (pre_row1) pre_v1 = pre_row1[e];
+    }
+    // ---- actions of this environment step (rl/builders.py:264-352; setters link.py:121-126, 462-478) --------
+    // Each thread derives the new width of its own link and of its mate's from the old widths, so neither waits
+    // for the other; its own store happens behind the sending-flow barrier, after the mate has read the old value.
+    bool gate_changed = false, np64_now = false;
+    if (ENV && flw && (act_own >= 0 || act_mate >= 0)) {
+        const double old_own = gate, old_rev = gate_rev;
+        const float* act = x.actions + (size_t)rep * x.env.n_act;
+        double v_own = 0.0, v_mate = 0.0;
+        if (act_own >= 0) v_own = clipped_action(x.env, act_own, (double)act[act_own], old_own);
+        if (act_mate >= 0) v_mate = clipped_action(x.env, act_mate, (double)act[act_mate], old_rev);
+        const bool sep_own = act_own >= 0 && __ldg(x.env.act_sep + act_own) != 0;
+        const bool sep_mate = act_mate >= 0 && __ldg(x.env.act_sep + act_mate) != 0;
+        if (act_own >= 0) { gate = v_own; gate_changed = true; np64_now = sep_own; }
+        else if (sep_mate) { gate = x.env.act_total_width[act_mate] - v_mate; gate_changed = true; np64_now = true; }
+        if (act_mate >= 0) gate_rev = v_mate;
+        else if (sep_own) gate_rev = x.env.act_total_width[act_own] - v_own;
+    }
+    const Area ar = link_area(c, p, e, gate, np64_now);
+    const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
+    const uint32_t rkey = (uint32_t)rep + c.io.replica_base;
+
+    if (upd) {
+        cin_tau = cin_prev + din;                                           // link.py:19-25
+        cou_tau = cou_prev + dout;
+        if (valid) { c.n_cin[e] = cin_tau; c.n_cout[e] = cou_tau; }
+        me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
+        me.dens = div_by_area(me.num, ar);                                  // link.py:136
+        const bool noisy = p.sigma > 0.0;
+        double z = 0.0;
+        sh_num[threadIdx.x] = me.num; sh_dens[threadIdx.x] = me.dens;
+        if (noisy) {
+            if (MODE == PNS_RNG_TABLE) z = c.draw_n[e];
+            else if (dir == 0) {
+                // one Philox block and one Box-Muller pair per corridor: the forward warp draws, keeps the cosine
+                // branch and hands the sine branch to its mate
+                pns::DrawKey key;
+                key.t = (uint32_t)c.t; key.link = (uint32_t)l; key.replica = rkey; key.k0 = k0; key.k1 = k1;
+                double g0, g1;
+                pns::normal_pair_philox(key, 4u, &g0, &g1);
+                z = g0;
+                sh_noise[threadIdx.x] = g1;
+            }
+        }
+        __syncthreads();
+        num_rev = sh_num[mate];
+        const float dens_rev = sh_dens[mate];
+        if (noisy) {
+            if (MODE != PNS_RNG_TABLE && dir == 1) z = sh_noise[mate];
+            if (MODE != PNS_RNG_TABLE) z = p.sigma * z;
+        }
+        float tt;
+        const float v = speed_and_travel_time(p, me.dens, is_sep(p) ? 0.0f : dens_rev, noisy, z, &tt);
+        float sum = rs + tt;                                                // link.py:183-186
+        if (windowed) {
+            sum = sum - tt_old;
+            me.avg_tt = sum / (float)c.n.window;
+        } else {
+            me.avg_tt = p.tt0;
+        }
+        if (valid) {
+            c.u_num[e] = me.num; c.u_dens[e] = me.dens; c.u_speed[e] = v; c.u_tt[e] = tt;
+            c.u_flow[e] = v * me.dens;                                      // functions.py:97-101
+            if (windowed) c.u_avg[e] = me.avg_tt;
+            c.s.runsum[e] = sum;
+            c.u_bgw[e] = gate;                                              // link.py:188, 451-452
+            if (is_sep(p)) c.u_sepw[e] = gate;
+        }
+        if (ENV && x.obs && valid) {
+            // ObservationBuilder (rl/builders.py:68-177): the entries this directed link contributes
+            for (int k = obs0; k < obs1; ++k) {
+                float f;
+                switch (__ldg(x.env.lk_obs_src + k)) {
+                    case PNS_OBS_INFLOW: f = (float)din; break;
+                    case PNS_OBS_OUTFLOW: f = (float)dout; break;
+                    case PNS_OBS_SHARED_DENSITY: f = is_sep(p) ? me.dens : div_by_area(me.num + num_rev, ar); break;
+                    case PNS_OBS_SHARED_DENSITY_OVER_KJ:
+                        f = (is_sep(p) ? me.dens : div_by_area(me.num + num_rev, ar)) / p.kj32; break;
+                    case PNS_OBS_SPEED: f = v; break;
+                    default: f = (float)gate; break;
+                }
+                const float d = __ldg(x.env.lk_obs_div + k);
+                if (d != 1.0f) f = f / d;
+                x.obs[(size_t)rep * x.env.n_obs + __ldg(x.env.lk_obs_col + k)] = f;
+            }
+            // reward: needs the rows of all reward links of the replica; whichever of their threads finishes last
+            // evaluates it, reading the others' values around L1
+            if (rewarded) {
+                __threadfence();
+                const int seen = atomicAdd(x.env.reward_count + rep, 1);
+                if (seen == 2 * x.env.n_reward_links - 1) {
+                    x.env.reward_count[rep] = 0;
+                    __threadfence();
+                    const float total = env_reward<true>(x, rep, c.t);
+                    x.reward[rep] = total;
+                    if (x.cum_reward) x.cum_reward[rep] = x.cum_reward[rep] + total;
+                }
+            }
+        }
+    }
+    if (!flw) return;
+    // occupied links will probably smooth their outflow over four lagged inflow rows (get_outflow,
+    // link.py:199-214) of a lag known only deep inside the sending-flow computation: request the five candidate
+    // rows now
+    if (me.num > 0.0f && tau >= fftau) {
+        const double* row = H64(c, PNS_F64_INFLOW, tau - fftau + 1) + e;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (tau - fftau + 1 - k >= 0) prefetch_l1(row - (size_t)k * c.row64);
+    }
+    pns::DrawKey key;
+    key.t = (uint32_t)c.t_flows; key.link = (uint32_t)l; key.replica = rkey; key.k0 = k0; key.k1 = k1;
+    const double front = is_sep(p) ? gate : gate_rev;                       // link.py:110-126, 462-478
+    pns::LinkDraws dr;          // one Philox block serves the link's release (R1) and blockers (R3) draws
+    dr.u1 = 0.0; dr.u3 = 0.0;
+    if (MODE == PNS_RNG_PHILOX && (me.num > 0.0f || num_rev >= 1.0f || cin_tau != cou_tau)) dr = pns::link_draws(key);
+    SendOut s;
+    // nobody on the link and nobody in transit: boundary flow 0, only the smoothing with the previous sending
+    // flow remains (link.py:363-364); exact, see k_link_lane
+    if (me.num == 0.0f && cin_tau == cou_tau && front >= 0.0 && tau >= fftau) {
+        s.kind = 0; s.n1 = 0; s.rf = 0.0f; s.sval = 0.0;
+        s.flow = pymin(floor(0.8 * 0.0 + 0.2 * snd_prev), 0.0);
+        if (s.flow < 0.0) atomicOr(c.s.err + rep, PNS_ERR_NEG_SENDING);
+    } else {
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, rep, key, dr, pre_i0, pre_v0,
+                               pre_i1, pre_v1);
+    }
+    int n3 = -1;
+    const double r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, dr, &n3);
+    sh_send[threadIdx.x] = s.flow;
+    __syncthreads();
+    const double s_rev = sh_send[mate];
+    if (valid) {
+        // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
+        const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
+        c.f_snd[e] = s.flow;
+        c.f_rcv[e] = rcv;
+        c.s.nm_s[(size_t)slots.x * R + rep] = s.flow;
+        c.s.nm_r[(size_t)slots.y * R + rep] = rcv;
+        if (ENV && gate_changed) {
+            c.s.gate[e] = gate;
+            if (np64_now) c.s.sep_np64[e] = 1;   // np.clip returns numpy float64: the lane area becomes a float64
+        }
+    }
+}
+#endif  // !PNS_HOST_EMULATION
 
 // =================================================================================================
 // Initial state (link.py:12-17, 56, 82-97, 425)
@@ -1409,6 +1725,27 @@ __global__ void __launch_bounds__(kBlock) k_kpi_reduce(const __grid_constant__ C
     for (int i = 0; i < PNS_KPI_COUNT; ++i) out[(size_t)rep * PNS_KPI_COUNT + i] = k[i];
 }
 
+// sampler tables of pns_rng.cuh, once per device and process
+__global__ void k_init_sampler_tables() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= (PNS_MODE_TABLE_N > PNS_INV_TABLE ? PNS_MODE_TABLE_N : PNS_INV_TABLE)) pns::init_sampler_table_entry(i);
+}
+void ensure_sampler_tables(cudaStream_t s) {
+#ifndef PNS_HOST_EMULATION
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    done[dev] = true;
+#else
+    static bool done = false;
+    if (done) return;
+    done = true;
+#endif
+    const int n = (PNS_MODE_TABLE_N > PNS_INV_TABLE ? PNS_MODE_TABLE_N : PNS_INV_TABLE) + 1;
+    PNS_LAUNCH(k_init_sampler_tables, (n + 127) / 128, 128, s);
+}
+
 __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t,
                                int site, int32_t* out_i, double* out_d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1417,6 +1754,10 @@ __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const d
     key.t = (uint32_t)t; key.link = (uint32_t)i; key.replica = 0;
     key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
     if (kind == 0) out_i[i] = pns::binomial_philox(key, (uint32_t)site, n_trials[i], p[i]);
+    else if (kind == 3) {          // the shared block of a link's draws: site 1 -> R1 (any p), site 3 -> R3 (p = 0.9)
+        const pns::LinkDraws dr = pns::link_draws(key);
+        out_i[i] = site == 3 ? pns::binomial09_u(n_trials[i], dr.u3) : pns::binomial_u(n_trials[i], p[i], dr.u1);
+    }
     else if (kind == 1) {
         float g[4];
         pns::normal_quad_philox(key, (uint32_t)site, g);
@@ -1483,6 +1824,8 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
     c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
+    c.draw_exp = (io && io->draw_exp && mode == PNS_RNG_TABLE)
+                     ? io->draw_exp + (size_t)(stride * row_flows) * net->n_opts * net->replicas : nullptr;
     return c;
 }
 
@@ -1536,8 +1879,59 @@ void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
     }
 }
 #endif
-void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
+// batched replicas on the GPU: one thread per (directed link, replica), optionally with the environment riding along
+template <int PHASE, bool ENV>
+void launch_rep_mode(const pns_net* net, cudaStream_t s, const EnvCtx& x) {
+    const dim3 nb((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)(net->n_links / 2) + (unsigned)x.route_blocks);
+    const bool one = net->n_classes == 1;
+    if (x.c.mode == PNS_RNG_PHILOX) {
+        if (one) PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_PHILOX, true, ENV>), nb, kRepBlock, s, x);
+        else PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_PHILOX, false, ENV>), nb, kRepBlock, s, x);
+    } else {
+        if (one) PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_TABLE, true, ENV>), nb, kRepBlock, s, x);
+        else PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_TABLE, false, ENV>), nb, kRepBlock, s, x);
+    }
+}
+bool rep_kernel_applies(const pns_net* net, int mode) {
+    return net->replicas > 1 && mode != PNS_RNG_REQUEST && !getenv("PNS_PAIR_THREADS");
+}
+// the environment part of a launch: null members = nothing to do in that phase
+struct EnvRide {
+    const pns_env* env;
+    const float* actions;     // FLOWS phase
+    float *obs, *reward, *cum_reward;   // UPDATE phase
+};
+void launch_rep(const pns_net* net, cudaStream_t s, const Ctx& c, const EnvRide* ride, bool with_route) {
+    EnvCtx x;
+    memset(&x, 0, sizeof x);
+    x.c = c;
+    if (with_route && c.phase == PH_FLOWS) {
+        x.route_blocks = (net->n_rows + 1) / 2;        // extra grid rows: two route rows per CTA
+        x.route_t = c.t_flows;
+    }
+    const bool env_flows = ride && ride->actions && (c.phase & PH_FLOWS);
+    const bool env_update = ride && ride->obs && (c.phase & PH_UPDATE);
+    if (env_flows || env_update) {
+        x.env = *ride->env;
+        x.actions = env_flows ? ride->actions : nullptr;
+        if (env_update) { x.obs = ride->obs; x.reward = ride->reward; x.cum_reward = ride->cum_reward; }
+        if (c.phase == PH_FLOWS) launch_rep_mode<PH_FLOWS, true>(net, s, x);
+        else if (c.phase == PH_UPDATE) launch_rep_mode<PH_UPDATE, true>(net, s, x);
+        else launch_rep_mode<PH_UPDATE | PH_FLOWS, true>(net, s, x);
+        return;
+    }
+    if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_rep_mode<PH_UPDATE | PH_FLOWS, false>(net, s, x);
+    else if (c.phase == PH_UPDATE) launch_rep_mode<PH_UPDATE, false>(net, s, x);
+    else if (c.phase == PH_FLOWS) launch_rep_mode<PH_FLOWS, false>(net, s, x);
+}
+#else
+struct EnvRide { const pns_env* env; const float* actions; float *obs, *reward, *cum_reward; };
+#endif
+void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, const EnvRide* ride = nullptr,
+                 bool with_route = false) {
+#ifndef PNS_HOST_EMULATION
+    if (rep_kernel_applies(net, c.mode)) { launch_rep(net, s, c, ride, with_route); return; }
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
         if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
         else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
@@ -1564,7 +1958,7 @@ struct StepSizes { size_t n_pair, n_grp, n_node; };
 StepSizes sizes_of(const pns_net* net) {
     StepSizes z;
     z.n_pair = (size_t)(net->n_links / 2) * net->replicas;
-    z.n_grp = (size_t)net->n_groups * net->replicas;
+    z.n_grp = (size_t)net->n_rows * net->replicas;       // route choice: one thread per routed upstream slot and replica
     z.n_node = (size_t)net->n_nodes * net->replicas;
     return z;
 }
@@ -1595,10 +1989,12 @@ struct Streamed {           // per-step host traffic of pns_step_streamed
 };
 
 int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps, int rng_mode,
-              cudaStream_t s, double* ms, int64_t* launches, const Streamed* sx = nullptr) {
+              cudaStream_t s, double* ms, int64_t* launches, const Streamed* sx = nullptr,
+              const EnvRide* ride = nullptr) {
     if (n_steps <= 0) return 0;
     if (check_common(net, st, t0) || check_common(net, st, t0 + n_steps - 1)) return 1;
     if (check_step_io(net, io, rng_mode)) return 1;
+    ensure_sampler_tables(s);
     const StepSizes z = sizes_of(net);
 #ifndef PNS_HOST_EMULATION
     static SideStream side;
@@ -1654,8 +2050,15 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
             if (k + kSyncGroup < n_steps) demand_next = copy_group(k + kSyncGroup);
         }
 #endif
+        // batched replicas: the route choice of step t0+k is independent of the link pass of the same step, so in a
+        // FLOWS-only launch it rides along as extra CTAs (not at step 1, where it reads the widths this launch sets)
+        bool route_rides = false;
+#ifndef PNS_HOST_EMULATION
+        route_rides = phase == PH_FLOWS && z.n_grp && z.n_pair && t0 + k >= 2 && !ev && !getenv("PNS_ROUTE_SEPARATE") &&
+                      rep_kernel_applies(net, rng_mode);
+#endif
         PNS_MARK(k, 0);
-        if (z.n_pair) launch_pair(net, z.n_pair, s, cp);
+        if (z.n_pair) launch_pair(net, z.n_pair, s, cp, ride, route_rides);
         PNS_MARK(k, 1);
 #ifndef PNS_HOST_EMULATION
         if (sx && k > 0) {          // result of step t0+k-1: partial sums reduced on the device
@@ -1674,7 +2077,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
 #endif
         if (k == n_steps) break;
         const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
-        if (z.n_grp) PNS_LAUNCH_CHAIN(k_route_probs, blocks_for(z.n_grp), kBlock, s, cn);
+        if (z.n_grp && !route_rides) PNS_LAUNCH_CHAIN(k_route_fractions, blocks_for(z.n_grp), kBlock, s, cn);
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);
@@ -1719,6 +2122,7 @@ int pns_state_init(const pns_net* net, const pns_state* st, void* stream) {
     if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
     if (cudaMemsetAsync(st->err, 0, sizeof(int32_t) * net->replicas, (cudaStream_t)stream) != cudaSuccess)
         return fail("memset err", cudaGetLastError());
+    ensure_sampler_tables((cudaStream_t)stream);
     const Ctx c = make_ctx(net, st, nullptr, 0, 1, 1, PNS_RNG_TABLE, 0, 0);
     PNS_LAUNCH(k_state_init, 148 * 8, 256, (cudaStream_t)stream, c);
     return launched("k_state_init");
@@ -1733,18 +2137,26 @@ int pns_link_flows(const pns_net* net, const pns_state* st, const pns_step_io* i
         return fail("REQUEST mode needs the req_* buffers");
     const size_t n = sizes_of(net).n_pair;
     if (n == 0) return 0;
+    ensure_sampler_tables((cudaStream_t)stream);
     const Ctx c = make_ctx(net, st, io, PH_FLOWS, t, t, rng_mode, 0, 0);
     launch_pair(net, n, (cudaStream_t)stream, c);
+    if (rng_mode == PNS_RNG_REQUEST && io->req_exp && net->n_routed > 0) {
+        const size_t nr = sizes_of(net).n_grp;
+        PNS_LAUNCH(k_route_fractions, blocks_for(nr), kBlock, (cudaStream_t)stream, c);
+    }
     return launched("k_link_pair[flows]");
 }
 
-int pns_route_probs(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, void* stream) {
+int pns_route_fractions(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, int rng_mode,
+                        void* stream) {
     if (check_common(net, st, t)) return 1;
     const size_t n = sizes_of(net).n_grp;
     if (n == 0) return 0;
-    const Ctx c = make_ctx(net, st, io, 0, t, t, PNS_RNG_TABLE, 0, 0);
-    PNS_LAUNCH(k_route_probs, blocks_for(n), kBlock, (cudaStream_t)stream, c);
-    return launched("k_route_probs");
+    if (rng_mode == PNS_RNG_REQUEST && !(io && io->req_exp)) return fail("REQUEST mode needs req_exp");
+    if (rng_mode != PNS_RNG_REQUEST && !(io && io->od_w)) return fail("od weight table missing");
+    const Ctx c = make_ctx(net, st, io, 0, t, t, rng_mode, 0, 0);
+    PNS_LAUNCH(k_route_fractions, blocks_for(n), kBlock, (cudaStream_t)stream, c);
+    return launched("k_route_fractions");
 }
 
 int pns_node_flows(const pns_net* net, const pns_state* st, const pns_step_io* io, int t, void* stream) {
@@ -1809,9 +2221,18 @@ int pns_env_step(const pns_net* net, const pns_state* st, const pns_step_io* io,
                  const float* actions, int t, int rng_mode, float* obs, float* reward, float* cum_reward,
                  void* stream) {
     if (!net || !st || !env || !obs || !reward) return fail("pns_env_step: null argument");
+    if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_step: too many reward links");
+#ifndef PNS_HOST_EMULATION
+    if (env->lk_act && env->lk_obs_ptr && env->lk_reward && env->reward_count && rep_kernel_applies(net, rng_mode)) {
+        // batched replicas: actions ride in the FLOWS launch, observations and reward in the UPDATE launch
+        EnvRide ride;
+        ride.env = env; ride.actions = (actions && env->n_act > 0) ? actions : nullptr;
+        ride.obs = obs; ride.reward = reward; ride.cum_reward = cum_reward;
+        return step_impl(net, st, io, t, 1, rng_mode, (cudaStream_t)stream, nullptr, nullptr, nullptr, &ride);
+    }
+#endif
     if (actions && env->n_act > 0 && pns_env_apply_actions(net, st, env, actions, stream)) return 1;
     if (step_impl(net, st, io, t, 1, rng_mode, (cudaStream_t)stream, nullptr, nullptr)) return 1;
-    if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_step: too many reward links");
     const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
     EnvCtx x;
     x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
@@ -1863,6 +2284,7 @@ int pns_kpi(const pns_net* net, const pns_state* st, const pns_step_io* io, int 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,
                      int32_t* out_i, double* out_d, void* stream) {
     if (n <= 0) return 0;
+    ensure_sampler_tables((cudaStream_t)stream);
     PNS_LAUNCH(k_rng_selftest, (n + 127) / 128, 128, (cudaStream_t)stream, kind, n, n_trials, p, seed, t, site, out_i,
                out_d);
     return launched("k_rng_selftest");

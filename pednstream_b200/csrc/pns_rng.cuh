@@ -7,8 +7,9 @@
 // (seed, replica; t, link, site), so results do not depend on thread scheduling.
 //
 // Every arithmetic step below is a single IEEE-754 operation (the library is compiled with
-// -fmad=false) and uses no libdevice transcendental, so `oracle/philox.py`, which restates the
-// same operation sequence in Python floats, reproduces the device samples bit for bit.
+// -fmad=false; the fused multiply-adds that are wanted are written explicitly) and uses no libdevice
+// transcendental, so `oracle/philox.py`, which restates the same operation sequence in Python floats
+// (fused multiply-adds through exact rationals), reproduces the device samples bit for bit.
 #pragma once
 #include <stdint.h>
 
@@ -169,169 +170,236 @@ struct DrawKey {
     uint32_t t, link, replica, k0, k1;
 };
 
-// 1/k, k = 1..512, correctly rounded (what the host's 1.0 / k gives): the pmf recurrence of the
-// inversion multiplies by these instead of dividing.  On the device they come from a 4 KB table:
-// a division or __drcp_rn is an 80-130 cycle dependent chain per step, and the 120-step walk of
-// a jammed link's blockers draw then keeps its CTA alive for 9 us (measured: the whole step got
-// 9 us slower once the first links jammed); a table load is off the critical path.
+// ---- sampler tables (filled on the device by init_sampler_tables, once per device) ------------
+// kInvK[k] = 1/k correctly rounded, k = 1..PNS_INV_TABLE: the pmf recurrences multiply by these instead of
+// dividing (a division is an 80-130 cycle dependent chain per step; a table load is off the critical path).
+// kPmfMode09[n] = pmf of Binomial(n, 1 - 0.9) at its mode, n <= PNS_MODE_TABLE_N: the blockers draw
+// (link.py:382) always has p = 0.9, so its mode-centred search starts from a table load.
+#define PNS_INV_TABLE 2048
+#define PNS_MODE_TABLE_N 4096
+#define PNS_MODE_MEAN_TABULATED 12.0   // mean from which the search starts at the mode (mode pmf tabulated)
+#define PNS_MODE_MEAN_GENERIC 48.0     // ... for any other probability (mode pmf evaluated per draw)
+// kPow09[n] = 0.9^n as binomial_from_zero forms it (by squaring), n <= PNS_MODE_TABLE_N: pmf(0) of a blockers draw.
 #ifdef __CUDACC__
-__device__ const double kInvK[513] = {
-    0x0p+0, 0x1.0000000000000p+0, 0x1.0000000000000p-1, 0x1.5555555555555p-2, 0x1.0000000000000p-2, 0x1.999999999999ap-3,
-    0x1.5555555555555p-3, 0x1.2492492492492p-3, 0x1.0000000000000p-3, 0x1.c71c71c71c71cp-4, 0x1.999999999999ap-4, 0x1.745d1745d1746p-4,
-    0x1.5555555555555p-4, 0x1.3b13b13b13b14p-4, 0x1.2492492492492p-4, 0x1.1111111111111p-4, 0x1.0000000000000p-4, 0x1.e1e1e1e1e1e1ep-5,
-    0x1.c71c71c71c71cp-5, 0x1.af286bca1af28p-5, 0x1.999999999999ap-5, 0x1.8618618618618p-5, 0x1.745d1745d1746p-5, 0x1.642c8590b2164p-5,
-    0x1.5555555555555p-5, 0x1.47ae147ae147bp-5, 0x1.3b13b13b13b14p-5, 0x1.2f684bda12f68p-5, 0x1.2492492492492p-5, 0x1.1a7b9611a7b96p-5,
-    0x1.1111111111111p-5, 0x1.0842108421084p-5, 0x1.0000000000000p-5, 0x1.f07c1f07c1f08p-6, 0x1.e1e1e1e1e1e1ep-6, 0x1.d41d41d41d41dp-6,
-    0x1.c71c71c71c71cp-6, 0x1.bacf914c1bad0p-6, 0x1.af286bca1af28p-6, 0x1.a41a41a41a41ap-6, 0x1.999999999999ap-6, 0x1.8f9c18f9c18fap-6,
-    0x1.8618618618618p-6, 0x1.7d05f417d05f4p-6, 0x1.745d1745d1746p-6, 0x1.6c16c16c16c17p-6, 0x1.642c8590b2164p-6, 0x1.5c9882b931057p-6,
-    0x1.5555555555555p-6, 0x1.4e5e0a72f0539p-6, 0x1.47ae147ae147bp-6, 0x1.4141414141414p-6, 0x1.3b13b13b13b14p-6, 0x1.3521cfb2b78c1p-6,
-    0x1.2f684bda12f68p-6, 0x1.29e4129e4129ep-6, 0x1.2492492492492p-6, 0x1.1f7047dc11f70p-6, 0x1.1a7b9611a7b96p-6, 0x1.15b1e5f75270dp-6,
-    0x1.1111111111111p-6, 0x1.0c9714fbcda3bp-6, 0x1.0842108421084p-6, 0x1.0410410410410p-6, 0x1.0000000000000p-6, 0x1.f81f81f81f820p-7,
-    0x1.f07c1f07c1f08p-7, 0x1.e9131abf0b767p-7, 0x1.e1e1e1e1e1e1ep-7, 0x1.dae6076b981dbp-7, 0x1.d41d41d41d41dp-7, 0x1.cd85689039b0bp-7,
-    0x1.c71c71c71c71cp-7, 0x1.c0e070381c0e0p-7, 0x1.bacf914c1bad0p-7, 0x1.b4e81b4e81b4fp-7, 0x1.af286bca1af28p-7, 0x1.a98ef606a63bep-7,
-    0x1.a41a41a41a41ap-7, 0x1.9ec8e951033d9p-7, 0x1.999999999999ap-7, 0x1.948b0fcd6e9e0p-7, 0x1.8f9c18f9c18fap-7, 0x1.8acb90f6bf3aap-7,
-    0x1.8618618618618p-7, 0x1.8181818181818p-7, 0x1.7d05f417d05f4p-7, 0x1.78a4c8178a4c8p-7, 0x1.745d1745d1746p-7, 0x1.702e05c0b8170p-7,
-    0x1.6c16c16c16c17p-7, 0x1.6816816816817p-7, 0x1.642c8590b2164p-7, 0x1.6058160581606p-7, 0x1.5c9882b931057p-7, 0x1.58ed2308158edp-7,
-    0x1.5555555555555p-7, 0x1.51d07eae2f815p-7, 0x1.4e5e0a72f0539p-7, 0x1.4afd6a052bf5bp-7, 0x1.47ae147ae147bp-7, 0x1.446f86562d9fbp-7,
-    0x1.4141414141414p-7, 0x1.3e22cbce4a902p-7, 0x1.3b13b13b13b14p-7, 0x1.3813813813814p-7, 0x1.3521cfb2b78c1p-7, 0x1.323e34a2b10bfp-7,
-    0x1.2f684bda12f68p-7, 0x1.2c9fb4d812ca0p-7, 0x1.29e4129e4129ep-7, 0x1.27350b8812735p-7, 0x1.2492492492492p-7, 0x1.21fb78121fb78p-7,
-    0x1.1f7047dc11f70p-7, 0x1.1cf06ada2811dp-7, 0x1.1a7b9611a7b96p-7, 0x1.1811811811812p-7, 0x1.15b1e5f75270dp-7, 0x1.135c81135c811p-7,
-    0x1.1111111111111p-7, 0x1.0ecf56be69c90p-7, 0x1.0c9714fbcda3bp-7, 0x1.0a6810a6810a7p-7, 0x1.0842108421084p-7, 0x1.0624dd2f1a9fcp-7,
-    0x1.0410410410410p-7, 0x1.0204081020408p-7, 0x1.0000000000000p-7, 0x1.fc07f01fc07f0p-8, 0x1.f81f81f81f820p-8, 0x1.f44659e4a4271p-8,
-    0x1.f07c1f07c1f08p-8, 0x1.ecc07b301ecc0p-8, 0x1.e9131abf0b767p-8, 0x1.e573ac901e574p-8, 0x1.e1e1e1e1e1e1ep-8, 0x1.de5d6e3f8868ap-8,
-    0x1.dae6076b981dbp-8, 0x1.d77b654b82c34p-8, 0x1.d41d41d41d41dp-8, 0x1.d0cb58f6ec074p-8, 0x1.cd85689039b0bp-8, 0x1.ca4b3055ee191p-8,
-    0x1.c71c71c71c71cp-8, 0x1.c3f8f01c3f8f0p-8, 0x1.c0e070381c0e0p-8, 0x1.bdd2b899406f7p-8, 0x1.bacf914c1bad0p-8, 0x1.b7d6c3dda338bp-8,
-    0x1.b4e81b4e81b4fp-8, 0x1.b2036406c80d9p-8, 0x1.af286bca1af28p-8, 0x1.ac5701ac5701bp-8, 0x1.a98ef606a63bep-8, 0x1.a6d01a6d01a6dp-8,
-    0x1.a41a41a41a41ap-8, 0x1.a16d3f97a4b02p-8, 0x1.9ec8e951033d9p-8, 0x1.9c2d14ee4a102p-8, 0x1.999999999999ap-8, 0x1.970e4f80cb872p-8,
-    0x1.948b0fcd6e9e0p-8, 0x1.920fb49d0e229p-8, 0x1.8f9c18f9c18fap-8, 0x1.8d3018d3018d3p-8, 0x1.8acb90f6bf3aap-8, 0x1.886e5f0abb04ap-8,
-    0x1.8618618618618p-8, 0x1.83c977ab2beddp-8, 0x1.8181818181818p-8, 0x1.7f405fd017f40p-8, 0x1.7d05f417d05f4p-8, 0x1.7ad2208e0ecc3p-8,
-    0x1.78a4c8178a4c8p-8, 0x1.767dce434a9b1p-8, 0x1.745d1745d1746p-8, 0x1.724287f46debcp-8, 0x1.702e05c0b8170p-8, 0x1.6e1f76b4337c7p-8,
-    0x1.6c16c16c16c17p-8, 0x1.6a13cd1537290p-8, 0x1.6816816816817p-8, 0x1.661ec6a5122f9p-8, 0x1.642c8590b2164p-8, 0x1.623fa77016240p-8,
-    0x1.6058160581606p-8, 0x1.5e75bb8d015e7p-8, 0x1.5c9882b931057p-8, 0x1.5ac056b015ac0p-8, 0x1.58ed2308158edp-8, 0x1.571ed3c506b3ap-8,
-    0x1.5555555555555p-8, 0x1.5390948f40febp-8, 0x1.51d07eae2f815p-8, 0x1.5015015015015p-8, 0x1.4e5e0a72f0539p-8, 0x1.4cab88725af6ep-8,
-    0x1.4afd6a052bf5bp-8, 0x1.49539e3b2d067p-8, 0x1.47ae147ae147bp-8, 0x1.460cbc7f5cf9ap-8, 0x1.446f86562d9fbp-8, 0x1.42d6625d51f87p-8,
-    0x1.4141414141414p-8, 0x1.3fb013fb013fbp-8, 0x1.3e22cbce4a902p-8, 0x1.3c995a47babe7p-8, 0x1.3b13b13b13b14p-8, 0x1.3991c2c187f63p-8,
-    0x1.3813813813814p-8, 0x1.3698df3de0748p-8, 0x1.3521cfb2b78c1p-8, 0x1.33ae45b57bcb2p-8, 0x1.323e34a2b10bfp-8, 0x1.30d190130d190p-8,
-    0x1.2f684bda12f68p-8, 0x1.2e025c04b8097p-8, 0x1.2c9fb4d812ca0p-8, 0x1.2b404ad012b40p-8, 0x1.29e4129e4129ep-8, 0x1.288b01288b013p-8,
-    0x1.27350b8812735p-8, 0x1.25e22708092f1p-8, 0x1.2492492492492p-8, 0x1.23456789abcdfp-8, 0x1.21fb78121fb78p-8, 0x1.20b470c67c0d9p-8,
-    0x1.1f7047dc11f70p-8, 0x1.1e2ef3b3fb874p-8, 0x1.1cf06ada2811dp-8, 0x1.1bb4a4046ed29p-8, 0x1.1a7b9611a7b96p-8, 0x1.19453808ca29cp-8,
-    0x1.1811811811812p-8, 0x1.16e0689427379p-8, 0x1.15b1e5f75270dp-8, 0x1.1485f0e0acd3bp-8, 0x1.135c81135c811p-8, 0x1.12358e75d3033p-8,
-    0x1.1111111111111p-8, 0x1.0fef010fef011p-8, 0x1.0ecf56be69c90p-8, 0x1.0db20a88f4696p-8, 0x1.0c9714fbcda3bp-8, 0x1.0b7e6ec259dc8p-8,
-    0x1.0a6810a6810a7p-8, 0x1.0953f39010954p-8, 0x1.0842108421084p-8, 0x1.073260a47f7c6p-8, 0x1.0624dd2f1a9fcp-8, 0x1.05197f7d73404p-8,
-    0x1.0410410410410p-8, 0x1.03091b51f5e1ap-8, 0x1.0204081020408p-8, 0x1.0101010101010p-8, 0x1.0000000000000p-8, 0x1.fe01fe01fe020p-9,
-    0x1.fc07f01fc07f0p-9, 0x1.fa11caa01fa12p-9, 0x1.f81f81f81f820p-9, 0x1.f6310aca0dbb5p-9, 0x1.f44659e4a4271p-9, 0x1.f25f644230ab5p-9,
-    0x1.f07c1f07c1f08p-9, 0x1.ee9c7f8458e02p-9, 0x1.ecc07b301ecc0p-9, 0x1.eae807aba01ebp-9, 0x1.e9131abf0b767p-9, 0x1.e741aa59750e4p-9,
-    0x1.e573ac901e574p-9, 0x1.e3a9179dc1a73p-9, 0x1.e1e1e1e1e1e1ep-9, 0x1.e01e01e01e01ep-9, 0x1.de5d6e3f8868ap-9, 0x1.dca01dca01dcap-9,
-    0x1.dae6076b981dbp-9, 0x1.d92f2231e7f8ap-9, 0x1.d77b654b82c34p-9, 0x1.d5cac807572b2p-9, 0x1.d41d41d41d41dp-9, 0x1.d272ca3fc5b1ap-9,
-    0x1.d0cb58f6ec074p-9, 0x1.cf26e5c44bfc6p-9, 0x1.cd85689039b0bp-9, 0x1.cbe6d9601cbe7p-9, 0x1.ca4b3055ee191p-9, 0x1.c8b265afb8a42p-9,
-    0x1.c71c71c71c71cp-9, 0x1.c5894d10d4986p-9, 0x1.c3f8f01c3f8f0p-9, 0x1.c26b5392ea01cp-9, 0x1.c0e070381c0e0p-9, 0x1.bf583ee868d8bp-9,
-    0x1.bdd2b899406f7p-9, 0x1.bc4fd65883e7bp-9, 0x1.bacf914c1bad0p-9, 0x1.b951e2b18ff23p-9, 0x1.b7d6c3dda338bp-9, 0x1.b65e2e3beee05p-9,
-    0x1.b4e81b4e81b4fp-9, 0x1.b37484ad806cep-9, 0x1.b2036406c80d9p-9, 0x1.b094b31d922a4p-9, 0x1.af286bca1af28p-9, 0x1.adbe87f94905ep-9,
-    0x1.ac5701ac5701bp-9, 0x1.aaf1d2f87ebfdp-9, 0x1.a98ef606a63bep-9, 0x1.a82e65130e159p-9, 0x1.a6d01a6d01a6dp-9, 0x1.a574107688a4ap-9,
-    0x1.a41a41a41a41ap-9, 0x1.a2c2a87c51ca0p-9, 0x1.a16d3f97a4b02p-9, 0x1.a01a01a01a01ap-9, 0x1.9ec8e951033d9p-9, 0x1.9d79f176b682dp-9,
-    0x1.9c2d14ee4a102p-9, 0x1.9ae24ea5510dap-9, 0x1.999999999999ap-9, 0x1.9852f0d8ec0ffp-9, 0x1.970e4f80cb872p-9, 0x1.95cbb0be377aep-9,
-    0x1.948b0fcd6e9e0p-9, 0x1.934c67f9b2ce6p-9, 0x1.920fb49d0e229p-9, 0x1.90d4f120190d5p-9, 0x1.8f9c18f9c18fap-9, 0x1.8e6527af1373fp-9,
-    0x1.8d3018d3018d3p-9, 0x1.8bfce8062ff3ap-9, 0x1.8acb90f6bf3aap-9, 0x1.899c0f601899cp-9, 0x1.886e5f0abb04ap-9, 0x1.87427bcc092b9p-9,
-    0x1.8618618618618p-9, 0x1.84f00c2780614p-9, 0x1.83c977ab2beddp-9, 0x1.82a4a0182a4a0p-9, 0x1.8181818181818p-9, 0x1.8060180601806p-9,
-    0x1.7f405fd017f40p-9, 0x1.7e225515a4f1dp-9, 0x1.7d05f417d05f4p-9, 0x1.7beb3922e017cp-9, 0x1.7ad2208e0ecc3p-9, 0x1.79baa6bb6398bp-9,
-    0x1.78a4c8178a4c8p-9, 0x1.77908119ac60dp-9, 0x1.767dce434a9b1p-9, 0x1.756cac201756dp-9, 0x1.745d1745d1746p-9, 0x1.734f0c541fe8dp-9,
-    0x1.724287f46debcp-9, 0x1.713786d9c7c09p-9, 0x1.702e05c0b8170p-9, 0x1.6f26016f26017p-9, 0x1.6e1f76b4337c7p-9, 0x1.6d1a62681c861p-9,
-    0x1.6c16c16c16c17p-9, 0x1.6b1490aa31a3dp-9, 0x1.6a13cd1537290p-9, 0x1.691473a88d0c0p-9, 0x1.6816816816817p-9, 0x1.6719f3601671ap-9,
-    0x1.661ec6a5122f9p-9, 0x1.6524f853b4aa3p-9, 0x1.642c8590b2164p-9, 0x1.63356b88ac0dep-9, 0x1.623fa77016240p-9, 0x1.614b36831ae94p-9,
-    0x1.6058160581606p-9, 0x1.5f66434292dfcp-9, 0x1.5e75bb8d015e7p-9, 0x1.5d867c3ece2a5p-9, 0x1.5c9882b931057p-9, 0x1.5babcc647fa91p-9,
-    0x1.5ac056b015ac0p-9, 0x1.59d61f123ccaap-9, 0x1.58ed2308158edp-9, 0x1.5805601580560p-9, 0x1.571ed3c506b3ap-9, 0x1.56397ba7c52e2p-9,
-    0x1.5555555555555p-9, 0x1.54725e6bb82fep-9, 0x1.5390948f40febp-9, 0x1.52aff56a8054bp-9, 0x1.51d07eae2f815p-9, 0x1.50f22e111c4c5p-9,
-    0x1.5015015015015p-9, 0x1.4f38f62dd4c9bp-9, 0x1.4e5e0a72f0539p-9, 0x1.4d843bedc2c4cp-9, 0x1.4cab88725af6ep-9, 0x1.4bd3edda68fe1p-9,
-    0x1.4afd6a052bf5bp-9, 0x1.4a27fad76014ap-9, 0x1.49539e3b2d067p-9, 0x1.4880522014880p-9, 0x1.47ae147ae147bp-9, 0x1.46dce34596066p-9,
-    0x1.460cbc7f5cf9ap-9, 0x1.453d9e2c776cap-9, 0x1.446f86562d9fbp-9, 0x1.43a2730abee4dp-9, 0x1.42d6625d51f87p-9, 0x1.420b5265e5951p-9,
-    0x1.4141414141414p-9, 0x1.40782d10e6566p-9, 0x1.3fb013fb013fbp-9, 0x1.3ee8f42a5af07p-9, 0x1.3e22cbce4a902p-9, 0x1.3d5d991aa75c6p-9,
-    0x1.3c995a47babe7p-9, 0x1.3bd60d9232955p-9, 0x1.3b13b13b13b14p-9, 0x1.3a524387ac822p-9, 0x1.3991c2c187f63p-9, 0x1.38d22d366088ep-9,
-    0x1.3813813813814p-9, 0x1.3755bd1c945eep-9, 0x1.3698df3de0748p-9, 0x1.35dce5f9f2af8p-9, 0x1.3521cfb2b78c1p-9, 0x1.34679ace01346p-9,
-    0x1.33ae45b57bcb2p-9, 0x1.32f5ced6a1dfap-9, 0x1.323e34a2b10bfp-9, 0x1.3187758e9ebb6p-9, 0x1.30d190130d190p-9, 0x1.301c82ac40260p-9,
-    0x1.2f684bda12f68p-9, 0x1.2eb4ea1fed14bp-9, 0x1.2e025c04b8097p-9, 0x1.2d50a012d50a0p-9, 0x1.2c9fb4d812ca0p-9, 0x1.2bef98e5a3711p-9,
-    0x1.2b404ad012b40p-9, 0x1.2a91c92f3c105p-9, 0x1.29e4129e4129ep-9, 0x1.293725bb804a5p-9, 0x1.288b01288b013p-9, 0x1.27dfa38a1ce4dp-9,
-    0x1.27350b8812735p-9, 0x1.268b37cd60127p-9, 0x1.25e22708092f1p-9, 0x1.2539d7e9177b2p-9, 0x1.2492492492492p-9, 0x1.23eb79717605bp-9,
-    0x1.23456789abcdfp-9, 0x1.22a0122a0122ap-9, 0x1.21fb78121fb78p-9, 0x1.21579804855e6p-9, 0x1.20b470c67c0d9p-9, 0x1.2012012012012p-9,
-    0x1.1f7047dc11f70p-9, 0x1.1ecf43c7fb84cp-9, 0x1.1e2ef3b3fb874p-9, 0x1.1d8f5672e4abdp-9, 0x1.1cf06ada2811dp-9, 0x1.1c522fc1ce059p-9,
-    0x1.1bb4a4046ed29p-9, 0x1.1b17c67f2bae3p-9, 0x1.1a7b9611a7b96p-9, 0x1.19e0119e0119ep-9, 0x1.19453808ca29cp-9, 0x1.18ab083902bdbp-9,
-    0x1.1811811811812p-9, 0x1.1778a191bd684p-9, 0x1.16e0689427379p-9, 0x1.1648d50fc3201p-9, 0x1.15b1e5f75270dp-9, 0x1.151b9a3fdd5c9p-9,
-    0x1.1485f0e0acd3bp-9, 0x1.13f0e8d344724p-9, 0x1.135c81135c811p-9, 0x1.12c8b89edc0acp-9, 0x1.12358e75d3033p-9, 0x1.11a3019a74826p-9,
-    0x1.1111111111111p-9, 0x1.107fbbe011080p-9, 0x1.0fef010fef011p-9, 0x1.0f5edfab325a2p-9, 0x1.0ecf56be69c90p-9, 0x1.0e40655826011p-9,
-    0x1.0db20a88f4696p-9, 0x1.0d24456359e3ap-9, 0x1.0c9714fbcda3bp-9, 0x1.0c0a7868b4171p-9, 0x1.0b7e6ec259dc8p-9, 0x1.0af2f722eecb5p-9,
-    0x1.0a6810a6810a7p-9, 0x1.09ddba6af8360p-9, 0x1.0953f39010954p-9, 0x1.08cabb37565e2p-9, 0x1.0842108421084p-9, 0x1.07b9f29b8eae2p-9,
-    0x1.073260a47f7c6p-9, 0x1.06ab59c7912fbp-9, 0x1.0624dd2f1a9fcp-9, 0x1.059eea0727586p-9, 0x1.05197f7d73404p-9, 0x1.04949cc1664c5p-9,
-    0x1.0410410410410p-9, 0x1.038c6b78247fcp-9, 0x1.03091b51f5e1ap-9, 0x1.02864fc7729e9p-9, 0x1.0204081020408p-9, 0x1.0182436517a37p-9,
-    0x1.0101010101010p-9, 0x1.0080402010080p-9, 0x1.0000000000000p-9,
-};
+__device__ double kInvK[PNS_INV_TABLE + 1];
+__device__ double kPmfMode09[PNS_MODE_TABLE_N + 1];
+__device__ double kPow09[PNS_MODE_TABLE_N + 1];
+#define PNS_TABLE(a, i) __ldg((a) + (i))
+#else
+static double kInvK[PNS_INV_TABLE + 1];
+static double kPmfMode09[PNS_MODE_TABLE_N + 1];
+static double kPow09[PNS_MODE_TABLE_N + 1];
+#define PNS_TABLE(a, i) ((a)[i])
 #endif
-__host__ __device__ inline double pns_inv_k(int k) {   // 1 <= k <= 512
+__host__ __device__ inline double pns_inv_k(int k) {   // k >= 1
 #ifdef __CUDA_ARCH__
-    return __ldg(kInvK + k);
+    return k <= PNS_INV_TABLE ? __ldg(kInvK + k) : 1.0 / (double)k;
 #else
     return 1.0 / (double)k;
 #endif
 }
+__host__ __device__ inline double pns_fma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+__host__ __device__ inline double pns_sqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(x);
+#else
+    return __builtin_sqrt(x);
+#endif
+}
 
-// Binomial(m, pp) by CDF inversion, m <= 512, 0 < pp <= 0.5, u in [0, 1).  The pmf recurrence is
-// pmf(k) = pmf(k-1) * f_k with f_k = (ratio * (m-k+1)) * (1/k), the factor formed off the critical
-// path: the loop-carried chain is one multiply, one subtract and a compare.  Four steps per trip,
-// because an in-order warp cannot overlap loop trips by itself (restated in oracle/philox.py).
-__host__ __device__ inline int binomial_inversion(int m, double pp, double u) {
-    const double q = 1.0 - pp;
-    const double ratio = pp / q;
+// Binomial(n, pp) by CDF inversion from 0, 0 < pp <= 0.5, u in [0, 1); used for small means n*pp, where q^n is
+// far from underflow.  pmf(k) = pmf(k-1) * f_k with f_k = ratio*(n-k+1)/k = A/k - ratio, A = ratio*(n+1): one
+// table load and one fused multiply-add, formed off the critical path (the loop-carried chain is one multiply,
+// one subtract and a compare).  Four steps per trip, because an in-order warp cannot overlap loop trips by
+// itself (restated in oracle/philox.py).
+__host__ __device__ inline double pow_by_squaring(double q, int n) {
     double pk = 1.0, b = q;
-    for (int e = m; e; e >>= 1) {
+    for (int e = n; e; e >>= 1) {
         if (e & 1) pk = pk * b;
         b = b * b;
     }
+    return pk;
+}
+__host__ __device__ inline int binomial_from_zero(int n, double pp, double u, double p0_tabulated = -1.0) {
+    const double q = 1.0 - pp;
+    const double ratio = pp / q;
+    const double A = ratio * (double)(n + 1);
+    double pk = p0_tabulated >= 0.0 ? p0_tabulated : pow_by_squaring(q, n);
     int k = 0;
-    double mk = (double)m;                                   // m - k, exact
-    while (u > pk && k < m) {
-        const double f1 = (ratio * mk) * pns_inv_k(k + 1);
-        const double f2 = (ratio * (mk - 1.0)) * pns_inv_k(k + 2 <= 512 ? k + 2 : 512);
-        const double f3 = (ratio * (mk - 2.0)) * pns_inv_k(k + 3 <= 512 ? k + 3 : 512);
-        const double f4 = (ratio * (mk - 3.0)) * pns_inv_k(k + 4 <= 512 ? k + 4 : 512);
+    while (u > pk && k < n) {
+        const double f1 = pns_fma(A, pns_inv_k(k + 1), -ratio);
+        const double f2 = pns_fma(A, pns_inv_k(k + 2), -ratio);
+        const double f3 = pns_fma(A, pns_inv_k(k + 3), -ratio);
+        const double f4 = pns_fma(A, pns_inv_k(k + 4), -ratio);
         u = u - pk; k += 1; pk = pk * f1;
-        if (!(u > pk && k < m)) break;
+        if (!(u > pk && k < n)) break;
         u = u - pk; k += 1; pk = pk * f2;
-        if (!(u > pk && k < m)) break;
+        if (!(u > pk && k < n)) break;
         u = u - pk; k += 1; pk = pk * f3;
-        if (!(u > pk && k < m)) break;
+        if (!(u > pk && k < n)) break;
         u = u - pk; k += 1; pk = pk * f4;
-        mk = mk - 4.0;
     }
     return k;
 }
 
-// Exact Binomial(n, p), 0 < p < 1, n > 0; chunks of 512 trials keep q^m representable (binomial
-// additivity).  Out of line and with scalar arguments: it is called on a minority of the links and
-// must not bloat the callers' register footprint.  (A rejection sampler for large means -- BTRS,
-// 1.2 rounds instead of n*min(p,1-p) inversion steps -- was tried: its register needs made ptxas
-// spill 170 bytes per thread on the link kernels' main path, and behind a separately compiled ABI
-// boundary the call overhead cost as much as it saved; see DESIGN.md.)
+// log(x!) - log(sqrt(2 pi x) (x/e)^x) for an integer-valued x >= 0 (Loader, "Fast and accurate computation of
+// binomial probabilities", 2000): table below 16, the asymptotic series above
+__host__ __device__ inline double pns_stirlerr(double x) {
+    if (x < 16.0) {
+        const int i = (int)x;
+        const double sfe[16] = {
+            0x0.0p+0, 0x1.4c071bcda0a5bp-4, 0x1.52a9b923ea649p-5, 0x1.c579a268d80b3p-6, 0x1.54a2662fd78a9p-6,
+            0x1.10b4e513fcbedp-6, 0x1.c6b167bebdf36p-7, 0x1.85d4d612e4a86p-7, 0x1.552805e7b3076p-7,
+            0x1.2f4871b12ab64p-7, 0x1.10f9d4c0743a7p-7, 0x1.f0593088014f8p-8, 0x1.c7018733aa9c6p-8,
+            0x1.a40514700f36cp-8, 0x1.86076c002d4a7p-8, 0x1.6c08f6f194a10p-8};
+        return sfe[i];
+    }
+    const double r = 1.0 / x;
+    const double rr = r * r;
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0) * rr) * rr) * rr) * rr) * r;
+}
+
+// deviance term x*log(x/np) + np - x by its series in v = (x-np)/(x+np) (|x - np| << x + np at the mode)
+__host__ __device__ inline double pns_bd0(double x, double np) {
+    const double d = x - np;
+    double v = d / (x + np);
+    double s = d * v;
+    if (fabs(s) < 2.2250738585072014e-308) return s;
+    double ej = (2.0 * x) * v;
+    v = v * v;
+    for (int j = 1; j < 64; ++j) {
+        ej = ej * v;
+        const double s1 = s + ej * (1.0 / (double)(2 * j + 1));
+        if (s1 == s) return s1;
+        s = s1;
+    }
+    return s;
+}
+
+// pmf of Binomial(n, pp) at m (0 < m < n), saddle-point form (Loader 2000); relative error ~2e-15
+__host__ __device__ inline double binomial_pmf_mode(int n, int m, double pp, double q) {
+    const double nd = (double)n, md = (double)m, kd = (double)(n - m);
+    const double lc = (((pns_stirlerr(nd) - pns_stirlerr(md)) - pns_stirlerr(kd)) - pns_bd0(md, nd * pp)) -
+                      pns_bd0(kd, nd * q);
+    return det_exp(lc) * pns_sqrt(nd / ((6.283185307179586 * md) * kd));
+}
+
+// Binomial(n, pp) for large means: search outward from the mode m = floor((n+1) pp) -- m, then the pairs
+// {m+1, m-1}, {m+2, m-2}, ... -- subtracting the pmf values from u.  Expected work ~1.6 standard deviations instead of the mean (a jammed link's
+// blockers draw, Binomial(1200, 0.9): ~17 candidates instead of a 120-step walk).  Up and down recurrences:
+// pmf(k+1)/pmf(k) = A/(k+1) - ratio, pmf(k-1)/pmf(k) = B/(n-k+1) - 1/ratio, A = ratio (n+1), B = (n+1)/ratio.
+__host__ __device__ inline int binomial_from_mode(int n, double pp, double u, double pm_tabulated) {
+    const double q = 1.0 - pp;
+    const double ratio = pp / q;
+    const double iratio = q / pp;
+    const int m = (int)((double)(n + 1) * pp);
+    const double pm = pm_tabulated > 0.0 ? pm_tabulated : binomial_pmf_mode(n, m, pp, q);
+    if (!(u > pm)) return m;
+    u = u - pm;
+    const double A = ratio * (double)(n + 1);
+    const double B = iratio * (double)(n + 1);
+    double pu = pm, pd = pm;
+    // candidates m+i and m-i are tested as a pair: one subtraction and one compare for two pmf values.  Both
+    // exist for i <= m (the mode is at most n/2), which covers all but the far tail of u.
+    const int paired = m < n - m ? m : n - m;
+    int i = 1;
+    for (; i <= paired; ++i) {
+        pu = pu * pns_fma(A, pns_inv_k(m + i), -ratio);
+        pd = pd * pns_fma(B, pns_inv_k(n - m + i), -iratio);
+        const double both = pu + pd;
+        if (!(u > both)) return !(u > pu) ? m + i : m - i;
+        u = u - both;
+    }
+    // far tail: one side is exhausted
+    int ku = m + paired, kd = m - paired;
+    for (;;) {
+        if (ku < n) {
+            ku += 1;
+            pu = pu * pns_fma(A, pns_inv_k(ku), -ratio);
+            if (!(u > pu)) return ku;
+            u = u - pu;
+        } else {
+            pu = 0.0;
+        }
+        if (kd > 0) {
+            pd = pd * pns_fma(B, pns_inv_k(n - kd + 1), -iratio);
+            kd -= 1;
+            if (!(u > pd)) return kd;
+            u = u - pd;
+        } else {
+            pd = 0.0;
+        }
+        if (!(pu > 0.0) && !(pd > 0.0)) return m;   // u fell into the rounding leftover of the total mass
+    }
+}
+
+// Exact Binomial(n, p), 0 < p < 1, n > 0, from one uniform u in [0, 1).  Out of line and with scalar arguments:
+// it is called on a minority of the links and must not bloat the callers' register footprint.  (A rejection
+// sampler for large means -- BTRS -- was tried in round 1: spills on the main path, and a warp runs its slow
+// path almost every time because some lane always needs it.)
 #ifdef __CUDACC__
 __device__ __noinline__
 #else
 inline
 #endif
-int binomial_philox_core(uint32_t t, uint32_t link, uint32_t replica, uint32_t k0, uint32_t k1, uint32_t site,
-                         int n, double p) {
+int binomial_core(int n, double p, double u) {
     const bool flip = p > 0.5;
     const double pp = flip ? 1.0 - p : p;
-    int total = 0, left = n;
-    uint32_t chunk = 0;
-    while (left > 0) {
-        const Philox4 w = philox4x32_10(t, link, site | ((chunk >> 1) << 8), replica, k0, k1);
-        for (int h = 0; h < 2 && left > 0; ++h) {
-            const int m = left < 512 ? left : 512;
-            total += binomial_inversion(m, pp, u53(w.v[2 * h], w.v[2 * h + 1]));
-            left -= m;
-            chunk += 1;
-        }
-    }
-    return flip ? n - total : total;
+    const double mean = (double)n * pp;
+    const bool tabulated = pp == (1.0 - 0.9) && n <= PNS_MODE_TABLE_N;
+    int k;
+    if (mean >= (tabulated ? PNS_MODE_MEAN_TABULATED : PNS_MODE_MEAN_GENERIC))
+        k = binomial_from_mode(n, pp, u, tabulated ? PNS_TABLE(kPmfMode09, n) : 0.0);
+    else
+        k = binomial_from_zero(n, pp, u, tabulated ? PNS_TABLE(kPow09, n) : -1.0);
+    return flip ? n - k : k;
 }
 
+#ifdef __CUDACC__
+__device__ __forceinline__
+#else
+inline
+#endif
+int binomial_u(int n, double p, double u) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    return binomial_core(n, p, u);
+}
+
+// The blockers draw, Binomial(n, 0.9) (link.py:382): same algorithm with every constant of p = 0.9 folded and the
+// short walks of lightly occupied links inline (most draws of a step are of this kind: a handful of pedestrians
+// on the reverse link, two or three steps from a tabulated 0.9^n).
+#ifdef __CUDACC__
+__device__ __forceinline__
+#else
+inline
+#endif
+int binomial09_u(int n, double u) {
+    if (n <= 0) return 0;
+    const double pp = 1.0 - 0.9;
+    if (n > PNS_MODE_TABLE_N || (double)n * pp >= PNS_MODE_MEAN_TABULATED) return binomial_core(n, 0.9, u);
+    return n - binomial_from_zero(n, pp, u, PNS_TABLE(kPow09, n));
+}
+
+// The uniforms of one link's release (R1) and blockers (R3) draws of a step: one Philox block, words 0,1 and 2,3.
+struct LinkDraws {
+    double u1, u3;
+};
+__host__ __device__ inline LinkDraws link_draws(const DrawKey& key) {
+    const Philox4 w = philox4x32_10(key.t, key.link, 1u, key.replica, key.k0, key.k1);
+    LinkDraws d;
+    d.u1 = u53(w.v[0], w.v[1]);
+    d.u3 = u53(w.v[2], w.v[3]);
+    return d;
+}
+
+// A draw with a block of its own (site in the counter): the activity draw R2, test hooks.
 #ifdef __CUDACC__
 __device__ __forceinline__
 #else
@@ -340,7 +408,23 @@ inline
 int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
     if (n <= 0 || !(p > 0.0)) return 0;
     if (p >= 1.0) return n;
-    return binomial_philox_core(key.t, key.link, key.replica, key.k0, key.k1, site, n, p);
+    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
+    return binomial_core(n, p, u53(w.v[0], w.v[1]));
+}
+
+// one entry of the sampler tables (see kInvK / kPmfMode09)
+#ifdef __CUDACC__
+__device__
+#endif
+inline void init_sampler_table_entry(int i) {
+    if (i >= 1 && i <= PNS_INV_TABLE) kInvK[i] = 1.0 / (double)i;
+    if (i == 0) kInvK[0] = 0.0;
+    if (i <= PNS_MODE_TABLE_N) {
+        const double pp = 1.0 - 0.9, q = 1.0 - pp;
+        const int m = (int)((double)(i + 1) * pp);
+        kPmfMode09[i] = (m > 0 && m < i) ? binomial_pmf_mode(i, m, pp, q) : 0.0;
+        kPow09[i] = pow_by_squaring(q, i);
+    }
 }
 
 // Poisson(lam), 0 <= lam <= 700, by CDF inversion from 0 (demand draws of the batched environment:

@@ -22,7 +22,7 @@ from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
 _NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
-               "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_grp_node", "rt_grp_up",
+               "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
                "rt_term_row_entry")
@@ -134,6 +134,15 @@ class Engine:
         io.draw_b, io.draw_n = d, d + 16 * n32
         io.draw_row_stride = 0
         io.seed = self.seed
+        # route-choice exponentials of numpy-compatible stepping: arguments out, numpy's exp back in
+        self._exp_arg = self._exp_val = self._exp_arg_host = self._exp_val_host = None
+        if rng == "numpy" and net.n_opts > 0:
+            n_exp = net.n_opts * R
+            self._exp_arg = torch.zeros((n_exp,), dtype=torch.float64, device=dev)
+            self._exp_val = torch.zeros((n_exp,), dtype=torch.float64, device=dev)
+            self._exp_arg_host = torch.zeros((n_exp,), dtype=torch.float64, pin_memory=not emulation)
+            self._exp_val_host = torch.zeros((n_exp,), dtype=torch.float64, pin_memory=not emulation)
+            io.req_exp, io.draw_exp = _ptr(self._exp_arg), _ptr(self._exp_val)
         self.io = io
         self._table_io = None
         self._od_per_replica = False
@@ -331,6 +340,8 @@ class Engine:
         n32 = self.L
         ops.ltm_draw_requests(self.hist64, self.hist32, self._req, self.err, self.handle, t)
         self._req_host.copy_(self._req, non_blocking=not self.emulation)
+        if self._exp_arg is not None:
+            self._exp_arg_host.copy_(self._exp_arg, non_blocking=not self.emulation)
         err = self.err.cpu() if self.emulation else self.err.to("cpu", non_blocking=False)
         self._raise_on_error(err)
         req = self._req_host.numpy()
@@ -371,6 +382,11 @@ class Engine:
         if len(self._noisy):
             noise[self._noisy] = np.random.normal(0, self._sigma[self._noisy])
         self._draw.copy_(self._draw_host, non_blocking=not self.emulation)
+        if self._exp_arg is not None:
+            # the logit's exponentials with the host's numpy, as the reference evaluates them
+            # (path_finder.py:585; elementwise, so one call over all groups gives the same values)
+            np.exp(self._exp_arg_host.numpy(), out=self._exp_val_host.numpy())
+            self._exp_val.copy_(self._exp_val_host, non_blocking=not self.emulation)
 
     # ------------------------------------------------------------------ batched / multi-step driving
     def run(self, t0: int, n_steps: int, rng_mode: int = _native.RNG_PHILOX):

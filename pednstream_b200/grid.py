@@ -151,8 +151,10 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     for key in ("routed_nodes", "routed_edge0", "routed_row0", "grp_node", "grp_up", "grp_od",
                 "grp_has_virtual", "opt_link", "opt_slot", "row_od", "term_opt", "term_row_entry"):
         plan["rt_" + key] = i32([])
-    for key in ("opt_ptr", "row_ptr", "term_ptr"):
+    for key in ("opt_ptr", "row_ptr", "term_ptr", "row_grp_ptr"):
         plan["rt_" + key] = i32([0])
+    for key in ("row_routed", "row_grp", "term_od"):
+        plan["rt_" + key] = i32([])
     plan["rt_opt_dist"] = np.zeros(0)
     plan["rt_scalars"] = np.array([0.1, 1.0, 0.05, 0.05, 0.0])
 

@@ -152,6 +152,27 @@ def lane_block_order(nd_meta, nd_in_link, n_links, stride, block, hops=4):
     return np.concatenate([np.nonzero(first)[0], np.nonzero(~first)[0]]).astype(np.int32)
 
 
+def route_row_tables(p):
+    """Per-row views of the route plan for the route kernel (one thread per upstream slot of a routed node):
+    rt_row_routed[row] the routed node of the row, rt_row_grp_ptr / rt_row_grp the (od, upstream) groups
+    registered at it, rt_term_od the OD column of every accumulation term."""
+    routed_nodes, row0 = np.asarray(p["rt_routed_nodes"]), np.asarray(p["rt_routed_row0"])
+    n_rows = len(p["rt_row_ptr"]) - 1
+    row_routed = np.zeros(n_rows, dtype=np.int32)
+    bounds = list(row0) + [n_rows]
+    for i in range(len(routed_nodes)):
+        row_routed[bounds[i]:bounds[i + 1]] = i
+    pos = {int(n): i for i, n in enumerate(routed_nodes)}
+    grp_row = np.array([row0[pos[int(n)]] + int(u) for n, u in zip(p["rt_grp_node"], p["rt_grp_up"])], dtype=np.int64)
+    order = np.argsort(grp_row, kind="stable").astype(np.int32)
+    ptr = np.zeros(n_rows + 1, dtype=np.int32)
+    if len(grp_row):
+        ptr[1:] = np.cumsum(np.bincount(grp_row, minlength=n_rows))
+    term_od = np.asarray(p["rt_row_od"], dtype=np.int32)[np.asarray(p["rt_term_row_entry"], dtype=np.int64)] \
+        if len(p["rt_term_row_entry"]) else np.zeros(0, dtype=np.int32)
+    return dict(rt_row_routed=row_routed, rt_row_grp_ptr=ptr, rt_row_grp=order, rt_term_od=_i32(term_od))
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -238,6 +259,7 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
         p["rt_scalars"] = _f64([0.1, 1.0, 0.05, 0.05, 0.0])
         p["n_od"] = 0
         p["od_keys"] = []
+    p.update(route_row_tables(p))
     # per-node routed index (-1 = static fractions)
     routed_of = np.full(len(nodes), -1, dtype=np.int32)
     routed_of[p["rt_routed_nodes"]] = np.arange(len(p["rt_routed_nodes"]), dtype=np.int32)

@@ -120,10 +120,39 @@ class BatchedPedNetEnv:
                            act_max_delta=to(act_md, np.float64), act_total_width=to(act_w, np.float64),
                            obs_link=to(obs_link, np.int32), obs_src=to(obs_src, np.int32),
                            obs_div=to(obs_div, np.float32), reward_link=to(reward_links, np.int32))
+        # the same programs indexed by directed link (the batched link kernel applies actions and emits
+        # observations itself): REV_* entries are produced by the reverse link as its own inflow / outflow
+        L = len(net.links)
+        lk_act = np.full(L, -1, dtype=np.int32)
+        for a, l in enumerate(act_link):
+            if lk_act[l] >= 0:
+                raise ValueError(f"link {l} is set by two actions")
+            lk_act[l] = a
+        by_link = [[] for _ in range(L)]
+        rev_of = {_native.OBS_SRC["rev.inflow"]: _native.OBS_SRC["inflow"],
+                  _native.OBS_SRC["rev.outflow"]: _native.OBS_SRC["outflow"]}
+        for col, (l, src, d) in enumerate(zip(obs_link, obs_src, obs_div)):
+            if src in rev_of:
+                by_link[l ^ 1].append((col, rev_of[src], d))
+            else:
+                by_link[l].append((col, src, d))
+        lk_obs_ptr = np.concatenate([[0], np.cumsum([len(b) for b in by_link])]).astype(np.int32)
+        flat = [x for b in by_link for x in b]
+        lk_reward = np.zeros(L, dtype=np.int32)
+        for l in reward_links:
+            lk_reward[l] = lk_reward[l ^ 1] = 1
+        assert int(lk_reward.sum()) == 2 * len(reward_links)
+        self._env_t.update(lk_act=to(lk_act, np.int32), lk_obs_ptr=to(lk_obs_ptr, np.int32),
+                           lk_obs_col=to([x[0] for x in flat], np.int32),
+                           lk_obs_src=to([x[1] for x in flat], np.int32),
+                           lk_obs_div=to([x[2] for x in flat], np.float32), lk_reward=to(lk_reward, np.int32),
+                           reward_count=torch.zeros((self.R,), dtype=torch.int32, device=dev))
         env = _native.PnsEnv()
         env.n_act, env.n_obs, env.n_reward_links = self.n_act, self.n_obs, len(reward_links)
         for k, t in self._env_t.items():
             setattr(env, k, _ptr(t))
+        if not len(flat):                 # keep the per-link pointers non-null: they select the fused path
+            env.lk_obs_col = env.lk_obs_src = env.lk_obs_div = _ptr(self._env_t["lk_obs_ptr"])
         self._env = env
         self.obs = torch.zeros((self.R, max(1, self.n_obs)), dtype=torch.float32, device=dev)
         self.reward = torch.zeros((self.R,), dtype=torch.float32, device=dev)
@@ -294,5 +323,8 @@ class BatchedPedNetEnv:
         return {a: obs[:, s] for a, s in self.obs_slices.items()}
 
     def launches_per_step(self):
+        """Kernel launches of one environment step."""
         routed = 1 if len(self.network.plan["rt_grp_node"]) else 0
+        if self.R > 1 and not self.engine.emulation:
+            return 3 + routed          # flows (+actions) | [route] | node | update (+observations, reward)
         return 1 + 3 + routed + 1      # actions, flows | [route] | node | update, observe+reward

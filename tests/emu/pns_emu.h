@@ -32,6 +32,7 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline int atomicOr(int32_t* p, int v) { int o = *p; *p = o | v; return o; }
 static inline int __float2int_rn(float x) { return (int)lrintf(x); }   // default rounding: nearest even
 using std::max;

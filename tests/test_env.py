@@ -12,7 +12,9 @@ ENV_CASES = {"env_nine_intersections": ("nine_intersections", "option3", False),
              "env_45_intersections": ("45_intersections", "option3", False),
              "env_long_corridor": ("long_corridor", "option1", False),
              "env_nine_intersections_opt2n": ("nine_intersections", "option2", True),
-             "env_butterfly_opt5": ("butterfly_scA", "option5", False)}
+             "env_butterfly_opt5": ("butterfly_scA", "option5", False),
+             "env_nine_intersections_opt4": ("nine_intersections", "option4", False),
+             "env_45_intersections_opt4": ("45_intersections", "option4", False)}
 
 
 def run_env_case(name, **engine_kw):
@@ -201,7 +203,9 @@ def test_batched_env_separator_emulated(emu_lib):
 @pytest.mark.parametrize("dataset,obs_mode,norm,steps,R,picks", [
     ("45_intersections", "option3", False, 80, 64, (0, 33, 63)),
     ("nine_intersections", "option2", True, 60, 40, (7,)),
-    ("long_corridor", "option1", False, 80, 33, (32,))])
+    ("long_corridor", "option1", False, 80, 33, (32,)),
+    ("butterfly_scA", "option5", False, 90, 70, (3, 69)),
+    ("nine_intersections", "option4", False, 70, 65, (0, 64))])
 def test_batched_env_matches_facade_cuda(dataset, obs_mode, norm, steps, R, picks):
     _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, device="cuda:0")
 
@@ -222,3 +226,40 @@ def test_batched_env_full_episode_and_reset():
     assert float(env.cumulative_reward.std()) > 0          # replicas differ (independent demand / draws)
     first = env.reset()
     assert env.sim_step == 1 and float(first[:, :4].abs().sum()) == 0.0 and float(first[0, 4]) == 4.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dataset,obs_mode,R,steps", [("45_intersections", "option3", 96, 260),
+                                                      ("nine_intersections", "option5", 130, 150),
+                                                      ("long_corridor", "option2", 33, 200)])
+def test_batched_env_fused_kernel_equals_standalone_kernels(dataset, obs_mode, R, steps, monkeypatch):
+    """The batched link kernel (one thread per directed link and replica; actions, observations and reward
+    ride along) against the pair-per-thread kernel with the stand-alone environment kernels: same
+    observations, rewards and history, bit for bit."""
+    outs = []
+    for standalone in (False, True):
+        if standalone:
+            monkeypatch.setenv("PNS_PAIR_THREADS", "1")
+        else:
+            monkeypatch.delenv("PNS_PAIR_THREADS", raising=False)
+        env = BatchedPedNetEnv(dataset, replicas=R, obs_mode=obs_mode, seed=9, device="cuda:0")
+        gen = torch.Generator(device="cuda:0")
+        gen.manual_seed(3)
+        lo = torch.tensor([float(x) for x in env._env_t["act_lo"].cpu()], device="cuda:0")
+        hi = torch.tensor([float(x) for x in env._env_t["act_hi"].cpu()], device="cuda:0")
+        obs, rew = [env.obs.clone()], []
+        for k in range(steps):
+            a = (lo + (hi - lo) * torch.rand((R, env.n_act), generator=gen, device="cuda:0")).float()
+            o, r, _, _ = env.step(a)
+            obs.append(o.clone()); rew.append(r.clone())
+        env.engine.check_errors()
+        outs.append((torch.stack(obs).cpu(), torch.stack(rew).cpu(), env.cumulative_reward.cpu().clone(),
+                     env.engine.hist64[:, : steps + 1].cpu(), env.engine.hist32[:, : steps + 1].cpu(),
+                     env.engine.gate.cpu().clone()))
+        del env
+        torch.cuda.empty_cache()
+    monkeypatch.delenv("PNS_PAIR_THREADS", raising=False)
+    names = ("obs", "reward", "cumulative reward", "hist64", "hist32", "gate")
+    for name, a, b in zip(names, outs[0], outs[1]):
+        assert torch.equal(a, b), name
+    assert float(outs[0][1].abs().sum()) > 0 or dataset == "long_corridor"

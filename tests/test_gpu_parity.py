@@ -33,7 +33,9 @@ def run_numpy_mode(case, steps):
                                          ("delft", 120), ("melbourne_2000", 1999),
                                          # randomised scenarios (randomize_network, env_loader.py:160-424)
                                          ("45_intersections_rand7", 400), ("nine_intersections_rand3", 300),
-                                         ("delft_rand11", 80)])
+                                         ("delft_rand11", 80),
+                                         # smulders fundamental diagram (functions.py:124-128)
+                                         ("nine_intersections_smulders", 499), ("45_intersections_smulders", 400)])
 def test_cuda_numpy_mode_matches_reference_fixture(case, steps):
     gold = load_golden(case)
     net = run_numpy_mode(case, steps)
@@ -85,13 +87,17 @@ def test_philox_samplers_match_python_restatement():
     oi = torch.zeros(n, dtype=torch.int32, device="cuda")
     od = torch.zeros(4 * n, dtype=torch.float64, device="cuda")
     seed, t = 0x1234567890ABCDEF, 77
-    for kind, site in ((0, 1), (0, 3), (1, 4), (2, 0)):
+    for kind, site in ((0, 1), (0, 3), (3, 1), (3, 3), (1, 4), (2, 0)):
         rc = lib.pns_rng_selftest(kind, n, C.c_void_p(dt.data_ptr()), C.c_void_p(dp.data_ptr()), seed, t, site,
                                   C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()), None)
         assert rc == 0
         torch.cuda.synchronize()
         if kind == 0:
             want = [ph.binomial_philox(seed, t, i, 0, site, int(trials[i]), float(p[i])) for i in range(n)]
+            assert oi.cpu().numpy().tolist() == want
+        elif kind == 3:     # release / blockers draws from the link's shared block
+            want = [ph.binomial_u(int(trials[i]), 0.9 if site == 3 else float(p[i]),
+                                  ph.link_draws(seed, t, i, 0)[site // 2]) for i in range(n)]
             assert oi.cpu().numpy().tolist() == want
         elif kind == 1:
             want = np.array([ph.normal_quad_philox(seed, t, i, 0, site) for i in range(n)]).reshape(-1)

@@ -20,7 +20,8 @@ def attach(net, emu_lib, rng="numpy", seed=0):
 
 @pytest.mark.parametrize("case,steps", [("long_corridor", 599), ("nine_intersections", 499),
                                          ("butterfly_scA", 599), ("45_intersections", 250),
-                                         ("delft", 40), ("melbourne_2000", 120)])
+                                         ("delft", 40), ("melbourne_2000", 120),
+                                         ("nine_intersections_smulders", 499), ("45_intersections_smulders", 200)])
 def test_emulated_kernels_match_reference_fixture(case, steps, emu_lib):
     gold = load_golden(case)
     net = make_network(case)

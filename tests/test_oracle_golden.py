@@ -8,7 +8,8 @@ from oracle.ltm_oracle import LtmOracle
 # (case, steps simulated here) -- prefixes keep the CPU suite short; the fixture has every row
 CASES = [("long_corridor_example", 499), ("long_corridor", 599), ("nine_intersections", 200),
          ("butterfly_scA", 300), ("small_network", 300), ("one_intersection_v0", 300),
-         ("od_flow_example", 300), ("45_intersections", 120), ("delft", 12), ("melbourne_2000", 40)]
+         ("od_flow_example", 300), ("45_intersections", 120), ("delft", 12), ("melbourne_2000", 40),
+         ("nine_intersections_smulders", 499), ("45_intersections_smulders", 150)]
 
 
 @pytest.mark.parametrize("case,steps", CASES)

@@ -35,6 +35,12 @@ def test_emulated_samplers_match_python_restatement(emu_lib):
         oi, _ = _selftest(emu_lib, 0, site, trials, p, seed, t)
         want = [ph.binomial_philox(seed, t, i, 0, site, int(trials[i]), float(p[i])) for i in range(n)]
         assert oi.tolist() == want
+    # a link's release (any p) and blockers (p = 0.9, tabulated fast path) draws share one Philox block
+    for site in (1, 3):
+        oi, _ = _selftest(emu_lib, 3, site, trials, p, seed, t)
+        want = [ph.binomial_u(int(trials[i]), 0.9 if site == 3 else float(p[i]), ph.link_draws(seed, t, i, 0)[site // 2])
+                for i in range(n)]
+        assert oi.tolist() == want
     _, od = _selftest(emu_lib, 1, 4, trials, p, seed, t)
     want = np.array([ph.normal_quad_philox(seed, t, i, 0, 4) for i in range(n)]).reshape(-1)
     assert np.array_equal(od, want)
@@ -44,9 +50,10 @@ def test_emulated_samplers_match_python_restatement(emu_lib):
         assert ph.normal_pair_philox(seed, t, link, 0, 4) == (quad[2:] if link & 2 else quad[:2])
 
 
-@pytest.mark.parametrize("n,p", [(1200, 0.9), (88, 0.775), (40, 0.25), (300, 0.5), (2000, 0.02), (9, 0.3)])
+@pytest.mark.parametrize("n,p", [(1200, 0.9), (130, 0.9), (88, 0.775), (40, 0.25), (300, 0.5), (2000, 0.02), (9, 0.3),
+                                 (5000, 0.6)])
 def test_binomial_sampler_follows_the_binomial_law(n, p):
-    """Chunked CDF inversion (with the p > 0.5 flip) against scipy's pmf: moments within 5 standard
+    """CDF inversion (from zero / outward from the mode, with the p > 0.5 flip) against scipy's pmf: moments within 5 standard
     errors and a chi-square test over pooled cells."""
     from scipy import stats
     N = 6000
