@@ -1,18 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the LTM timestep (BASELINE.json metric: link-timesteps/sec, fp64 state).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid SIZE] [--no-env] [--no-cpu-baseline]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid SIZE]
+                    [--no-env] [--no-cpu-baseline] [--no-variants] [--no-small]
 
 Workload at N=1 (`config.workload`): BASELINE config 4, the synthetic 512x512-node lattice of
 data/create_grid.py's rule (1 046 528 directed links, default_link of data/45_intersections, 35
-origins = 4 corners + every 64th boundary node, gaussian-peak Poisson demand pre-drawn on the host (lattice),
-uniform turning fractions), single replica, on-device Philox draws.  configs[1] (nine_intersections,
-24 links) is a parity-test case: at 24 links a step is pure launch latency and says nothing about the
-HBM roofline the metric is quoted against; the 512x512 grid is the largest single-GPU configuration.
-A "step" is one `network_loading(t)` over the whole network.  With N>1 every rank runs an
-independent replica of the grid (replicas only, no data-path collective; weak scaling).
+origins = 4 corners + every 64th boundary node, gaussian-peak Poisson demand pre-drawn on the host,
+uniform turning fractions), single replica, on-device Philox draws.  A "step" is one
+`network_loading(t)` over the whole network.  With N>1 every rank runs an independent replica of the
+grid (replicas only, no data-path collective; weak scaling).
 
-One JSON line on stdout (rank 0).  See the tier contract in the task brief for the keys.
+Further blocks of the JSON line (rank 0):
+  roofline.variants   the dominant kernel in the timed region, late in the run (t ~ 950) and on the dense-boundary
+                      workload (every boundary node an origin)
+  batched_env         BASELINE config 5 at its stated size: data/45_intersections, 8192 replicas in total
+                      (8192/N per GPU), random gate actions, with its own roofline and end-to-end figures
+  small_configs       BASELINE configs 1-3 (long_corridor, nine_intersections, melbourne@2000): GPU wall time per
+                      step in numpy-compatible and philox draw modes
+  cpu_baseline        the reference's own code (baseline/_ref, kind "reference"; the oracle port when the
+                      reference is not installed) on one host core, bounded sample
+
+`--impl reference` times the reference's own CPU implementation on all host cores: the config-4 sample (one 32x32
+lattice per core -- the reference cannot build a 512x512 network from a dense adjacency matrix) as the line's
+value, plus configs 1, 2, 3 (sample) and 5 (one episode per core) in `reference_configs`.
 """
 from __future__ import annotations
 
@@ -28,12 +39,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 B_ALG = 176.0            # algorithmic bytes per link-timestep, SURVEY.md section 8(d)
-# split of B_ALG by kernel (DESIGN.md "kernels"; sums to 176): the fused link-pair kernel carries the
+# split of B_ALG by kernel (DESIGN.md "kernels"; sums to 176): the fused link kernel carries the
 # 96 B of lagged / previous-row reads and 48 B of link-state + sending/receiving writes, the node kernel
 # the 32 B of flow / cumulative-count writes.  Intermediate re-reads between kernels are not algorithmic.
 B_ALG_PASS = {"link_pair": 144.0, "route_probs": 0.0, "node_flows": 32.0}
 GRID_SIZE = 512
 REF_SAMPLE_SIZE = 32
+ENV_REPLICAS_TOTAL = 8192          # BASELINE.json configs[4]
+LATE_T, LATE_K = 950, 40           # late-time window of the lattice run
+DENSE_WARM, DENSE_K = 600, 40      # dense-boundary variant: steps before / inside its window
 
 
 def measured_peak():
@@ -47,13 +61,15 @@ def measured_peak():
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this build
-    (profiles/r1_final_traffic.json; measured offline -- never under this run), or None."""
-    try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-        return rec[{"link_pair": "k_link_lane", "node_flows": "k_node_flows"}[kernel]]["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed single-pass ncu capture of this build
+    (measured offline -- never under this run), or None."""
+    for name in ("r2_final_traffic.json", "r1_final_traffic.json"):
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return rec[{"link_pair": "k_link_lane", "node_flows": "k_node_flows"}[kernel]]["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -102,119 +118,201 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# --------------------------------------------------------------------------------- reference arm
-def oracle_sample(steps, warmup):
-    """The reference's algorithm on the host: the Python oracle (kind 'port'; the reference itself is
-    Python and does not travel to the GPU box) on a 32x32 lattice with the workload's link
-    parameters, origin rule and demand pattern.  Per-link-step cost of this code is size-independent
-    (12.2k vs 12.7k link-steps/s at 16x16 / 32x32)."""
-    import numpy as np
-    from oracle.ltm_oracle import LtmOracle
-    from pednstream_b200 import Network
-    from pednstream_b200.grid import DEFAULT_LINK, default_origins, grid_adjacency
-    size = REF_SAMPLE_SIZE
+# ================================================================================= reference arm
+def _lattice_params(size, S):
+    from pednstream_b200.grid import DEFAULT_LINK, default_origins
     origins = default_origins(size, stride=64)
-    S = max(1000, warmup + steps + 1)
     params = {"unit_time": 10, "simulation_steps": S, "default_link": dict(DEFAULT_LINK),
               "demand": {f"origin_{o}": {"peak_lambda": 50, "base_lambda": 30} for o in origins}}
+    return origins, params
+
+
+def reference_installed():
+    from oracle import ref_harness as rh
+    return rh.reference_available()
+
+
+def lattice_sample(steps, warmup, kind):
+    """`steps` steps of a 32x32 lattice with the workload's link parameters, origin rule and demand pattern on the
+    host: kind "reference" = the reference's own Network (baseline/_ref), kind "port" = the Python oracle.
+    Per-link-step cost of this code is size-independent.  Returns
+    (link-timesteps/s, seconds, links)."""
+    import numpy as np
+    from pednstream_b200.grid import grid_adjacency
+    size = REF_SAMPLE_SIZE
+    S = max(1000, warmup + steps + 1)
+    origins, params = _lattice_params(size, S)
     np.random.seed(0)
-    net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
-    o = LtmOracle(net)
+    if kind == "reference":
+        from oracle import ref_harness as rh
+        Network, _ = rh.import_reference()
+        net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
+        step = net.network_loading
+    else:
+        from oracle.ltm_oracle import LtmOracle
+        from pednstream_b200 import Network
+        net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
+        step = LtmOracle(net).network_loading
     for t in range(1, warmup + 1):
-        o.network_loading(t)
+        step(t)
     t0 = time.perf_counter()
     for t in range(warmup + 1, warmup + steps + 1):
-        o.network_loading(t)
+        step(t)
     dt = time.perf_counter() - t0
     L = len(net.links)
     return L * steps / dt, dt, L
 
 
-def _oracle_worker(job):
-    steps, warmup = job
-    t0 = time.perf_counter()
-    value, dt, L = oracle_sample(steps, warmup)
-    return L * steps, dt, L, time.perf_counter() - t0
+def _lattice_worker(job):
+    steps, warmup, kind = job
+    value, dt, L = lattice_sample(steps, warmup, kind)
+    return L * steps, dt, L
 
 
-def oracle_sample_all_cores(steps, warmup):
-    """The reference algorithm is single-threaded; its only parallelism is independent replicas
-    (the reference's RLlib workers), so the best case on the host is one replica per core."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    with mp.get_context("spawn").Pool(cores) as pool:
-        out = pool.map(_oracle_worker, [(steps, warmup)] * cores)
-    work = sum(o[0] for o in out)
-    slowest = max(o[1] for o in out)
-    return work / slowest, slowest, out[0][2], cores
+def reference_dataset_run(job):
+    """One reference run of a shipped scenario: (links * steps, seconds, links, steps).  `env`: through the
+    reference's own PedNetParallelEnv with random gate actions (config 5), else network_loading directly."""
+    import numpy as np
+    from oracle import ref_harness as rh
+    name, steps, steps_override, env = job
+    np.random.seed(0)
+    if env:
+        e = rh.make_reference_env(name, obs_mode="option3", seed=0)
+        e.reset()
+        L = len(e.network.links)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e.step({a: e.action_space(a).sample() for a in e.possible_agents})
+        dt = time.perf_counter() - t0
+    else:
+        net, _ = rh.create_network(name, steps_override=steps_override, verbose=False)
+        L = len(net.links)
+        t0 = time.perf_counter()
+        for t in range(1, steps + 1):
+            net.network_loading(t)
+        dt = time.perf_counter() - t0
+    return L * steps, dt, L, steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 60)
-    value, dt, L, cores = oracle_sample_all_cores(steps, min(args.warmup, 3))
+    import multiprocessing as mp
+    kind = "reference" if reference_installed() else "port"
+    steps = max(5, min(args.steps, 40))
+    warmup = min(args.warmup, 3)
+    cores = os.cpu_count() or 1
+    ref_cfg = {}
+    with mp.get_context("spawn").Pool(cores) as pool:
+        # config 4 sample: the reference algorithm is single-threaded; its only parallelism is independent
+        # replicas (the reference's RLlib workers), so the best case on the host is one lattice per core
+        out = pool.map(_lattice_worker, [(steps, warmup, kind)] * cores)
+        work, slowest, L = sum(o[0] for o in out), max(o[1] for o in out), out[0][2]
+        if kind == "reference" and not args.no_small:
+            jobs = {"config1_long_corridor": ("long_corridor", 500, None, False),
+                    "config2_nine_intersections": ("nine_intersections", 499, None, False),
+                    "config3_melbourne_2000_sample": ("melbourne", 150, 2000, False)}
+            res = pool.map(reference_dataset_run, list(jobs.values()))
+            for key, (w, dt, l, n) in zip(jobs, res):
+                ref_cfg[key] = {"links": l, "steps": n, "seconds": dt, "ms_per_step": 1e3 * dt / n,
+                                "link_timesteps_per_s": w / dt, "cores": 1}
+            # config 5: one full episode of the reference's own env per core
+            ep = pool.map(reference_dataset_run, [("45_intersections", 700, None, True)] * cores)
+            dt5 = max(o[1] for o in ep)
+            ref_cfg["config5_45_intersections_env"] = {
+                "links": ep[0][2], "steps": 700, "episodes": cores, "cores": cores, "seconds": dt5,
+                "env_steps_per_s": cores * 700 / dt5, "link_timesteps_per_s": sum(o[0] for o in ep) / dt5,
+                "note": "reference rl/pz_pednet_env.PedNetParallelEnv, obs option3, action_space.sample() every step; "
+                        "one episode per host core"}
+    value = work / slowest
+    src = ("the reference's own Network (baseline/_ref, unmodified)" if kind == "reference"
+           else "the Python oracle port (baseline/_ref not installed)")
     sample = (f"{cores} independent {REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattices ({L} links each), {steps} steps, same "
-              f"link parameters / origin rule / demand pattern as the workload; one Python process per host core")
+              f"link parameters / origin rule / demand pattern as the workload; one Python process per host core; {src}")
     line = {"impl": "reference", "metric": "link-timesteps/sec", "value": value, "unit": "link-timesteps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
-            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * slowest / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"grid{GRID_SIZE} (config 4: synthetic {GRID_SIZE}x{GRID_SIZE}-node lattice, 1046528 "
                                    f"directed links, 1 replica per GPU, philox draws, uniform turning fractions)",
                        "reference_sample": sample},
-            "cpu_baseline": {"value": value, "unit": "link-timesteps/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "link-timesteps/s", "cores": cores, "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": "link-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if ref_cfg:
+        line["reference_configs"] = ref_cfg
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------------- batched env (config 5)
-def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup):
+# ================================================================================= batched env (config 5)
+def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, congested=True):
     """BASELINE config 5: data/45_intersections, batched replicas with random gate actions in [0, 4] m,
-    obs_mode option3, action_gap 1.  Returns (env-steps/s device-resident, env-steps/s end-to-end with the
-    actions coming from pinned host memory and observations + rewards copied back every step)."""
+    obs_mode option3, action_gap 1.  Device-resident and end-to-end (actions from pinned host memory, observations
+    and rewards back to pinned host memory every step, `BatchedPedNetEnv.rollout_host`) env-steps/s at the start of
+    an episode, and device-resident again in the congested state around step 300."""
     from pednstream_b200.rl import BatchedPedNetEnv
-    env = BatchedPedNetEnv("45_intersections", replicas=replicas, obs_mode="option3", seed=1000 + rank,
+    env = BatchedPedNetEnv("45_intersections", replicas=replicas, obs_mode="option3", seed=1000,
                            replica_base=rank * replicas, device=dev)
     R, A = env.R, env.n_act
+    links = env.engine.L
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank)
-    actions = torch.rand((warmup + 2 * steps, R, A), generator=gen, device=dev, dtype=torch.float32) * 4.0
+    pool = torch.rand((16, R, A), generator=gen, device=dev, dtype=torch.float32) * 4.0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in range(n):
+            env.step(pool[k & 15])
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     for k in range(warmup):
-        env.step(actions[k])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(steps):
-        env.step(actions[warmup + k])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    host_actions = actions[warmup + steps:].cpu().pin_memory()
-    host_obs = torch.zeros((R, env.n_obs), dtype=torch.float32).pin_memory()
-    host_rew = torch.zeros((R,), dtype=torch.float32).pin_memory()
-    dev_act = torch.zeros((R, A), dtype=torch.float32, device=dev)
-    barrier()
+        env.step(pool[k & 15])
+    ms = timed(steps)
+    # end to end: every step its own H2D (actions) and D2H (observations + rewards), pipelined on two copy streams
+    host_actions = (torch.rand((steps, R, A), dtype=torch.float32) * 4.0).pin_memory()
+    host_obs = torch.zeros((steps, R, env.n_obs), dtype=torch.float32).pin_memory()
+    host_rew = torch.zeros((steps, R), dtype=torch.float32).pin_memory()
+    env.rollout_host(host_actions[:2], host_obs[:2], host_rew[:2])          # creates the streams / buffers
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e2.record()
-    for k in range(steps):
-        dev_act.copy_(host_actions[k], non_blocking=True)
-        obs, rew, done, _ = env.step(dev_act)
-        host_obs.copy_(obs, non_blocking=True)
-        host_rew.copy_(rew, non_blocking=False)
+    env.rollout_host(host_actions, host_obs, host_rew)
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    # congested state (queues at the gater and the origins; blockers draws of jammed links)
+    ms_late, late_from = None, None
+    if congested and env.sim_step + steps < 330:
+        while env.sim_step < 300:
+            env.step(pool[env.sim_step & 15])
+        late_from = env.sim_step
+        ms_late = timed(steps)
     env.engine.check_errors()
+    # cross-GPU gather of the per-replica episode statistic (NCCL all-gather over NVLink), timed on the device
+    gather_us = None
+    if world > 1:
+        from pednstream_b200 import parallel
+        parallel.gather_replica_values(env.cumulative_reward)               # warm-up (communicator set-up)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        for _ in range(10):
+            allr = parallel.gather_replica_values(env.cumulative_reward)
+        g1.record()
+        barrier()
+        gather_us = 1e3 * g0.elapsed_time(g1) / 10
+        assert allr.shape[0] == world * R
     # episode turnover: reset = state init + demand of the next episode drawn on the device (wall clock, it
     # has host work in it)
     torch.cuda.synchronize()
@@ -222,34 +320,93 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup):
     env.reset()
     torch.cuda.synchronize()
     reset_ms = (time.perf_counter() - w0) * 1e3
-    t = torch.tensor([ms, ms_e2e, reset_ms], dtype=torch.float64, device=dev)
+    vals = [ms, ms_e2e, reset_ms, ms_late if ms_late is not None else 0.0, gather_us or 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, reset_ms = float(t[0]), float(t[1]), float(t[2])
+    ms, ms_e2e, reset_ms, ms_late_max, gather_us_max = [float(v) for v in t]
     S_ep = env.simulation_steps
     episode_ms = S_ep * ms / steps + reset_ms
-    links = env.engine.L
-    return {"env_steps_per_s": world * R * steps / (ms * 1e-3),
-            "env_steps_per_s_e2e": world * R * steps / (ms_e2e * 1e-3),
-            "env_steps_per_s_with_resets": world * R * S_ep / (episode_ms * 1e-3),
-            "reset_ms": reset_ms, "steps_per_episode": S_ep,
-            "link_timesteps_per_s": world * R * links * steps / (ms * 1e-3),
-            "replicas_per_gpu": R, "replicas_total": world * R, "env_steps": steps, "ms_per_env_step": ms / steps,
-            "launches_per_env_step": env.launches_per_step(), "links": links,
-            "h2d_bytes_per_step": R * A * 4, "d2h_bytes_per_step": R * (env.n_obs + 1) * 4,
-            "workload": "config 5: data/45_intersections, obs option3, uniform random gate actions, philox draws, "
-                        "per-replica demand drawn on the device at reset",
-            "mean_reward_last_step": float(host_rew.mean())}
+
+    def roof(ms_window):
+        gbs = B_ALG * world * R * links * steps / (ms_window * 1e-3) / 1e9
+        return {"achieved": gbs, "frac": gbs / (peak * world), "link_timesteps_per_s": world * R * links * steps / (ms_window * 1e-3),
+                "us_per_env_step": 1e3 * ms_window / steps}
+
+    out = {"env_steps_per_s": world * R * steps / (ms * 1e-3),
+           "env_steps_per_s_e2e": world * R * steps / (ms_e2e * 1e-3),
+           "env_steps_per_s_with_resets": world * R * S_ep / (episode_ms * 1e-3),
+           "reset_ms": reset_ms, "steps_per_episode": S_ep,
+           "link_timesteps_per_s": world * R * links * steps / (ms * 1e-3),
+           "replicas_per_gpu": R, "replicas_total": world * R, "scaling": "strong (8192 replicas in total)",
+           "env_steps": steps, "ms_per_env_step": ms / steps,
+           "launches_per_env_step": env.launches_per_step(), "links": links,
+           "h2d_bytes_per_step": R * A * 4, "d2h_bytes_per_step": R * (env.n_obs + 1) * 4,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak * world, "alg_bytes_per_link_step": B_ALG,
+                        "note": "whole env step (link flows + route choice + node model + link update with actions, "
+                                "observations and reward riding in the link kernels): 176 B x links x replicas / step time",
+                        "episode_start": roof(ms)},
+           "workload": "config 5: data/45_intersections, obs option3, uniform random gate actions, philox draws, "
+                       "per-replica demand drawn on the device at reset",
+           "e2e_note": "BatchedPedNetEnv.rollout_host: per step H2D of the actions and D2H of observations + rewards "
+                       "(pinned host memory), double-buffered on two copy streams",
+           "mean_reward_last_step": float(host_rew[-1].mean())}
+    if ms_late is not None:
+        out["roofline"]["congested_t%d" % late_from] = roof(ms_late_max)
+    if world > 1:
+        out["reward_gather_us"] = gather_us_max
+        out["reward_gather_note"] = "all-gather of one float32 per replica over NCCL (per call, device-timed)"
+    del env
+    return out
 
 
-# --------------------------------------------------------------------------------- our arm
+# ================================================================================= small configs (1-3)
+def bench_small_configs(torch, dev):
+    """BASELINE configs 1-3 on the GPU through the facade: wall time per network_loading(t) in the numpy-compatible
+    draw mode (bit-identical to the reference; one host round trip per step) and in philox mode (no host in the
+    loop; one native call for the whole run)."""
+    import numpy as np
+    from pednstream_b200 import NetworkEnvGenerator, _native
+    out = {}
+    for key, name, steps, override in (("config1_long_corridor", "long_corridor", 500, None),
+                                       ("config2_nine_intersections", "nine_intersections", 499, None),
+                                       ("config3_melbourne_2000", "melbourne", 1999, 2000)):
+        rec = {}
+        for mode in ("numpy", "philox"):
+            np.random.seed(0)
+            g = NetworkEnvGenerator()
+            if override:
+                g.network_data = g.load_network_data(name)
+                g.config["params"]["simulation_steps"] = override
+            net = g.create_network(name, verbose=False, rng=mode, seed=0, device=dev)
+            eng = net.engine
+            net.network_loading(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if mode == "numpy":
+                for t in range(2, steps + 1):
+                    net.network_loading(t)
+            else:
+                eng._push_all_demand(net)
+                eng.run(2, steps - 1, _native.RNG_PHILOX)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            eng.check_errors()
+            L = len(net.links)
+            rec[mode] = {"ms_per_step": 1e3 * dt / (steps - 1), "link_timesteps_per_s": L * (steps - 1) / dt}
+            rec["links"], rec["steps"] = L, steps
+        out[key] = rec
+    return out
+
+
+# ================================================================================= our arm
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from pednstream_b200 import _native
     from pednstream_b200.engine import Engine
-    from pednstream_b200.grid import build_grid_plan
+    from pednstream_b200.grid import build_grid_plan, default_origins
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,15 +415,21 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = measured_peak()
 
     K, W = args.steps, max(args.warmup, 3)
     size = args.grid
     Kp, Ke = min(K, 50), min(K, 100)                     # profiled / end-to-end region lengths
-    S = W + K + Kp + Ke + 2                              # history rows: 80 B x links x (S+1) of HBM
-    if 80.0 * (S + 1) * (2 * 2 * size * (size - 1)) > 150e9:
-        raise SystemExit(f"--steps {K}: the {size}x{size} history would not fit in HBM; use <= 1500 steps")
+    want_late = not args.no_variants and W + K + Kp + Ke + 8 < LATE_T
+    S = max(W + K + Kp + Ke + 10, LATE_T + LATE_K + 2 if want_late else 0)   # history rows: 80 B x links x (S+1)
+    n_links_est = 2 * 2 * size * (size - 1)
+    if 80.0 * (S + 1) * n_links_est > 150e9:
+        if want_late:
+            want_late = False
+            S = W + K + Kp + Ke + 10
+        if 80.0 * (S + 1) * n_links_est > 150e9:
+            raise SystemExit(f"--steps {K}: the {size}x{size} history would not fit in HBM; use <= 1500 steps")
     link_over = {"speed_noise_std": args.sigma} if args.sigma is not None else None
-    from pednstream_b200.grid import default_origins
     plan, gate, tf, demand = build_grid_plan(size, S, demand_seed=rank, locality_order=True, link=link_over,
                                              origins=default_origins(size, args.origin_stride))
     L = plan["n_links"]
@@ -278,6 +441,20 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    names = ("link_pair", "route_probs", "node_flows")
+
+    def profiled(engine, t0, n):
+        k_ms, k_cnt = engine.run_profiled(t0, n)
+        return {nm: (k_ms[i] / k_cnt[i] if k_cnt[i] else None) for i, nm in enumerate(names)}
+
+    def roof_of(per_kernel, links):
+        dom = max((n for n in names if per_kernel[n]), key=lambda n: per_kernel[n])
+        gbs = B_ALG_PASS[dom] * links / (per_kernel[dom] * 1e-3) / 1e9
+        step_ms = sum(v for v in per_kernel.values() if v)
+        return dom, {"kernel": "k_link_lane" if dom == "link_pair" else "k_" + dom, "achieved": gbs, "frac": gbs / peak,
+                     "kernel_ms": {k: v for k, v in per_kernel.items() if v},
+                     "step_serialised": {"ms": step_ms, "frac": B_ALG * links / (step_ms * 1e-3) / 1e9 / peak}}
 
     # ---- warm-up, then the timed region: inputs resident in HBM, K steps in one native call ----
     eng.run(1, W)
@@ -294,17 +471,25 @@ def run_ours(args):
     t_next = W + K + 1
 
     # ---- per-kernel durations (CUDA events on the launching stream, inside the library) --------
-    k_ms, k_cnt = eng.run_profiled(t_next, Kp)
+    per_kernel = profiled(eng, t_next, Kp)
     t_next += Kp
-    names = ("link_pair", "route_probs", "node_flows")
-    per_kernel = {n: (k_ms[i] / k_cnt[i] if k_cnt[i] else None) for i, n in enumerate(names)}
+
+    # stores the exact shortcuts skipped in the last step (idle nodes leave the zero inflow / outflow rows alone):
+    # what the step really moved, next to the 176 algorithmic bytes it is credited with
+    stride = int(plan["nd_stride"])
+    active = (eng.nm_s.view(-1, stride) != 0).any(dim=1)
+    slot_node = torch.from_numpy(np.ascontiguousarray(plan["lk_slots"]) // stride).to(dev)
+    skipped = int((~active[slot_node[:, 0]]).sum()) + int((~active[slot_node[:, 1]]).sum())
+    moved_bytes = B_ALG - 8.0 * skipped / L
 
     # ---- end to end through the public call, host buffers: every step copies its demand row from
     # pinned host memory, launches the step, and reads the network-wide pedestrian count back ----
     pinned = torch.zeros((eng.demand.shape[0], eng.demand.shape[1]), dtype=torch.float64).pin_memory()
     pinned[: demand.shape[0], : demand.shape[1]] = torch.from_numpy(np.ascontiguousarray(demand))
     from pednstream_b200 import _native as _nat
-    result_host = torch.zeros((Ke, _nat.METRIC_ROW), dtype=torch.float64).pin_memory()
+    result_host = torch.zeros((Ke + 4, _nat.METRIC_ROW), dtype=torch.float64).pin_memory()
+    eng.run_streamed(t_next, 4, pinned, result_host)      # untimed: creates the copy stream and its events
+    t_next += 4
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -312,42 +497,83 @@ def run_ours(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
-    num_hist = None
+    t_next += Ke
     eng.check_errors()
     total_peds = float(eng.streamed_metric(result_host, Ke)[-1])
+
+    # ---- roofline variants: late in the run, and the dense-boundary workload ----------------------------------
+    variants = {}
+    dom, rf = roof_of(per_kernel, L)
+    rf["window"] = f"t = {W + K + 1} .. {W + K + Kp}"
+    variants["timed_region"] = rf
+    if want_late and rank == 0:
+        eng.run(t_next, LATE_T - t_next)
+        torch.cuda.synchronize()
+        _, rl = roof_of(profiled(eng, LATE_T, LATE_K), L)
+        rl["window"] = f"t = {LATE_T} .. {LATE_T + LATE_K - 1}"
+        rl["pedestrians_on_links"] = float(eng.history("num_pedestrians")[LATE_T + LATE_K - 1].sum())
+        variants["late"] = rl
 
     t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
 
-    # free the lattice history before the batched environment allocates its own
+    # free the lattice history before the next allocation
     h2d_bytes = int(plan["n_demand_rows"] * 8)
-    del num_hist, pinned
+    n_nodes, n_origins = plan["n_nodes"], plan["n_demand_rows"]
+    routed = bool(plan["rt_grp_node"].size)
+    del pinned, active, slot_node
     eng = None
     torch.cuda.empty_cache()
+
+    if not args.no_variants and rank == 0 and world == 1:
+        Sd = DENSE_WARM + DENSE_K + 4
+        if 80.0 * (Sd + 1) * n_links_est < 150e9:
+            pl2, g2, tf2, d2 = build_grid_plan(size, Sd, demand_seed=0, locality_order=True, link=link_over,
+                                               origins=default_origins(size, 1))
+            e2_ = Engine(pl2, replicas=1, rng="philox", seed=0, device=dev)
+            e2_.initialise(g2, None, tf2, d2, None)
+            e2_.run(1, DENSE_WARM)
+            torch.cuda.synchronize()
+            _, rd = roof_of(profiled(e2_, DENSE_WARM + 1, DENSE_K), pl2["n_links"])
+            rd["window"] = f"every boundary node an origin ({pl2['n_demand_rows']} origins), t = {DENSE_WARM + 1} .. {DENSE_WARM + DENSE_K}"
+            rd["pedestrians_on_links"] = float(e2_.history("num_pedestrians")[DENSE_WARM + DENSE_K].sum())
+            variants["dense_boundary"] = rd
+            e2_ = None
+            del pl2, g2, tf2, d2
+            torch.cuda.empty_cache()
+
     env_stats = None
     if not args.no_env:
-        env_stats = bench_env45(torch, dist, world, rank, dev, args.env_replicas, min(K, 300), 10)
+        per_gpu = max(1, args.env_replicas // world)
+        env_stats = bench_env45(torch, dist, world, rank, dev, per_gpu, max(10, min(K, 200)), 10, peak)
+        torch.cuda.empty_cache()
+
+    small = None
+    if rank == 0 and world == 1 and not args.no_small:
+        small = bench_small_configs(torch, dev)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         value = world * L * K / (ms * 1e-3)
         e2e = world * L * Ke / (ms_e2e * 1e-3)
-        dom = max((n for n in names if per_kernel[n]), key=lambda n: per_kernel[n])
         step_gbs = B_ALG * L / (ms / K * 1e-3) / 1e9
-        dom_gbs = B_ALG_PASS[dom] * L / (per_kernel[dom] * 1e-3) / 1e9
-        cpu_v, cpu_dt, cpu_L = (None, None, None)
+        cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_steps = 150                   # ~13 s of single-core work (the brief asks for 10-30 s)
-            cpu_v, cpu_dt, cpu_L = oracle_sample(cpu_steps, 2)
+            kind = "reference" if reference_installed() else "port"
+            cpu_steps = 40 if kind == "reference" else 150     # ~13 s of single-core work (the brief asks for 10-30 s)
+            cpu_v, cpu_dt, cpu_L = lattice_sample(cpu_steps, 2, kind)
+            cpu = {"value": cpu_v, "unit": "link-timesteps/s", "cores": 1, "kind": kind,
+                   "sample": f"{'the reference (baseline/_ref, unmodified)' if kind == 'reference' else 'Python oracle port'}, "
+                             f"{REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({cpu_L} links), {cpu_steps} steps, {cpu_dt:.1f} s; "
+                             f"host has {os.cpu_count()} cores, the reference algorithm is single-threaded"}
         line = {
             "metric": "link-timesteps/sec", "value": value, "unit": "link-timesteps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"grid{size} (config 4: synthetic {size}x{size}-node lattice, {L} directed links, "
                                    f"1 replica per GPU, philox draws, uniform turning fractions)",
-                       "links": L, "nodes": plan["n_nodes"], "origins": plan["n_demand_rows"],
+                       "links": L, "nodes": n_nodes, "origins": n_origins,
                        "l2_policy": "inputs larger than L2: one step touches >= 176 B x links = "
                                     f"{B_ALG * L / 1e6:.0f} MB of history",
                        "multi_gpu": "replicas only: one independent grid per rank, no data-path collective"},
@@ -357,23 +583,28 @@ def run_ours(args):
                             "pinned host memory, runs the step (whose link kernel also reduces the network-wide "
                             "pedestrian count to 64 partial sums) and copies those to pinned host memory; "
                             "stream-ordered, one host wait at the end"},
-            "gpu_launches": int(2 * K + 1 + (K if plan["rt_grp_node"].size else 0)),
+            "gpu_launches": int(2 * K + 1 + (K if routed else 0)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_link_lane" if dom == "link_pair" else "k_" + dom, "achieved": dom_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": dom_gbs / peak, "traffic": measured_traffic(dom),
+            "roofline": {"bound": "hbm", "kernel": variants["timed_region"]["kernel"],
+                         "achieved": variants["timed_region"]["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": variants["timed_region"]["frac"], "traffic": measured_traffic(dom),
                          "peak_source": peak_src,
                          "alg_bytes_per_link_step": B_ALG_PASS[dom],
-                         "kernel_ms": {k: v for k, v in per_kernel.items() if v},
-                         "step": {"achieved": step_gbs, "frac": step_gbs / peak, "alg_bytes_per_link_step": B_ALG}},
+                         "kernel_ms": variants["timed_region"]["kernel_ms"],
+                         "step": {"achieved": step_gbs, "frac": step_gbs / peak, "alg_bytes_per_link_step": B_ALG,
+                                  "moved_bytes_per_link_step": moved_bytes,
+                                  "moved_frac": step_gbs / peak * moved_bytes / B_ALG,
+                                  "note": "moved = 176 B minus the inflow/outflow stores that idle nodes skip (rows are "
+                                          "zero by contract), counted in the last profiled step"},
+                         "variants": variants},
             "check": {"pedestrians_on_links_last_step": total_peds},
         }
         if env_stats is not None:
             line["batched_env"] = env_stats
-        if cpu_v is not None:
-            line["cpu_baseline"] = {"value": cpu_v, "unit": "link-timesteps/s", "cores": 1, "kind": "port",
-                                    "sample": f"Python oracle, {REF_SAMPLE_SIZE}x{REF_SAMPLE_SIZE} lattice ({cpu_L} links), "
-                                              f"{cpu_steps} steps, {cpu_dt:.1f} s; host has {os.cpu_count()} cores, the "
-                                              f"reference algorithm is single-threaded"}
+        if small is not None:
+            line["small_configs"] = small
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -382,7 +613,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_SIZE)
@@ -390,7 +621,10 @@ def main():
     ap.add_argument("--sigma", type=float, default=None, help="override speed_noise_std of the lattice (experiments)")
     ap.add_argument("--origin-stride", type=int, default=64, help="every n-th boundary node is an origin")
     ap.add_argument("--no-env", action="store_true", help="skip the batched 45_intersections environment section")
-    ap.add_argument("--env-replicas", type=int, default=1024, help="replicas per GPU of the batched environment")
+    ap.add_argument("--no-variants", action="store_true", help="skip the late-time / dense-boundary roofline variants")
+    ap.add_argument("--no-small", action="store_true", help="skip BASELINE configs 1-3")
+    ap.add_argument("--env-replicas", type=int, default=ENV_REPLICAS_TOTAL,
+                    help="replicas of the batched environment in total (divided over the GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

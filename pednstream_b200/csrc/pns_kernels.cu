@@ -328,8 +328,8 @@ template <int MODE>
 __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, size_t e, int tau, const LinkNow& me,
                                                 float num_rev, const Area& ar, double front_gate, double cum_out_tau,
                                                 double snd_prev, int replica, const pns::DrawKey& key,
-                                                const pns::LinkDraws& dr, int pre_idx0 = -1, double pre_val0 = 0.0,
-                                                int pre_idx1 = -1, double pre_val1 = 0.0) {
+                                                int pre_idx0 = -1, double pre_val0 = 0.0, int pre_idx1 = -1,
+                                                double pre_val1 = 0.0) {
     SendOut o;
     o.kind = 0; o.n1 = 0; o.rf = 0.0f; o.sval = 0.0; o.flow = 0.0;
     if (tau < p.fftau) return o;                                          // link.py:267-269
@@ -367,7 +367,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
                 flow = (double)c.draw_b[e];
             } else if (MODE == PNS_RNG_PHILOX) {
                 const float p32 = 0.7f + 0.15f * pns::det_pow08(rf);
-                flow = (double)pns::binomial_u(trials, (double)p32, dr.u1);
+                flow = (double)pns::binomial_release(key, trials, (double)p32);
             } else {
                 return o;   // REQUEST: the host draws R1 (and R2, which depends on it)
             }
@@ -394,7 +394,7 @@ __device__ __forceinline__ SendOut sending_flow(const Ctx& c, const LinkP& p, si
 template <int MODE>
 __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, size_t e, int tau, float num_rev,
                                                  const Area& ar, double back_gate, double cum_in_tau,
-                                                 double cum_out_lag, double rcv_prev, const pns::LinkDraws& dr,
+                                                 double cum_out_lag, double rcv_prev, const pns::DrawKey& key,
                                                  int* n3) {
     const int lag_i = tau + 1 - p.swtau;   // cum_out_lag = cumulative_outflow[lag_i] when lag_i >= 0
     double bound;
@@ -407,7 +407,7 @@ __device__ __forceinline__ double receiving_flow(const Ctx& c, const LinkP& p, s
         *n3 = trials;
         int blockers = 0;
         if (MODE == PNS_RNG_TABLE) blockers = c.draw_b[2 * c.row32 + e];
-        else if (MODE == PNS_RNG_PHILOX) blockers = pns::binomial09_u(trials, dr.u3);
+        else if (MODE == PNS_RNG_PHILOX) blockers = pns::binomial_blockers(key, trials);
         else return 0.0;
         if (lag_i < 0) {
             bound = ar.space - (double)blockers;
@@ -613,16 +613,10 @@ __device__ __forceinline__ void link_pair_body(const Ctx& c) {
         // front gate of a plain link is the back gate of its reverse (link.py:110-126); a separator's
         // gates both equal its lane width (link.py:462-478)
         const double front = is_sep(p) ? gate[a] : gate[1 - a];
-        // one Philox block per link and step serves its release (R1) and blockers (R3) draws; a link with nobody
-        // on it, in transit or opposite draws nothing
-        pns::LinkDraws dr;
-        dr.u1 = 0.0; dr.u3 = 0.0;
-        if (MODE == PNS_RNG_PHILOX && (now[a].num > 0.0f || now[1 - a].num >= 1.0f || cin_tau[a] != cou_tau[a]))
-            dr = pns::link_draws(key);
         s[a] = sending_flow<MODE>(c, p, e[a], tau, now[a], now[1 - a].num, ar[a], front, cou_tau[a], snd_prev[a], rep,
-                                  key, dr);
+                                  key);
         r[a] = receiving_flow<MODE>(c, p, e[a], tau, now[1 - a].num, ar[a], gate[a], cin_tau[a], cou_lag[a],
-                                    rcv_prev[a], dr, &n3[a]);
+                                    rcv_prev[a], key, &n3[a]);
     }
     if (MODE == PNS_RNG_REQUEST) {
 #pragma unroll
@@ -1161,10 +1155,6 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     SendOut s;
     double r = 0.0;
     int n3 = -1;
-    pns::LinkDraws dr;          // one Philox block serves the link's release (R1) and blockers (R3) draws
-    dr.u1 = 0.0; dr.u3 = 0.0;
-    if (MODE == PNS_RNG_PHILOX && valid && (me.num > 0.0f || num_rev >= 1.0f || cin_tau != cou_tau))
-        dr = pns::link_draws(key);
     if (valid) {
         // A link with nobody on it and nobody in transit (everything that entered has left) sends nothing:
         // arrived <= cin[tau] - cout[tau] = 0, so boundary = 0 and only the smoothing with the previous
@@ -1176,9 +1166,9 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
             if (MODE != PNS_RNG_REQUEST && f < 0.0) atomicOr(c.s.err, PNS_ERR_NEG_SENDING);
             s.flow = MODE == PNS_RNG_REQUEST ? 0.0 : f;
         } else
-        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, dr, pre_i0, pre_v0,
-                               pre_i1, pre_v1);
-        r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, dr, &n3);
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, 0, key, pre_i0, pre_v0, pre_i1,
+                               pre_v1);
+        r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
     } else {
         s.flow = 0; s.sval = 0; s.kind = 0; s.n1 = 0; s.rf = 0;
     }
@@ -1532,9 +1522,6 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     pns::DrawKey key;
     key.t = (uint32_t)c.t_flows; key.link = (uint32_t)l; key.replica = rkey; key.k0 = k0; key.k1 = k1;
     const double front = is_sep(p) ? gate : gate_rev;                       // link.py:110-126, 462-478
-    pns::LinkDraws dr;          // one Philox block serves the link's release (R1) and blockers (R3) draws
-    dr.u1 = 0.0; dr.u3 = 0.0;
-    if (MODE == PNS_RNG_PHILOX && (me.num > 0.0f || num_rev >= 1.0f || cin_tau != cou_tau)) dr = pns::link_draws(key);
     SendOut s;
     // nobody on the link and nobody in transit: boundary flow 0, only the smoothing with the previous sending
     // flow remains (link.py:363-364); exact, see k_link_lane
@@ -1543,11 +1530,11 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
         s.flow = pymin(floor(0.8 * 0.0 + 0.2 * snd_prev), 0.0);
         if (s.flow < 0.0) atomicOr(c.s.err + rep, PNS_ERR_NEG_SENDING);
     } else {
-        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, rep, key, dr, pre_i0, pre_v0,
+        s = sending_flow<MODE>(c, p, e, tau, me, num_rev, ar, front, cou_tau, snd_prev, rep, key, pre_i0, pre_v0,
                                pre_i1, pre_v1);
     }
     int n3 = -1;
-    const double r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, dr, &n3);
+    const double r = receiving_flow<MODE>(c, p, e, tau, num_rev, ar, gate, cin_tau, cou_lag, rcv_prev, key, &n3);
     sh_send[threadIdx.x] = s.flow;
     __syncthreads();
     const double s_rev = sh_send[mate];
@@ -1755,8 +1742,7 @@ __global__ void k_rng_selftest(int kind, int n, const int32_t* n_trials, const d
     key.k0 = (uint32_t)seed; key.k1 = (uint32_t)(seed >> 32);
     if (kind == 0) out_i[i] = pns::binomial_philox(key, (uint32_t)site, n_trials[i], p[i]);
     else if (kind == 3) {          // the shared block of a link's draws: site 1 -> R1 (any p), site 3 -> R3 (p = 0.9)
-        const pns::LinkDraws dr = pns::link_draws(key);
-        out_i[i] = site == 3 ? pns::binomial09_u(n_trials[i], dr.u3) : pns::binomial_u(n_trials[i], p[i], dr.u1);
+        out_i[i] = site == 3 ? pns::binomial_blockers(key, n_trials[i]) : pns::binomial_release(key, n_trials[i], p[i]);
     }
     else if (kind == 1) {
         float g[4];

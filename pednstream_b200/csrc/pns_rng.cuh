@@ -250,23 +250,29 @@ __host__ __device__ inline int binomial_from_zero(int n, double pp, double u, do
 
 // log(x!) - log(sqrt(2 pi x) (x/e)^x) for an integer-valued x >= 0 (Loader, "Fast and accurate computation of
 // binomial probabilities", 2000): table below 16, the asymptotic series above
-__host__ __device__ inline double pns_stirlerr(double x) {
-    if (x < 16.0) {
-        const int i = (int)x;
-        const double sfe[16] = {
-            0x0.0p+0, 0x1.4c071bcda0a5bp-4, 0x1.52a9b923ea649p-5, 0x1.c579a268d80b3p-6, 0x1.54a2662fd78a9p-6,
-            0x1.10b4e513fcbedp-6, 0x1.c6b167bebdf36p-7, 0x1.85d4d612e4a86p-7, 0x1.552805e7b3076p-7,
-            0x1.2f4871b12ab64p-7, 0x1.10f9d4c0743a7p-7, 0x1.f0593088014f8p-8, 0x1.c7018733aa9c6p-8,
-            0x1.a40514700f36cp-8, 0x1.86076c002d4a7p-8, 0x1.6c08f6f194a10p-8};
-        return sfe[i];
-    }
+#ifdef __CUDACC__
+__device__
+#endif
+const double kStirlingErr[16] = {
+    0x0.0p+0, 0x1.4c071bcda0a5bp-4, 0x1.52a9b923ea649p-5, 0x1.c579a268d80b3p-6, 0x1.54a2662fd78a9p-6,
+    0x1.10b4e513fcbedp-6, 0x1.c6b167bebdf36p-7, 0x1.85d4d612e4a86p-7, 0x1.552805e7b3076p-7,
+    0x1.2f4871b12ab64p-7, 0x1.10f9d4c0743a7p-7, 0x1.f0593088014f8p-8, 0x1.c7018733aa9c6p-8,
+    0x1.a40514700f36cp-8, 0x1.86076c002d4a7p-8, 0x1.6c08f6f194a10p-8};
+#ifdef __CUDACC__
+__device__
+#endif
+inline double pns_stirlerr(double x) {
+    if (x < 16.0) return kStirlingErr[(int)x];
     const double r = 1.0 / x;
     const double rr = r * r;
     return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0) * rr) * rr) * rr) * rr) * r;
 }
 
 // deviance term x*log(x/np) + np - x by its series in v = (x-np)/(x+np) (|x - np| << x + np at the mode)
-__host__ __device__ inline double pns_bd0(double x, double np) {
+#ifdef __CUDACC__
+__device__
+#endif
+inline double pns_bd0(double x, double np) {
     const double d = x - np;
     double v = d / (x + np);
     double s = d * v;
@@ -283,7 +289,10 @@ __host__ __device__ inline double pns_bd0(double x, double np) {
 }
 
 // pmf of Binomial(n, pp) at m (0 < m < n), saddle-point form (Loader 2000); relative error ~2e-15
-__host__ __device__ inline double binomial_pmf_mode(int n, int m, double pp, double q) {
+#ifdef __CUDACC__
+__device__
+#endif
+inline double binomial_pmf_mode(int n, int m, double pp, double q) {
     const double nd = (double)n, md = (double)m, kd = (double)(n - m);
     const double lc = (((pns_stirlerr(nd) - pns_stirlerr(md)) - pns_stirlerr(kd)) - pns_bd0(md, nd * pp)) -
                       pns_bd0(kd, nd * q);
@@ -294,7 +303,10 @@ __host__ __device__ inline double binomial_pmf_mode(int n, int m, double pp, dou
 // {m+1, m-1}, {m+2, m-2}, ... -- subtracting the pmf values from u.  Expected work ~1.6 standard deviations instead of the mean (a jammed link's
 // blockers draw, Binomial(1200, 0.9): ~17 candidates instead of a 120-step walk).  Up and down recurrences:
 // pmf(k+1)/pmf(k) = A/(k+1) - ratio, pmf(k-1)/pmf(k) = B/(n-k+1) - 1/ratio, A = ratio (n+1), B = (n+1)/ratio.
-__host__ __device__ inline int binomial_from_mode(int n, double pp, double u, double pm_tabulated) {
+#ifdef __CUDACC__
+__device__
+#endif
+inline int binomial_from_mode(int n, double pp, double u, double pm_tabulated) {
     const double q = 1.0 - pp;
     const double ratio = pp / q;
     const double iratio = q / pp;
@@ -339,78 +351,60 @@ __host__ __device__ inline int binomial_from_mode(int n, double pp, double u, do
     }
 }
 
-// Exact Binomial(n, p), 0 < p < 1, n > 0, from one uniform u in [0, 1).  Out of line and with scalar arguments:
-// it is called on a minority of the links and must not bloat the callers' register footprint.  (A rejection
-// sampler for large means -- BTRS -- was tried in round 1: spills on the main path, and a warp runs its slow
-// path almost every time because some lane always needs it.)
+// Exact Binomial(n, p), 0 < p < 1, n > 0: CDF inversion of one uniform -- from zero for small means n*min(p,1-p),
+// outward from the mode for large ones; 0.9^n and the mode pmf of the blockers draw (p = 0.9) come from tables.
+// The two searches are separate out-of-line functions with scalar arguments (Philox block included): draws happen
+// on a minority of the links and must not bloat the callers' register footprint, and the rare, register-hungry
+// mode search must not tax the call site of the common one (inlined, or behind one shared entry point, the
+// 64-register link kernels spill).  (A rejection sampler for large means -- BTRS -- was tried in round 1: spills on
+// the main path, and a warp runs its slow path almost every time because some lane needs it.)
+// The release (R1) and blockers (R3) draws of a link and step take their uniforms from one Philox block (site 1):
+// words 0,1 and words 2,3; a draw with a block of its own (the activity draw R2, test hooks) names its site.
+__host__ __device__ inline double site_uniform(uint32_t t, uint32_t link, uint32_t replica, uint32_t k0, uint32_t k1,
+                                               uint32_t site, uint32_t word) {
+    const Philox4 w = philox4x32_10(t, link, site, replica, k0, k1);
+    return word ? u53(w.v[2], w.v[3]) : u53(w.v[0], w.v[1]);
+}
 #ifdef __CUDACC__
 __device__ __noinline__
 #else
 inline
 #endif
-int binomial_core(int n, double p, double u) {
+int binomial_zero_core(uint32_t t, uint32_t link, uint32_t replica, uint32_t k0, uint32_t k1, uint32_t site,
+                       uint32_t word, int n, double pp, bool tabulated) {
+    return binomial_from_zero(n, pp, site_uniform(t, link, replica, k0, k1, site, word),
+                              tabulated ? PNS_TABLE(kPow09, n) : -1.0);
+}
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+inline
+#endif
+int binomial_mode_core(uint32_t t, uint32_t link, uint32_t replica, uint32_t k0, uint32_t k1, uint32_t site,
+                       uint32_t word, int n, double pp, bool tabulated) {
+    return binomial_from_mode(n, pp, site_uniform(t, link, replica, k0, k1, site, word),
+                              tabulated ? PNS_TABLE(kPmfMode09, n) : 0.0);
+}
+
+#ifdef __CUDACC__
+#define PNS_DEVFN __device__ __forceinline__
+#else
+#define PNS_DEVFN inline
+#endif
+PNS_DEVFN int binomial_draw(const DrawKey& key, uint32_t site, uint32_t word, int n, double p) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
     const bool flip = p > 0.5;
     const double pp = flip ? 1.0 - p : p;
-    const double mean = (double)n * pp;
     const bool tabulated = pp == (1.0 - 0.9) && n <= PNS_MODE_TABLE_N;
-    int k;
-    if (mean >= (tabulated ? PNS_MODE_MEAN_TABULATED : PNS_MODE_MEAN_GENERIC))
-        k = binomial_from_mode(n, pp, u, tabulated ? PNS_TABLE(kPmfMode09, n) : 0.0);
-    else
-        k = binomial_from_zero(n, pp, u, tabulated ? PNS_TABLE(kPow09, n) : -1.0);
+    const int k = (double)n * pp >= (tabulated ? PNS_MODE_MEAN_TABULATED : PNS_MODE_MEAN_GENERIC)
+                      ? binomial_mode_core(key.t, key.link, key.replica, key.k0, key.k1, site, word, n, pp, tabulated)
+                      : binomial_zero_core(key.t, key.link, key.replica, key.k0, key.k1, site, word, n, pp, tabulated);
     return flip ? n - k : k;
 }
-
-#ifdef __CUDACC__
-__device__ __forceinline__
-#else
-inline
-#endif
-int binomial_u(int n, double p, double u) {
-    if (n <= 0 || !(p > 0.0)) return 0;
-    if (p >= 1.0) return n;
-    return binomial_core(n, p, u);
-}
-
-// The blockers draw, Binomial(n, 0.9) (link.py:382): same algorithm with every constant of p = 0.9 folded and the
-// short walks of lightly occupied links inline (most draws of a step are of this kind: a handful of pedestrians
-// on the reverse link, two or three steps from a tabulated 0.9^n).
-#ifdef __CUDACC__
-__device__ __forceinline__
-#else
-inline
-#endif
-int binomial09_u(int n, double u) {
-    if (n <= 0) return 0;
-    const double pp = 1.0 - 0.9;
-    if (n > PNS_MODE_TABLE_N || (double)n * pp >= PNS_MODE_MEAN_TABULATED) return binomial_core(n, 0.9, u);
-    return n - binomial_from_zero(n, pp, u, PNS_TABLE(kPow09, n));
-}
-
-// The uniforms of one link's release (R1) and blockers (R3) draws of a step: one Philox block, words 0,1 and 2,3.
-struct LinkDraws {
-    double u1, u3;
-};
-__host__ __device__ inline LinkDraws link_draws(const DrawKey& key) {
-    const Philox4 w = philox4x32_10(key.t, key.link, 1u, key.replica, key.k0, key.k1);
-    LinkDraws d;
-    d.u1 = u53(w.v[0], w.v[1]);
-    d.u3 = u53(w.v[2], w.v[3]);
-    return d;
-}
-
-// A draw with a block of its own (site in the counter): the activity draw R2, test hooks.
-#ifdef __CUDACC__
-__device__ __forceinline__
-#else
-inline
-#endif
-int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) {
-    if (n <= 0 || !(p > 0.0)) return 0;
-    if (p >= 1.0) return n;
-    const Philox4 w = philox4x32_10(key.t, key.link, site, key.replica, key.k0, key.k1);
-    return binomial_core(n, p, u53(w.v[0], w.v[1]));
-}
+PNS_DEVFN int binomial_philox(const DrawKey& key, uint32_t site, int n, double p) { return binomial_draw(key, site, 0u, n, p); }
+PNS_DEVFN int binomial_release(const DrawKey& key, int n, double p) { return binomial_draw(key, 1u, 0u, n, p); }   // R1
+PNS_DEVFN int binomial_blockers(const DrawKey& key, int n) { return binomial_draw(key, 1u, 1u, n, 0.9); }          // R3
 
 // one entry of the sampler tables (see kInvK / kPmfMode09)
 #ifdef __CUDACC__

@@ -318,6 +318,19 @@ class Engine:
             row = np.array([float(a[t]) for a in self._od_arrays], dtype=np.float64)
             self.od_w[t, : len(row)].copy_(torch.from_numpy(row))
 
+    def _push_all_demand(self, net):
+        """Upload every origin's whole demand series and every OD weight series (multi-step `run` on a facade
+        network: no host edits between the steps)."""
+        if self._demand_nodes:
+            table = np.zeros((self.S + 1, len(self._demand_nodes)))
+            for k, node in enumerate(self._demand_nodes):
+                d = np.asarray(node.demand, dtype=np.float64)
+                table[: len(d), k] = d[: self.S + 1]
+            self.set_demand(table)
+        if self._od_arrays and not self._od_per_replica:
+            od = np.stack([np.asarray(a, dtype=np.float64)[: self.S + 1] for a in self._od_arrays], axis=1)
+            self.od_w[: od.shape[0], : od.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(od)))
+
     def step_network(self, net, t: int):
         if not (1 <= t <= self.S):
             raise IndexError(f"time step {t} outside [1, {self.S}]")

@@ -287,9 +287,15 @@ class BatchedPedNetEnv:
                                                            int(row), _ptr(self.obs), _ptr(self.reward),
                                                            self._stream()), "pns_env_observe")
 
-    def step(self, actions: torch.Tensor):
-        """actions [R, n_act] float32 on the env's device.  Returns (obs, reward, done, info)."""
+    def step(self, actions: torch.Tensor, obs_out: torch.Tensor = None, reward_out: torch.Tensor = None):
+        """actions [R, n_act] float32 on the env's device.  Returns (obs, reward, done, info).
+        obs_out / reward_out: device tensors to receive this step's observations / rewards instead of the
+        env's own buffers (pipelined host loops keep two sets, see `rollout_host`)."""
         eng = self.engine
+        obs = self.obs if obs_out is None else obs_out
+        reward = self.reward if reward_out is None else reward_out
+        if obs.shape != self.obs.shape or obs.dtype != torch.float32 or reward.shape != self.reward.shape:
+            raise ValueError("obs_out / reward_out must match the env's obs / reward tensors")
         if self.sim_step > self.simulation_steps:
             raise RuntimeError("episode finished: call reset()")
         act_ptr = C.c_void_p(0)
@@ -302,12 +308,61 @@ class BatchedPedNetEnv:
             eng._begin_steps(self.sim_step, 1)
             _native.check(eng.lib, eng.lib.pns_env_step(
                 C.byref(eng.net), C.byref(eng.state), C.byref(eng.io), C.byref(self._env), act_ptr,
-                int(self.sim_step), _native.RNG_PHILOX, _ptr(self.obs), _ptr(self.reward),
+                int(self.sim_step), _native.RNG_PHILOX, _ptr(obs), _ptr(reward),
                 _ptr(self.cumulative_reward), self._stream()), "pns_env_step")
         eng.t_done = self.sim_step
         done = self.sim_step >= self.simulation_steps           # tested before the increment (quirk Q8)
         self.sim_step += 1
-        return self.obs, self.reward, done, {"step": self.sim_step - 1}
+        return obs, reward, done, {"step": self.sim_step - 1}
+
+    def rollout_host(self, host_actions: torch.Tensor, host_obs: torch.Tensor, host_reward: torch.Tensor):
+        """K environment steps driven from host memory: step k takes `host_actions[k]` ([K, R, n_act] pinned
+        float32) and delivers its observations and rewards to `host_obs[k]` ([K, R, n_obs]) / `host_reward[k]`
+        ([K, R]), both pinned.  Every step has its own host->device and device->host copies; they run on two
+        copy streams, double-buffered against the step kernels (actions of step k+1 go up and results of step
+        k come down while the other step computes).  Returns after everything is enqueued; synchronise the
+        device (or the current stream) before reading the host tensors."""
+        K = int(host_actions.shape[0])
+        if not (host_actions.is_pinned() and host_obs.is_pinned() and host_reward.is_pinned()):
+            raise ValueError("rollout_host needs pinned host tensors")
+        if host_obs.shape[0] < K or host_reward.shape[0] < K:
+            raise ValueError("host_obs / host_reward are shorter than host_actions")
+        dev = self.device
+        if not hasattr(self, "_pipe"):
+            mk = lambda shape: [torch.zeros(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._pipe = dict(act=mk((self.R, max(1, self.n_act))), obs=mk(tuple(self.obs.shape)), rew=mk((self.R,)),
+                              up=torch.cuda.Stream(dev), down=torch.cuda.Stream(dev),
+                              up_done=[torch.cuda.Event() for _ in range(2)],
+                              step_done=[torch.cuda.Event() for _ in range(2)],
+                              down_done=[torch.cuda.Event() for _ in range(2)])
+        P = self._pipe
+        main = torch.cuda.current_stream(dev)
+        up, down = P["up"], P["down"]
+        up.wait_stream(main)
+        down.wait_stream(main)
+        with torch.cuda.stream(up):                                  # actions of the first step
+            P["act"][0][:, : self.n_act].copy_(host_actions[0], non_blocking=True)
+            P["up_done"][0].record(up)
+        for k in range(K):
+            s = k & 1
+            main.wait_event(P["up_done"][s])
+            if k >= 2:
+                main.wait_event(P["down_done"][s])                    # results of step k-2 have left this buffer set
+            self.step(P["act"][s][:, : self.n_act] if self.n_act else None, obs_out=P["obs"][s], reward_out=P["rew"][s])
+            P["step_done"][s].record(main)
+            if k + 1 < K:
+                with torch.cuda.stream(up):                          # next step's actions (its buffer was read by step k-1)
+                    if k >= 1:
+                        up.wait_event(P["step_done"][1 - s])
+                    P["act"][1 - s][:, : self.n_act].copy_(host_actions[k + 1], non_blocking=True)
+                    P["up_done"][1 - s].record(up)
+            with torch.cuda.stream(down):                            # this step's results
+                down.wait_event(P["step_done"][s])
+                host_obs[k].copy_(P["obs"][s], non_blocking=True)
+                host_reward[k].copy_(P["rew"][s], non_blocking=True)
+                P["down_done"][s].record(down)
+        main.wait_stream(down)
+        main.wait_stream(up)
 
     def kpis(self, t_last: int = None) -> torch.Tensor:
         """Per-replica episode KPIs from the device history up to row t_last (default: the last simulated
