@@ -186,6 +186,83 @@ def generate_env(name):
           f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+# ---- turning fractions per step (reference node.turning_fractions after every network_loading) -------------
+TF_CASES = {"tf_nine_intersections": dict(dataset="nine_intersections", run=220, seed=0),
+            "tf_45_intersections": dict(dataset="45_intersections", run=160, seed=1)}
+
+
+def generate_tf(name):
+    """Every routed node's turning fractions after each step, recorded from the live reference
+    (path_finder.update_turning_fractions + check_fractions, path_finder.py:591-715) -- idle steps included."""
+    case = TF_CASES[name]
+    net = build_reference_network(case)
+    routed = [n for n in net.nodes.values()
+              if net.path_finder is not None and n.node_id in net.path_finder.nodes_in_paths and n.source_num > 2]
+    series = {n.node_id: [] for n in routed}
+    for t in range(1, case["run"] + 1):
+        net.network_loading(t)
+        for n in routed:
+            series[n.node_id].append(np.array(n.turning_fractions, dtype=np.float64).copy())
+    out = {"steps_run": np.int64(case["run"]), "seed": np.int64(case["seed"]),
+           "routed_nodes": np.asarray([n.node_id for n in routed], dtype=np.int64)}
+    for k, v in series.items():
+        out[f"tf_{k}"] = np.stack(v)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {len(routed)} routed nodes, {case['run']} steps -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)",
+          flush=True)
+
+
+# ---- on-device (Philox) draw mode on jammed lattices: digests of the oracle run with the Python restatement of
+# the device samplers.  No reference involved (the reference has no counter-based mode): these pin the
+# single-replica lattice kernel path (k_link_lane, one parameter class, host-resolved lag rows, launch order)
+# against the CPU restatement at sizes the unit tests do not reach.
+LATTICE_CASES = {"lattice32_philox": dict(size=32, stride=2, run=320, seed=5, base=30, peak=50),
+                 "lattice64_philox": dict(size=64, stride=8, run=300, seed=7, base=40, peak=70)}
+
+
+def lattice_network(case):
+    from pednstream_b200 import Network
+    from pednstream_b200.grid import DEFAULT_LINK, default_origins, grid_adjacency
+    size = case["size"]
+    origins = default_origins(size, stride=case["stride"])
+    params = {"unit_time": 10, "simulation_steps": case["run"] + 30, "default_link": dict(DEFAULT_LINK),
+              "demand": {f"origin_{o}": {"peak_lambda": case["peak"], "base_lambda": case["base"]} for o in origins}}
+    np.random.seed(case["seed"])
+    return Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False), origins
+
+
+def generate_lattice(name):
+    from oracle.ltm_oracle import F32_FIELDS, F64_FIELDS, LtmOracle
+    from oracle.philox import PhiloxDraws
+    case = LATTICE_CASES[name]
+    net, origins = lattice_network(case)
+    t0 = time.time()
+    h = LtmOracle(net, draws=PhiloxDraws(seed=case["seed"])).run(case["run"])
+    L = len(net.links)
+    out = {"steps_run": np.int64(case["run"]), "seed": np.int64(case["seed"]), "n_links": np.int64(L),
+           "sim_steps": np.int64(net.simulation_steps), "origins": np.asarray(origins, dtype=np.int64),
+           "max_pedestrians": np.float64(h["num_pedestrians"][: case["run"] + 1].max()),
+           "jammed_link_steps": np.int64((h["num_pedestrians"][: case["run"] + 1] >= 1100).sum())}
+    for f in F64_FIELDS[:7] + F32_FIELDS:
+        out["rows_" + f] = row_digests(np.ascontiguousarray(h[f][: case["run"] + 1, :L]))
+    dem = net.plan["demand_nodes"]
+    out["demand"] = np.stack([np.asarray(n.demand, dtype=np.float64)[: net.simulation_steps] for n in dem], axis=1)
+    out["demand_node_ids"] = np.asarray([n.node_id for n in dem], dtype=np.int64)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {L} links, {case['run']} steps, oracle {time.time() - t0:.0f}s, max pedestrians on a link "
+          f"{out['max_pedestrians']:.0f}, jammed link-steps {int(out['jammed_link_steps'])} -> {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or list(CASES) + list(ENV_CASES)):
-        (generate_env if nm in ENV_CASES else generate)(nm)
+    for nm in (sys.argv[1:] or list(CASES) + list(ENV_CASES) + list(TF_CASES) + list(LATTICE_CASES)):
+        if nm in ENV_CASES:
+            generate_env(nm)
+        elif nm in TF_CASES:
+            generate_tf(nm)
+        elif nm in LATTICE_CASES:
+            generate_lattice(nm)
+        else:
+            generate(nm)

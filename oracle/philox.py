@@ -132,9 +132,30 @@ def det_pow08(x32):
     return np.float32(det_exp(float(np.float32(0.8)) * det_log(x)))   # numpy demotes the exponent to float32
 
 
-def fma(a, b, c):
+def _fma_exact(a, b, c):
     """Correctly rounded a*b + c (what __fma_rn / fma() give): exact through rationals."""
     return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def _load_libm_fma():
+    """C99 fma() of the host's libm (correctly rounded by definition) when it can be loaded and agrees with the
+    exact evaluation on a few probes; it is ~50x faster than going through rationals."""
+    try:
+        import ctypes
+        import ctypes.util
+        lib = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        f = lib.fma
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_double] * 3
+        probes = [(0.1, 0.3, -0.03), (1.0 + 2.0 ** -52, 1.0 - 2.0 ** -53, -1.0), (3.7e10, 1.0 / 1153.0, -0.1111111111111111)]
+        if all(f(*p) == _fma_exact(*p) for p in probes):
+            return f
+    except Exception:
+        pass
+    return _fma_exact
+
+
+fma = _load_libm_fma()
 
 
 INV_TABLE = 2048          # pns_rng.cuh kInvK: correctly rounded reciprocals of 1 .. 2048

@@ -466,12 +466,15 @@ class Engine:
                                                      _ptr(out), self._stream()), "pns_kpi")
         return out
 
-    def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor):
-        """draw_b [rows, 3, L*R] int32, draw_n [rows, L*R] float64; row k serves step t0+k of `run`."""
-        self._table = (draw_b, draw_n)
+    def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor, draw_exp: torch.Tensor = None):
+        """draw_b [rows, 3, L*R] int32, draw_n [rows, L*R] float64; row k serves step t0+k of `run`.
+        draw_exp [rows, n_opts*R] float64 (optional): the route-choice exponentials of every step as the host
+        evaluated them (without it the device evaluates them)."""
+        self._table = (draw_b, draw_n, draw_exp)
         io = _native.PnsStepIO()
         C.memmove(C.byref(io), C.byref(self.io), C.sizeof(io))
         io.draw_b, io.draw_n = draw_b.data_ptr(), draw_n.data_ptr()
+        io.draw_exp = draw_exp.data_ptr() if draw_exp is not None else 0
         io.draw_row_stride = 1
         self._table_io = io
 

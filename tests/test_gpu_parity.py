@@ -154,14 +154,16 @@ def test_table_mode_multi_step_replays_numpy_mode():
     L = len(a.links)
     rows_b = np.zeros((steps, 3, L), dtype=np.int32)
     rows_n = np.zeros((steps, L), dtype=np.float64)
+    rows_e = np.zeros((steps, a.engine.net.n_opts), dtype=np.float64)
     for t in range(1, steps + 1):
         a.network_loading(t)
         host = a.engine._draw_host.numpy()
         rows_b[t - 1] = host[: 3 * L].reshape(3, L)
         rows_n[t - 1] = host[4 * L: 6 * L].view(np.float64)
+        rows_e[t - 1] = a.engine._exp_val_host.numpy()         # the logit exponentials, from the host's numpy
     b = make_network("45_intersections")
     eng = _engine_from_network(b, 1, "table", 0)
-    eng.set_draw_table(torch.from_numpy(rows_b).cuda(), torch.from_numpy(rows_n).cuda())
+    eng.set_draw_table(torch.from_numpy(rows_b).cuda(), torch.from_numpy(rows_n).cuda(), torch.from_numpy(rows_e).cuda())
     eng.run(1, steps, _native.RNG_TABLE)
     eng.check_errors()
     for f in FIELDS:
