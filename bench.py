@@ -14,6 +14,7 @@ grid (replicas only, no data-path collective; weak scaling).
 Further blocks of the JSON line (rank 0):
   roofline.variants   the dominant kernel in the timed region, late in the run (t ~ 950) and on the dense-boundary
                       workload (every boundary node an origin)
+  config4b_routed_lattice   the routed variant of config 4 (8 OD pairs, k_paths 3): sparse setup time, step time, roofline
   batched_env         BASELINE config 5 at its stated size: data/45_intersections, 8192 replicas in total
                       (8192/N per GPU), random gate actions, with its own roofline and end-to-end figures
   small_configs       BASELINE configs 1-3 (long_corridor, nine_intersections, melbourne@2000): GPU wall time per
@@ -48,6 +49,9 @@ REF_SAMPLE_SIZE = 32
 ENV_REPLICAS_TOTAL = 8192          # BASELINE.json configs[4]
 LATE_T, LATE_K = 950, 40           # late-time window of the lattice run
 DENSE_WARM, DENSE_K = 600, 40      # dense-boundary variant: steps before / inside its window
+ROUTED_WARM = 200                  # config 4b: steps before its timed window
+ROUTED_ORIGIN_COLS = (112, 128, 144, 160)      # config 4b: origins on row 0 ...
+ROUTED_DEST_ROW, ROUTED_DEST_COLS = 32, (120, 152)   # ... destinations on row 32: 8 OD pairs, 40-72 links apart
 
 
 def measured_peak():
@@ -544,6 +548,48 @@ def run_ours(args):
             del pl2, g2, tf2, d2
             torch.cuda.empty_cache()
 
+    # ---- config 4b: the routed lattice (8 OD pairs, k_paths = 3): route-choice kernel + routed node kernel ----
+    cfg4b = None
+    if not args.no_variants and rank == 0 and world == 1:
+        from pednstream_b200.grid import build_routed_grid_plan
+        W4, K4 = ROUTED_WARM, max(20, min(K, 100))
+        S4 = W4 + 2 * K4 + 8
+        if 80.0 * (S4 + 1) * n_links_est < 150e9:
+            w0 = time.perf_counter()
+            orig4 = [c for c in ROUTED_ORIGIN_COLS if c < size]
+            dest4 = [ROUTED_DEST_ROW * size + c for c in ROUTED_DEST_COLS if c < size and ROUTED_DEST_ROW < size]
+            pl4, g4, tf4, d4, od4 = build_routed_grid_plan(size, S4, orig4, dest4, demand_seed=0, locality_order=True,
+                                                          link=link_over)
+            setup_s = time.perf_counter() - w0
+            e4 = Engine(pl4, replicas=1, rng="philox", seed=0, device=dev)
+            e4.initialise(g4, None, tf4, d4, od4)
+            e4.run(1, W4)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            e4.run(W4 + 1, K4)
+            a1.record()
+            torch.cuda.synchronize()
+            ms4 = a0.elapsed_time(a1)
+            _, r4 = roof_of(profiled(e4, W4 + K4 + 1, K4), pl4["n_links"])
+            e4.check_errors()
+            gbs4 = B_ALG * pl4["n_links"] / (ms4 / K4 * 1e-3) / 1e9
+            cfg4b = {"workload": f"config 4b: {size}x{size} routed lattice, {len(pl4['od_keys'])} OD pairs "
+                                 f"(origins row 0, columns {list(ROUTED_ORIGIN_COLS)}; destinations row {ROUTED_DEST_ROW}, "
+                                 f"columns {list(ROUTED_DEST_COLS)}), k_paths 3, {len(pl4['rt_routed_nodes'])} routed nodes, "
+                                 f"{len(pl4['rt_opt_link'])} route options; steps {W4 + 1}..{W4 + K4}",
+                     "value": pl4["n_links"] * K4 / (ms4 * 1e-3), "unit": "link-timesteps/s", "ms_per_step": ms4 / K4,
+                     "steps": K4, "setup_seconds": setup_s,
+                     "setup_note": "sparse constructor: lattice plan + networkx k-shortest simple paths and turn structures "
+                                   "(grid.build_routed_grid_plan), no dense adjacency matrix",
+                     "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "step": {"achieved": gbs4, "frac": gbs4 / peak},
+                                  **r4},
+                     "arrivals_at_destinations": float(e4.history("cumulative_outflow")[W4 + K4].sum()),
+                     "pedestrians_on_links": float(e4.history("num_pedestrians")[W4 + K4].sum())}
+            e4 = None
+            del pl4, g4, tf4, d4, od4
+            torch.cuda.empty_cache()
+
     env_stats = None
     if not args.no_env:
         per_gpu = max(1, args.env_replicas // world)
@@ -599,6 +645,8 @@ def run_ours(args):
                          "variants": variants},
             "check": {"pedestrians_on_links_last_step": total_peds},
         }
+        if cfg4b is not None:
+            line["config4b_routed_lattice"] = cfg4b
         if env_stats is not None:
             line["batched_env"] = env_stats
         if small is not None:

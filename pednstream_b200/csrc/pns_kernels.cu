@@ -138,6 +138,12 @@ struct Ctx {
     const double *c0_pre0, *c0_pre1;                    // cumulative_inflow rows of the two likeliest arrival lags
     int c0_pre_i0, c0_pre_i1;                           // their indices (-1: not applicable)
     double* metric;                                     // streamed runs: PNS_METRIC_SLOTS partial sums of num_pedestrians[t]
+    // Route choice riding in a link launch that computes FLOWS(route_t): route_blocks extra CTAs (lane kernel: at the
+    // front of the grid; batched kernel: extra grid rows) run route_thread for step route_t next to the link CTAs.  It
+    // is independent of the FLOWS part; when the launch also runs UPDATE(route_t-1) (route_recompute), the pedestrian
+    // counts of row route_t-1 are being written by the link CTAs, and the route threads rebuild the few they need from
+    // the UPDATE inputs (num[t-2], inflow[t-1], outflow[t-1]) with the same arithmetic.
+    int route_blocks, route_t, route_recompute;
 };
 
 // Control environment (reference rl/builders.py, rl/pz_pednet_env.py): the step context plus the action /
@@ -149,9 +155,6 @@ struct EnvCtx {
     float* obs;
     float* reward;
     float* cum_reward;      // optional running sum of the rewards (null: not kept)
-    // route choice riding in a FLOWS-only launch of k_link_rep: route_blocks extra grid rows run route_thread for
-    // step route_t (independent of the link pass: it reads rows <= t-1 and writes probs / tf_routed)
-    int route_blocks, route_t;
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -665,6 +668,13 @@ __device__ __forceinline__ void group_probs(const Ctx& c, int g, int rep, int t)
     const float* num = H32(c, PNS_F32_NUM_PED, tm1);
     const float* dens_row = H32(c, PNS_F32_DENSITY, tm1);
     const double* rcv = H64(c, PNS_F64_RECEIVING, tm2);
+    // pedestrians at t-1; rebuilt from the inputs of UPDATE(t-1) when that update runs in the same launch
+    // (link.py:134-135: float32(num[t-2] + (inflow[t-1] - outflow[t-1])))
+    const bool rebuild = c.route_recompute != 0;
+    const float* num_prev = rebuild ? H32(c, PNS_F32_NUM_PED, tm1 - 1) : nullptr;
+    const double* in_row = rebuild ? H64(c, PNS_F64_INFLOW, tm1) : nullptr;
+    const double* out_row = rebuild ? H64(c, PNS_F64_OUTFLOW, tm1) : nullptr;
+#define PNS_NUM_AT(x) (rebuild ? (float)((double)num_prev[x] + (in_row[x] - out_row[x])) : num[x])
 
     float dens[PNS_MAX_DEGREE];
     double cap[PNS_MAX_DEGREE];
@@ -676,12 +686,9 @@ __device__ __forceinline__ void group_probs(const Ctx& c, int g, int rep, int t)
             const LinkP& p = c.n.classes[class_of(c, l, rep)];
             const size_t e = (size_t)l * R + rep;
             const double gate = c.s.gate[e];
-            if (is_sep(p)) {
-                dens[k] = dens_row[e];
-            } else {
-                const Area ar = link_area(c, p, e, gate);
-                dens[k] = div_by_area(num[e] + num[(size_t)(l ^ 1) * R + rep], ar);
-            }
+            const Area ar = link_area(c, p, e, gate);
+            if (is_sep(p)) dens[k] = rebuild ? div_by_area(PNS_NUM_AT(e), ar) : dens_row[e];
+            else dens[k] = div_by_area(PNS_NUM_AT(e) + PNS_NUM_AT((size_t)(l ^ 1) * R + rep), ar);
             const double last = rcv[e];
             cap[k] = last >= 0.0 ? last : ((gate * p.vf) * p.kc) * c.n.unit_time;
         } else {
@@ -714,6 +721,7 @@ __device__ __forceinline__ void group_probs(const Ctx& c, int g, int rep, int t)
               : c.draw_exp ? c.draw_exp[(size_t)(o0 + k) * R + rep] : exp(arg);
         sum_e = k == 0 ? ex[0] : sum_e + ex[k];
     }
+#undef PNS_NUM_AT
     if (c.mode == PNS_RNG_REQUEST) return;
     for (int k = 0; k < n; ++k) c.s.probs[(size_t)(o0 + k) * R + rep] = ex[k] / sum_e;
 }
@@ -976,10 +984,20 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     constexpr unsigned FULL = 0xffffffffu;
     // launch order (pns_net.lane_order): CTA i works on link block order[i]; blocks likely to hold long
     // sampler walks come first so that they overlap the rest of the grid
+    unsigned bx = blockIdx.x, n_link_ctas = gridDim.x;
+    if (flw && c.route_blocks > 0) {                     // route choice rides along (see Ctx::route_blocks)
+        if (bx < (unsigned)c.route_blocks) {
+            const unsigned row = bx * (unsigned)PNS_LANE_BLOCK + threadIdx.x;
+            if (row < (unsigned)c.n.n_rows) route_thread(c, c.route_t, (int)row, 0);
+            return;
+        }
+        bx -= (unsigned)c.route_blocks;
+        n_link_ctas -= (unsigned)c.route_blocks;
+    }
     const bool ordered = c.n.lane_order != nullptr && c.n.lane_order_block == PNS_LANE_BLOCK;
-    const unsigned blk = ordered ? (unsigned)__ldg(c.n.lane_order + blockIdx.x) : blockIdx.x;
-    const unsigned pf_slot = blockIdx.x + (unsigned)PNS_PF_AHEAD_CTAS;       // the CTA this one prefetches for (below)
-    const unsigned pf_blk = pf_slot < gridDim.x ? (ordered ? (unsigned)__ldg(c.n.lane_order + pf_slot) : pf_slot) : 0xffffffu;
+    const unsigned blk = ordered ? (unsigned)__ldg(c.n.lane_order + bx) : bx;
+    const unsigned pf_slot = bx + (unsigned)PNS_PF_AHEAD_CTAS;       // the CTA this one prefetches for (below)
+    const unsigned pf_blk = pf_slot < n_link_ctas ? (ordered ? (unsigned)__ldg(c.n.lane_order + pf_slot) : pf_slot) : 0xffffffu;
     const unsigned gid = blk * blockDim.x + threadIdx.x;
     const bool valid = gid < (unsigned)c.n.n_links;           // whole pairs: a lane and its partner agree
     const int l = valid ? (int)gid : 0;
@@ -1048,7 +1066,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     if (PNS_PF_AHEAD_CTAS > 0 && threadIdx.x < 32u) {
         // the CTA's first warp covers the PNS_LANE_BLOCK links of the target CTA, 16 bytes apart
         const unsigned ga = pf_blk * (unsigned)PNS_LANE_BLOCK + (unsigned)(PNS_LANE_BLOCK / 32) * threadIdx.x;
-        if (pf_slot < gridDim.x && ga < (unsigned)c.n.n_links) {
+        if (pf_slot < n_link_ctas && ga < (unsigned)c.n.n_links) {
             const size_t ea = ga;
             prefetch_l2(reinterpret_cast<const int2*>(c.n.lk_slots) + ea);
             prefetch_l2(c.s.gate + ea);
@@ -1337,9 +1355,9 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     const unsigned dir = threadIdx.x >> 5;
     const int rep_raw = (int)(blockIdx.x * 32u + (threadIdx.x & 31u));
     const unsigned n_pairs = (unsigned)c.n.n_links >> 1;
-    if (PHASE == PH_FLOWS && blockIdx.y >= n_pairs) {       // route choice rides along: two rows per CTA
+    if (flw && blockIdx.y >= n_pairs) {                     // route choice rides along: two rows per CTA
         const unsigned row = 2u * (blockIdx.y - n_pairs) + dir;
-        if (row < (unsigned)c.n.n_rows && rep_raw < R) route_thread(c, x.route_t, (int)row, rep_raw);
+        if (row < (unsigned)c.n.n_rows && rep_raw < R) route_thread(c, c.route_t, (int)row, rep_raw);
         return;
     }
     const unsigned pair = blockIdx.y;
@@ -1807,6 +1825,7 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
         }
     }
     c.metric = nullptr;
+    c.route_blocks = 0; c.route_t = 0; c.route_recompute = 0;
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
     c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
@@ -1853,7 +1872,7 @@ void launch_pair_phase(size_t n, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
 template <int PHASE>
 void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
-    const unsigned nb = (unsigned)((n_links + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK);
+    const unsigned nb = (unsigned)((n_links + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK) + (unsigned)c.route_blocks;
     if (c.n.n_classes == 1) {
         if (c.mode == PNS_RNG_PHILOX) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_PHILOX, true>), nb, PNS_LANE_BLOCK, s, c);
         else if (c.mode == PNS_RNG_TABLE) PNS_LAUNCH_CHAIN((k_link_lane<PHASE, PNS_RNG_TABLE, true>), nb, PNS_LANE_BLOCK, s, c);
@@ -1869,7 +1888,7 @@ void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
 // batched replicas on the GPU: one thread per (directed link, replica), optionally with the environment riding along
 template <int PHASE, bool ENV>
 void launch_rep_mode(const pns_net* net, cudaStream_t s, const EnvCtx& x) {
-    const dim3 nb((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)(net->n_links / 2) + (unsigned)x.route_blocks);
+    const dim3 nb((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)(net->n_links / 2) + (unsigned)x.c.route_blocks);
     const bool one = net->n_classes == 1;
     if (x.c.mode == PNS_RNG_PHILOX) {
         if (one) PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_PHILOX, true, ENV>), nb, kRepBlock, s, x);
@@ -1892,9 +1911,10 @@ void launch_rep(const pns_net* net, cudaStream_t s, const Ctx& c, const EnvRide*
     EnvCtx x;
     memset(&x, 0, sizeof x);
     x.c = c;
-    if (with_route && c.phase == PH_FLOWS) {
-        x.route_blocks = (net->n_rows + 1) / 2;        // extra grid rows: two route rows per CTA
-        x.route_t = c.t_flows;
+    if (with_route && (c.phase & PH_FLOWS)) {
+        x.c.route_blocks = (net->n_rows + 1) / 2;      // extra grid rows: two route rows per CTA
+        x.c.route_t = c.t_flows;
+        x.c.route_recompute = (c.phase & PH_UPDATE) ? 1 : 0;
     }
     const bool env_flows = ride && ride->actions && (c.phase & PH_FLOWS);
     const bool env_update = ride && ride->obs && (c.phase & PH_UPDATE);
@@ -1919,9 +1939,15 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, con
 #ifndef PNS_HOST_EMULATION
     if (rep_kernel_applies(net, c.mode)) { launch_rep(net, s, c, ride, with_route); return; }
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
-        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, c);
-        else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, c);
-        else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, c);
+        Ctx cl = c;
+        if (with_route && (c.phase & PH_FLOWS)) {
+            cl.route_blocks = (net->n_rows + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK;
+            cl.route_t = c.t_flows;
+            cl.route_recompute = (c.phase & PH_UPDATE) ? 1 : 0;
+        }
+        if (c.phase == (PH_UPDATE | PH_FLOWS)) launch_lane_mode<PH_UPDATE | PH_FLOWS>(2 * n, s, cl);
+        else if (c.phase == PH_UPDATE) launch_lane_mode<PH_UPDATE>(2 * n, s, cl);
+        else if (c.phase == PH_FLOWS) launch_lane_mode<PH_FLOWS>(2 * n, s, cl);
         return;
     }
 #endif
@@ -2036,12 +2062,14 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
             if (k + kSyncGroup < n_steps) demand_next = copy_group(k + kSyncGroup);
         }
 #endif
-        // batched replicas: the route choice of step t0+k is independent of the link pass of the same step, so in a
-        // FLOWS-only launch it rides along as extra CTAs (not at step 1, where it reads the widths this launch sets)
+        // GPU link kernels: the route choice of step t0+k is independent of the FLOWS part of the link pass and needs
+        // only a few pedestrian counts of its UPDATE part, so it rides along as extra CTAs of the link launch (not at
+        // step 1 of an environment, where it reads the widths this launch sets)
         bool route_rides = false;
 #ifndef PNS_HOST_EMULATION
-        route_rides = phase == PH_FLOWS && z.n_grp && z.n_pair && t0 + k >= 2 && !ev && !getenv("PNS_ROUTE_SEPARATE") &&
-                      rep_kernel_applies(net, rng_mode);
+        route_rides = (phase & PH_FLOWS) && z.n_grp && z.n_pair && !ev && !getenv("PNS_ROUTE_SEPARATE") &&
+                      !(t0 + k == 1 && ride && ride->actions) &&
+                      (rep_kernel_applies(net, rng_mode) || (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")));
 #endif
         PNS_MARK(k, 0);
         if (z.n_pair) launch_pair(net, z.n_pair, s, cp, ride, route_rides);

@@ -178,6 +178,23 @@ class Engine:
         _native.check(self.lib, self.lib.pns_step(C.byref(self.net), C.byref(self.state), C.byref(io),
                                                   t0, n_steps, rng_mode, self._stream()), "pns_step")
 
+    def _native_step_streamed(self, t0, n_steps, rng_mode):
+        host_demand, host_metric = self._streamed_host
+        _native.check(self.lib, self.lib.pns_step_streamed(
+            C.byref(self.net), C.byref(self.state), C.byref(self.io), t0, n_steps, rng_mode,
+            _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")
+
+    def _native_env_step(self, actions, obs, reward, cum_reward, t):
+        _native.check(self.lib, self.lib.pns_env_step(
+            C.byref(self.net), C.byref(self.state), C.byref(self.io), C.byref(self._env_struct),
+            _ptr(actions) if actions is not None else C.c_void_p(0), int(t), _native.RNG_PHILOX, _ptr(obs), _ptr(reward),
+            _ptr(cum_reward), self._stream()), "pns_env_step")
+
+    def _native_kpi(self, role, scratch, out, t_last, any_od_path):
+        _native.check(self.lib, self.lib.pns_kpi(C.byref(self.net), C.byref(self.state), C.byref(self.io),
+                                                 int(t_last), _ptr(role), int(bool(any_od_path)), _ptr(scratch),
+                                                 _ptr(out), self._stream()), "pns_kpi")
+
     # ------------------------------------------------------------------ setup
     def initialise(self, gate: np.ndarray, sep_np64: np.ndarray = None, tf_static: np.ndarray = None,
                    demand: np.ndarray = None, od_w: np.ndarray = None, tf_supplied: np.ndarray = None):
@@ -440,11 +457,11 @@ class Engine:
             raise ValueError("host_demand must cover rows [0, t0+n_steps-1) with the device table's width")
         if not hasattr(self, "_dev_metric") or self._dev_metric.numel() < n_steps * _native.METRIC_ROW:
             self._dev_metric = torch.zeros(n_steps * _native.METRIC_ROW, dtype=torch.float64, device=self.device)
+        self._streamed_host = (host_demand, host_metric)
         with self._guard():
             self._begin_steps(t0, n_steps)
-            _native.check(self.lib, self.lib.pns_step_streamed(
-                C.byref(self.net), C.byref(self.state), C.byref(self.io), t0, n_steps, rng_mode,
-                _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")
+            ops.ltm_step_streamed(self.hist64, self.hist32, self.runsum, self.tf_routed, self.probs, self.err,
+                                  self._dev_metric, self.handle, t0, n_steps, rng_mode)
         self.t_done = t0 + n_steps - 1
 
     @staticmethod
@@ -461,9 +478,8 @@ class Engine:
         scratch = torch.empty((max(1, self.L * self.R) * 8,), dtype=torch.float64, device=self.device)
         out = torch.zeros((self.R, len(_native.KPI_NAMES)), dtype=torch.float64, device=self.device)
         with self._guard():
-            _native.check(self.lib, self.lib.pns_kpi(C.byref(self.net), C.byref(self.state), C.byref(self.io),
-                                                     int(t_last), _ptr(role), int(bool(any_od_path)), _ptr(scratch),
-                                                     _ptr(out), self._stream()), "pns_kpi")
+            ops.episode_kpis(self.hist64, self.hist32, self.demand, role, scratch, out, self.handle, int(t_last),
+                             bool(any_od_path))
         return out
 
     def set_draw_table(self, draw_b: torch.Tensor, draw_n: torch.Tensor, draw_exp: torch.Tensor = None):

@@ -43,9 +43,12 @@ def default_origins(size: int, stride: int = 64):
 
 
 def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=None,
-                    peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False):
+                    peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False, destinations=()):
     """Returns (plan, gate[L], tf_static[n_edges], demand[S, rows]) for `Engine`.
-    locality_order=True lists nodes by id instead of the reference's creation order."""
+    locality_order=True lists nodes by id instead of the reference's creation order.
+    destinations: nodes that get virtual O/D links like origins but draw no demand (network.py:139-167); the
+    route plan of a routed lattice is attached by `build_routed_grid_plan`.  demand_seed=None: the caller has
+    positioned numpy's global stream (the reference draws demand from it while it creates the nodes)."""
     lk = dict(DEFAULT_LINK)
     lk.update(link or {})
     n = size
@@ -53,6 +56,8 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     origins = default_origins(n) if origins is None else sorted(origins)
     is_origin = np.zeros(N, dtype=bool)
     is_origin[origins] = True
+    is_od = is_origin.copy()
+    is_od[list(destinations)] = True
 
     ids = np.arange(N)
     r, c = ids // n, ids % n
@@ -85,8 +90,8 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
 
     degree = (r > 0).astype(int) + (c > 0) + has_right + has_down
     # network.py:141-167: degree 2 -> one-to-one unless O/D; degree 1 -> one-to-one + virtual; else regular
-    virtual = is_origin | (degree == 1)
-    kind = np.where((degree == 2) & ~is_origin, 0, np.where(degree == 1, 0, 1)).astype(np.int32)
+    virtual = is_od | (degree == 1)
+    kind = np.where((degree == 2) & ~is_od, 0, np.where(degree == 1, 0, 1)).astype(np.int32)
     vrank = np.full(N, -1, dtype=np.int64)           # rank among virtual-link owners, creation order
     vo = order[virtual[order]]
     vrank[vo] = np.arange(len(vo))
@@ -147,16 +152,10 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
         n_virtual=2 * int(virtual.sum()), n_demand_rows=int(virtual.sum()), n_edges=int(tf_ptr[-1]),
         n_od=0, od_keys=[], demand_nodes=[], node_order=order,
     )
-    i32 = lambda a: np.asarray(a, dtype=np.int32)
-    for key in ("routed_nodes", "routed_edge0", "routed_row0", "grp_node", "grp_up", "grp_od",
-                "grp_has_virtual", "opt_link", "opt_slot", "row_od", "term_opt", "term_row_entry"):
-        plan["rt_" + key] = i32([])
-    for key in ("opt_ptr", "row_ptr", "term_ptr", "row_grp_ptr"):
-        plan["rt_" + key] = i32([0])
-    for key in ("row_routed", "row_grp", "term_od"):
-        plan["rt_" + key] = i32([])
-    plan["rt_opt_dist"] = np.zeros(0)
-    plan["rt_scalars"] = np.array([0.1, 1.0, 0.05, 0.05, 0.0])
+    from .plan import attach_empty_route_plan
+    attach_empty_route_plan(plan)
+    plan["lattice"] = dict(size=n, pair_right=pair_right, pair_down=pair_down, virtual=virtual, vrank=vrank,
+                           length=float(lk["length"]))
 
     gate = np.full(L, float(lk["width"]))
     tf_static = np.repeat(1.0 / np.maximum(m_o - 1, 1), edges)      # uniform 1/(m-1), network.py:269-271
@@ -169,8 +168,134 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     width2 = 2 * (S / 20) ** 2
     lam = (base_lambda + peak_lambda * np.exp(-(tgrid - S / 4) ** 2 / width2)
            + peak_lambda * np.exp(-(tgrid - 3 * S / 4) ** 2 / width2))
-    np.random.seed(demand_seed)
+    if demand_seed is not None:
+        np.random.seed(demand_seed)
     for node in vo:
         if is_origin[node]:
             demand[:, vrank[node]] = np.random.poisson(lam=lam)
     return plan, gate, tf_static, demand
+
+
+# ---- routed lattices (BASELINE config 4b) ------------------------------------------------------------------
+class _Stub:
+    """Attribute bag standing in for a Node / Link of the generic constructor (PathFinder reads a handful of
+    attributes and hangs its per-node route structures on the node)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class _LatticeLinks:
+    """`network.links` of a lattice without per-link objects: iteration in the reference's order ((i,j),(j,i) by
+    ascending i, then j), membership and index by arithmetic."""
+
+    def __init__(self, lat):
+        self.n, self.pair_right, self.pair_down, self.length = lat["size"], lat["pair_right"], lat["pair_down"], lat["length"]
+        self._link = _Stub(length=self.length)
+
+    def index(self, key):
+        u, v = key
+        a, b = (u, v) if u < v else (v, u)
+        n = self.n
+        if a < 0 or b >= n * n:
+            return -1
+        if b == a + 1 and a % n != n - 1:
+            p = self.pair_right[a]
+        elif b == a + n:
+            p = self.pair_down[a]
+        else:
+            return -1
+        return int(2 * p + (0 if u < v else 1))
+
+    def __contains__(self, key):
+        return self.index(key) >= 0
+
+    def __getitem__(self, key):
+        k = self.index(key)
+        if k < 0:
+            raise KeyError(key)
+        return k if self._as_index else self._link
+
+    _as_index = False
+
+    def as_index(self):
+        view = _LatticeLinks.__new__(_LatticeLinks)
+        view.__dict__.update(self.__dict__)
+        view._as_index = True
+        return view
+
+    def items(self):
+        n = self.n
+        for i in range(n * n):
+            if i % n != n - 1:
+                yield (i, i + 1), self._link
+                yield (i + 1, i), self._link
+            if i + n < n * n:
+                yield (i, i + n), self._link
+                yield (i + n, i), self._link
+
+
+class _LatticeNodes:
+    """`network.nodes` of a lattice, materialised on demand (only nodes on OD paths are ever touched): slot order
+    is the reference's -- the virtual O/D link first, then neighbours by ascending id."""
+
+    def __init__(self, lat, index_of):
+        self.lat, self.index_of, self._made = lat, index_of, {}
+
+    def __getitem__(self, i):
+        node = self._made.get(i)
+        if node is not None:
+            return node
+        n = self.lat["size"]
+        r, c = divmod(int(i), n)
+        nbrs = [j for j, ok in ((i - n, r > 0), (i - 1, c > 0), (i + 1, c < n - 1), (i + n, r < n - 1)) if ok]
+        me = _Stub(node_id=int(i), index=int(self.index_of[i]), ods_in_turns={})
+        inc, out = [], []
+        if self.lat["virtual"][i]:
+            inc.append(_Stub(start_node=None, end_node=me))
+            out.append(_Stub(start_node=me, end_node=None))
+        for j in nbrs:
+            other = _Stub(node_id=int(j))
+            inc.append(_Stub(start_node=other, end_node=me))
+            out.append(_Stub(start_node=me, end_node=other))
+        me.incoming_links, me.outgoing_links = inc, out
+        me.source_num = me.dest_num = len(inc)
+        self._made[i] = me
+        return me
+
+
+def build_routed_grid_plan(size: int, sim_steps: int, origins, destinations, params=None, unit_time=10, link=None,
+                           peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False):
+    """A routed lattice (BASELINE config 4b) without the dense adjacency matrix and per-link objects of the generic
+    constructor: `build_grid_plan` for topology and demand, then the reference's own route setup -- networkx
+    k-shortest simple paths on a graph whose edges are inserted in `network.links` order, turn structures per path
+    node (path_finder.py:114-142, 199-234, 460-546; `PathFinder` is shared with the generic constructor, so ties
+    are broken identically) -- over lazily materialised nodes.  Returns (plan, gate, tf_static, demand, od_w);
+    equal to the plan the generic constructor compiles (tests/test_grid.py)."""
+    from .od_manager import ODManager
+    from .path_finder import PathFinder
+    from .plan import attach_route_plan
+    origins, destinations = list(origins), list(destinations)
+    plan, gate, tf, demand = build_grid_plan(size, sim_steps, unit_time=unit_time, link=link, origins=origins,
+                                             peak_lambda=peak_lambda, base_lambda=base_lambda,
+                                             demand_seed=demand_seed, locality_order=locality_order,
+                                             destinations=destinations)
+    lat = plan["lattice"]
+    order = plan["node_order"]
+    index_of = np.empty(size * size, dtype=np.int64)
+    index_of[order] = np.arange(size * size)
+    links = _LatticeLinks(lat)
+    nodes = _LatticeNodes(lat, index_of)
+    odm = ODManager(sim_steps)
+    odm.logger.disabled = True
+    odm.init_od_flows(origins, destinations, None)
+    pf = PathFinder(links, params=params or {}, controller_nodes=set(), controller_links=[], logger=None)
+    pf.find_od_paths(od_pairs=odm.od_flows.keys(), nodes=nodes)
+    on_path = sorted((nodes[i] for i in pf.nodes_in_paths), key=lambda nd: nd.index)
+    attach_route_plan(plan, pf, odm, on_path, links.as_index())
+    routed_of = np.full(size * size, -1, dtype=np.int32)
+    routed_of[plan["rt_routed_nodes"]] = np.arange(len(plan["rt_routed_nodes"]), dtype=np.int32)
+    plan["nd_routed"] = routed_of
+    plan["od_paths"] = pf.od_paths
+    od_w = np.stack([odm.od_flows[k] for k in plan["od_keys"]], axis=1)
+    return plan, gate, tf, demand, od_w

@@ -173,6 +173,37 @@ def route_row_tables(p):
     return dict(rt_row_routed=row_routed, rt_row_grp_ptr=ptr, rt_row_grp=order, rt_term_od=_i32(term_od))
 
 
+def attach_empty_route_plan(p):
+    for k in ("routed_nodes", "routed_edge0", "routed_row0", "grp_node", "grp_up", "grp_od",
+              "grp_has_virtual", "opt_link", "opt_slot", "row_od", "term_opt", "term_row_entry"):
+        p["rt_" + k] = _i32([])
+    for k in ("opt_ptr", "row_ptr", "term_ptr"):
+        p["rt_" + k] = _i32([0])
+    p["rt_opt_dist"] = _f64([])
+    p["rt_scalars"] = _f64([0.1, 1.0, 0.05, 0.05, 0.0])
+    p["n_od"] = 0
+    p["od_keys"] = []
+    p.update(route_row_tables(p))
+
+
+def attach_route_plan(p, path_finder, od_manager, nodes_in_order, link_index):
+    """Adds the route-choice tables of `path_finder` to plan `p` (and marks the routed nodes in nd_meta).
+    nodes_in_order: Node-like objects in plan node order with `.index` = plan node index (only nodes on OD paths
+    need to be present); link_index: mapping (u, v) -> physical link index."""
+    od_keys = list(od_manager.od_flows.keys())
+    od_index = {k: i for i, k in enumerate(od_keys)}
+    rp = path_finder.export_route_plan(nodes_in_order, od_index, link_index)
+    p.update({"rt_" + k: v for k, v in rp.items()})
+    p["rt_scalars"] = _f64([path_finder.temp, path_finder.alpha, path_finder.beta,
+                            path_finder.omega, path_finder.epsilon])
+    p["n_od"] = len(od_keys)
+    p["od_keys"] = od_keys
+    p.update(route_row_tables(p))
+    meta = p["nd_meta"]
+    routed = np.asarray(p["rt_routed_nodes"], dtype=np.int64)
+    meta[routed, 1] = (meta[routed, 1] & 0xffff) | (2 << 16)
+
+
 def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
     order, .index set).  Returns dict name -> numpy array / python scalar."""
@@ -239,27 +270,10 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
 
     # ---- route plan -------------------------------------------------------------------
     if path_finder is not None:
-        od_keys = list(od_manager.od_flows.keys())
-        od_index = {k: i for i, k in enumerate(od_keys)}
         link_index = {(l.start_node.node_id, l.end_node.node_id): l.index for l in links}
-        rp = path_finder.export_route_plan(nodes, od_index, link_index)
-        p.update({"rt_" + k: v for k, v in rp.items()})
-        p["rt_scalars"] = _f64([path_finder.temp, path_finder.alpha, path_finder.beta,
-                                path_finder.omega, path_finder.epsilon])
-        p["n_od"] = len(od_keys)
-        p["od_keys"] = od_keys
+        attach_route_plan(p, path_finder, od_manager, nodes, link_index)
     else:
-        from .path_finder import PathFinder  # noqa: F401  (empty plan, same keys)
-        for k in ("routed_nodes", "routed_edge0", "routed_row0", "grp_node", "grp_up", "grp_od",
-                  "grp_has_virtual", "opt_link", "opt_slot", "row_od", "term_opt", "term_row_entry"):
-            p["rt_" + k] = _i32([])
-        for k in ("opt_ptr", "row_ptr", "term_ptr"):
-            p["rt_" + k] = _i32([0])
-        p["rt_opt_dist"] = _f64([])
-        p["rt_scalars"] = _f64([0.1, 1.0, 0.05, 0.05, 0.0])
-        p["n_od"] = 0
-        p["od_keys"] = []
-    p.update(route_row_tables(p))
+        attach_empty_route_plan(p)
     # per-node routed index (-1 = static fractions)
     routed_of = np.full(len(nodes), -1, dtype=np.int32)
     routed_of[p["rt_routed_nodes"]] = np.arange(len(p["rt_routed_nodes"]), dtype=np.int32)

@@ -29,7 +29,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _native
+from .. import _native, ops
 from ..engine import Engine, _ptr
 from ..env_loader import NetworkEnvGenerator
 from .builders import DENSITY_NORM, FLOW_NORM, OBS_LAYOUT
@@ -154,6 +154,8 @@ class BatchedPedNetEnv:
         if not len(flat):                 # keep the per-link pointers non-null: they select the fused path
             env.lk_obs_col = env.lk_obs_src = env.lk_obs_div = _ptr(self._env_t["lk_obs_ptr"])
         self._env = env
+        eng._env_struct = env
+        self._no_actions = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.obs = torch.zeros((self.R, max(1, self.n_obs)), dtype=torch.float32, device=dev)
         self.reward = torch.zeros((self.R,), dtype=torch.float32, device=dev)
         self.cumulative_reward = torch.zeros((self.R,), dtype=torch.float32, device=dev)
@@ -298,18 +300,16 @@ class BatchedPedNetEnv:
             raise ValueError("obs_out / reward_out must match the env's obs / reward tensors")
         if self.sim_step > self.simulation_steps:
             raise RuntimeError("episode finished: call reset()")
-        act_ptr = C.c_void_p(0)
         if actions is not None and self.n_act:
             if actions.shape != (self.R, self.n_act) or actions.dtype != torch.float32:
                 raise ValueError(f"actions must be float32 [{self.R}, {self.n_act}]")
             actions = actions.contiguous()
-            act_ptr = _ptr(actions)
-        with eng._guard():      # actions, the LTM step, observations + reward: one native call
+        with eng._guard():      # actions, the LTM step, observations + reward: one native call behind one custom op
             eng._begin_steps(self.sim_step, 1)
-            _native.check(eng.lib, eng.lib.pns_env_step(
-                C.byref(eng.net), C.byref(eng.state), C.byref(eng.io), C.byref(self._env), act_ptr,
-                int(self.sim_step), _native.RNG_PHILOX, _ptr(obs), _ptr(reward),
-                _ptr(self.cumulative_reward), self._stream()), "pns_env_step")
+            has_actions = actions is not None and self.n_act > 0
+            ops.env_step(eng.hist64, eng.hist32, eng.runsum, eng.tf_routed, eng.probs, eng.err, eng.gate,
+                         actions if has_actions else self._no_actions, obs, reward, self.cumulative_reward,
+                         eng.handle, int(self.sim_step), has_actions)
         eng.t_done = self.sim_step
         done = self.sim_step >= self.simulation_steps           # tested before the increment (quirk Q8)
         self.sim_step += 1

@@ -53,3 +53,68 @@ def test_lane_block_order_is_a_permutation_that_starts_next_to_the_origins():
     # nothing to schedule without origins
     meta2 = meta.copy(); meta2[:, 2] = -1
     assert lane_block_order(meta2, plan["nd_in_link"], L, stride, block) is None
+
+
+def _routed_pair(size, S, origins, dests, seed):
+    """(generic Network, sparse routed plan tuple) of the same routed lattice, same position of numpy's stream."""
+    from pednstream_b200.grid import build_routed_grid_plan
+    params = {"unit_time": 10, "simulation_steps": S, "default_link": dict(DEFAULT_LINK),
+              "demand": {f"origin_{o}": {"peak_lambda": 50, "base_lambda": 30} for o in origins}}
+    np.random.seed(seed)
+    net = Network(grid_adjacency(size), params, origin_nodes=list(origins), destination_nodes=list(dests), verbose=False)
+    np.random.seed(seed)
+    sparse = build_routed_grid_plan(size, S, origins, dests, demand_seed=None)
+    return net, sparse
+
+
+@pytest.mark.parametrize("size,origins,dests", [(8, [0, 7], [63]), (12, [0, 5, 77, 143], [11, 130]),
+                                                (16, [3, 100, 255], [240, 15])])
+def test_routed_grid_plan_equals_generic_plan(size, origins, dests):
+    """BASELINE config 4b's constructor: k-shortest paths and turn structures of a routed lattice built without the
+    dense adjacency matrix or per-link objects give the plan the generic constructor compiles -- every table."""
+    net, (got, gate, tf, demand, od_w) = _routed_pair(size, 60, origins, dests, seed=4)
+    want = net.plan
+    assert len(want["rt_routed_nodes"]) > 0 and want["od_keys"] == got["od_keys"]
+    for k, v in want.items():
+        if isinstance(v, np.ndarray):
+            if v.dtype.names:
+                assert v.tobytes() == got[k].tobytes(), k
+            else:
+                assert v.dtype == got[k].dtype and np.array_equal(v, got[k]), k
+    for k in ("n_links", "n_nodes", "n_virtual", "n_demand_rows", "n_edges", "n_od", "window", "unit_time"):
+        assert want[k] == got[k], k
+    assert {k: [list(map(int, p)) for p in v] for k, v in net.path_finder.od_paths.items()} == \
+           {k: [list(map(int, p)) for p in v] for k, v in got["od_paths"].items()}
+    want_od = np.stack([net.od_manager.od_flows[k] for k in want["od_keys"]], axis=1)
+    assert np.array_equal(want_od, od_w)
+    for row, node in enumerate(want["demand_nodes"]):
+        assert np.array_equal(np.asarray(node.demand, dtype=np.float64)[:60], demand[:, row]), node.node_id
+
+
+def _routed_lattice_vs_oracle(size, steps, origins, dests, **engine_kw):
+    from oracle.ltm_oracle import F32_FIELDS, F64_FIELDS, LtmOracle
+    from oracle.philox import PhiloxDraws
+    from pednstream_b200.engine import Engine
+    net, (plan, gate, tf, demand, od_w) = _routed_pair(size, steps + 20, origins, dests, seed=9)
+    want = LtmOracle(net, draws=PhiloxDraws(seed=21)).run(steps)
+    eng = Engine(plan, replicas=1, rng="philox", seed=21, **engine_kw)
+    eng.initialise(gate, None, tf, demand, od_w)
+    eng.run(1, steps)
+    eng.check_errors()
+    L = plan["n_links"]
+    for f in F64_FIELDS[:7] + F32_FIELDS:
+        got = eng.history(f)[: steps + 1, :, 0].cpu().numpy()
+        upto = steps if f in ("sending_flow", "receiving_flow") else steps + 1
+        assert np.array_equal(want[f][:upto], got[:upto]), f
+    assert want["cumulative_outflow"][steps, :L].sum() > 0
+
+
+def test_routed_lattice_sparse_plan_matches_oracle_emulated(emu_lib):
+    _routed_lattice_vs_oracle(10, 60, [0, 9], [95, 90], lib=emu_lib, emulation=True)
+
+
+@pytest.mark.gpu
+def test_routed_lattice_sparse_plan_matches_oracle_cuda():
+    """32x32 routed lattice from the sparse constructor on the GPU (route kernel + routed node kernel on the
+    single-replica path) against the oracle stepping the generic constructor's network."""
+    _routed_lattice_vs_oracle(32, 70, [5, 20, 12 * 32 + 3], [8 * 32 + 16, 14 * 32 + 30], device="cuda:0")
