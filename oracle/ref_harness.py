@@ -128,17 +128,51 @@ def reference_copy() -> str:
     return _REF_COPY
 
 
+_PREFIXES = ("src", "rl", "handlers")
+_REF_MODULES = {}          # module name -> reference module object, kept out of sys.modules between uses
+
+
+def _is_ref_name(name):
+    return any(name == p or name.startswith(p + ".") for p in _PREFIXES)
+
+
+class reference_modules:
+    """Context manager: while active, the names `src.*`, `rl.*`, `handlers.*` in sys.modules are the reference's own
+    modules (this repository has import-path shims under the same `src` name, which must not be what the
+    reference's `from src.LTM...` statements find); afterwards whatever was there before is put back.  The
+    reference module objects stay alive in `_REF_MODULES`, so classes handed out keep working."""
+
+    def __enter__(self):
+        _install_stubs()
+        self.root = reference_copy()
+        self.saved = {k: v for k, v in sys.modules.items() if _is_ref_name(k)}
+        for k in self.saved:
+            del sys.modules[k]
+        sys.modules.update(_REF_MODULES)
+        sys.path.insert(0, self.root)
+        return self
+
+    def __exit__(self, *exc):
+        for k in [k for k in sys.modules if _is_ref_name(k)]:
+            _REF_MODULES[k] = sys.modules.pop(k)
+        sys.modules.update(self.saved)
+        try:
+            sys.path.remove(self.root)
+        except ValueError:
+            pass
+        return False
+
+
 def import_reference():
     """Returns (Network class, NetworkEnvGenerator class) of the live reference."""
     if not reference_available():
         raise RuntimeError("reference tree not present")
-    _install_stubs()
-    root = reference_copy()
-    if root not in sys.path:
-        sys.path.insert(0, root)
     import logging
-    from src.LTM.network import Network  # noqa
-    from src.utils.env_loader import NetworkEnvGenerator  # noqa
+    with reference_modules():
+        from src.LTM.network import Network  # noqa
+        from src.utils.env_loader import NetworkEnvGenerator  # noqa
+    assert "pednstream_b200" not in Network.__module__ and Network.__module__ == "src.LTM.network"
+    assert not hasattr(Network, "engine"), "resolved to this repository's facade instead of the reference"
     logging.getLogger("src.LTM.network").setLevel(logging.ERROR)
     return Network, NetworkEnvGenerator
 
@@ -159,8 +193,9 @@ def make_reference_env(dataset, **kw):
 
         create_network._accepts_verbose = True
         Gen.create_network = create_network
-    from rl.pz_pednet_env import PedNetParallelEnv
-    return PedNetParallelEnv(dataset, **kw)
+    with reference_modules():
+        from rl.pz_pednet_env import PedNetParallelEnv
+        return PedNetParallelEnv(dataset, **kw)
 
 
 def create_network(name: str, steps_override: int | None = None, verbose: bool = True, default_link: dict = None,
@@ -197,7 +232,9 @@ class DrawRecorder:
         self._k = 0
 
     def install(self):
-        import src.LTM.link as rl
+        with reference_modules():
+            import src.LTM.link as rl
+        self._rl = rl
         self._orig = (np.random.binomial, np.random.normal,
                       rl.Link.cal_sending_flow, rl.Link.cal_receiving_flow, rl.Link.update_speeds,
                       rl.Separator.cal_receiving_flow, rl.Separator.update_speeds)
@@ -245,7 +282,7 @@ class DrawRecorder:
         return self
 
     def uninstall(self):
-        import src.LTM.link as rl
+        rl = self._rl
         (np.random.binomial, np.random.normal, rl.Link.cal_sending_flow, rl.Link.cal_receiving_flow,
          rl.Link.update_speeds, rl.Separator.cal_receiving_flow, rl.Separator.update_speeds) = self._orig
 

@@ -494,6 +494,24 @@ class Engine:
         io.draw_row_stride = 1
         self._table_io = io
 
+    def release(self):
+        """Drop the device tensors and the reference to the network (the engine <-> network cycle would otherwise
+        keep an episode's history alive until the garbage collector finds it; environments that rebuild their
+        network at every reset call this on the old one, and torch's caching allocator hands the blocks to the
+        next engine)."""
+        net = self._net_ref
+        if net is not None:
+            if getattr(net, "_engine", None) is self:
+                net._engine = None
+            if getattr(net._store, "engine", None) is self:
+                net._store.engine = None
+        self._net_ref = None
+        for name in ("hist64", "hist32", "gate", "sep_np64", "runsum", "tf_static", "tf_routed", "probs", "nm_s",
+                     "nm_r", "demand", "od_w", "_req", "_draw", "_exp_arg", "_exp_val", "_dev_metric"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self._net_t = {}
+
     # ------------------------------------------------------------------ reading back
     def _raise_on_error(self, err_host):
         bits = int(np.bitwise_or.reduce(err_host.numpy())) if err_host.numel() else 0

@@ -59,6 +59,12 @@ def class_record(length, width, vf, kc, kj, gamma, act, bi, sigma, fd_type, is_s
     rec["tt0"] = tt0
     rec["fftau"] = round(tt0 / unit_time)                   # link.py:86
     rec["swtau"] = round(length / (shock * unit_time))      # link.py:380
+    if int(rec["swtau"]) == 0:
+        # a zero shock-wave lag makes cal_receiving_flow read cumulative_outflow[t], which the reference fills in
+        # node-visiting order during the same step: the result depends on that order and has no parallel
+        # counterpart (the travel-time lag has the same hazard; the kernels flag it as PNS_ERR_ZERO_LAG)
+        raise ValueError(f"link of length {length} m: shock-wave lag round(length / (w * unit_time)) is 0 with "
+                         f"w = {shock:.4g} m/s and unit_time = {unit_time}; use a smaller unit_time")
     rec["flags"] = (1 if is_sep else 0) | (FD_TYPES[fd_type] << 1)
     return rec
 

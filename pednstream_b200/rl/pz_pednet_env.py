@@ -92,6 +92,9 @@ class PedNetParallelEnv(_Base):
 
     # ------------------------------------------------------------------ episode control
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None) -> Tuple[Dict, Dict]:
+        old = getattr(self, "network", None)             # the reference rebuilds the network at every reset (Q10);
+        if old is not None and getattr(old, "_engine", None) is not None:
+            old._engine.release()                        # ... so hand the old episode's device history back first
         if options and options.get("randomize", False):
             # the reference passes `verbose=` to a randomize_network that does not take it and raises
             # TypeError (pz_pednet_env.py:163-165); this is the evident intent of that branch
@@ -169,11 +172,19 @@ class PedNetParallelEnv(_Base):
                 for a in self.possible_agents}
 
     def render(self, *a, **k):
+        """Nothing to draw without a render mode (reference pz_pednet_env.py:644-648); the plotting itself is
+        the reference's NetworkVisualizer, which reads `env.network` or a directory written by `save`."""
+        if getattr(self, "render_mode", None) is None:
+            return None
         raise NotImplementedError("rendering is outside the accelerated path; use the reference's "
-                                  "NetworkVisualizer on env.network")
+                                  "NetworkVisualizer on env.network or on a directory written by env.save()")
 
-    def save(self, simulation_dir: str):
-        raise NotImplementedError("use the reference's OutputHandler on env.network")
+    def save(self, simulation_dir: str, base_dir: str = "../outputs"):
+        """Save the current network state (reference pz_pednet_env.py:688-691): the directory layout and JSON
+        schema of the reference's OutputHandler, under `base_dir/simulation_dir`."""
+        import os
+        from ..output import save_network_state
+        return save_network_state(self.network, os.path.join(base_dir, simulation_dir))
 
     def close(self):
         pass

@@ -115,6 +115,6 @@ def test_routed_lattice_sparse_plan_matches_oracle_emulated(emu_lib):
 
 @pytest.mark.gpu
 def test_routed_lattice_sparse_plan_matches_oracle_cuda():
-    """32x32 routed lattice from the sparse constructor on the GPU (route kernel + routed node kernel on the
-    single-replica path) against the oracle stepping the generic constructor's network."""
-    _routed_lattice_vs_oracle(32, 70, [5, 20, 12 * 32 + 3], [8 * 32 + 16, 14 * 32 + 30], device="cuda:0")
+    """20x20 routed lattice from the sparse constructor on the GPU (route choice riding in the single-replica link
+    kernel + routed node kernel) against the oracle stepping the generic constructor's network."""
+    _routed_lattice_vs_oracle(20, 70, [5, 12, 7 * 20 + 0], [6 * 20 + 14, 11 * 20 + 19], device="cuda:0")

@@ -62,3 +62,26 @@ def test_reference_output_handler_saves_facade_network(case, steps, emu_lib, tmp
     assert data["network_params"]["simulation_steps"] == net.simulation_steps
     ts = (tmp_path / "sim" / "time_series.csv").read_text().splitlines()
     assert len(ts) == 1 + len(keys) * net.simulation_steps
+
+
+def test_env_save_writes_the_reference_layout(emu_lib, tmp_path):
+    """PedNetParallelEnv.save (reference rl/pz_pednet_env.py:688-691): the directory the package writes is read by
+    the reference's own loader and equals, entry by entry, what the reference's own OutputHandler saves from the
+    same network."""
+    from pednstream_b200.rl import PedNetParallelEnv
+    env = PedNetParallelEnv("long_corridor", obs_mode="option1", seed=3, _lib=emu_lib, _emulation=True)
+    env.reset()
+    for k in range(60):
+        env.step({a: env.action_space(a).sample() for a in env.agents})
+    assert env.render() is None                                 # no render mode: nothing to draw
+    out = env.save("mine", base_dir=str(tmp_path))
+    mod = _load_handler()
+    mod.OutputHandler(base_dir=str(tmp_path), simulation_dir="theirs").save_network_state(env.network)
+    mine = mod.OutputHandler.load_simulation(out)
+    theirs = mod.OutputHandler.load_simulation(str(tmp_path / "theirs"))
+    assert mine["network_params"] == theirs["network_params"]
+    assert mine["node_data"] == theirs["node_data"]
+    assert set(mine["link_data"]) == set(theirs["link_data"])
+    for key, entry in theirs["link_data"].items():
+        assert mine["link_data"][key] == entry, key
+    assert any(e.get("is_separator") for e in mine["link_data"].values())
