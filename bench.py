@@ -324,6 +324,21 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
     env.reset()
     torch.cuda.synchronize()
     reset_ms = (time.perf_counter() - w0) * 1e3
+    # domain randomisation drawn on the device: episode turnover with a new scenario per replica
+    rand_reset_ms = None
+    if world == 1:
+        del env
+        torch.cuda.empty_cache()
+        env = BatchedPedNetEnv("45_intersections", replicas=replicas, obs_mode="option3", seed=1000,
+                               replica_base=rank * replicas, device=dev, randomize="device")
+        for k in range(3):
+            env.step(pool[k])
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        env.reset()
+        torch.cuda.synchronize()
+        rand_reset_ms = (time.perf_counter() - w0) * 1e3
+        env.engine.check_errors()
     vals = [ms, ms_e2e, reset_ms, ms_late if ms_late is not None else 0.0, gather_us or 0.0]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
@@ -357,6 +372,11 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
            "mean_reward_last_step": float(host_rew[-1].mean())}
     if ms_late is not None:
         out["roofline"]["congested_t%d" % late_from] = roof(ms_late_max)
+    if rand_reset_ms is not None:
+        out["randomized_reset_ms"] = rand_reset_ms
+        out["randomized_reset_note"] = ("BatchedPedNetEnv(randomize='device'): per-replica link bottlenecks, OD weights and "
+                                        "demand patterns drawn by one kernel launch (pns_env_randomize), then state init and "
+                                        "demand draw; wall clock")
     if world > 1:
         out["reward_gather_us"] = gather_us_max
         out["reward_gather_note"] = "all-gather of one float32 per replica over NCCL (per call, device-timed)"

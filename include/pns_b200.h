@@ -313,6 +313,22 @@ int pns_env_draw_demand(int sim_steps, int rows, int replicas, uint32_t replica_
                         const double *bump1, const double *bump2, const double *base, const double *peak,
                         const int32_t *pattern, double *demand, void *stream);
 
+/* Domain randomisation on the device: per-replica scenarios of one episode without a host loop over replicas
+ * (reference NetworkEnvGenerator.generate_random_link_params / generate_random_od_flows / generate_random_demand_params,
+ * env_loader.py:183-258, 363-424; same distributions, counter-based draws keyed (seed; replica_base + r)):
+ *   classes      [n_base_classes + R*n_change]: on entry the first n_base_classes hold the unperturbed parameter
+ *                classes; the call appends the classes of every replica's n_change perturbed corridors
+ *                (n_change = int(0.2 * corridors), at most 32);
+ *   lk_class     [n_links*R] (replica fastest): base_class[l], or the replica's own class on a perturbed corridor;
+ *   od_w         [sim_steps+1][n_od*R]: one weight ~ U[1, 10) per OD pair and replica, constant over the episode;
+ *   dem_base / dem_peak / dem_pattern  [n_demand_rows*R]: the inputs of pns_env_draw_demand (rows with
+ *                row_is_origin == 0 get pattern -1).
+ * The caller then points pns_net.classes / lk_class at these arrays with per_replica_scenario = 1. */
+int pns_env_randomize(const pns_net *net, pns_link_class *classes, int n_base_classes, const int32_t *base_class,
+                      int n_change, int32_t *lk_class, double *od_w, int n_demand_rows, const int32_t *row_is_origin,
+                      double *dem_base, double *dem_peak, int32_t *dem_pattern, uint64_t seed, uint32_t replica_base,
+                      void *stream);
+
 /* Episode KPIs of every replica from the history rows 0..t_last (reference rl/rl_utils.py, which computes them
  * from the JSON that handlers/output_handler.py saves): out[replica][PNS_KPI_COUNT].
  *   TOTAL_DEMAND     sum of the origin demand                                  (compute_network_throughput :827-835)

@@ -339,6 +339,44 @@ def normal_philox(seed, t, link, replica, site):
     return math.sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2)
 
 
+def device_scenario(seed, replica, n_corridors, n_change, base_params, n_od, origin_rows):
+    """Restatement of pns_kernels.cu k_scenario_draw for one replica (global replica index `replica`):
+    base_params[c] = (k_critical, k_jam, free_flow_speed) of corridor c; origin_rows = indices of the demand rows
+    that are origins.  Returns (corridor overrides {c: (kc, kj, vf)} in draw order, OD weights [n_od],
+    demand parameters {row: (pattern code, base, peak)})."""
+    k0, k1 = seed & M32, (seed >> 32) & M32
+    order = list(range(n_corridors))
+    over = {}
+    for k in range(n_change):
+        w = philox4x32_10(k, 0, 10, replica, k0, k1)
+        j = min(k + int(u53(w[0], w[1]) * float(n_corridors - k)), n_corridors - 1)
+        order[k], order[j] = order[j], order[k]
+        c = order[k]
+        a = philox4x32_10(k, 0, 11, replica, k0, k1)
+        b = philox4x32_10(k, 0, 12, replica, k0, k1)
+        kc, kj, vf = (float(x) for x in base_params[c])
+        if a[0] & 1:
+            f = 0.6 + 0.6 * u53(a[2], a[3])
+            kc_new = max(0.5, kc * f)
+            kj = max(kc_new * 2.0, kj * f)
+            kc = kc_new
+        if a[1] & 1:
+            vf = vf * (0.6 + 0.3 * u53(b[0], b[1]))
+        over[c] = (kc, kj, vf)
+    weights = []
+    for od in range(n_od):
+        w = philox4x32_10(od, 0, 13, replica, k0, k1)
+        weights.append(1.0 + 9.0 * u53(w[0], w[1]))
+    demand = {}
+    for row in origin_rows:
+        w = philox4x32_10(row, 0, 14, replica, k0, k1)
+        v = philox4x32_10(row, 0, 15, replica, k0, k1)
+        base = 2.0 + 8.0 * u53(w[1], w[2])
+        peak = max(10.0 + 20.0 * u53(v[0], v[1]), base + 5.0)
+        demand[row] = (w[0] % 3, base, peak)
+    return over, weights, demand
+
+
 # ---- float32 Box-Muller with exact fused multiply-adds (mirrors pns_rng.cuh) -----------------------
 
 F32 = np.float32

@@ -33,6 +33,7 @@
 #include "pns_emu.h"   // tests/emu: sequential host build of these kernels for CPU-side unit tests
 #else
 #include <cuda_runtime.h>
+#include <mutex>
 #define PNS_LAUNCH(kern, nblk, nthr, stream, ...) kern<<<(nblk), (nthr), 0, (stream)>>>(__VA_ARGS__)
 // Programmatic dependent launch (sm_90+): the kernels of a step form a strict chain on one stream.
 // Each kernel lets its successor start launching at once (TRIGGER) and waits for its predecessor's
@@ -1663,6 +1664,115 @@ __global__ void __launch_bounds__(kBlock) k_demand_draw(const DemandCtx d) {
 }
 
 // =================================================================================================
+// Domain randomisation on the device (reference NetworkEnvGenerator.generate_random_link_params /
+// generate_random_od_flows / generate_random_demand_params, env_loader.py:183-258, 363-424): every replica and
+// episode gets its own scenario without a host loop over replicas.  Same distributions as the reference's
+// generators, drawn from Philox blocks keyed (seed; replica) instead of numpy's stream (restated in
+// oracle/philox.py: device_scenario):
+//   * n_change = int(0.2 * corridors) corridors chosen uniformly without replacement (partial Fisher-Yates);
+//     each, with probability 1/2, gets a capacity factor f ~ U[0.6, 1.2): k_c' = max(0.5, k_c f),
+//     k_j' = max(2 k_c', k_j f), and, with probability 1/2, a free-flow speed factor ~ U[0.6, 0.9);
+//   * every OD pair a weight ~ U[1, 10), constant over the episode;
+//   * every origin a demand pattern (gaussian_peaks / constant / sudden_demand, equally likely), a base rate
+//     ~ U[2, 10) and a peak rate ~ U[10, 30), raised to base + 5 when it is closer than that.
+// One thread per replica; the parameter classes of its perturbed corridors are built here with the arithmetic
+// of plan.class_record.
+struct ScenarioCtx {
+    int n_links, R, n_change, n_base, n_od, S, rows;
+    uint32_t replica_base;
+    uint64_t seed;
+    double unit_time;
+    pns_link_class* classes;       // [n_base + R*n_change]; the first n_base are the unperturbed classes
+    int32_t* lk_class;             // [n_links*R]
+    const int32_t* base_class;     // [n_links]
+    const double* lk_width;        // [n_links]
+    double* od_w;                  // [S+1][n_od*R]
+    double *dem_base, *dem_peak;   // [rows*R]
+    int32_t* dem_pattern;          // [rows*R]; rows that are not origins keep -1
+    const int32_t* row_is_origin;  // [rows]
+};
+
+__device__ __forceinline__ pns_link_class make_link_class(const pns_link_class& b, double width, double vf, double kc,
+                                                          double kj, double unit_time) {
+    pns_link_class r = b;                                       // length, gamma, act, bi, sigma, flags unchanged
+    const double area = b.length * width;                       // link.py:131
+    const double slow = b.length / 0.05;                        // link.py:63
+    const double free = b.length / vf;
+    const float tt0 = (float)(free < slow ? free : slow);       // link.py:83
+    const double shock = (vf * kc) / (kj - kc);                 // link.py:58,61
+    r.area = area; r.space = kj * area;
+    r.kc = kc; r.vf = vf; r.kj = kj;
+    r.kc32 = (float)kc; r.kj32 = (float)kj; r.kj_minus_kc32 = (float)(kj - kc);
+    r.area32 = (float)area;
+    r.yp_coef32 = (float)((kc * vf) / (kj - kc));
+    r.neg_vf32 = (float)(-vf);
+    r.vf32 = (float)vf;
+    r.sm_gamma32 = (float)(vf * kc);
+    r.inv_kj32 = (float)(1.0 / kj);
+    r.max_tt32 = (float)slow;
+    r.tt0 = tt0;
+    r.fftau = __float2int_rn(tt0 / (float)unit_time);           // link.py:86
+    r.swtau = (int)rint(b.length / (shock * unit_time));        // link.py:380
+    return r;
+}
+
+__global__ void __launch_bounds__(kBlock) k_scenario_draw(const ScenarioCtx x) {
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= x.R) return;
+    const uint32_t rkey = x.replica_base + (uint32_t)rep, k0 = (uint32_t)x.seed, k1 = (uint32_t)(x.seed >> 32);
+    const int R = x.R, C = x.n_links / 2;
+    for (int l = 0; l < x.n_links; ++l) x.lk_class[(size_t)l * R + rep] = x.base_class[l];
+    // corridors to perturb: partial Fisher-Yates over 0..C-1, positions swapped so far kept in a short list
+    int moved_pos[64], moved_val[64];
+    int n_moved = 0;
+    const int n_change = x.n_change < 32 ? x.n_change : 32;
+    for (int k = 0; k < n_change; ++k) {
+        const pns::Philox4 w = pns::philox4x32_10((uint32_t)k, 0u, 10u, rkey, k0, k1);
+        int j = k + (int)(pns::u53(w.v[0], w.v[1]) * (double)(C - k));
+        if (j >= C) j = C - 1;
+        int vj = j, vk = k, ij = -1, ik = -1;                   // current contents of positions j and k
+        for (int q = 0; q < n_moved; ++q) {
+            if (moved_pos[q] == j) { vj = moved_val[q]; ij = q; }
+            if (moved_pos[q] == k) { vk = moved_val[q]; ik = q; }
+        }
+        if (ij >= 0) moved_val[ij] = vk; else { moved_pos[n_moved] = j; moved_val[n_moved] = vk; ++n_moved; }
+        if (ik >= 0) moved_val[ik] = vj; else if (j != k) { moved_pos[n_moved] = k; moved_val[n_moved] = vj; ++n_moved; }
+        const int corridor = vj;                                 // chosen: links 2*corridor, 2*corridor + 1
+        const pns::Philox4 a = pns::philox4x32_10((uint32_t)k, 0u, 11u, rkey, k0, k1);
+        const pns::Philox4 b = pns::philox4x32_10((uint32_t)k, 0u, 12u, rkey, k0, k1);
+        const pns_link_class base = x.classes[x.base_class[2 * corridor]];
+        double kc = base.kc, kj = base.kj, vf = base.vf;
+        if (a.v[0] & 1u) {
+            const double f = 0.6 + 0.6 * pns::u53(a.v[2], a.v[3]);
+            kc = fmax(0.5, base.kc * f);
+            kj = fmax(kc * 2.0, base.kj * f);
+        }
+        if (a.v[1] & 1u) vf = base.vf * (0.6 + 0.3 * pns::u53(b.v[0], b.v[1]));
+        const int slot = x.n_base + rep * x.n_change + k;
+        x.classes[slot] = make_link_class(base, x.lk_width[2 * corridor], vf, kc, kj, x.unit_time);
+        x.lk_class[(size_t)(2 * corridor) * R + rep] = slot;
+        x.lk_class[(size_t)(2 * corridor + 1) * R + rep] = slot;
+    }
+    for (int od = 0; od < x.n_od; ++od) {
+        const pns::Philox4 w = pns::philox4x32_10((uint32_t)od, 0u, 13u, rkey, k0, k1);
+        const double weight = 1.0 + 9.0 * pns::u53(w.v[0], w.v[1]);
+        for (int t = 0; t <= x.S; ++t) x.od_w[((size_t)t * x.n_od + od) * R + rep] = weight;
+    }
+    for (int row = 0; row < x.rows; ++row) {
+        const size_t col = (size_t)row * R + rep;
+        if (!x.row_is_origin[row]) { x.dem_pattern[col] = -1; x.dem_base[col] = 0.0; x.dem_peak[col] = 0.0; continue; }
+        const pns::Philox4 w = pns::philox4x32_10((uint32_t)row, 0u, 14u, rkey, k0, k1);
+        const pns::Philox4 v = pns::philox4x32_10((uint32_t)row, 0u, 15u, rkey, k0, k1);
+        const double base = 2.0 + 8.0 * pns::u53(w.v[1], w.v[2]);
+        double peak = 10.0 + 20.0 * pns::u53(v.v[0], v.v[1]);
+        if (peak < base + 5.0) peak = base + 5.0;
+        x.dem_pattern[col] = (int32_t)(w.v[0] % 3u);            // 0 gaussian_peaks, 1 constant, 2 sudden_demand
+        x.dem_base[col] = base;
+        x.dem_peak[col] = peak;
+    }
+}
+
+// =================================================================================================
 // Episode KPIs per replica (reference rl/rl_utils.py:770-1512, which reads them from the JSON that
 // OutputHandler saves): reductions over the whole history, rows 0..t_last.
 // Pass 1: one thread per (link, replica) walks its column through time (coalesced over replicas).
@@ -1977,22 +2087,31 @@ StepSizes sizes_of(const pns_net* net) {
 
 constexpr size_t kMetricRow = (size_t)PNS_METRIC_SLOTS * PNS_METRIC_STRIDE;   // doubles per step in the metric buffers
 #ifndef PNS_HOST_EMULATION
-// copy stream + event ring of pns_step_streamed (per device; a re-recorded event does not disturb
-// waits that were enqueued on its earlier record)
+// copy stream + event ring of pns_step_streamed, one per device (created on first use, kept for the life of the
+// process; a re-recorded event does not disturb waits that were enqueued on its earlier record).  The table is
+// guarded by a mutex: ctypes callers release the GIL, so two host threads may be inside the library at once.
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t ring[256];
-    int dev = -1, next = 0;
-    void ensure() {
-        int d = 0;
-        cudaGetDevice(&d);
-        if (stream && d == dev) return;
-        dev = d;
-        cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-        for (auto& e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    }
+    int next = 0;
+    bool ok = false;
     cudaEvent_t event() { next = (next + 1) & 255; return ring[next]; }
 };
+SideStream* side_stream_for_current_device() {
+    static SideStream table[64];
+    static std::mutex guard;
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(guard);
+    SideStream& s = table[d];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (auto& e : s.ring)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
 #endif
 struct Streamed {           // per-step host traffic of pns_step_streamed
     const double* host_demand;   // pinned [rows][n_demand_rows*R]
@@ -2009,13 +2128,15 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     ensure_sampler_tables(s);
     const StepSizes z = sizes_of(net);
 #ifndef PNS_HOST_EMULATION
-    static SideStream side;
     constexpr int kSyncGroup = 8;
     cudaEvent_t demand_next = nullptr;
     int results_copied = 0;
+    SideStream* side_p = sx ? side_stream_for_current_device() : nullptr;
+    if (sx && !side_p) return fail("pns_step_streamed: copy stream / events could not be created", cudaGetLastError());
+    SideStream dummy;
+    SideStream& side = side_p ? *side_p : dummy;
     if (sx) {
         cudaMemsetAsync(sx->dev_metric, 0, (size_t)n_steps * kMetricRow * sizeof(double), s);
-        side.ensure();
         cudaEvent_t e = side.event();                  // the side stream starts after everything queued so far
         cudaEventRecord(e, s);
         cudaStreamWaitEvent(side.stream, e, 0);
@@ -2279,6 +2400,27 @@ int pns_env_draw_demand(int sim_steps, int rows, int replicas, uint32_t replica_
     const size_t n = (size_t)(sim_steps + 1) * rows * replicas;
     PNS_LAUNCH(k_demand_draw, blocks_for(n), kBlock, (cudaStream_t)stream, d);
     return launched("k_demand_draw");
+}
+
+int pns_env_randomize(const pns_net* net, pns_link_class* classes, int n_base_classes, const int32_t* base_class,
+                      int n_change, int32_t* lk_class, double* od_w, int n_demand_rows, const int32_t* row_is_origin,
+                      double* dem_base, double* dem_peak, int32_t* dem_pattern, uint64_t seed, uint32_t replica_base,
+                      void* stream) {
+    if (!net || !classes || !base_class || !lk_class) return fail("pns_env_randomize: null argument");
+    if (net->abi_version != PNS_ABI_VERSION) return fail("pns_net.abi_version mismatch");
+    if (n_change < 0 || n_change > 32) return fail("pns_env_randomize: at most 32 perturbed corridors per replica");
+    if (net->n_od > 0 && !od_w) return fail("pns_env_randomize: od weight table missing");
+    if (n_demand_rows > 0 && !(row_is_origin && dem_base && dem_peak && dem_pattern))
+        return fail("pns_env_randomize: demand parameter arrays missing");
+    ScenarioCtx x;
+    x.n_links = net->n_links; x.R = net->replicas; x.n_change = n_change; x.n_base = n_base_classes;
+    x.n_od = net->n_od; x.S = net->sim_steps; x.rows = n_demand_rows;
+    x.replica_base = replica_base; x.seed = seed; x.unit_time = net->unit_time;
+    x.classes = classes; x.lk_class = lk_class; x.base_class = base_class; x.lk_width = net->lk_width;
+    x.od_w = od_w; x.dem_base = dem_base; x.dem_peak = dem_peak; x.dem_pattern = dem_pattern;
+    x.row_is_origin = row_is_origin;
+    PNS_LAUNCH(k_scenario_draw, blocks_for((size_t)net->replicas), kBlock, (cudaStream_t)stream, x);
+    return launched("k_scenario_draw");
 }
 
 int pns_kpi(const pns_net* net, const pns_state* st, const pns_step_io* io, int t_last, const int32_t* lk_role,

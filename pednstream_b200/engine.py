@@ -261,6 +261,23 @@ class Engine:
         if self._table_io is not None:
             self._table_io.od_w = _ptr(self.od_w)
 
+    def set_replica_scenarios_device(self, classes: torch.Tensor, n_classes: int, lk_class: torch.Tensor,
+                                     od_w: torch.Tensor = None):
+        """Per-replica scenarios whose tables already live on the device (pns_env_randomize): `classes` a uint8
+        tensor of n_classes pns_link_class records, `lk_class` int32 [L*R] (replica fastest), `od_w` float64
+        [S+1, n_od*R].  Call before `initialise`."""
+        self._net_t["classes"], self._net_t["lk_class"] = classes, lk_class
+        net = self.net
+        net.classes, net.lk_class = _ptr(classes), _ptr(lk_class)
+        net.n_classes = int(n_classes)
+        net.per_replica_scenario = 1
+        if od_w is not None:
+            self.od_w = od_w
+            self.io.od_w = _ptr(od_w)
+            if self._table_io is not None:
+                self._table_io.od_w = _ptr(od_w)
+        self._od_per_replica = True
+
     def set_gate(self, gate, sep_np64=None):
         g = torch.from_numpy(np.ascontiguousarray(gate, dtype=np.float64).reshape(-1))
         if g.shape[0] == self.L and self.R > 1:

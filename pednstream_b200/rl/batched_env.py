@@ -62,7 +62,9 @@ class BatchedPedNetEnv:
         self.generator = NetworkEnvGenerator(data_dir)
         self.network = self.generator.create_network(dataset, verbose=False)
         np.random.set_state(state)
-        self.randomize = bool(randomize)
+        if randomize not in (False, True, "host", "device"):
+            raise ValueError("randomize must be False, True / 'host' or 'device'")
+        self.randomize = "host" if randomize is True else randomize
         self._scenarios = None
         net = self.network
         self.simulation_steps = S = net.simulation_steps
@@ -173,6 +175,10 @@ class BatchedPedNetEnv:
     def scenario(self, replica: int, episode: int = None) -> dict:
         """The overrides of local replica `replica` in `episode` (default: the current one), as the
         reference's generators produce them for `scenario_seed(replica, episode)`."""
+        if self.randomize == "device":
+            if episode is not None and episode != self._device_episode:
+                raise ValueError("device scenarios are kept for the current episode only")
+            return self._device_scenario(replica)
         episode = self.episode - 1 if episode is None else episode
         gen, s = self.generator, self.scenario_seed(replica, episode)
         state = np.random.get_state()
@@ -186,38 +192,137 @@ class BatchedPedNetEnv:
 
     def _apply_scenarios(self, episode: int):
         """Builds the class table, the per-replica class indices and OD weights of this episode and hands
-        them to the engine; keeps the per-replica demand parameters for `_draw_demand`."""
+        them to the engine; keeps the per-replica demand parameters for `_draw_demand`.  Only the corridors a
+        scenario perturbs (20 % of them) are looked at per replica: every other link keeps the class of the
+        unperturbed scenario (create_network merges an override into the corridor's own block and nothing else,
+        env_loader.py:93-144)."""
         from ..plan import CLASS_DTYPE, class_record
         net, gen, R = self.network, self.generator, self.R
-        links = list(net.links.values())
-        L = len(links)
-        od_keys = list(net.plan["od_keys"])
-        table, rows = {}, []
-        lk_class = np.zeros((L, R), dtype=np.int32)
-        od_w = np.zeros((self.simulation_steps + 1, len(od_keys), R)) if od_keys else None
-        self._scenarios = []
         unit_time = net.params["unit_time"]
-        for r in range(R):
-            sc = self.scenario(r, episode)
-            self._scenarios.append(sc["demand_params_overrides"])
-            per_corridor = gen.scenario_link_params(sc["link_params_overrides"])
+        if not hasattr(self, "_scn_base"):
+            links = list(net.links.values())
+            per_corridor = gen.scenario_link_params(None)
+            table, rows = {}, []
+            base_idx = np.zeros(len(links), dtype=np.int32)
+            corridor_links, link_static = {}, {}
             for l in links:
                 u, v = l.start_node.node_id, l.end_node.node_id
-                kw = per_corridor[(min(u, v), max(u, v))]
-                key = (l.length, l._width, kw["free_flow_speed"], kw["k_critical"], kw["k_jam"], l.gamma,
-                       l.activity_probability, l.bi_factor, l.speed_noise_std, l.fd_type, bool(l.is_separator))
+                c = (min(u, v), max(u, v))
+                kw = per_corridor[c]
+                static = (l.length, l._width, l.gamma, l.activity_probability, l.bi_factor, l.speed_noise_std,
+                          l.fd_type, bool(l.is_separator))
+                key = (static, kw["free_flow_speed"], kw["k_critical"], kw["k_jam"])
                 k = table.get(key)
                 if k is None:
                     k = table[key] = len(rows)
-                    rows.append(class_record(*key, unit_time))
-                lk_class[l.index, r] = k
+                    rows.append(class_record(static[0], static[1], key[1], key[2], key[3], *static[2:], unit_time))
+                base_idx[l.index] = k
+                corridor_links.setdefault(c, []).append(l.index)
+                link_static[l.index] = static
+            self._scn_base = (per_corridor, base_idx, corridor_links, link_static, dict(table), list(rows))
+        per_corridor, base_idx, corridor_links, link_static, table0, rows0 = self._scn_base
+        table, rows = dict(table0), list(rows0)
+        od_keys = list(net.plan["od_keys"])
+        lk_class = np.repeat(base_idx[:, None], R, axis=1)
+        od_w = np.zeros((self.simulation_steps + 1, len(od_keys), R)) if od_keys else None
+        self._scenarios = []
+        for r in range(R):
+            sc = self.scenario(r, episode)
+            self._scenarios.append(sc["demand_params_overrides"])
+            for link_id, over in sc["link_params_overrides"].items():
+                u, v = (int(x) for x in link_id.split("_"))
+                c = (min(u, v), max(u, v))
+                kw = {**per_corridor[c], **over}
+                for li in corridor_links[c]:
+                    static = link_static[li]
+                    key = (static, kw["free_flow_speed"], kw["k_critical"], kw["k_jam"])
+                    k = table.get(key)
+                    if k is None:
+                        k = table[key] = len(rows)
+                        rows.append(class_record(static[0], static[1], key[1], key[2], key[3], *static[2:], unit_time))
+                    lk_class[li, r] = k
             if od_keys:
                 if set(sc["od_flows"]) != set(od_keys):
                     raise NotImplementedError("randomised OD weights need the scenario's full origin x destination set")
                 for j, key in enumerate(od_keys):
-                    od_w[:, j, r] = sc["od_flows"][key]
+                    od_w[:, j, r] = sc["od_flows"][key][0]          # constant over the episode (env_loader.py:236-243)
         classes = np.array(rows, dtype=CLASS_DTYPE).reshape(len(rows))
         self.engine.set_replica_scenarios(classes, lk_class, od_w)
+
+    # ------------------------------------------------------------------ per-replica scenarios drawn on the device
+    def device_scenario_seed(self, episode: int) -> int:
+        return (self.seed * 0xD1B54A32D192ED03 + 0x9E3779B97F4A7C15 * (episode + 1)) % (2 ** 64)
+
+    def _corridors(self):
+        """[(u, v)] with u < v in link-pair order: corridor c is links 2c (u -> v) and 2c + 1."""
+        keys = list(self.network.links.keys())
+        return [keys[2 * c] for c in range(len(keys) // 2)]
+
+    def _apply_scenarios_device(self, episode: int):
+        """randomize='device': the scenarios of all replicas drawn by one kernel launch (C-ABI pns_env_randomize; the
+        reference generators' distributions with counter-based draws keyed by the global replica index), so an
+        episode turnover has no host loop over replicas.  `scenario(r)` restates a replica's draws on the host."""
+        net, eng, R = self.network, self.engine, self.R
+        plan = net.plan
+        L, S, n_od = len(net.links), self.simulation_steps, int(plan["n_od"])
+        dev = eng.device
+        n_base = len(plan["classes"])
+        n_change = int((L // 2) * 0.2)                    # env_loader.py:401
+        rows = plan["demand_nodes"]
+        if not hasattr(self, "_dev_scn"):
+            from ..plan import CLASS_DTYPE
+            rec = CLASS_DTYPE.itemsize
+            classes = torch.zeros(((n_base + R * n_change) * rec,), dtype=torch.uint8, device=dev)
+            base_bytes = np.ascontiguousarray(plan["classes"]).view(np.uint8).reshape(-1)
+            classes[: n_base * rec].copy_(torch.from_numpy(base_bytes.copy()))
+            is_origin = np.array([1 if n.node_id in net.origin_nodes else 0 for n in rows], dtype=np.int32)
+            self._dev_scn = dict(
+                classes=classes, lk_class=torch.zeros((L * R,), dtype=torch.int32, device=dev),
+                base_class=torch.from_numpy(np.ascontiguousarray(plan["lk_class"], dtype=np.int32)).to(dev),
+                od_w=torch.zeros((S + 1, max(1, n_od) * R), dtype=torch.float64, device=dev),
+                row_is_origin=torch.from_numpy(is_origin).to(dev),
+                base=torch.zeros((max(1, len(rows)) * R,), dtype=torch.float64, device=dev),
+                peak=torch.zeros((max(1, len(rows)) * R,), dtype=torch.float64, device=dev),
+                pattern=torch.zeros((max(1, len(rows)) * R,), dtype=torch.int32, device=dev))
+        d = self._dev_scn
+        with eng._guard():
+            _native.check(eng.lib, eng.lib.pns_env_randomize(
+                C.byref(eng.net), _ptr(d["classes"]), n_base, _ptr(d["base_class"]), n_change, _ptr(d["lk_class"]),
+                _ptr(d["od_w"]) if n_od else C.c_void_p(0), len(rows), _ptr(d["row_is_origin"]), _ptr(d["base"]),
+                _ptr(d["peak"]), _ptr(d["pattern"]), C.c_uint64(self.device_scenario_seed(episode)),
+                self.replica_base, self._stream()), "pns_env_randomize")
+        eng.set_replica_scenarios_device(d["classes"], n_base + R * n_change, d["lk_class"], d["od_w"] if n_od else None)
+        self._scenarios = None
+        self._device_episode = episode
+
+    def _device_scenario(self, replica: int) -> dict:
+        """What the kernel drew for one replica in the current episode, read back from the device tables, in the
+        shape of the reference generators' results (so `create_network(dataset, **scenario)` builds that replica)."""
+        from ..plan import CLASS_DTYPE
+        net, R, d = self.network, self.R, self._dev_scn
+        n_base = len(net.plan["classes"])
+        L, S = len(net.links), self.simulation_steps
+        lk = d["lk_class"].view(L, R)[:, replica].cpu().numpy()
+        table = d["classes"].cpu().numpy().view(CLASS_DTYPE)
+        over = {}
+        for c, (u, v) in enumerate(self._corridors()):
+            k = int(lk[2 * c])
+            if k >= n_base:
+                rec = table[k]
+                over[f"{u}_{v}"] = {"k_critical": float(rec["kc"]), "k_jam": float(rec["kj"]),
+                                    "free_flow_speed": float(rec["vf"])}
+        od_keys = list(net.plan["od_keys"])
+        od_row = d["od_w"][0].view(-1, R)[:, replica].cpu().numpy() if od_keys else []
+        od_flows = {key: np.full(S + 1, float(od_row[j])) for j, key in enumerate(od_keys)}
+        names = {v: k for k, v in self._PATTERN_CODE.items()}
+        rows = net.plan["demand_nodes"]
+        base = d["base"].view(-1, R)[:, replica].cpu().numpy()
+        peak = d["peak"].view(-1, R)[:, replica].cpu().numpy()
+        pat = d["pattern"].view(-1, R)[:, replica].cpu().numpy()
+        demand = {f"origin_{n.node_id}": {"pattern": names[int(pat[k])], "base_lambda": float(base[k]),
+                                         "peak_lambda": float(peak[k])}
+                  for k, n in enumerate(rows) if pat[k] >= 0}
+        return {"link_params_overrides": over, "od_flows": od_flows, "demand_params_overrides": demand}
 
     # ------------------------------------------------------------------ demand
     _PATTERN_CODE = {"gaussian_peaks": 0, "constant": 1, "sudden_demand": 2}
@@ -235,6 +340,20 @@ class BatchedPedNetEnv:
         if not rows:
             return
         n = len(rows)
+        t = np.arange(S)
+        spread = 2 * (S / 20) ** 2
+        bump1 = np.exp(-(t - S / 4) ** 2 / spread)
+        bump2 = np.exp(-(t - 3 * S / 4) ** 2 / spread)
+        if self.randomize == "device":                    # parameters already on the device (pns_env_randomize)
+            d = self._dev_scn
+            if not hasattr(self, "_bumps_dev"):
+                self._bumps_dev = (torch.from_numpy(bump1).to(eng.device), torch.from_numpy(bump2).to(eng.device))
+            self._demand_args = (*self._bumps_dev, d["base"], d["peak"], d["pattern"])
+            with eng._guard():
+                _native.check(eng.lib, eng.lib.pns_env_draw_demand(
+                    S, n, R, self.replica_base, C.c_uint64(self.demand_seed(episode)),
+                    *[_ptr(x) for x in self._demand_args], _ptr(eng.demand), self._stream()), "pns_env_draw_demand")
+            return
         base = np.zeros((n, R)); peak = np.zeros((n, R)); pattern = np.full((n, R), -1, dtype=np.int32)
         gen = net.demand_generator
         for k, node in enumerate(rows):
@@ -252,10 +371,6 @@ class BatchedPedNetEnv:
                     if p is not None:
                         base[k, r], peak[k, r] = p["base_lambda"], p["peak_lambda"]
                         pattern[k, r] = self._PATTERN_CODE[str(p["pattern"])]
-        t = np.arange(S)
-        spread = 2 * (S / 20) ** 2
-        bump1 = np.exp(-(t - S / 4) ** 2 / spread)
-        bump2 = np.exp(-(t - 3 * S / 4) ** 2 / spread)
         dev = eng.device
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self._demand_args = (to(bump1), to(bump2), to(base.reshape(-1)), to(peak.reshape(-1)), to(pattern.reshape(-1)))
@@ -269,7 +384,9 @@ class BatchedPedNetEnv:
         """Start a new episode in every replica; returns obs [R, n_obs] at step 1 (all zeros + widths)."""
         eng, net = self.engine, self.network
         eng.io.seed = (self.seed + 0x9E3779B97F4A7C15 * self.episode) % (2 ** 64)
-        if self.randomize:
+        if self.randomize == "device":
+            self._apply_scenarios_device(self.episode)
+        elif self.randomize:
             self._apply_scenarios(self.episode)
         eng.initialise(net._store.gate, net._store.sep_np64, self._tf, None, self._od_w, self._supplied)
         self._draw_demand(self.episode)

@@ -136,11 +136,40 @@ def _batched_vs_facade(dataset, obs_mode, norm, steps, R, picks, lib=None, emula
             assert np.array_equal(want[: steps + 1], got[: steps + 1]), (f, rep)
 
 
-def _randomized_batched_vs_facade(dataset, steps, R, picks, lib=None, emulation=False, device=None):
-    """randomize=True: replica r must equal the facade network built from `scenario(r)` through
+def _check_device_scenarios_against_restatement(benv, picks):
+    """randomize='device': what the kernel drew (read back through `scenario`) equals the Python restatement of
+    k_scenario_draw (oracle/philox.py device_scenario), value for value."""
+    from oracle import philox as ph
+    net = benv.network
+    corridors = benv._corridors()
+    base = [(net.links[c].k_critical, net.links[c].k_jam, net.links[c].free_flow_speed) for c in corridors]
+    rows = net.plan["demand_nodes"]
+    origin_rows = [k for k, n in enumerate(rows) if n.node_id in net.origin_nodes]
+    od_keys = list(net.plan["od_keys"])
+    for rep in picks:
+        over, weights, demand = ph.device_scenario(benv.device_scenario_seed(benv.episode - 1), benv.replica_base + rep,
+                                                   len(corridors), int(len(corridors) * 0.2), base, len(od_keys), origin_rows)
+        sc = benv.scenario(rep)
+        want_over = {f"{corridors[c][0]}_{corridors[c][1]}": {"k_critical": v[0], "k_jam": v[1], "free_flow_speed": v[2]}
+                     for c, v in over.items()}
+        assert sc["link_params_overrides"] == want_over
+        assert len(want_over) == int(len(corridors) * 0.2)
+        for j, key in enumerate(od_keys):
+            assert np.array_equal(sc["od_flows"][key], np.full(benv.simulation_steps + 1, weights[j]))
+        names = {0: "gaussian_peaks", 1: "constant", 2: "sudden_demand"}
+        for row, (pat, b, p) in demand.items():
+            got = sc["demand_params_overrides"][f"origin_{rows[row].node_id}"]
+            assert (got["pattern"], got["base_lambda"], got["peak_lambda"]) == (names[pat], b, p)
+            assert 2.0 <= b < 10.0 and b + 5.0 <= p < 30.0 + 1e-9
+
+
+def _randomized_batched_vs_facade(dataset, steps, R, picks, lib=None, emulation=False, device=None, mode=True):
+    """randomize=True / 'device': replica r must equal the facade network built from `scenario(r)` through
     create_network's override arguments (what randomize_network does, minus the OD-node perturbation)."""
     kw = dict(_lib=lib, _emulation=emulation) if emulation else dict(device=device)
-    benv = BatchedPedNetEnv(dataset, replicas=R, obs_mode="option3", seed=5, randomize=True, **kw)
+    benv = BatchedPedNetEnv(dataset, replicas=R, obs_mode="option3", seed=5, randomize=mode, **kw)
+    if mode == "device":
+        _check_device_scenarios_against_restatement(benv, picks)
     dev = benv.device
     rs = np.random.RandomState(9)
     acts = rs.uniform(0.0, 4.0, size=(steps, R, benv.n_act)).astype(np.float32)
@@ -182,13 +211,15 @@ def _randomized_batched_vs_facade(dataset, steps, R, picks, lib=None, emulation=
     assert benv.scenario(0)["link_params_overrides"] != before["link_params_overrides"]
 
 
-def test_batched_env_randomized_scenarios_emulated(emu_lib):
-    _randomized_batched_vs_facade("45_intersections", 60, 3, (0, 2), lib=emu_lib, emulation=True)
+@pytest.mark.parametrize("mode", [True, "device"])
+def test_batched_env_randomized_scenarios_emulated(emu_lib, mode):
+    _randomized_batched_vs_facade("45_intersections", 60, 3, (0, 2), lib=emu_lib, emulation=True, mode=mode)
 
 
 @pytest.mark.gpu
-def test_batched_env_randomized_scenarios_cuda():
-    _randomized_batched_vs_facade("45_intersections", 150, 48, (0, 17, 47), device="cuda:0")
+@pytest.mark.parametrize("mode", [True, "device"])
+def test_batched_env_randomized_scenarios_cuda(mode):
+    _randomized_batched_vs_facade("45_intersections", 150, 48, (0, 17, 47), device="cuda:0", mode=mode)
 
 
 def test_batched_env_matches_facade_emulated(emu_lib):
