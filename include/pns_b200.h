@@ -120,6 +120,9 @@ typedef struct pns_net {
     const int32_t *rt_row_routed;     /* [n_rows] routed node (index into rt_routed_*) of each upstream-slot row */
     const int32_t *rt_row_grp_ptr, *rt_row_grp; /* [n_rows+1], [n_groups]: the (od, upstream) groups registered at each row */
     const int32_t *rt_term_od;        /* [n_terms] OD column of each accumulation term (= rt_row_od[rt_term_row_entry]) */
+    const int32_t *rt_dyn_rows;       /* [n_dyn_rows] rows whose fractions can change between steps (a group with several
+                                         options, or several registered ODs); the other rows evaluate to constants and
+                                         are computed only on a step with pns_step_io.route_all_rows set */
     const int32_t *rt_grp_node, *rt_grp_up, *rt_grp_od, *rt_grp_has_virtual, *rt_opt_ptr;
     const int32_t *rt_opt_link, *rt_opt_slot;
     const double *rt_opt_dist;
@@ -137,7 +140,7 @@ typedef struct pns_net {
      * [n_links*replicas] (replica fastest) -- every replica has its own parameter class per link -- and
      * pns_step_io.od_w is [sim_steps+1][n_od*replicas] (replica fastest).  Topology, widths, OD nodes and the
      * route plan are shared by all replicas. */
-    int32_t per_replica_scenario, pad2_;
+    int32_t per_replica_scenario, n_dyn_rows;
 } pns_net;
 
 /* Mutable simulation state; all device pointers, caller-owned. */
@@ -178,7 +181,8 @@ typedef struct pns_step_io {
     const double *draw_exp; /* TABLE input [rows][n_opts*R]: exp of those arguments (NULL: evaluated on the device) */
     uint64_t seed;          /* PHILOX */
     uint32_t replica_base;  /* PHILOX: global index of local replica 0 (replicas sharded over GPUs) */
-    uint32_t pad_;
+    uint32_t route_all_rows;/* non-zero: the first step of the call evaluates every route row, not only rt_dyn_rows (the
+                               first step after pns_state_init, a change of the route plan; step 1 always does) */
 } pns_step_io;
 
 /* Control environment over R replicas (reference rl/pz_pednet_env.py, rl/builders.py, rl/discovery.py).

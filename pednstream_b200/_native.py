@@ -41,13 +41,13 @@ class PnsNet(C.Structure):
         + [("unit_time", C.c_double)]
         + [("classes", _p), ("class0", PnsLinkClass)]
         + [(n, _p) for n in ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
-                             "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od",
+                             "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od", "rt_dyn_rows",
                              "rt_grp_node", "rt_grp_up", "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr",
                              "rt_opt_link", "rt_opt_slot", "rt_opt_dist",
                              "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
         + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
         + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32),
-           ("per_replica_scenario", _i32), ("pad2_", _i32)]
+           ("per_replica_scenario", _i32), ("n_dyn_rows", _i32)]
     )
 
 
@@ -61,7 +61,7 @@ class PnsStepIO(C.Structure):
                 ("draw_row_stride", C.c_int64),
                 ("req_kind", _p), ("req_n1", _p), ("req_rf", _p), ("req_sval", _p), ("req_n3", _p),
                 ("req_exp", _p), ("draw_exp", _p),
-                ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("pad_", C.c_uint32)]
+                ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("route_all_rows", C.c_uint32)]
 
 
 class PnsEnv(C.Structure):

@@ -145,6 +145,7 @@ struct Ctx {
     // counts of row route_t-1 are being written by the link CTAs, and the route threads rebuild the few they need from
     // the UPDATE inputs (num[t-2], inflow[t-1], outflow[t-1]) with the same arithmetic.
     int route_blocks, route_t, route_recompute;
+    int route_all;   // 1: every route row is evaluated; 0: only pns_net.rt_dyn_rows (the others hold constants)
 };
 
 // Control environment (reference rl/builders.py, rl/pz_pednet_env.py): the step context plus the action /
@@ -254,6 +255,7 @@ __device__ __forceinline__ int4 ld_meta(const int4* a, const L2Pol p) { if (PNS_
 struct L2Pol { };
 static inline L2Pol l2_policies() { return L2Pol(); }
 static inline void prefetch_l2(const void*) { }
+static inline void prefetch_l1(const void*) { }
 template <int S, typename T> static inline T ld_keep(const T* a, const L2Pol) { return *a; }
 template <int S, typename T> static inline void st_keep(T* a, T v, const L2Pol) { *a = v; }
 static inline int4 ld_meta(const int4* a, const L2Pol) { return *a; }
@@ -770,9 +772,11 @@ __device__ __forceinline__ void routed_row_fractions(const Ctx& c, int routed, i
 // groups registered at that slot, then the slot's row of turning fractions (tf_routed; read by the node pass of
 // the same step).  Runs for every routed node on every step, as the reference does (network.py:273-278), so the
 // fractions a caller reads back are those of the last step.
-__device__ __forceinline__ void route_thread(const Ctx& c, int t, int row, int rep) {
+__device__ __forceinline__ int route_rows(const Ctx& c) { return c.route_all ? c.n.n_rows : c.n.n_dyn_rows; }
+__device__ __forceinline__ void route_thread(const Ctx& c, int t, int row_index, int rep) {
     const int R = c.n.replicas;
     PNS_PDL_TRIGGER();
+    const int row = c.route_all ? row_index : __ldg(c.n.rt_dyn_rows + row_index);
     const int routed = __ldg(c.n.rt_row_routed + row);
     const int ga = __ldg(c.n.rt_row_grp_ptr + row), gb = __ldg(c.n.rt_row_grp_ptr + row + 1);
     const int i = row - __ldg(c.n.rt_routed_row0 + routed);
@@ -786,7 +790,7 @@ __device__ __forceinline__ void route_thread(const Ctx& c, int t, int row, int r
 __global__ void __launch_bounds__(kBlock) k_route_fractions(const __grid_constant__ Ctx c) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned R = (unsigned)c.n.replicas;
-    if (gid >= (size_t)c.n.n_rows * R) return;
+    if (gid >= (size_t)route_rows(c) * R) return;
     route_thread(c, c.t, (int)((unsigned)gid / R), (int)((unsigned)gid % R));
 }
 
@@ -816,6 +820,14 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     const size_t base = (size_t)node * c.n.nd_stride;
     double s[CAP], r[CAP];
     int in_link[CAP];                                                       // incoming link column of each slot
+    if (ROUTED && tf_mode == 2) {
+        // the m(m-1) routed fractions are read one by one deep inside the column loop: ask for them now, together
+        // with the hand-over loads, instead of paying a memory round trip each
+        const double* t0 = c.s.tf_routed + (size_t)tf_ptr * R + rep;
+#pragma unroll
+        for (int k = 0; k < CAP * (CAP - 1); ++k)
+            if (k < m * (m - 1)) prefetch_l1(t0 + (size_t)k * R);
+    }
     if (M == 4) {
         const int4 v = __ldg(reinterpret_cast<const int4*>(c.n.nd_in_link + base));
         in_link[0] = v.x; in_link[1 % CAP] = v.y; in_link[2 % CAP] = v.z; in_link[3 % CAP] = v.w;
@@ -989,7 +1001,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     if (flw && c.route_blocks > 0) {                     // route choice rides along (see Ctx::route_blocks)
         if (bx < (unsigned)c.route_blocks) {
             const unsigned row = bx * (unsigned)PNS_LANE_BLOCK + threadIdx.x;
-            if (row < (unsigned)c.n.n_rows) route_thread(c, c.route_t, (int)row, 0);
+            if (row < (unsigned)route_rows(c)) route_thread(c, c.route_t, (int)row, 0);
             return;
         }
         bx -= (unsigned)c.route_blocks;
@@ -1358,7 +1370,7 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     const unsigned n_pairs = (unsigned)c.n.n_links >> 1;
     if (flw && blockIdx.y >= n_pairs) {                     // route choice rides along: two rows per CTA
         const unsigned row = 2u * (blockIdx.y - n_pairs) + dir;
-        if (row < (unsigned)c.n.n_rows && rep_raw < R) route_thread(c, c.route_t, (int)row, rep_raw);
+        if (row < (unsigned)route_rows(c) && rep_raw < R) route_thread(c, c.route_t, (int)row, rep_raw);
         return;
     }
     const unsigned pair = blockIdx.y;
@@ -1936,6 +1948,7 @@ Ctx make_ctx(const pns_net* net, const pns_state* st, const pns_step_io* io, int
     }
     c.metric = nullptr;
     c.route_blocks = 0; c.route_t = 0; c.route_recompute = 0;
+    c.route_all = 1;
     const int64_t stride = io ? io->draw_row_stride : 0;
     c.draw_b = (io && io->draw_b) ? io->draw_b + (size_t)(stride * row_flows) * 3 * c.row32 : nullptr;
     c.draw_n = (io && io->draw_n) ? io->draw_n + (size_t)(stride * row_update) * c.row32 : nullptr;
@@ -2022,7 +2035,7 @@ void launch_rep(const pns_net* net, cudaStream_t s, const Ctx& c, const EnvRide*
     memset(&x, 0, sizeof x);
     x.c = c;
     if (with_route && (c.phase & PH_FLOWS)) {
-        x.c.route_blocks = (net->n_rows + 1) / 2;      // extra grid rows: two route rows per CTA
+        x.c.route_blocks = ((c.route_all ? net->n_rows : net->n_dyn_rows) + 1) / 2;   // extra grid rows: two route rows per CTA
         x.c.route_t = c.t_flows;
         x.c.route_recompute = (c.phase & PH_UPDATE) ? 1 : 0;
     }
@@ -2051,7 +2064,7 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, con
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
         Ctx cl = c;
         if (with_route && (c.phase & PH_FLOWS)) {
-            cl.route_blocks = (net->n_rows + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK;
+            cl.route_blocks = ((c.route_all ? net->n_rows : net->n_dyn_rows) + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK;
             cl.route_t = c.t_flows;
             cl.route_recompute = (c.phase & PH_UPDATE) ? 1 : 0;
         }
@@ -2156,6 +2169,10 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
     for (int k = 0; k <= n_steps; ++k) {
         const int phase = (k > 0 ? PH_UPDATE : 0) | (k < n_steps ? PH_FLOWS : 0);
         Ctx cp = make_ctx(net, st, io, phase, t0 + k - 1, t0 + k, rng_mode, k - 1, k);
+        // constant route rows are evaluated on step 1 and whenever the caller asks (first step after an init)
+        const int route_all = (t0 + k == 1 || (k == 0 && io && io->route_all_rows)) ? 1 : 0;
+        cp.route_all = route_all;
+        const size_t n_route = (size_t)(route_all ? net->n_rows : net->n_dyn_rows) * net->replicas;
 #ifndef PNS_HOST_EMULATION
         // streamed runs: the single-replica link kernel accumulates the step's pedestrian count itself
         const bool lane_metric = sx && k > 0 && net->replicas == 1 && !getenv("PNS_PAIR_THREADS");
@@ -2188,7 +2205,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         // step 1 of an environment, where it reads the widths this launch sets)
         bool route_rides = false;
 #ifndef PNS_HOST_EMULATION
-        route_rides = (phase & PH_FLOWS) && z.n_grp && z.n_pair && !ev && !getenv("PNS_ROUTE_SEPARATE") &&
+        route_rides = (phase & PH_FLOWS) && n_route && z.n_pair && !ev && !getenv("PNS_ROUTE_SEPARATE") &&
                       !(t0 + k == 1 && ride && ride->actions) &&
                       (rep_kernel_applies(net, rng_mode) || (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")));
 #endif
@@ -2211,8 +2228,9 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         }
 #endif
         if (k == n_steps) break;
-        const Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
-        if (z.n_grp && !route_rides) PNS_LAUNCH_CHAIN(k_route_fractions, blocks_for(z.n_grp), kBlock, s, cn);
+        Ctx cn = make_ctx(net, st, io, 0, t0 + k, t0 + k, rng_mode, k, k);
+        cn.route_all = route_all;
+        if (n_route && !route_rides) PNS_LAUNCH_CHAIN(k_route_fractions, blocks_for(n_route), kBlock, s, cn);
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
         PNS_MARK(k, 3);

@@ -22,7 +22,7 @@ from . import _native, ops
 from .state import F32_INDEX, F64_FIELDS, F64_INDEX
 
 _NET_ARRAYS = ("lk_class", "lk_width", "nd_meta", "nd_routed", "lk_slots", "nd_in_link",
-               "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od", "rt_grp_node", "rt_grp_up",
+               "rt_routed_nodes", "rt_routed_edge0", "rt_routed_row0", "rt_row_routed", "rt_row_grp_ptr", "rt_row_grp", "rt_term_od", "rt_dyn_rows", "rt_grp_node", "rt_grp_up",
                "rt_grp_od", "rt_grp_has_virtual", "rt_opt_ptr", "rt_opt_link", "rt_opt_slot",
                "rt_opt_dist", "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt",
                "rt_term_row_entry")
@@ -75,6 +75,7 @@ class Engine:
         net.n_opts = len(p["rt_opt_link"])
         net.n_rows = len(p["rt_row_ptr"]) - 1
         net.n_terms = len(p["rt_term_opt"])
+        net.n_dyn_rows = len(p["rt_dyn_rows"])
         net.n_classes = len(p["classes"])
         net.max_degree = int(p["max_degree"])
         net.nd_stride = int(p["nd_stride"])
@@ -177,18 +178,21 @@ class Engine:
         io = self._table_io if (rng_mode == _native.RNG_TABLE and self._table_io is not None) else self.io
         _native.check(self.lib, self.lib.pns_step(C.byref(self.net), C.byref(self.state), C.byref(io),
                                                   t0, n_steps, rng_mode, self._stream()), "pns_step")
+        self._route_all(False)
 
     def _native_step_streamed(self, t0, n_steps, rng_mode):
         host_demand, host_metric = self._streamed_host
         _native.check(self.lib, self.lib.pns_step_streamed(
             C.byref(self.net), C.byref(self.state), C.byref(self.io), t0, n_steps, rng_mode,
             _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")
+        self._route_all(False)
 
     def _native_env_step(self, actions, obs, reward, cum_reward, t):
         _native.check(self.lib, self.lib.pns_env_step(
             C.byref(self.net), C.byref(self.state), C.byref(self.io), C.byref(self._env_struct),
             _ptr(actions) if actions is not None else C.c_void_p(0), int(t), _native.RNG_PHILOX, _ptr(obs), _ptr(reward),
             _ptr(cum_reward), self._stream()), "pns_env_step")
+        self._route_all(False)
 
     def _native_kpi(self, role, scratch, out, t_last, any_od_path):
         _native.check(self.lib, self.lib.pns_kpi(C.byref(self.net), C.byref(self.state), C.byref(self.io),
@@ -214,6 +218,13 @@ class Engine:
         self.t_done = 0
         self._last_row = 0
         self._initialised = True
+        self._route_all(True)
+
+    def _route_all(self, flag: bool):
+        """Whether the next step call evaluates every route row (constant rows included) or only the dynamic ones."""
+        self.io.route_all_rows = 1 if flag else 0
+        if self._table_io is not None:
+            self._table_io.route_all_rows = self.io.route_all_rows
 
     def _begin_steps(self, t0: int, n_steps: int):
         """Row contract of the node pass (pns_b200.h, pns_node_flows): inflow/outflow rows of a step must be
@@ -455,6 +466,7 @@ class Engine:
             _native.check(self.lib, self.lib.pns_step_profiled(
                 C.byref(self.net), C.byref(self.state), C.byref(io), t0, n_steps, rng_mode, self._stream(),
                 ms, cnt), "pns_step_profiled")
+            self._route_all(False)
         self.t_done = t0 + n_steps - 1
         return list(ms), list(cnt)
 

@@ -176,7 +176,19 @@ def route_row_tables(p):
         ptr[1:] = np.cumsum(np.bincount(grp_row, minlength=n_rows))
     term_od = np.asarray(p["rt_row_od"], dtype=np.int32)[np.asarray(p["rt_term_row_entry"], dtype=np.int64)] \
         if len(p["rt_term_row_entry"]) else np.zeros(0, dtype=np.int32)
-    return dict(rt_row_routed=row_routed, rt_row_grp_ptr=ptr, rt_row_grp=order, rt_term_od=_i32(term_od))
+    # Rows whose fractions can change from step to step: a group with several options (the logit depends on
+    # densities and receiving flows) or several registered ODs (P(od | up) depends on the step's OD weights).
+    # Every other row -- nothing registered, or single-option groups of a single OD -- evaluates to the same
+    # constants on every step (P(down | up, od) = exp(x)/exp(x) = 1, P(od | up) = w/w = 1): the route kernel
+    # computes those once, on the first step after the state is initialised.
+    n_opt = np.diff(np.asarray(p["rt_opt_ptr"], dtype=np.int64)) if len(p["rt_opt_ptr"]) > 1 else np.zeros(0, dtype=np.int64)
+    row_ods = np.diff(np.asarray(p["rt_row_ptr"], dtype=np.int64))
+    dynamic = row_ods > 1
+    for g, row in enumerate(grp_row):
+        if n_opt[g] > 1:
+            dynamic[row] = True
+    return dict(rt_row_routed=row_routed, rt_row_grp_ptr=ptr, rt_row_grp=order, rt_term_od=_i32(term_od),
+                rt_dyn_rows=_i32(np.nonzero(dynamic)[0]))
 
 
 def attach_empty_route_plan(p):
