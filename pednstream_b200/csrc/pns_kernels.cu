@@ -107,6 +107,9 @@ constexpr int kBlock = 128;
 #ifndef PNS_NODE_BLOCK
 #define PNS_NODE_BLOCK 128     // threads per CTA of k_node_flows
 #endif
+#ifndef PNS_NODE_COLS_MAX_REPLICAS
+#define PNS_NODE_COLS_MAX_REPLICAS (1 << 30)   // k_node_cols up to this many replicas per GPU (measured faster at 1024 .. 8192)
+#endif
 #ifndef PNS_NODE_MIN_BLOCKS
 #define PNS_NODE_MIN_BLOCKS 4  // 72 registers, no spills; 4..8 measured within 1%
 #endif
@@ -820,13 +823,15 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
     const size_t base = (size_t)node * c.n.nd_stride;
     double s[CAP], r[CAP];
     int in_link[CAP];                                                       // incoming link column of each slot
-    if (ROUTED && tf_mode == 2) {
-        // the m(m-1) routed fractions are read one by one deep inside the column loop: ask for them now, together
-        // with the hand-over loads, instead of paying a memory round trip each
+    // The m(m-1) routed fractions are used one by one deep inside the column loop; read there, each costs its own
+    // memory round trip (measured: a third of the kernel's stall samples, 6 us of serial latency per CTA).  With a
+    // compile-time slot count they are fetched here in one batch with the hand-over loads.
+    constexpr bool PRELOAD = ROUTED && M > 0;
+    double tfv[PRELOAD ? M * (M - 1) : 1];
+    if (PRELOAD && tf_mode == 2) {
         const double* t0 = c.s.tf_routed + (size_t)tf_ptr * R + rep;
 #pragma unroll
-        for (int k = 0; k < CAP * (CAP - 1); ++k)
-            if (k < m * (m - 1)) prefetch_l1(t0 + (size_t)k * R);
+        for (int k = 0; k < M * (M - 1); ++k) tfv[k] = t0[(size_t)k * R];
     }
     if (M == 4) {
         const int4 v = __ldg(reinterpret_cast<const int4*>(c.n.nd_in_link + base));
@@ -908,7 +913,8 @@ __device__ __forceinline__ void node_body(const Ctx& c, int node, int rep, int m
             for (int i = 0; i < m; ++i) {
                 w[i] = 0.0;
                 if (i == j) continue;
-                w[i] = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i] : s[i];
+                if (PRELOAD && tf_mode == 2) w[i] = tfv[(i * (M - 1) + (j < i ? j : j - 1)) % (PRELOAD ? M * (M - 1) : 1)] * s[i];
+                else w[i] = tf ? tf[(size_t)(i * (m - 1) + (j < i ? j : j - 1)) * ts] * s[i] : s[i];
                 D = D + w[i];
             }
             D = D != 0.0 ? D : 1e-5;
@@ -983,6 +989,138 @@ __global__ void __launch_bounds__(PNS_NODE_BLOCK, PNS_NODE_MIN_BLOCKS) k_node_fl
         default: node_body_generic<R1, ROUTED>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
     }
 }
+
+#ifndef PNS_HOST_EMULATION
+// =================================================================================================
+// Batched replicas: the node model with one *warp per slot*.  A CTA is one node for 32 replicas; warp j owns slot j
+// (outgoing link j, receiving flow r[j]): it forms column j of the classic model -- W[i][j] = P[i][j] s[i],
+// D[j] = sum_i W[i][j] in slot order, f[i][j] = floor(min(W, r[j] (W/D))) -- and the inflow of its outgoing link,
+// q_in[j] = sum_i f[i][j]; the flows meet in shared memory, and after one barrier warp j adds up row j, the
+// outflow of its incoming link, q_out[j] = sum_j' f[j][j'] (same summation orders as node_body).  Against one
+// thread per node this is a quarter of the dependent arithmetic per thread, a third of the registers and four
+// times the warps: the thread-per-node kernel spent 25 us at 4096 replicas on 25 MB of traffic (9 us its loads,
+// 7 us the solve, 8 us the routed fractions), its duration almost independent of the replica count.
+// W = slots per node the launch provides warps for (pns_net.nd_stride: 4 or 8); warps beyond the node's slot count
+// leave at once, the others meet at a named barrier sized to the node.
+// Body for a node with M slots (compile-time: every loop is exact and every small array lives in registers).
+template <bool ROUTED, int W, int M>
+__device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][32], int node, int j, int lane, int rep,
+                                               bool valid, int kind, int tf_mode, int dem_row, int tf_ptr) {
+    const int R = c.n.replicas;
+    const size_t base = (size_t)node * c.n.nd_stride;
+    const int col = __ldg(c.n.nd_in_link + base + j);
+    PNS_PDL_WAIT();
+    // ---- one batch of loads: all sending flows, this slot's receiving flow, column j of the fractions ----
+    double s[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = c.s.nm_s[(base + i) * R + rep];
+    double r_j = c.s.nm_r[(base + j) * R + rep];
+    double r_other = (M == 2 && kind == 0) ? c.s.nm_r[(base + (1 - j)) * R + rep] : 0.0;
+    double P[M];
+    if (kind != 0) {
+        const double phi = 1.0 / (double)(M - 1);
+        const double* tf = nullptr;
+        size_t ts = 1;
+        if (ROUTED && tf_mode == 2) { tf = c.s.tf_routed + (size_t)tf_ptr * R + rep; ts = (size_t)R; }
+        else if (tf_mode == 1) tf = c.s.tf_static + tf_ptr;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            P[i] = i != j ? (tf ? tf[(size_t)(i * (M - 1) + (j < i ? j : j - 1)) * ts] : phi) : 0.0;
+    }
+    double v_cout = 0.0, v_cin = 0.0;          // counters of the virtual links (kept by warp 0, their slot)
+    size_t vin = 0;
+    if (dem_row >= 0) {                        // slot 0 is the virtual O/D link pair
+        s[0] = c.n_demand[(size_t)dem_row * R + rep];                       // node.py:176
+        vin = (size_t)(c.n.n_links + 2 * dem_row) * R + rep;
+        if (j == 0) r_j = 1e6;                                              // node.py:186
+        if (M == 2 && kind == 0 && j == 1) r_other = 1e6;
+        if (j == 0) { v_cout = c.n_coutp[vin]; v_cin = c.n_cinp[vin + R]; }
+    }
+    double s_j = 0.0, s_other = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) { if (i == j) s_j = s[i]; if (i == 1 - j) s_other = s[i]; }
+    if (valid && ((s_j < 0.0) | (r_j < 0.0))) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
+    bool any_flow = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) any_flow |= s[i] != 0.0;
+    double q_in = 0.0, q_out = 0.0;
+    if (M == 2 && kind == 0) {
+        // OneToOneNode.solve (node.py:230-242): exactly two slots
+        q_out = fmin(s_j, r_other);
+        q_in = fmin(s_other, r_j);
+    } else {
+        // RegularNode.solve, 'classic' (node.py:272-300), column j
+        double D = 0.0;                        // np.sum(axis=0): rows added in order (the diagonal adds an exact 0)
+        double w[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            w[i] = 0.0;
+            if (i == j) continue;
+            w[i] = P[i] * s[i];
+            D = D + w[i];
+        }
+        D = D != 0.0 ? D : 1e-5;
+        double in_j = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            if (i == j) continue;
+            const double f = turn_flow(w[i], r_j, D);
+            sh_f[j][i][lane] = f;
+            in_j += f;
+        }
+        q_in = fmax(0.0, in_j);
+        asm volatile("bar.sync 1, %0;" :: "r"(32 * M) : "memory");
+#pragma unroll
+        for (int jj = 0; jj < M; ++jj)
+            if (jj != j) q_out += sh_f[jj][j][lane];
+        q_out = fmax(0.0, q_out);
+    }
+    if (!valid) return;
+    // Node.update_links (node.py:146-162); a node that receives no sending flow stores nothing (rows are zero by
+    // contract, see pns_node_flows), only the counters of its virtual links carry forward
+    if (any_flow) {
+        c.n_outflow[(size_t)col * R + rep] = q_out;
+        c.n_inflow[(size_t)(col ^ 1) * R + rep] = q_in;
+    }
+    if (dem_row >= 0 && j == 0) {
+        // the virtual links have no link thread: slot 0's flows extend their counters (link.py:19-25)
+        c.n_cout[vin] = v_cout + (any_flow ? q_out : 0.0);
+        c.n_cin[vin + R] = v_cin + (any_flow ? q_in : 0.0);
+    }
+}
+
+template <bool ROUTED, int W>
+__global__ void __launch_bounds__(32 * W) k_node_cols(const __grid_constant__ Ctx c) {
+    __shared__ double sh_f[W][W][32];          // f[j][i][lane]: flow from slot i into slot j's outgoing link
+    const int R = c.n.replicas;
+    const int node = (int)blockIdx.y;
+    const int j = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    const int rep_raw = (int)blockIdx.x * 32 + lane;
+    const bool valid = rep_raw < R;
+    const int rep = valid ? rep_raw : R - 1;
+    PNS_PDL_TRIGGER();
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
+    const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
+    if (m < 2 || j >= m) return;               // dead end / isolated node; warps without a slot
+#define PNS_COLS(MM) node_cols_body<ROUTED, W, MM>(c, sh_f, node, j, lane, rep, valid, kind, tf_mode, meta.z, meta.w)
+    switch (m) {
+        case 2: PNS_COLS(2); break;
+        case 3: PNS_COLS(3); break;
+        case 4: PNS_COLS(4); break;
+        default:
+            if (W > 4) {
+                switch (m) {
+                    case 5: PNS_COLS((W > 4 ? 5 : 2)); break;
+                    case 6: PNS_COLS((W > 4 ? 6 : 2)); break;
+                    case 7: PNS_COLS((W > 4 ? 7 : 2)); break;
+                    default: PNS_COLS((W > 4 ? 8 : 2)); break;
+                }
+            }
+            break;
+    }
+#undef PNS_COLS
+}
+#endif
 
 #ifndef PNS_HOST_EMULATION
 // =================================================================================================
@@ -2079,6 +2217,22 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, con
 }
 void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     const bool routed = net->n_routed > 0;
+#ifndef PNS_HOST_EMULATION
+    static const int cols_max = getenv("PNS_NODE_COLS_MAX") ? atoi(getenv("PNS_NODE_COLS_MAX")) : PNS_NODE_COLS_MAX_REPLICAS;
+    if (net->replicas > 1 && net->replicas <= cols_max && !getenv("PNS_PAIR_THREADS")) {
+        // batched replicas, small batches: one warp per node slot (latency); large batches keep one thread per node
+        // (fewer instructions per node)
+        const dim3 grid((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)net->n_nodes);
+        if (net->nd_stride <= 4) {
+            if (routed) PNS_LAUNCH_CHAIN((k_node_cols<true, 4>), grid, 128, s, c);
+            else PNS_LAUNCH_CHAIN((k_node_cols<false, 4>), grid, 128, s, c);
+        } else {
+            if (routed) PNS_LAUNCH_CHAIN((k_node_cols<true, 8>), grid, 256, s, c);
+            else PNS_LAUNCH_CHAIN((k_node_cols<false, 8>), grid, 256, s, c);
+        }
+        return;
+    }
+#endif
     const unsigned nb = (unsigned)((n + PNS_NODE_BLOCK - 1) / PNS_NODE_BLOCK);
     if (net->replicas == 1) {
         if (routed) PNS_LAUNCH_CHAIN((k_node_flows<true, true>), nb, PNS_NODE_BLOCK, s, c);
