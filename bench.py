@@ -276,12 +276,16 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
             dist.barrier()
         torch.cuda.synchronize()
 
+    roll_obs = torch.empty((steps, R, env.n_obs), dtype=torch.float32, device=dev)
+    roll_rew = torch.empty((steps, R), dtype=torch.float32, device=dev)
+    roll_act = pool.repeat((steps + 15) // 16, 1, 1)[:steps].contiguous()
+
     def timed(n):
+        """n env steps with device-resident random actions in one native call (BatchedPedNetEnv.rollout)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for k in range(n):
-            env.step(pool[k & 15])
+        env.rollout(roll_act[:n], roll_obs[:n], roll_rew[:n])
         e1.record()
         barrier()
         return e0.elapsed_time(e1)

@@ -303,10 +303,22 @@ int pns_env_observe(const pns_net *net, const pns_state *st, const pns_env *env,
 
 /* One environment step (rl/pz_pednet_env.py:194-254 with action_gap 1) in one call: apply the actions (skipped when
  * `actions` is NULL), Network.network_loading(t), build observations and the reward; `cum_reward` (optional, [R])
- * accumulates the rewards.  Same launches as pns_env_apply_actions + pns_step + pns_env_observe. */
+ * accumulates the rewards.  Same results as pns_env_apply_actions + pns_step + pns_env_observe.
+ * Batched replicas with the per-link programs of pns_env run three launches: actions ride in the flow launch,
+ * observations and reward in the state-update launch. */
 int pns_env_step(const pns_net *net, const pns_state *st, const pns_step_io *io, const pns_env *env,
                  const float *actions, int t, int rng_mode, float *obs, float *reward, float *cum_reward,
                  void *stream);
+
+/* n_steps environment steps t0 .. t0+n_steps-1 in one call (a rollout with given actions, e.g. random gate actions).
+ * Device-resident form (host_* NULL): actions [n_steps][R*n_act], obs [n_steps][R*n_obs], reward [n_steps][R] on the
+ * device.  Host form: host_actions / host_obs / host_reward are pinned host arrays of those shapes and actions / obs /
+ * reward are device staging buffers for TWO steps ([2][...]); every step has its own host->device copy of its actions
+ * and device->host copy of its observations and rewards, on two internal copy streams, double-buffered against the
+ * step kernels.  Returns with everything enqueued; after synchronising `stream` the results are complete. */
+int pns_env_rollout(const pns_net *net, const pns_state *st, const pns_step_io *io, const pns_env *env, int t0,
+                    int n_steps, int rng_mode, const float *actions, float *obs, float *reward, float *cum_reward,
+                    const float *host_actions, float *host_obs, float *host_reward, void *stream);
 
 /* Origin demand of a batch of replicas, drawn on the device (reference od_manager.py:100-155): demand[t][row*R + r]
  * for t = 0..sim_steps.  pattern[row*R + r]: 0 gaussian_peaks = Poisson(base + peak*bump1[t] + peak*bump2[t]),

@@ -77,7 +77,7 @@ OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens"
 
 
 EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_fractions",
-           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_env_step", "pns_env_draw_demand", "pns_env_randomize", "pns_kpi",
+           "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_env_step", "pns_env_rollout", "pns_env_draw_demand", "pns_env_randomize", "pns_kpi",
            "pns_lane_block_size", "pns_rng_selftest")
 
 _LIB = None
@@ -102,6 +102,7 @@ def _declare(lib):
                                       C.c_uint32, _p]
     lib.pns_kpi.argtypes = [net_p, st_p, io_p, C.c_int, _p, C.c_int, _p, _p, _p]
     lib.pns_env_step.argtypes = [net_p, st_p, io_p, env_p, _p, C.c_int, C.c_int, _p, _p, _p, _p]
+    lib.pns_env_rollout.argtypes = [net_p, st_p, io_p, env_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
     lib.pns_env_observe.argtypes = [net_p, st_p, env_p, C.c_int, _p, _p, _p]
     lib.pns_rng_selftest.argtypes = [C.c_int, C.c_int, _p, _p, C.c_uint64, C.c_int, C.c_int, _p, _p, _p]
     for name in EXPORTS[2:]:

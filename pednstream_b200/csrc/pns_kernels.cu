@@ -2258,7 +2258,7 @@ constexpr size_t kMetricRow = (size_t)PNS_METRIC_SLOTS * PNS_METRIC_STRIDE;   //
 // process; a re-recorded event does not disturb waits that were enqueued on its earlier record).  The table is
 // guarded by a mutex: ctypes callers release the GIL, so two host threads may be inside the library at once.
 struct SideStream {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;    // host->device copies / device->host copies
     cudaEvent_t ring[256];
     int next = 0;
     bool ok = false;
@@ -2273,6 +2273,7 @@ SideStream* side_stream_for_current_device() {
     SideStream& s = table[d];
     if (!s.ok) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (auto& e : s.ring)
             if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         s.ok = true;
@@ -2524,28 +2525,116 @@ int pns_env_observe(const pns_net* net, const pns_state* st, const pns_env* env,
     return launched("k_env_observe");
 }
 
+namespace {
+bool env_fused_path(const pns_net* net, const pns_env* env, int rng_mode) {
+#ifndef PNS_HOST_EMULATION
+    return env->lk_act && env->lk_obs_ptr && env->lk_reward && env->reward_count && rep_kernel_applies(net, rng_mode);
+#else
+    (void)net; (void)env; (void)rng_mode;
+    return false;
+#endif
+}
+
+// one environment step
+int env_step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, const pns_env* env,
+                  const float* actions, int t, int rng_mode, float* obs, float* reward, float* cum_reward,
+                  cudaStream_t stream) {
+    if (env_fused_path(net, env, rng_mode)) {
+        // batched replicas: actions ride in the FLOWS launch, observations and reward in the UPDATE launch
+        EnvRide ride;
+        memset(&ride, 0, sizeof ride);
+        ride.env = env; ride.actions = (actions && env->n_act > 0) ? actions : nullptr;
+        ride.obs = obs; ride.reward = reward; ride.cum_reward = cum_reward;
+        return step_impl(net, st, io, t, 1, rng_mode, stream, nullptr, nullptr, nullptr, &ride);
+    }
+    if (actions && env->n_act > 0 && pns_env_apply_actions(net, st, env, actions, stream)) return 1;
+    if (step_impl(net, st, io, t, 1, rng_mode, stream, nullptr, nullptr)) return 1;
+    const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
+    EnvCtx x;
+    memset(&x, 0, sizeof x);
+    x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
+    x.env = *env; x.obs = obs; x.reward = reward; x.cum_reward = cum_reward;
+    PNS_LAUNCH_CHAIN(k_env_observe, blocks_for(n), kBlock, stream, x);
+    return launched("k_env_observe");
+}
+}  // namespace
+
 int pns_env_step(const pns_net* net, const pns_state* st, const pns_step_io* io, const pns_env* env,
                  const float* actions, int t, int rng_mode, float* obs, float* reward, float* cum_reward,
                  void* stream) {
     if (!net || !st || !env || !obs || !reward) return fail("pns_env_step: null argument");
     if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_step: too many reward links");
+    return env_step_impl(net, st, io, env, actions, t, rng_mode, obs, reward, cum_reward, (cudaStream_t)stream);
+}
+
+int pns_env_rollout(const pns_net* net, const pns_state* st, const pns_step_io* io, const pns_env* env, int t0,
+                    int n_steps, int rng_mode, const float* actions, float* obs, float* reward, float* cum_reward,
+                    const float* host_actions, float* host_obs, float* host_reward, void* stream) {
+    if (!net || !st || !env || !obs || !reward) return fail("pns_env_rollout: null argument");
+    if (env->n_reward_links > PNS_MAX_DEGREE) return fail("pns_env_rollout: too many reward links");
+    if (n_steps <= 0) return 0;
+    if (t0 < 1 || t0 + n_steps - 1 > net->sim_steps) return fail("pns_env_rollout: steps out of range");
+    const bool host = host_actions || host_obs || host_reward;
+    if (host && !(host_obs && host_reward && (host_actions || env->n_act == 0)))
+        return fail("pns_env_rollout: host form needs all host buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t na = (size_t)net->replicas * env->n_act, no = (size_t)net->replicas * env->n_obs, nr = (size_t)net->replicas;
 #ifndef PNS_HOST_EMULATION
-    if (env->lk_act && env->lk_obs_ptr && env->lk_reward && env->reward_count && rep_kernel_applies(net, rng_mode)) {
-        // batched replicas: actions ride in the FLOWS launch, observations and reward in the UPDATE launch
-        EnvRide ride;
-        ride.env = env; ride.actions = (actions && env->n_act > 0) ? actions : nullptr;
-        ride.obs = obs; ride.reward = reward; ride.cum_reward = cum_reward;
-        return step_impl(net, st, io, t, 1, rng_mode, (cudaStream_t)stream, nullptr, nullptr, nullptr, &ride);
+    SideStream* side = host ? side_stream_for_current_device() : nullptr;
+    if (host && !side) return fail("pns_env_rollout: copy streams / events could not be created", cudaGetLastError());
+    cudaEvent_t up_done[2] = {nullptr, nullptr}, step_done[2] = {nullptr, nullptr}, down_done[2] = {nullptr, nullptr};
+    if (host) {
+        cudaEvent_t e = side->event();                 // the copy streams start after everything queued so far
+        cudaEventRecord(e, s);
+        cudaStreamWaitEvent(side->stream, e, 0);
+        cudaStreamWaitEvent(side->stream2, e, 0);
+        if (na) cudaMemcpyAsync(const_cast<float*>(actions), host_actions, na * sizeof(float), cudaMemcpyHostToDevice, side->stream);
+        up_done[0] = side->event();
+        cudaEventRecord(up_done[0], side->stream);
+    }
+#else
+    if (host) return fail("pns_env_rollout: host form needs the CUDA build");
+#endif
+    for (int k = 0; k < n_steps; ++k) {
+        const int slot = host ? (k & 1) : k;
+#ifndef PNS_HOST_EMULATION
+        if (host) {
+            cudaStreamWaitEvent(s, up_done[k & 1], 0);                       // this step's actions are on the device
+            if (k >= 2) cudaStreamWaitEvent(s, down_done[k & 1], 0);         // results of step k-2 have left this slot
+        }
+#endif
+        if (env_step_impl(net, st, io, env, env->n_act ? actions + (size_t)slot * na : nullptr, t0 + k, rng_mode,
+                          obs + (size_t)slot * no, reward + (size_t)slot * nr, cum_reward, s))
+            return 1;
+#ifndef PNS_HOST_EMULATION
+        if (host) {
+            step_done[k & 1] = side->event();
+            cudaEventRecord(step_done[k & 1], s);
+            if (k + 1 < n_steps) {                     // next step's actions (its slot was read by step k-1)
+                if (k >= 1) cudaStreamWaitEvent(side->stream, step_done[(k + 1) & 1], 0);
+                if (na) cudaMemcpyAsync(const_cast<float*>(actions) + (size_t)((k + 1) & 1) * na, host_actions + (size_t)(k + 1) * na,
+                                        na * sizeof(float), cudaMemcpyHostToDevice, side->stream);
+                up_done[(k + 1) & 1] = side->event();
+                cudaEventRecord(up_done[(k + 1) & 1], side->stream);
+            }
+            cudaStreamWaitEvent(side->stream2, step_done[k & 1], 0);          // this step's results
+            cudaMemcpyAsync(host_obs + (size_t)k * no, obs + (size_t)(k & 1) * no, no * sizeof(float), cudaMemcpyDeviceToHost, side->stream2);
+            cudaMemcpyAsync(host_reward + (size_t)k * nr, reward + (size_t)(k & 1) * nr, nr * sizeof(float), cudaMemcpyDeviceToHost, side->stream2);
+            down_done[k & 1] = side->event();
+            cudaEventRecord(down_done[k & 1], side->stream2);
+        }
+#endif
+    }
+#ifndef PNS_HOST_EMULATION
+    if (host) {                                        // the caller synchronises `stream` only
+        cudaEvent_t e1 = side->event(), e2 = side->event();
+        cudaEventRecord(e1, side->stream);
+        cudaEventRecord(e2, side->stream2);
+        cudaStreamWaitEvent(s, e1, 0);
+        cudaStreamWaitEvent(s, e2, 0);
     }
 #endif
-    if (actions && env->n_act > 0 && pns_env_apply_actions(net, st, env, actions, stream)) return 1;
-    if (step_impl(net, st, io, t, 1, rng_mode, (cudaStream_t)stream, nullptr, nullptr)) return 1;
-    const size_t n = (size_t)env->n_obs * net->replicas + (size_t)net->replicas;
-    EnvCtx x;
-    x.c = make_ctx(net, st, nullptr, 0, t, t, PNS_RNG_TABLE, 0, 0);
-    x.env = *env; x.actions = nullptr; x.obs = obs; x.reward = reward; x.cum_reward = cum_reward;
-    PNS_LAUNCH_CHAIN(k_env_observe, blocks_for(n), kBlock, (cudaStream_t)stream, x);
-    return launched("k_env_observe");
+    return launched("pns_env_rollout");
 }
 
 int pns_step_streamed(const pns_net* net, const pns_state* st, const pns_step_io* io, int t0, int n_steps,

@@ -194,6 +194,14 @@ class Engine:
             _ptr(cum_reward), self._stream()), "pns_env_step")
         self._route_all(False)
 
+    def _native_env_rollout(self, actions, obs, reward, cum_reward, t0, n_steps, host=None):
+        h = [_ptr(x) if x is not None else C.c_void_p(0) for x in (host or (None, None, None))]
+        _native.check(self.lib, self.lib.pns_env_rollout(
+            C.byref(self.net), C.byref(self.state), C.byref(self.io), C.byref(self._env_struct), int(t0), int(n_steps),
+            _native.RNG_PHILOX, _ptr(actions) if actions is not None else C.c_void_p(0), _ptr(obs), _ptr(reward),
+            _ptr(cum_reward), h[0], h[1], h[2], self._stream()), "pns_env_rollout")
+        self._route_all(False)
+
     def _native_kpi(self, role, scratch, out, t_last, any_od_path):
         _native.check(self.lib, self.lib.pns_kpi(C.byref(self.net), C.byref(self.state), C.byref(self.io),
                                                  int(t_last), _ptr(role), int(bool(any_od_path)), _ptr(scratch),

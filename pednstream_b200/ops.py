@@ -69,6 +69,13 @@ def _env_step(hist64, hist32, runsum, tf_routed, probs, err, gate, actions, obs,
     _engine(handle)._native_env_step(actions if has_actions else None, obs, reward, cum_reward, t)
 
 
+def _env_rollout(hist64, hist32, runsum, tf_routed, probs, err, gate, actions, obs, reward, cum_reward, handle, t0,
+                 n_steps, has_actions):
+    """n_steps environment steps with given device-resident actions [n_steps, R, n_act] in one native call
+    (C-ABI pns_env_rollout): obs [n_steps, R, n_obs], reward [n_steps, R]."""
+    _engine(handle)._native_env_rollout(actions if has_actions else None, obs, reward, cum_reward, t0, n_steps)
+
+
 def _episode_kpis(hist64, hist32, demand, role, scratch, out, handle, t_last, any_od_path):
     """Per-replica episode KPIs from history rows 0..t_last (reference rl/rl_utils.py:770-1512; C-ABI pns_kpi)."""
     _engine(handle)._native_kpi(role, scratch, out, t_last, any_od_path)
@@ -91,6 +98,10 @@ env_step = _define(
     "env_step(Tensor(a!) hist64, Tensor(b!) hist32, Tensor(c!) runsum, Tensor(d!) tf_routed, Tensor(e!) probs, "
     "Tensor(f!) err, Tensor(g!) gate, Tensor actions, Tensor(h!) obs, Tensor(i!) reward, Tensor(j!) cum_reward, "
     "int handle, int t, bool has_actions) -> ()", _env_step)
+env_rollout = _define(
+    "env_rollout(Tensor(a!) hist64, Tensor(b!) hist32, Tensor(c!) runsum, Tensor(d!) tf_routed, Tensor(e!) probs, "
+    "Tensor(f!) err, Tensor(g!) gate, Tensor actions, Tensor(h!) obs, Tensor(i!) reward, Tensor(j!) cum_reward, "
+    "int handle, int t0, int n_steps, bool has_actions) -> ()", _env_rollout)
 episode_kpis = _define(
     "episode_kpis(Tensor hist64, Tensor hist32, Tensor demand, Tensor role, Tensor(a!) scratch, Tensor(b!) out, "
     "int handle, int t_last, bool any_od_path) -> ()", _episode_kpis)

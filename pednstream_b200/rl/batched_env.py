@@ -432,54 +432,59 @@ class BatchedPedNetEnv:
         self.sim_step += 1
         return obs, reward, done, {"step": self.sim_step - 1}
 
+    def rollout(self, actions: torch.Tensor, obs_out: torch.Tensor = None, reward_out: torch.Tensor = None):
+        """K environment steps with given actions ([K, R, n_act] float32 on the device) in one native call
+        (`torch.ops.pednstream.env_rollout` -> pns_env_rollout): returns (obs [K, R, n_obs], reward [K, R], done)."""
+        eng = self.engine
+        K = int(actions.shape[0])
+        if self.sim_step + K - 1 > self.simulation_steps:
+            raise RuntimeError("rollout runs past the end of the episode")
+        if tuple(actions.shape[1:]) != (self.R, self.n_act) or actions.dtype != torch.float32:
+            raise ValueError(f"actions must be float32 [K, {self.R}, {self.n_act}]")
+        actions = actions.contiguous()
+        obs = obs_out if obs_out is not None else torch.empty((K, self.R, self.obs.shape[1]), dtype=torch.float32, device=self.device)
+        rew = reward_out if reward_out is not None else torch.empty((K, self.R), dtype=torch.float32, device=self.device)
+        with eng._guard():
+            eng._begin_steps(self.sim_step, K)
+            has_actions = self.n_act > 0
+            ops.env_rollout(eng.hist64, eng.hist32, eng.runsum, eng.tf_routed, eng.probs, eng.err, eng.gate,
+                            actions if has_actions else self._no_actions, obs, rew, self.cumulative_reward,
+                            eng.handle, int(self.sim_step), K, has_actions)
+        self.sim_step += K
+        eng.t_done = self.sim_step - 1
+        self.obs.copy_(obs[K - 1]); self.reward.copy_(rew[K - 1])
+        return obs, rew, self.sim_step > self.simulation_steps
+
     def rollout_host(self, host_actions: torch.Tensor, host_obs: torch.Tensor, host_reward: torch.Tensor):
-        """K environment steps driven from host memory: step k takes `host_actions[k]` ([K, R, n_act] pinned
-        float32) and delivers its observations and rewards to `host_obs[k]` ([K, R, n_obs]) / `host_reward[k]`
-        ([K, R]), both pinned.  Every step has its own host->device and device->host copies; they run on two
-        copy streams, double-buffered against the step kernels (actions of step k+1 go up and results of step
-        k come down while the other step computes).  Returns after everything is enqueued; synchronise the
-        device (or the current stream) before reading the host tensors."""
+        """K environment steps driven from host memory in one native call (pns_env_rollout, host form): step k takes
+        `host_actions[k]` ([K, R, n_act] pinned float32) and delivers its observations and rewards to `host_obs[k]`
+        ([K, R, n_obs]) / `host_reward[k]` ([K, R]), both pinned.  Every step has its own host->device and
+        device->host copies; they run on two copy streams, double-buffered against the step kernels (actions of step
+        k+1 go up and results of step k come down while the other step computes).  Returns after everything is
+        enqueued; synchronise the device (or the current stream) before reading the host tensors."""
         K = int(host_actions.shape[0])
         if not (host_actions.is_pinned() and host_obs.is_pinned() and host_reward.is_pinned()):
             raise ValueError("rollout_host needs pinned host tensors")
         if host_obs.shape[0] < K or host_reward.shape[0] < K:
             raise ValueError("host_obs / host_reward are shorter than host_actions")
-        dev = self.device
-        if not hasattr(self, "_pipe"):
-            mk = lambda shape: [torch.zeros(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-            self._pipe = dict(act=mk((self.R, max(1, self.n_act))), obs=mk(tuple(self.obs.shape)), rew=mk((self.R,)),
-                              up=torch.cuda.Stream(dev), down=torch.cuda.Stream(dev),
-                              up_done=[torch.cuda.Event() for _ in range(2)],
-                              step_done=[torch.cuda.Event() for _ in range(2)],
-                              down_done=[torch.cuda.Event() for _ in range(2)])
-        P = self._pipe
-        main = torch.cuda.current_stream(dev)
-        up, down = P["up"], P["down"]
-        up.wait_stream(main)
-        down.wait_stream(main)
-        with torch.cuda.stream(up):                                  # actions of the first step
-            P["act"][0][:, : self.n_act].copy_(host_actions[0], non_blocking=True)
-            P["up_done"][0].record(up)
-        for k in range(K):
-            s = k & 1
-            main.wait_event(P["up_done"][s])
-            if k >= 2:
-                main.wait_event(P["down_done"][s])                    # results of step k-2 have left this buffer set
-            self.step(P["act"][s][:, : self.n_act] if self.n_act else None, obs_out=P["obs"][s], reward_out=P["rew"][s])
-            P["step_done"][s].record(main)
-            if k + 1 < K:
-                with torch.cuda.stream(up):                          # next step's actions (its buffer was read by step k-1)
-                    if k >= 1:
-                        up.wait_event(P["step_done"][1 - s])
-                    P["act"][1 - s][:, : self.n_act].copy_(host_actions[k + 1], non_blocking=True)
-                    P["up_done"][1 - s].record(up)
-            with torch.cuda.stream(down):                            # this step's results
-                down.wait_event(P["step_done"][s])
-                host_obs[k].copy_(P["obs"][s], non_blocking=True)
-                host_reward[k].copy_(P["rew"][s], non_blocking=True)
-                P["down_done"][s].record(down)
-        main.wait_stream(down)
-        main.wait_stream(up)
+        if self.sim_step + K - 1 > self.simulation_steps:
+            raise RuntimeError("rollout runs past the end of the episode")
+        if (host_actions.dtype != torch.float32 or tuple(host_actions.shape[1:]) != (self.R, self.n_act)
+                or not host_actions.is_contiguous() or not host_obs.is_contiguous() or not host_reward.is_contiguous()
+                or tuple(host_obs.shape[1:]) != tuple(self.obs.shape) or tuple(host_reward.shape[1:]) != (self.R,)):
+            raise ValueError("host tensors must be contiguous float32 [K, R, n_act] / [K, R, n_obs] / [K, R]")
+        dev, eng = self.device, self.engine
+        if not hasattr(self, "_stage"):
+            self._stage = (torch.zeros((2, self.R, max(1, self.n_act)), dtype=torch.float32, device=dev),
+                           torch.zeros((2,) + tuple(self.obs.shape), dtype=torch.float32, device=dev),
+                           torch.zeros((2, self.R), dtype=torch.float32, device=dev))
+        act, obs, rew = self._stage
+        with eng._guard():
+            eng._begin_steps(self.sim_step, K)
+            eng._native_env_rollout(act if self.n_act else None, obs, rew, self.cumulative_reward, self.sim_step, K,
+                                    host=(host_actions if self.n_act else None, host_obs, host_reward))
+        self.sim_step += K
+        eng.t_done = self.sim_step - 1
 
     def kpis(self, t_last: int = None) -> torch.Tensor:
         """Per-replica episode KPIs from the device history up to row t_last (default: the last simulated
@@ -498,5 +503,7 @@ class BatchedPedNetEnv:
         """Kernel launches of one environment step."""
         routed = 1 if len(self.network.plan["rt_grp_node"]) else 0
         if self.R > 1 and not self.engine.emulation:
-            return 3 + routed          # flows (+actions) | [route] | node | update (+observations, reward)
+            # flows (+actions, + route choice as extra CTAs) | node | update (+observations, reward); only the first
+            # step of an episode with actions runs the route choice as its own launch
+            return 3
         return 1 + 3 + routed + 1      # actions, flows | [route] | node | update, observe+reward

@@ -294,3 +294,45 @@ def test_batched_env_fused_kernel_equals_standalone_kernels(dataset, obs_mode, R
     for name, a, b in zip(names, outs[0], outs[1]):
         assert torch.equal(a, b), name
     assert float(outs[0][1].abs().sum()) > 0 or dataset == "long_corridor"
+
+
+def _rollout_equals_steps(R, K, host, **kw):
+    """`rollout` / `rollout_host` (K steps in one native call) against K calls of `step` with the same actions."""
+    envs = [BatchedPedNetEnv("nine_intersections", replicas=R, obs_mode="option3", seed=4, **kw) for _ in range(2)]
+    dev = envs[0].device
+    rs = np.random.RandomState(2)
+    actions = torch.from_numpy(rs.uniform(0.0, 4.0, size=(K, R, envs[0].n_act)).astype(np.float32))
+    want_obs, want_rew = [], []
+    for k in range(K):
+        o, r, _, _ = envs[0].step(actions[k].to(dev))
+        want_obs.append(o.cpu().clone()); want_rew.append(r.cpu().clone())
+    if host:
+        ha = actions.pin_memory()
+        ho = torch.zeros((K, R, envs[1].n_obs), dtype=torch.float32).pin_memory()
+        hr = torch.zeros((K, R), dtype=torch.float32).pin_memory()
+        envs[1].rollout_host(ha[: K // 2], ho[: K // 2], hr[: K // 2])          # two calls: the look-ahead state carries over
+        envs[1].rollout_host(ha[K // 2:], ho[K // 2:], hr[K // 2:])
+        torch.cuda.synchronize()
+        got_obs, got_rew = ho, hr
+    else:
+        o1, r1, _ = envs[1].rollout(actions[: K // 2].to(dev))
+        o2, r2, _ = envs[1].rollout(actions[K // 2:].to(dev))
+        got_obs, got_rew = torch.cat([o1, o2]).cpu(), torch.cat([r1, r2]).cpu()
+    assert torch.equal(torch.stack(want_obs), got_obs) and torch.equal(torch.stack(want_rew), got_rew)
+    assert envs[0].sim_step == envs[1].sim_step == K + 1
+    assert torch.equal(envs[0].cumulative_reward.cpu(), envs[1].cumulative_reward.cpu())
+    assert torch.equal(envs[0].engine.hist64[:, : K + 1].cpu(), envs[1].engine.hist64[:, : K + 1].cpu())
+    assert torch.equal(envs[0].engine.hist32[:, : K + 1].cpu(), envs[1].engine.hist32[:, : K + 1].cpu())
+    o, r, _, _ = envs[1].step(actions[0].to(dev))                              # and stepping continues from there
+    o0, r0, _, _ = envs[0].step(actions[0].to(dev))
+    assert torch.equal(o.cpu(), o0.cpu()) and torch.equal(r.cpu(), r0.cpu())
+
+
+def test_batched_env_rollout_equals_steps_emulated(emu_lib):
+    _rollout_equals_steps(3, 30, False, _lib=emu_lib, _emulation=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [False, True])
+def test_batched_env_rollout_equals_steps_cuda(host):
+    _rollout_equals_steps(70, 120, host, device="cuda:0")
