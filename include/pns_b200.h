@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNS_ABI_VERSION 7
+#define PNS_ABI_VERSION 8
 #define PNS_MAX_DEGREE 8 /* link slots per node handled by the node kernel */
 
 /* fp64 history fields (reference src/LTM/link.py:12-17, 56, 425) */
@@ -66,7 +66,9 @@ enum {
     PNS_ERR_NEG_SENDING = 1,     /* link.py:346,366 ValueError */
     PNS_ERR_NEG_NODE_FLOW = 2,   /* node.py:194,219,238 Warning */
     PNS_ERR_HISTORY_INDEX = 4,   /* numpy IndexError in link.py:210-212 */
-    PNS_ERR_ZERO_LAG = 8         /* tau == 0: the reference result depends on node visiting order */
+    PNS_ERR_ZERO_LAG = 8,        /* tau == 0: the reference result depends on node visiting order */
+    PNS_ERR_LP_FAILED = 16       /* 'optimal' node model: the simplex ended unbounded or at its pivot limit (the
+                                    reference keeps the previous step's q when linprog fails, node.py:265) */
 };
 
 /* One parameter class of links (reference src/LTM/link.py:52-100): networks have few distinct
@@ -106,7 +108,8 @@ typedef struct pns_net {
     const int32_t *nd_meta;     /* [n_nodes][4]: slot offset (host use), m | kind<<8 | tf_mode<<16, demand row
                                    (-1 none; the node's virtual in/out links are columns n_links + 2*row, +1),
                                    offset of the node's m(m-1) turning fractions.
-                                   kind: 0 one-to-one (node.py:230), 1 regular/classic (node.py:272);
+                                   kind: 0 one-to-one (node.py:230), 1 regular/classic (node.py:272), 2 regular/optimal
+                                   (node.py:249-271, the linear program; such nodes are also listed in lp_nodes);
                                    tf_mode: 0 uniform 1/(m-1) (network.py:269-271), 1 tf_static, 2 routed */
     const int32_t *nd_routed;   /* [n_nodes] index into the routed-node arrays, -1 = none */
     const int32_t *lk_slots;    /* [n_links][2] node-major exchange slots of each link: where its sending flow goes
@@ -141,6 +144,11 @@ typedef struct pns_net {
      * pns_step_io.od_w is [sim_steps+1][n_od*replicas] (replica fastest).  Topology, widths, OD nodes and the
      * route plan are shared by all replicas. */
     int32_t per_replica_scenario, n_dyn_rows;
+    /* assign_flows_type 'optimal' (node.py:249-271): the nodes of kind 2, the largest slot count among them and the
+     * weight of the turning-fraction penalty (Node.w = 0.01, node.py:14) */
+    const int32_t *lp_nodes;   /* [n_lp_nodes] */
+    int32_t n_lp_nodes, lp_max_m;
+    double lp_w;
 } pns_net;
 
 /* Mutable simulation state; all device pointers, caller-owned. */
@@ -183,6 +191,8 @@ typedef struct pns_step_io {
     uint32_t replica_base;  /* PHILOX: global index of local replica 0 (replicas sharded over GPUs) */
     uint32_t route_all_rows;/* non-zero: the first step of the call evaluates every route row, not only rt_dyn_rows (the
                                first step after pns_state_init, a change of the route plan; step 1 always does) */
+    double *lp_x;           /* optional output [n_edges*R]: the turn flows x of the step's linear programs before the
+                               floor (nodes of kind 2; indexed like tf_routed); NULL = not kept */
 } pns_step_io;
 
 /* Control environment over R replicas (reference rl/pz_pednet_env.py, rl/builders.py, rl/discovery.py).
@@ -363,6 +373,16 @@ enum { PNS_KPI_TOTAL_DEMAND = 0, PNS_KPI_TOTAL_OUTFLOW, PNS_KPI_TOTAL_INFLOW, PN
        PNS_KPI_CONGESTED_STEPS, PNS_KPI_AVG_TRAVEL_TIME, PNS_KPI_COUNT };
 int pns_kpi(const pns_net *net, const pns_state *st, const pns_step_io *io, int t_last, const int32_t *lk_role,
             int any_od_path, double *scratch, double *out, void *stream);
+
+/* RegularNode.solve(type='optimal') (node.py:249-271) for a batch of `n` independent nodes of `m` link slots: the
+ * linear program that the reference gives to scipy.optimize.linprog (constraint matrices node.py:73-104, :110-137;
+ * objective -sum x + w sum |phi X - x|), one warp per program.  s, r: [n][m] sending / receiving flows (>= 0), phi:
+ * [n][m(m-1)] turning fractions; x: [n][m(m-1)] turn flows at the optimum (before the reference's floor), objective:
+ * [n], info: [n] pivot count, | 1<<28 when a non-basic reduced cost is zero (the optimum may not be unique), | 1<<29
+ * unbounded, | 1<<30 pivot limit.  All pointers are device memory.  Inside a step the same solver runs for the nodes
+ * of kind 2 (pns_node_flows / pns_step). */
+int pns_lp_solve(int m, int n, const double *s, const double *r, const double *phi, double w, double *x,
+                 double *objective, int32_t *info, void *stream);
 
 /* Links per CTA of the single-replica link kernel (the granularity of pns_net.lane_order). */
 int pns_lane_block_size(void);

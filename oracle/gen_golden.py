@@ -47,7 +47,15 @@ CASES = {
                                         default_link={"fd_type": "smulders"}),
     "45_intersections_smulders": dict(dataset="45_intersections", run=400, seed=2,
                                       default_link={"fd_type": "smulders", "speed_noise_std": 0.2}),
+    # the 'optimal' node model (reference src/LTM/node.py:249-271: one scipy.optimize.linprog per regular node and
+    # step): no shipped scenario selects it, so the simulation block's assign_flows_type is overridden
+    "nine_intersections_optimal": dict(dataset="nine_intersections", run=300, seed=0,
+                                       params={"assign_flows_type": "optimal"}),
+    "45_intersections_optimal": dict(dataset="45_intersections", run=150, seed=1,
+                                     params={"assign_flows_type": "optimal"}),
 }
+LP_CASES = ("nine_intersections_optimal", "45_intersections_optimal")
+LP_PER_SHAPE = 400          # programs kept per slot count in tests/golden/lp_programs.npz
 
 # parameters of reference examples/long_corridor.py:25-63 (scenario 1), restated as data
 LONG_CORRIDOR_EXAMPLE = dict(
@@ -79,7 +87,7 @@ def build_reference_network(case):
         net.logger.setLevel(logging.ERROR)
         return net
     net, gen = rh.create_network(case["dataset"], steps_override=case.get("steps_override"),
-                                 default_link=case.get("default_link"))
+                                 default_link=case.get("default_link"), params=case.get("params"))
     if case.get("randomize") is not None:
         import logging
         net = gen.randomize_network(case["dataset"], seed=case["randomize"])
@@ -117,6 +125,62 @@ def generate(name):
     np.savez_compressed(path, **out)
     print(f"{name}: {L} links, {case['run']} steps, reference {wall:.1f}s -> {path} "
           f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
+def generate_lp_programs():
+    """Programs that the reference's 'optimal' node model hands to scipy.optimize.linprog while it runs LP_CASES,
+    with the solutions linprog returned (node.py:262): per slot count m the right-hand sides (s, r), the turning
+    fractions, x and the objective.  Every second program kept comes from a step where a receiving flow binds."""
+    import sys
+    rng = np.random.RandomState(0)
+    kept = {}
+    for name in LP_CASES:
+        case = CASES[name]
+        net = build_reference_network(case)
+        recs = []
+        with rh.reference_modules():
+            nodemod = sys.modules["src.LTM.node"]
+            solver = nodemod.linprog
+
+            def spy(c, **kw):
+                res = solver(c, **kw)
+                if res.success:
+                    recs.append((kw["b_ub"].copy(), kw["A_eq"].copy(), res.x.copy(), float(res.fun)))
+                return res
+            nodemod.linprog = spy
+            try:
+                for t in range(1, case["run"] + 1):
+                    net.network_loading(t)
+            finally:
+                nodemod.linprog = solver
+        for b, A_eq, x, fun in recs:
+            m = len(b) // 2
+            E = m * (m - 1)
+            phi = A_eq[np.arange(E), np.arange(E)] + 1                       # node.py:131: the diagonal holds phi - 1
+            xe = x[:E].reshape(m, m - 1)
+            inflow = np.zeros(m)
+            for i in range(m):
+                for k in range(m - 1):
+                    inflow[k if k < i else k + 1] += xe[i, k]
+            binding = bool(np.any(inflow >= b[m:] - 1e-9)) and b[:m].sum() > 0
+            kept.setdefault((m, binding), []).append((b[:m], b[m:], phi, x[:E], fun))
+    out = {}
+    for m in sorted({k[0] for k in kept}):
+        rows = []
+        for binding in (True, False):
+            pool = kept.get((m, binding), [])
+            take = rng.permutation(len(pool))[:LP_PER_SHAPE // 2]
+            rows += [pool[i] for i in take]
+        out[f"s_{m}"] = np.array([r[0] for r in rows])
+        out[f"r_{m}"] = np.array([r[1] for r in rows])
+        out[f"phi_{m}"] = np.array([r[2] for r in rows])
+        out[f"x_{m}"] = np.array([r[3] for r in rows])
+        out[f"objective_{m}"] = np.array([r[4] for r in rows])
+        print(f"lp_programs: m={m}: {len(rows)} programs "
+              f"({len(kept.get((m, True), []))} binding / {len(kept.get((m, False), []))} free recorded)", flush=True)
+    path = os.path.join(GOLDEN_DIR, "lp_programs.npz")
+    np.savez_compressed(path, **out)
+    print(f"-> {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
 # ---- control-environment fixtures (reference rl/pz_pednet_env.py with scripted actions) -----------
@@ -257,8 +321,10 @@ def generate_lattice(name):
 
 
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or list(CASES) + list(ENV_CASES) + list(TF_CASES) + list(LATTICE_CASES)):
-        if nm in ENV_CASES:
+    for nm in (sys.argv[1:] or list(CASES) + list(ENV_CASES) + list(TF_CASES) + list(LATTICE_CASES) + ["lp_programs"]):
+        if nm == "lp_programs":
+            generate_lp_programs()
+        elif nm in ENV_CASES:
             generate_env(nm)
         elif nm in TF_CASES:
             generate_tf(nm)

@@ -11,6 +11,7 @@ in the reference), the algorithm of `Network.network_loading(t)`:
     sending flow           src/LTM/link.py:216-370, 199-214      -> _sending_flow, _diffusion_outflow
     receiving flow         src/LTM/link.py:372-416, 480-512      -> _receiving_flow
     node models            src/LTM/node.py:164-221, 230-242, 272-300 -> _assign_flows
+    'optimal' node model   src/LTM/node.py:73-137, 249-271         -> lp_matrices, scipy_lp, _assign_flows
     logit route choice     src/LTM/path_finder.py:561-737        -> _turning_fractions
     density / speed        src/LTM/link.py:133-188, 430-452; src/utils/functions.py:112-134
                                                                    -> _update_link_states
@@ -29,6 +30,40 @@ import numpy as np
 F64_FIELDS = ("inflow", "outflow", "cumulative_inflow", "cumulative_outflow",
               "sending_flow", "receiving_flow", "back_gate_width_data", "separator_width_data")
 F32_FIELDS = ("num_pedestrians", "density", "speed", "travel_time", "avg_travel_time", "link_flow")
+
+
+# ----------------------------------------------------------------------------- 'optimal' node model
+def lp_matrices(m, turning_fractions, w=1e-2):
+    """The linear program of RegularNode.solve(type='optimal') for a node with m incoming = m outgoing slots:
+    cost vector, A_ub (Node.get_matrix_A, node.py:73-104) and A_eq (Node.update_matrix_A_eq, node.py:110-137).
+    Variables: E = m(m-1) turn flows, then (p_e, n_e) penalty pairs interleaved."""
+    E = m * m - m
+    A_ub = np.zeros((2 * m, E + m + 2 * E))
+    for i in range(m):                                                                 # node.py:86-89
+        e = np.ones(m)
+        e[i] = 0
+        A_ub[i, i * m:(i + 1) * m] = e
+    for j in range(m):                                                                 # node.py:92-97
+        for k in range(m):
+            A_ub[m + j, j + k * m] = 1 if k != j else 0
+    A_ub = np.delete(A_ub, [i * m + i for i in range(m)], axis=1)                      # node.py:100-101
+    A_eq = np.zeros((E, 3 * E))
+    for i in range(E):                                                                 # node.py:127-135
+        start = (i // (m - 1)) * (m - 1)
+        A_eq[i, start:start + m - 1] = turning_fractions[i]
+        A_eq[i, i] = turning_fractions[i] - 1
+        A_eq[i, E + 2 * i:E + 2 * i + 2] = np.array([1, -1])
+    c = np.concatenate((-1 * np.ones(E), w * np.ones(2 * E)))                          # node.py:252-254
+    return c, A_ub, A_eq
+
+
+def scipy_lp(m, s, r, turning_fractions, w=1e-2):
+    """node.py:262: the reference's own solver call (scipy.optimize.linprog, default method and bounds).
+    Returns (x, objective) or None when linprog reports failure."""
+    from scipy.optimize import linprog
+    c, A_ub, A_eq = lp_matrices(m, turning_fractions, w)
+    res = linprog(c, A_ub=A_ub, A_eq=A_eq, b_ub=np.concatenate((s, r)), b_eq=np.zeros(m * m - m))
+    return (res.x, res.fun) if res.success else None
 
 
 # ----------------------------------------------------------------------------- draw providers
@@ -109,11 +144,17 @@ class _OLink:
 class LtmOracle:
     """Scalar restatement of the reference step on [S+1, columns] history arrays."""
 
-    def __init__(self, net, draws=None):
+    def __init__(self, net, draws=None, lp_solver=None):
         """net: a host-side `pednstream_b200.Network` (topology, parameters, demand, route
-        structures -- all built on the host and verified against the reference's own setup)."""
+        structures -- all built on the host and verified against the reference's own setup).
+        lp_solver(node, t, m, s, r, tf) -> x or None replaces the scipy call of the 'optimal' node model
+        (tests replay the device's optimal vertices through it: where a program's optimum is a face, two
+        solvers legitimately return different x)."""
         self.net = net
         self.draws = draws or NumpyDraws()
+        self.node_model = getattr(net, "assign_flows_type", "classic")
+        self.lp_solver = lp_solver
+        self.last_q = {}
         self.S = S = net.simulation_steps
         self.unit_time = net.unit_time
         links = list(net.links.values())
@@ -357,6 +398,21 @@ class LtmOracle:
             q = np.array([a, b, b, a])
             if np.any(q < 0):
                 raise Warning(f"Negative flows detected: {q}")
+        elif self.node_model == "optimal":                                             # node.py:249-271
+            tf = self.tf[node.node_id]
+            if self.lp_solver is not None:
+                x = self.lp_solver(node, t, m, s, r, tf)
+            else:
+                sol = scipy_lp(m, s, r, tf, getattr(node, "w", 1e-2))
+                x = None if sol is None else sol[0]
+            if x is None:                      # node.py:265: `if res.success` -- q keeps its previous value
+                q = self.last_q[node.node_id]
+            else:
+                _, A_ub, _ = lp_matrices(m, tf)
+                xf = np.zeros(A_ub.shape[1])
+                xf[:len(x)] = np.floor(x)
+                q = np.maximum(0, A_ub @ xf)                                           # node.py:266-268
+            self.last_q[node.node_id] = q
         else:                                                                          # node.py:272-300
             tf = self.tf[node.node_id]
             P = np.zeros((m, m))

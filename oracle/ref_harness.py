@@ -199,18 +199,20 @@ def make_reference_env(dataset, **kw):
 
 
 def create_network(name: str, steps_override: int | None = None, verbose: bool = True, default_link: dict = None,
-                   **kw):
+                   params: dict = None, **kw):
     """reference NetworkEnvGenerator.create_network(name) (env_loader.py:81), optional
     simulation_steps override and overrides of the scenario's default_link block."""
     import logging
     Network, Gen = import_reference()
     g = Gen()
-    if steps_override is not None or default_link:
+    if steps_override is not None or default_link or params:
         g.network_data = g.load_network_data(name)
         if steps_override is not None:
             g.config["params"]["simulation_steps"] = steps_override
         if default_link:
             g.config["params"]["default_link"].update(default_link)
+        if params:
+            g.config["params"].update(params)
     net = g.create_network(name, **kw)
     if net.logger is not None:
         net.logger.setLevel(logging.ERROR)

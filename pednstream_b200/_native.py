@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpns_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 METRIC_SLOTS, METRIC_STRIDE = 64, 4          # PNS_METRIC_SLOTS / PNS_METRIC_STRIDE of pns_step_streamed
 METRIC_ROW = METRIC_SLOTS * METRIC_STRIDE
 KPI_NAMES = ("total_demand", "total_outflow", "total_inflow", "person_time", "person_time_moving", "total_delay",
@@ -20,7 +20,8 @@ RNG_TABLE, RNG_PHILOX, RNG_REQUEST = 0, 1, 2
 ERR_BITS = {1: "negative sending flow (reference link.py:346,366 ValueError)",
             2: "negative node flow (reference node.py:194,219,238 Warning)",
             4: "history index out of range (numpy IndexError in reference link.py:210-212)",
-            8: "zero travel-time lag: the reference result depends on node visiting order"}
+            8: "zero travel-time lag: the reference result depends on node visiting order",
+            16: "'optimal' node model: the linear program of a node did not reach an optimum (reference node.py:265)"}
 
 _p = C.c_void_p
 _i32 = C.c_int32
@@ -47,7 +48,8 @@ class PnsNet(C.Structure):
                              "rt_row_ptr", "rt_row_od", "rt_term_ptr", "rt_term_opt", "rt_term_row_entry")]
         + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
         + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32),
-           ("per_replica_scenario", _i32), ("n_dyn_rows", _i32)]
+           ("per_replica_scenario", _i32), ("n_dyn_rows", _i32),
+           ("lp_nodes", _p), ("n_lp_nodes", _i32), ("lp_max_m", _i32), ("lp_w", C.c_double)]
     )
 
 
@@ -61,7 +63,8 @@ class PnsStepIO(C.Structure):
                 ("draw_row_stride", C.c_int64),
                 ("req_kind", _p), ("req_n1", _p), ("req_rf", _p), ("req_sval", _p), ("req_n3", _p),
                 ("req_exp", _p), ("draw_exp", _p),
-                ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("route_all_rows", C.c_uint32)]
+                ("seed", C.c_uint64), ("replica_base", C.c_uint32), ("route_all_rows", C.c_uint32),
+                ("lp_x", _p)]
 
 
 class PnsEnv(C.Structure):
@@ -78,7 +81,7 @@ OBS_SRC = {"inflow": 0, "outflow": 1, "rev.inflow": 2, "rev.outflow": 3, "gdens"
 
 EXPORTS = ("pns_abi_version", "pns_last_error", "pns_state_init", "pns_link_flows", "pns_route_fractions",
            "pns_node_flows", "pns_link_update", "pns_step", "pns_step_profiled", "pns_step_streamed", "pns_env_apply_actions", "pns_env_observe", "pns_env_step", "pns_env_rollout", "pns_env_draw_demand", "pns_env_randomize", "pns_kpi",
-           "pns_lane_block_size", "pns_rng_selftest")
+           "pns_lp_solve", "pns_lane_block_size", "pns_rng_selftest")
 
 _LIB = None
 
@@ -104,6 +107,7 @@ def _declare(lib):
     lib.pns_env_step.argtypes = [net_p, st_p, io_p, env_p, _p, C.c_int, C.c_int, _p, _p, _p, _p]
     lib.pns_env_rollout.argtypes = [net_p, st_p, io_p, env_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
     lib.pns_env_observe.argtypes = [net_p, st_p, env_p, C.c_int, _p, _p, _p]
+    lib.pns_lp_solve.argtypes = [C.c_int, C.c_int, _p, _p, _p, C.c_double, _p, _p, _p, _p]
     lib.pns_rng_selftest.argtypes = [C.c_int, C.c_int, _p, _p, C.c_uint64, C.c_int, C.c_int, _p, _p, _p]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int

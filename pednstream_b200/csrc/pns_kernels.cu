@@ -42,9 +42,10 @@
 #define PNS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define PNS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 template <typename K>
-static inline void pns_launch_chain(K kern, dim3 nblk, unsigned nthr, cudaStream_t stream, const void* ctx_arg) {
+static inline void pns_launch_chain(K kern, dim3 nblk, unsigned nthr, cudaStream_t stream, const void* ctx_arg,
+                                    size_t smem = 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = nblk; cfg.blockDim = dim3(nthr); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.gridDim = nblk; cfg.blockDim = dim3(nthr); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -67,6 +68,7 @@ static inline void pns_launch_chain(K kern, dim3 nblk, unsigned nthr, cudaStream
 
 #include "../../include/pns_b200.h"
 #include "pns_rng.cuh"
+#include "pns_lp.cuh"
 
 namespace {
 
@@ -981,6 +983,7 @@ __global__ void __launch_bounds__(PNS_NODE_BLOCK, PNS_NODE_MIN_BLOCKS) k_node_fl
             prefetch_l2(c.s.nm_r + na * c.n.nd_stride);
         }
     }
+    if (kind == 2) return;       // 'optimal' node model: k_node_lp
     switch (m) {
         case 0: case 1: break;   // isolated node / dead end without any turn
         case 2: node_body<2, R1, ROUTED>(c, node, rep, 2, kind, tf_mode, meta.z, meta.w, pol); break;
@@ -989,6 +992,119 @@ __global__ void __launch_bounds__(PNS_NODE_BLOCK, PNS_NODE_MIN_BLOCKS) k_node_fl
         default: node_body_generic<R1, ROUTED>(c, node, rep, m, kind, tf_mode, meta.z, meta.w); break;
     }
 }
+
+// =================================================================================================
+// RegularNode.solve(type='optimal') (node.py:249-271): nodes of kind 2 solve the linear program of pns_lp.cuh, one
+// warp per node and replica (a sequential "thread" in the host build), then floor the turn flows and add them up
+// per link like the classic model (`A_ub @ np.floor(res.x)`, node.py:266-268).  Loads, the zero-flow shortcut (no
+// sending flow: X_i <= 0 forces x = 0), the stores into the history rows and the counters of the virtual links are
+// those of node_body.
+constexpr int kLpHeader = 24;   // doubles in front of the solver's scratch: s[8], r[8], uniform fraction
+template <int LANES>
+__device__ __forceinline__ void node_lp_body(const Ctx& c, int node, int rep, int lane, double* scratch) {
+    const int R = c.n.replicas;
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);
+    const int m = meta.y & 0xff, tf_mode = (meta.y >> 16) & 0xff, dem_row = meta.z, tf_ptr = meta.w;
+    const size_t base = (size_t)node * c.n.nd_stride;
+    double *sv = scratch, *rv = scratch + 8;
+    for (int i = lane; i < m; i += LANES) {
+        sv[i] = c.s.nm_s[(base + i) * R + rep];
+        rv[i] = c.s.nm_r[(base + i) * R + rep];
+    }
+    double v_cout = 0.0, v_cin = 0.0;
+    const size_t vin = dem_row >= 0 ? (size_t)(c.n.n_links + 2 * dem_row) * R + rep : 0, vout = vin + R;
+    if (dem_row >= 0 && lane == 0) {
+        sv[0] = c.n_demand[(size_t)dem_row * R + rep];                       // node.py:176
+        rv[0] = 1e6;                                                         // node.py:186
+        v_cout = c.n_coutp[vin]; v_cin = c.n_cinp[vout];
+    }
+    if (lane == 0) scratch[16] = 1.0 / (double)(m - 1);                      // network.py:269-271
+    PNS_LP_SYNC();
+    bool negative = false, any_flow = false;
+    for (int i = 0; i < m; ++i) { negative |= (sv[i] < 0.0) | (rv[i] < 0.0); any_flow |= sv[i] != 0.0; }
+    if (negative && lane == 0) atomicOr(c.s.err + rep, PNS_ERR_NEG_NODE_FLOW);
+    if (negative || !any_flow) {
+        if (dem_row >= 0 && lane == 0) { c.n_cout[vin] = v_cout; c.n_cin[vout] = v_cin; }
+        return;
+    }
+    const double* phi = scratch + 16;
+    size_t phi_stride = 0;
+    if (tf_mode == 2) { phi = c.s.tf_routed + (size_t)tf_ptr * R + rep; phi_stride = (size_t)R; }
+    else if (tf_mode == 1) { phi = c.s.tf_static + tf_ptr; phi_stride = 1; }
+    double* x = nullptr;
+    double objective = 0.0;
+    const int info = pns::lp_node_solve<LANES>(m, sv, rv, phi, phi_stride, c.n.lp_w, lane, scratch + kLpHeader, &x,
+                                               &objective);
+    if ((info & (pns::LP_UNBOUNDED | pns::LP_PIVOT_LIMIT)) && lane == 0) atomicOr(c.s.err + rep, PNS_ERR_LP_FAILED);
+    if (c.io.lp_x)
+        for (int e = lane; e < m * (m - 1); e += LANES) c.io.lp_x[(size_t)(tf_ptr + e) * R + rep] = x[e];
+    double q0_out = 0.0, q0_in = 0.0;
+    for (int i = lane; i < m; i += LANES) {
+        double q_out = 0.0, q_in = 0.0;
+        for (int k = 0; k < m - 1; ++k) q_out += floor(x[i * (m - 1) + k]);              // row i of A_ub
+        for (int k = 0; k < m; ++k)
+            if (k != i) q_in += floor(x[k * (m - 1) + (i < k ? i : i - 1)]);             // row m + i of A_ub
+        q_out = fmax(0.0, q_out); q_in = fmax(0.0, q_in);
+        const int col = __ldg(c.n.nd_in_link + base + i);
+        c.n_outflow[(size_t)col * R + rep] = q_out;                                      // node.py:146-162
+        c.n_inflow[(size_t)(col ^ 1) * R + rep] = q_in;
+        if (i == 0) { q0_out = q_out; q0_in = q_in; }
+    }
+    if (dem_row >= 0 && lane == 0) { c.n_cout[vin] = v_cout + q0_out; c.n_cin[vout] = v_cin + q0_in; }
+}
+
+__host__ __device__ inline size_t node_lp_warp_doubles(int max_m) {
+    return (size_t)kLpHeader + pns::lp_scratch_bytes(max_m) / sizeof(double);
+}
+
+#ifdef PNS_HOST_EMULATION
+__global__ void k_node_lp(const Ctx c) {
+    static thread_local double* scratch = nullptr;
+    if (!scratch) scratch = (double*)malloc(node_lp_warp_doubles(PNS_MAX_DEGREE) * sizeof(double));
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)c.n.n_lp_nodes * c.n.replicas) return;
+    node_lp_body<1>(c, c.n.lp_nodes[gid / c.n.replicas], (int)(gid % c.n.replicas), 0, scratch);
+}
+// batch of stand-alone programs (pns_lp_solve)
+struct LpBatch { int m, n; const double *s, *r, *phi; double w; double *x, *objective; int32_t* info; };
+__global__ void k_lp_batch(const LpBatch b) {
+    static thread_local double* scratch = nullptr;
+    if (!scratch) scratch = (double*)malloc(node_lp_warp_doubles(PNS_MAX_DEGREE) * sizeof(double));
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)b.n) return;
+    const int E = b.m * (b.m - 1);
+    double* x = nullptr;
+    b.info[k] = pns::lp_node_solve<1>(b.m, b.s + k * b.m, b.r + k * b.m, b.phi + k * E, 1, b.w, 0, scratch, &x,
+                                      b.objective + k);
+    for (int e = 0; e < E; ++e) b.x[k * E + e] = x[e];
+}
+#else
+__global__ void __launch_bounds__(256) k_node_lp(const __grid_constant__ Ctx c) {
+    extern __shared__ double lp_smem[];
+    const unsigned warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+    const unsigned R = (unsigned)c.n.replicas;
+    PNS_PDL_TRIGGER();
+    PNS_PDL_WAIT();
+    if (warp >= (size_t)c.n.n_lp_nodes * R) return;
+    const int node = __ldg(c.n.lp_nodes + (unsigned)(warp / R));
+    node_lp_body<32>(c, node, (int)(warp % R), (int)lane, lp_smem + warp_in_cta * node_lp_warp_doubles(c.n.lp_max_m));
+}
+struct LpBatch { int m, n; const double *s, *r, *phi; double w; double *x, *objective; int32_t* info; };
+__global__ void __launch_bounds__(256) k_lp_batch(const LpBatch b) {
+    extern __shared__ double lp_smem[];
+    const unsigned warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t k = (size_t)blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+    if (k >= (size_t)b.n) return;
+    const int E = b.m * (b.m - 1);
+    double* x = nullptr;
+    double objective = 0.0;
+    const int info = pns::lp_node_solve<32>(b.m, b.s + k * b.m, b.r + k * b.m, b.phi + k * E, 1, b.w, (int)lane,
+                                            lp_smem + warp_in_cta * node_lp_warp_doubles(b.m), &x, &objective);
+    for (int e = (int)lane; e < E; e += 32) b.x[k * E + e] = x[e];
+    if (lane == 0) { b.objective[k] = objective; b.info[k] = info; }
+}
+#endif
 
 #ifndef PNS_HOST_EMULATION
 // =================================================================================================
@@ -1101,7 +1217,7 @@ __global__ void __launch_bounds__(32 * W) k_node_cols(const __grid_constant__ Ct
     PNS_PDL_TRIGGER();
     const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
-    if (m < 2 || j >= m) return;               // dead end / isolated node; warps without a slot
+    if (m < 2 || j >= m || kind == 2) return;  // dead end / isolated node; warps without a slot; k_node_lp's nodes
 #define PNS_COLS(MM) node_cols_body<ROUTED, W, MM>(c, sh_f, node, j, lane, rep, valid, kind, tf_mode, meta.z, meta.w)
     switch (m) {
         case 2: PNS_COLS(2); break;
@@ -2243,6 +2359,37 @@ void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     }
 }
 
+// warps per CTA and dynamic shared memory of the LP kernels for programs of up to max_m slots
+struct LpLaunch { unsigned warps; size_t smem; };
+LpLaunch lp_launch_shape(int max_m) {
+    const size_t per_warp = node_lp_warp_doubles(max_m) * sizeof(double);
+    size_t warps = (96 * 1024) / per_warp;
+    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+    return {(unsigned)warps, warps * per_warp};
+}
+#ifndef PNS_HOST_EMULATION
+template <typename K>
+int lp_allow_smem(K kern, size_t smem) {
+    if (smem <= 48 * 1024) return 0;
+    if (smem > 227 * 1024) return fail("linear program too large for shared memory");
+    const cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_node_lp)", e);
+}
+#endif
+// nodes of kind 2 ('optimal' node model), after the classic pass
+int launch_node_lp(const pns_net* net, cudaStream_t s, const Ctx& c) {
+    if (net->n_lp_nodes <= 0) return 0;
+    const size_t n = (size_t)net->n_lp_nodes * net->replicas;
+#ifdef PNS_HOST_EMULATION
+    PNS_LAUNCH(k_node_lp, (unsigned)n, 1, s, c);
+#else
+    const LpLaunch z = lp_launch_shape(net->lp_max_m);
+    if (lp_allow_smem(k_node_lp, z.smem)) return 1;
+    pns_launch_chain(k_node_lp, dim3((unsigned)((n + z.warps - 1) / z.warps)), z.warps * 32, s, &c, z.smem);
+#endif
+    return 0;
+}
+
 struct StepSizes { size_t n_pair, n_grp, n_node; };
 StepSizes sizes_of(const pns_net* net) {
     StepSizes z;
@@ -2388,6 +2535,7 @@ int step_impl(const pns_net* net, const pns_state* st, const pns_step_io* io, in
         if (n_route && !route_rides) PNS_LAUNCH_CHAIN(k_route_fractions, blocks_for(n_route), kBlock, s, cn);
         PNS_MARK(k, 2);
         if (z.n_node) launch_node(net, z.n_node, s, cn);
+        if (launch_node_lp(net, s, cn)) return 1;
         PNS_MARK(k, 3);
     }
 #undef PNS_MARK
@@ -2475,6 +2623,7 @@ int pns_node_flows(const pns_net* net, const pns_state* st, const pns_step_io* i
     if (n == 0) return 0;
     const Ctx c = make_ctx(net, st, io, 0, t, t, PNS_RNG_TABLE, 0, 0);
     launch_node(net, n, (cudaStream_t)stream, c);
+    if (launch_node_lp(net, (cudaStream_t)stream, c)) return 1;
     return launched("k_node_flows");
 }
 
@@ -2696,6 +2845,22 @@ int pns_kpi(const pns_net* net, const pns_state* st, const pns_step_io* io, int 
     PNS_LAUNCH(k_kpi_reduce, blocks_for((size_t)net->replicas), kBlock, (cudaStream_t)stream, c, t_last,
                (const double*)scratch, lk_role, any_od_path, out);
     return launched("k_kpi");
+}
+
+int pns_lp_solve(int m, int n, const double* s, const double* r, const double* phi, double w, double* x,
+                 double* objective, int32_t* info, void* stream) {
+    if (m < 2 || m > PNS_MAX_DEGREE) return fail("pns_lp_solve: 2 <= m <= PNS_MAX_DEGREE");
+    if (!s || !r || !phi || !x || !objective || !info) return fail("pns_lp_solve: null argument");
+    if (n <= 0) return 0;
+    const LpBatch b = {m, n, s, r, phi, w, x, objective, info};
+#ifdef PNS_HOST_EMULATION
+    PNS_LAUNCH(k_lp_batch, (unsigned)n, 1, (cudaStream_t)stream, b);
+#else
+    const LpLaunch z = lp_launch_shape(m);
+    if (lp_allow_smem(k_lp_batch, z.smem)) return 1;
+    k_lp_batch<<<(unsigned)((n + z.warps - 1) / z.warps), z.warps * 32, z.smem, (cudaStream_t)stream>>>(b);
+#endif
+    return launched("k_lp_batch");
 }
 
 int pns_rng_selftest(int kind, int n, const int32_t* n_trials, const double* p, uint64_t seed, int t, int site,

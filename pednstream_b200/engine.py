@@ -84,6 +84,14 @@ class Engine:
             setattr(net, k, _ptr(self._net_t[k]))
         C.memmove(C.byref(net.class0), np.ascontiguousarray(p["classes"][:1]).ctypes.data, C.sizeof(net.class0))
         net.rt_temp, net.rt_alpha, net.rt_beta, net.rt_omega, net.rt_eps = [float(x) for x in p["rt_scalars"]]
+        # assign_flows_type 'optimal': the nodes that solve the linear program (kind 2 in nd_meta)
+        kinds = (np.asarray(p["nd_meta"])[:, 1] >> 8) & 0xff if self.N else np.zeros(0, dtype=np.int64)
+        lp_nodes = np.nonzero(kinds == 2)[0].astype(np.int32)
+        self._lp_nodes = torch.from_numpy(lp_nodes if len(lp_nodes) else np.zeros(1, np.int32)).to(dev)
+        net.lp_nodes, net.n_lp_nodes = _ptr(self._lp_nodes), len(lp_nodes)
+        net.lp_max_m = int((np.asarray(p["nd_meta"])[lp_nodes, 1] & 0xff).max()) if len(lp_nodes) else 0
+        net.lp_w = float(p.get("lp_w", 0.01))
+        self.lp_x = None                                  # keep_lp_solutions(): the step's turn flows before the floor
         # launch order of the single-replica link kernel (a schedule; results do not depend on it)
         self._lane_order = None
         if R == 1 and not emulation and L > 0:
@@ -530,6 +538,15 @@ class Engine:
         io.draw_exp = draw_exp.data_ptr() if draw_exp is not None else 0
         io.draw_row_stride = 1
         self._table_io = io
+
+    def keep_lp_solutions(self, keep=True):
+        """'optimal' node model: keep the turn flows x of every step's linear programs (before the floor) in
+        `self.lp_x` [n_edges * R], indexed like the turning fractions -- a test hook."""
+        if keep and self.lp_x is None:
+            self.lp_x = torch.zeros((max(1, self.net.n_edges) * self.R,), dtype=torch.float64, device=self.device)
+        self.io.lp_x = _ptr(self.lp_x) if keep else None
+        if self._table_io is not None:
+            self._table_io.lp_x = self.io.lp_x
 
     def release(self):
         """Drop the device tensors and the reference to the network (the engine <-> network cycle would otherwise

@@ -43,12 +43,15 @@ def default_origins(size: int, stride: int = 64):
 
 
 def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=None,
-                    peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False, destinations=()):
+                    peak_lambda=50, base_lambda=30, demand_seed=0, locality_order=False, destinations=(),
+                    node_model="classic"):
     """Returns (plan, gate[L], tf_static[n_edges], demand[S, rows]) for `Engine`.
     locality_order=True lists nodes by id instead of the reference's creation order.
     destinations: nodes that get virtual O/D links like origins but draw no demand (network.py:139-167); the
     route plan of a routed lattice is attached by `build_routed_grid_plan`.  demand_seed=None: the caller has
-    positioned numpy's global stream (the reference draws demand from it while it creates the nodes)."""
+    positioned numpy's global stream (the reference draws demand from it while it creates the nodes).
+    node_model: Network.assign_flows_type -- 'optimal' makes every regular node solve the linear program of
+    node.py:249-271 (kind 2)."""
     lk = dict(DEFAULT_LINK)
     lk.update(link or {})
     n = size
@@ -92,6 +95,8 @@ def build_grid_plan(size: int, sim_steps: int, unit_time=10, link=None, origins=
     # network.py:141-167: degree 2 -> one-to-one unless O/D; degree 1 -> one-to-one + virtual; else regular
     virtual = is_od | (degree == 1)
     kind = np.where((degree == 2) & ~is_od, 0, np.where(degree == 1, 0, 1)).astype(np.int32)
+    if node_model == "optimal":
+        kind[kind == 1] = 2
     vrank = np.full(N, -1, dtype=np.int64)           # rank among virtual-link owners, creation order
     vo = order[virtual[order]]
     vrank[vo] = np.arange(len(vo))

@@ -60,10 +60,9 @@ class Network:
         self.od_manager = None
         self.pos = pos
         self.assign_flows_type = params.get("assign_flows_type", "classic")
-        if self.assign_flows_type != "classic":
-            raise NotImplementedError(
-                "assign_flows_type='optimal' (per-node LP, reference node.py:249-271) is outside "
-                "the accelerated path; every shipped scenario uses 'classic'")
+        if self.assign_flows_type not in ("classic", "optimal"):
+            raise ValueError(f"unknown assign_flows_type {self.assign_flows_type!r} (reference node.py:248-300 "
+                             "knows 'classic' and 'optimal')")
         self._info(f"Network initialization started, assign flows type: {self.assign_flows_type}")
 
         self.rng_mode = rng
@@ -264,7 +263,7 @@ class Network:
         if self._plan is None:
             self._plan = compile_plan(list(self.nodes.values()), list(self.links.values()),
                                       self.unit_time, self.simulation_steps,
-                                      self.path_finder, self.od_manager)
+                                      self.path_finder, self.od_manager, node_model=self.assign_flows_type)
         return self._plan
 
     @property

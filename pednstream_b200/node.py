@@ -24,6 +24,7 @@ class Node:
         self.virtual_incoming_link = None
         self.virtual_outgoing_link = None
         self.M = 1e6                    # receiving flow of a virtual destination link
+        self.w = 1e-2                   # weight of the turning-fraction penalty of the 'optimal' model (node.py:14)
         self.demand = None
         self.source_num = None
         self.dest_num = None
@@ -69,8 +70,8 @@ class Node:
 
     def update_matrix_A_eq(self, turning_fractions):
         """External fractions setter used by Network.update_turning_fractions_per_node
-        (reference node.py:110-118; the LP matrix itself belongs to the out-of-scope
-        'optimal' node model)."""
+        (reference node.py:110-118; the matrices of the 'optimal' node model are built on the device from these
+        fractions, csrc/pns_lp.cuh)."""
         tf = np.asarray(turning_fractions, dtype=np.float64)
         assert len(tf) == self.edge_num
         self.turning_fractions = tf

@@ -222,9 +222,10 @@ def attach_route_plan(p, path_finder, od_manager, nodes_in_order, link_index):
     meta[routed, 1] = (meta[routed, 1] & 0xffff) | (2 << 16)
 
 
-def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None):
+def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od_manager=None, node_model="classic"):
     """nodes: list of Node (network.nodes order, .index set); links: list of Link (network.links
-    order, .index set).  Returns dict name -> numpy array / python scalar."""
+    order, .index set).  node_model: Network.assign_flows_type -- with 'optimal' every regular node solves the
+    linear program of reference node.py:249-271 (kind 2).  Returns dict name -> numpy array / python scalar."""
     L = len(links)
     for l in links:
         assert links[l.index ^ 1] is l.reverse_link, "links must come in forward/reverse pairs"
@@ -272,7 +273,8 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
         tf_mode = 2 if n.node_id in routed_ids else 0
         if dem_row >= 0:
             assert n.incoming_links[0]._col == L + 2 * dem_row, "virtual columns follow the demand rows"
-        meta.append((slot0, m | (n.kind << 8) | (tf_mode << 16), dem_row, tf_ptr))
+        kind = 2 if (node_model == "optimal" and n.kind == 1 and m >= 2) else n.kind
+        meta.append((slot0, m | (kind << 8) | (tf_mode << 16), dem_row, tf_ptr))
         slot0 += m
         tf_ptr += m * (m - 1)
     p["nd_meta"] = _i32(meta).reshape(-1, 4)
@@ -285,6 +287,7 @@ def compile_plan(nodes, links, unit_time, simulation_steps, path_finder=None, od
     p["n_demand_rows"] = len(demand_nodes)
     p["demand_nodes"] = demand_nodes
     p["n_edges"] = tf_ptr
+    p["lp_w"] = float(next((n.w for n in nodes if hasattr(n, "w")), 0.01))     # Node.w (node.py:14)
 
     # ---- route plan -------------------------------------------------------------------
     if path_finder is not None:

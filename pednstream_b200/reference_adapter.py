@@ -32,13 +32,13 @@ _LINK_FIELDS = F64_FIELDS[:7] + F32_FIELDS
 class B200Step:
     def __init__(self, network, rng: str = "numpy", seed: int = 0, device=None, _lib=None, _emulation: bool = False):
         self.network = network
-        if getattr(network, "assign_flows_type", "classic") != "classic":
-            raise NotImplementedError("only assign_flows_type='classic' runs on the device")
         od = getattr(network, "od_manager", None)
         od_flows = {k: np.array(v, dtype=np.float64) for k, v in od.od_flows.items()} if od is not None else None
         state = np.random.get_state()               # attaching must not move the reference's global stream
         try:
-            self.facade = Network(network.adjacency_matrix, copy.deepcopy(network.params),
+            params = copy.deepcopy(network.params)
+            params["assign_flows_type"] = getattr(network, "assign_flows_type", "classic")
+            self.facade = Network(network.adjacency_matrix, params,
                                   list(network.origin_nodes), list(network.destination_nodes),
                                   od_flows=od_flows, pos=getattr(network, "pos", None), verbose=False,
                                   rng=rng, seed=seed, device=device, _lib=_lib, _emulation=_emulation)

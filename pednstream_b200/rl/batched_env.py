@@ -52,7 +52,9 @@ def _gater_divisors(obs_mode, k):
 class BatchedPedNetEnv:
     def __init__(self, dataset: str, replicas: int, obs_mode: str = "option3", normalize_obs: bool = False,
                  seed: int = 0, replica_base: int = 0, device=None, data_dir="data", randomize: bool = False,
-                 _lib=None, _emulation: bool = False):
+                 params: dict = None, _lib=None, _emulation: bool = False):
+        """params: overrides of the scenario's parameter block (e.g. {"assign_flows_type": "optimal"}), applied
+        before the template network is built."""
         if obs_mode not in OBS_LAYOUT:
             raise ValueError(f"obs_mode must be one of {list(OBS_LAYOUT)}, got: {obs_mode}")
         self.dataset, self.R, self.obs_mode, self.seed = dataset, int(replicas), obs_mode, int(seed)
@@ -60,6 +62,9 @@ class BatchedPedNetEnv:
         state = np.random.get_state()                 # building the template must not disturb the caller's stream
         np.random.seed(self.seed)
         self.generator = NetworkEnvGenerator(data_dir)
+        if params:
+            self.generator.network_data = self.generator.load_network_data(dataset)
+            self.generator.config["params"].update(params)
         self.network = self.generator.create_network(dataset, verbose=False)
         np.random.set_state(state)
         if randomize not in (False, True, "host", "device"):

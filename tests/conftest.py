@@ -73,12 +73,14 @@ def make_network(case, **kw):
         return Network(np.array(spec["adjacency"]), spec["params"], origin_nodes=spec["origin_nodes"],
                        verbose=False, **kw)
     g = NetworkEnvGenerator()
-    if c.get("steps_override") or c.get("default_link"):
+    if c.get("steps_override") or c.get("default_link") or c.get("params"):
         g.network_data = g.load_network_data(c["dataset"])
         if c.get("steps_override"):
             g.config["params"]["simulation_steps"] = c["steps_override"]
         if c.get("default_link"):
             g.config["params"]["default_link"].update(c["default_link"])
+        if c.get("params"):
+            g.config["params"].update(c["params"])
     net = g.create_network(c["dataset"], verbose=False, **({} if c.get("randomize") is not None else kw))
     if c.get("randomize") is not None:
         net = g.randomize_network(c["dataset"], seed=c["randomize"], verbose=False, **kw)

