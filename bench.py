@@ -350,6 +350,30 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
         torch.cuda.synchronize()
         rand_reset_ms = (time.perf_counter() - w0) * 1e3
         env.engine.check_errors()
+        # scenario groups: per-group origin / destination nodes (generate_random_od_nodes), per-replica everything else
+        del env
+        torch.cuda.empty_cache()
+        from pednstream_b200.rl import GroupedPedNetEnv
+        n_groups = 8
+        genv = GroupedPedNetEnv("45_intersections", replicas=replicas, groups=n_groups, obs_mode="option3", seed=1000,
+                                device=dev, randomize="device")
+        for k in range(warmup):
+            genv.step(pool[k % len(pool)])
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(steps):
+            genv.step(pool[k % len(pool)])
+        g1.record()
+        torch.cuda.synchronize()
+        genv.check_errors()
+        grouped = {"groups": n_groups, "replicas": replicas, "ms_per_env_step": g0.elapsed_time(g1) / steps,
+                   "env_steps_per_s": replicas / (g0.elapsed_time(g1) / steps * 1e-3),
+                   "distinct_od_node_sets": len({str(od) for od in genv.od_nodes}),
+                   "note": "GroupedPedNetEnv: every group perturbs the origin / destination nodes with its own seed "
+                           "(reference generate_random_od_nodes) and runs its own plan on its own stream; scenarios "
+                           "inside a group are per replica, drawn on the device"}
+        env = genv.envs[0]
     vals = [ms, ms_e2e, reset_ms, ms_late if ms_late is not None else 0.0, gather_us or 0.0]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
@@ -388,6 +412,8 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
         out["randomized_reset_note"] = ("BatchedPedNetEnv(randomize='device'): per-replica link bottlenecks, OD weights and "
                                         "demand patterns drawn by one kernel launch (pns_env_randomize), then state init and "
                                         "demand draw; wall clock")
+    if rand_reset_ms is not None:
+        out["od_node_groups"] = grouped
     if world > 1:
         out["reward_gather_us"] = gather_us_max
         out["reward_gather_note"] = "all-gather of one float32 per replica over NCCL (per call, device-timed)"

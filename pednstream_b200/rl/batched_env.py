@@ -52,9 +52,11 @@ def _gater_divisors(obs_mode, k):
 class BatchedPedNetEnv:
     def __init__(self, dataset: str, replicas: int, obs_mode: str = "option3", normalize_obs: bool = False,
                  seed: int = 0, replica_base: int = 0, device=None, data_dir="data", randomize: bool = False,
-                 params: dict = None, _lib=None, _emulation: bool = False):
+                 params: dict = None, od_nodes_seed: int = None, _lib=None, _emulation: bool = False):
         """params: overrides of the scenario's parameter block (e.g. {"assign_flows_type": "optimal"}), applied
-        before the template network is built."""
+        before the template network is built.  od_nodes_seed: perturb the scenario's origin / destination nodes as
+        the reference's generate_random_od_nodes(seed) does (env_loader.py:261-361) -- all replicas of this
+        environment share that topology; `GroupedPedNetEnv` runs several such groups side by side."""
         if obs_mode not in OBS_LAYOUT:
             raise ValueError(f"obs_mode must be one of {list(OBS_LAYOUT)}, got: {obs_mode}")
         self.dataset, self.R, self.obs_mode, self.seed = dataset, int(replicas), obs_mode, int(seed)
@@ -66,6 +68,23 @@ class BatchedPedNetEnv:
             self.generator.network_data = self.generator.load_network_data(dataset)
             self.generator.config["params"].update(params)
         self.network = self.generator.create_network(dataset, verbose=False)
+        self.od_nodes = self.od_nodes_seed = None
+        if od_nodes_seed is not None:
+            cfg = self.generator.config
+            own = (list(cfg.get("origin_nodes", [])), list(cfg.get("destination_nodes", [])))
+            for attempt in range(64):
+                # a perturbation may leave no origin -> destination pair at all (e.g. both sets shrink to the same
+                # node); the reference's network constructor fails on that (KeyError, path_finder.py:226): next seed
+                self.od_nodes_seed = (int(od_nodes_seed) + 1000003 * attempt) % (2 ** 32)
+                cfg["origin_nodes"], cfg["destination_nodes"] = list(own[0]), list(own[1])
+                self.od_nodes = self.generator.generate_random_od_nodes(self.od_nodes_seed)
+                if any(o != d for o in self.od_nodes["origin_nodes"] for d in self.od_nodes["destination_nodes"]):
+                    break
+            else:
+                raise RuntimeError("no usable origin / destination perturbation found")
+            od_flows = self.generator.generate_random_od_flows(self.od_nodes_seed)   # weights for the new OD pairs
+            np.random.seed(self.seed)
+            self.network = self.generator.create_network(dataset, od_flows=od_flows, verbose=False)
         np.random.set_state(state)
         if randomize not in (False, True, "host", "device"):
             raise ValueError("randomize must be False, True / 'host' or 'device'")

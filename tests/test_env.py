@@ -222,6 +222,74 @@ def test_batched_env_randomized_scenarios_cuda(mode):
     _randomized_batched_vs_facade("45_intersections", 150, 48, (0, 17, 47), device="cuda:0", mode=mode)
 
 
+def _grouped_vs_randomize_network(dataset, steps, R, G, lib=None, emulation=False, device=None):
+    """Scenario groups (per-group OD nodes): the first replica of every group must equal the network that
+    `randomize_network(dataset, seed)` builds -- OD nodes, bottlenecks, OD weights and demand pattern, the whole of
+    reference env_loader.py:160-181 -- and the groups' OD node sets must differ from each other."""
+    from pednstream_b200.rl import GroupedPedNetEnv
+    kw = dict(_lib=lib, _emulation=emulation) if emulation else dict(device=device)
+    genv = GroupedPedNetEnv(dataset, replicas=R, groups=G, obs_mode="option3", seed=5, randomize="host", **kw)
+    dev = genv.device
+    rs = np.random.RandomState(3)
+    acts = rs.uniform(0.0, 4.0, size=(steps, R, genv.n_act)).astype(np.float32)
+    obs_b, rew_b = [genv.obs.cpu().numpy().copy()], []
+    for k in range(steps):
+        o, r, _, _ = genv.step(torch.from_numpy(acts[k]).to(dev))
+        if not emulation:
+            torch.cuda.synchronize()
+        obs_b.append(o.cpu().numpy().copy())
+        rew_b.append(r.cpu().numpy().copy())
+    genv.check_errors()
+    assert len({str(od) for od in genv.od_nodes}) > 1, "the groups must not all share one OD node set"
+    base_od, exact = None, 0
+    for g, (benv, sl) in enumerate(zip(genv.envs, genv.slices)):
+        rep = sl.start                                    # global index of the group's first replica
+        seed_g = benv.scenario_seed(0, 0)
+        fkw = dict(_lib=lib, _emulation=True) if emulation else dict(device=device)
+        env = PedNetParallelEnv(dataset, obs_mode="option3", seed=5, rng="philox", **fkw)
+        if base_od is None:
+            base_od = (list(env.env_generator.config["origin_nodes"]), list(env.env_generator.config["destination_nodes"]))
+        state = np.random.get_state()
+        if benv.od_nodes_seed == seed_g:
+            exact += 1
+            env.network = env.env_generator.randomize_network(dataset, seed=seed_g, verbose=False, rng="philox", **fkw)
+        else:       # the perturbation of seed_g has no OD pair (the reference cannot build it): OD nodes of the next seed
+            env.env_generator.generate_random_od_nodes(benv.od_nodes_seed)
+            env.network = env.env_generator.create_network(dataset, verbose=False, rng="philox", **benv.scenario(0), **fkw)
+        np.random.set_state(state)
+        assert env.env_generator.config["origin_nodes"] == benv.od_nodes["origin_nodes"]
+        assert env.env_generator.config["destination_nodes"] == benv.od_nodes["destination_nodes"]
+        env._bind_network()
+        demand = benv.engine.demand.cpu().numpy().reshape(benv.simulation_steps + 1, -1, benv.R)
+        for row, node in enumerate(env.network.plan["demand_nodes"]):
+            node.demand = demand[:, row, 0].copy()
+        eng = env.network.engine
+        eng.io.seed = benv.engine.io.seed
+        eng.io.replica_base = benv.replica_base
+        agents = env.possible_agents
+        assert np.array_equal(np.concatenate([env._observe()[a] for a in agents]), obs_b[0][rep])
+        for k in range(steps):
+            obs, rew, *_ = env.step({a: acts[k, rep, genv.action_slices[a]] for a in agents})
+            assert np.array_equal(np.concatenate([obs[a] for a in agents]), obs_b[k + 1][rep]), (g, k)
+            assert np.float32(rew.get(agents[0], 0.0)) == rew_b[k][rep], (g, k)
+        for f in F64_FIELDS[:7] + F32_FIELDS:
+            want = env.network._store.field(f)
+            got = benv.engine.history(f)[:, :, 0].cpu().numpy()
+            assert np.array_equal(want[: steps + 1], got[: steps + 1]), (f, g)
+    assert any((od["origin_nodes"], od["destination_nodes"]) != base_od for od in genv.od_nodes)
+    assert exact >= G - 1, "most groups must be exactly randomize_network(seed)"
+    assert genv.kpis().shape[0] == R
+
+
+def test_grouped_env_od_node_perturbation_emulated(emu_lib):
+    _grouped_vs_randomize_network("45_intersections", 50, 5, 3, lib=emu_lib, emulation=True)
+
+
+@pytest.mark.gpu
+def test_grouped_env_od_node_perturbation_cuda():
+    _grouped_vs_randomize_network("45_intersections", 150, 40, 5, device="cuda:0")
+
+
 def test_batched_env_matches_facade_emulated(emu_lib):
     _batched_vs_facade("nine_intersections", "option3", False, 40, 3, (0, 2), lib=emu_lib, emulation=True)
 
