@@ -22,8 +22,9 @@ def timed(eng, t0, n):
 
 
 out = {}
+only_env = len(sys.argv) > 1 and sys.argv[1] == "env"          # `env`: the batched part only (ncu captures)
 for model in ("classic", "optimal"):
-    for size in (128, 512):
+    for size in (() if only_env else (128, 512)):
         S = 260
         plan, gate, tf, demand = build_grid_plan(size, S, node_model=model)
         eng = Engine(plan, replicas=1, rng="philox", seed=1, device="cuda:0")
