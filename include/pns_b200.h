@@ -149,6 +149,11 @@ typedef struct pns_net {
     const int32_t *lp_nodes;   /* [n_lp_nodes] */
     int32_t n_lp_nodes, lp_max_m;
     double lp_w;
+    /* optional schedule of the batched node kernel when nd_stride is 8: all nodes, those with at most 4 link slots
+     * first (n_nodes_small of them; they share a CTA in twos).  NULL = one CTA per node in index order.  A schedule,
+     * not a result. */
+    const int32_t *nd_cols_order;
+    int32_t n_nodes_small, pad3_;
 } pns_net;
 
 /* Mutable simulation state; all device pointers, caller-owned. */

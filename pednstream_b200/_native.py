@@ -49,7 +49,8 @@ class PnsNet(C.Structure):
         + [(n, C.c_double) for n in ("rt_temp", "rt_alpha", "rt_beta", "rt_omega", "rt_eps")]
         + [("lane_order", _p), ("lane_order_block", _i32), ("n_lane_blocks", _i32),
            ("per_replica_scenario", _i32), ("n_dyn_rows", _i32),
-           ("lp_nodes", _p), ("n_lp_nodes", _i32), ("lp_max_m", _i32), ("lp_w", C.c_double)]
+           ("lp_nodes", _p), ("n_lp_nodes", _i32), ("lp_max_m", _i32), ("lp_w", C.c_double),
+           ("nd_cols_order", _p), ("n_nodes_small", _i32), ("pad3_", _i32)]
     )
 
 

@@ -1121,7 +1121,8 @@ __global__ void __launch_bounds__(256) k_lp_batch(const LpBatch b) {
 // Body for a node with M slots (compile-time: every loop is exact and every small array lives in registers).
 template <bool ROUTED, int W, int M>
 __device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][32], int node, int j, int lane, int rep,
-                                               bool valid, int kind, int tf_mode, int dem_row, int tf_ptr) {
+                                               bool valid, int kind, int tf_mode, int dem_row, int tf_ptr,
+                                               int barrier_id = 1) {
     const int R = c.n.replicas;
     const size_t base = (size_t)node * c.n.nd_stride;
     const int col = __ldg(c.n.nd_in_link + base + j);
@@ -1185,7 +1186,7 @@ __device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][3
             in_j += f;
         }
         q_in = fmax(0.0, in_j);
-        asm volatile("bar.sync 1, %0;" :: "r"(32 * M) : "memory");
+        asm volatile("bar.sync %0, %1;" :: "r"(barrier_id), "r"(32 * M) : "memory");
 #pragma unroll
         for (int jj = 0; jj < M; ++jj)
             if (jj != j) q_out += sh_f[jj][j][lane];
@@ -1209,20 +1210,42 @@ template <bool ROUTED, int W>
 __global__ void __launch_bounds__(32 * W) k_node_cols(const __grid_constant__ Ctx c) {
     __shared__ double sh_f[W][W][32];          // f[j][i][lane]: flow from slot i into slot j's outgoing link
     const int R = c.n.replicas;
-    const int node = (int)blockIdx.y;
-    const int j = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
     const int rep_raw = (int)blockIdx.x * 32 + lane;
     const bool valid = rep_raw < R;
     const int rep = valid ? rep_raw : R - 1;
     PNS_PDL_TRIGGER();
+    // W == 8 (some node has more than 4 slots): registers are granted per CTA, so a 256-thread CTA for a node with
+    // 3 or 4 slots would hold half of them idle.  Nodes with at most 4 slots therefore share a CTA in twos (warps
+    // 0-3 / 4-7, named barriers 1 / 2, the two halves of sh_f); pns_net.nd_cols_order lists those nodes first.
+    int node, j, half = 0;
+    if (W == 8 && c.n.nd_cols_order) {
+        const int n_small = c.n.n_nodes_small, small_ctas = (n_small + 1) >> 1;
+        if ((int)blockIdx.y < small_ctas) {
+            half = warp >> 2;
+            const int k = 2 * (int)blockIdx.y + half;
+            if (k >= n_small) return;
+            node = __ldg(c.n.nd_cols_order + k);
+            j = warp & 3;
+        } else {
+            node = __ldg(c.n.nd_cols_order + n_small + ((int)blockIdx.y - small_ctas));
+            j = warp;
+        }
+    } else {
+        node = (int)blockIdx.y;
+        j = warp;
+    }
     const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + node);   // {-, m|kind|mode, demand row, tf offset}
     const int m = meta.y & 0xff, kind = (meta.y >> 8) & 0xff, tf_mode = (meta.y >> 16) & 0xff;
     if (m < 2 || j >= m || kind == 2) return;  // dead end / isolated node; warps without a slot; k_node_lp's nodes
+    // a node of <= 4 slots uses a 4 x 4 x 32 block of sh_f (the first or the second half of the array)
+    double (*sh4)[4][32] = reinterpret_cast<double (*)[4][32]>(&sh_f[0][0][0] + (size_t)half * 4 * 4 * 32);
+#define PNS_COLS4(MM) node_cols_body<ROUTED, 4, MM>(c, sh4, node, j, lane, rep, valid, kind, tf_mode, meta.z, meta.w, 1 + half)
 #define PNS_COLS(MM) node_cols_body<ROUTED, W, MM>(c, sh_f, node, j, lane, rep, valid, kind, tf_mode, meta.z, meta.w)
     switch (m) {
-        case 2: PNS_COLS(2); break;
-        case 3: PNS_COLS(3); break;
-        case 4: PNS_COLS(4); break;
+        case 2: PNS_COLS4(2); break;
+        case 3: PNS_COLS4(3); break;
+        case 4: PNS_COLS4(4); break;
         default:
             if (W > 4) {
                 switch (m) {
@@ -1235,6 +1258,7 @@ __global__ void __launch_bounds__(32 * W) k_node_cols(const __grid_constant__ Ct
             break;
     }
 #undef PNS_COLS
+#undef PNS_COLS4
 }
 #endif
 
@@ -2338,7 +2362,9 @@ void launch_node(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c) {
     if (net->replicas > 1 && net->replicas <= cols_max && !getenv("PNS_PAIR_THREADS")) {
         // batched replicas, small batches: one warp per node slot (latency); large batches keep one thread per node
         // (fewer instructions per node)
-        const dim3 grid((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)net->n_nodes);
+        dim3 grid((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)net->n_nodes);
+        if (net->nd_stride > 4 && net->nd_cols_order)          // nodes of <= 4 slots share a CTA in twos
+            grid.y = (unsigned)((net->n_nodes_small + 1) / 2 + (net->n_nodes - net->n_nodes_small));
         if (net->nd_stride <= 4) {
             if (routed) PNS_LAUNCH_CHAIN((k_node_cols<true, 4>), grid, 128, s, c);
             else PNS_LAUNCH_CHAIN((k_node_cols<false, 4>), grid, 128, s, c);

@@ -92,6 +92,13 @@ class Engine:
         net.lp_max_m = int((np.asarray(p["nd_meta"])[lp_nodes, 1] & 0xff).max()) if len(lp_nodes) else 0
         net.lp_w = float(p.get("lp_w", 0.01))
         self.lp_x = None                                  # keep_lp_solutions(): the step's turn flows before the floor
+        # schedule of the batched node kernel (nd_stride 8): nodes of <= 4 slots first, they share a CTA in twos
+        self._cols_order = None
+        if R > 1 and not emulation and int(p["nd_stride"]) > 4 and self.N:
+            slots = np.asarray(p["nd_meta"])[:, 1] & 0xff
+            order = np.concatenate([np.nonzero(slots <= 4)[0], np.nonzero(slots > 4)[0]]).astype(np.int32)
+            self._cols_order = torch.from_numpy(order).to(dev)
+            net.nd_cols_order, net.n_nodes_small = _ptr(self._cols_order), int((slots <= 4).sum())
         # launch order of the single-replica link kernel (a schedule; results do not depend on it)
         self._lane_order = None
         if R == 1 and not emulation and L > 0:

@@ -11,6 +11,7 @@ SRC = os.path.join(ROOT, "pednstream_b200", "csrc", "pns_kernels.cu")
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     deps = [SRC, os.path.join(ROOT, "pednstream_b200", "csrc", "pns_rng.cuh"),
+            os.path.join(ROOT, "pednstream_b200", "csrc", "pns_lp.cuh"),
             os.path.join(ROOT, "include", "pns_b200.h"), os.path.join(ROOT, "tests", "emu", "pns_emu.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) > os.path.getmtime(d) for d in deps):
         return OUT
