@@ -162,6 +162,10 @@ struct EnvCtx {
     float* obs;
     float* reward;
     float* cum_reward;      // optional running sum of the rewards (null: not kept)
+    // software prefetch of k_link_rep (a schedule): each CTA pulls the first-batch rows of the corridor `pf_pairs`
+    // further on (same replicas; about one resident wave of CTAs later) into L2, `pf_off` elements ahead; 0 = off
+    unsigned pf_pairs;
+    size_t pf_off;
 };
 
 template <bool R1> struct Lanes;   // how a thread's two links sit in a history row
@@ -1119,6 +1123,16 @@ __global__ void __launch_bounds__(256) k_lp_batch(const LpBatch b) {
 // W = slots per node the launch provides warps for (pns_net.nd_stride: 4 or 8); warps beyond the node's slot count
 // leave at once, the others meet at a named barrier sized to the node.
 // Body for a node with M slots (compile-time: every loop is exact and every small array lives in registers).
+#ifndef PNS_REP_L2
+#define PNS_REP_L2 0   // L2 eviction hints in the batched kernels (see k_link_rep): measured no gain, off
+#endif
+#if PNS_REP_L2
+#define NLD_ONCE(a) ldh((a), pol.once)
+#define NST_KEEP(a, v) sth((a), (v), pol.keep)
+#else
+#define NLD_ONCE(a) (*(a))
+#define NST_KEEP(a, v) (*(a) = (v))
+#endif
 template <bool ROUTED, int W, int M>
 __device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][32], int node, int j, int lane, int rep,
                                                bool valid, int kind, int tf_mode, int dem_row, int tf_ptr,
@@ -1128,10 +1142,12 @@ __device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][3
     const int col = __ldg(c.n.nd_in_link + base + j);
     PNS_PDL_WAIT();
     // ---- one batch of loads: all sending flows, this slot's receiving flow, column j of the fractions ----
+    const L2Pol pol = l2_policies();           // PNS_REP_L2: hand-over records read once, the answer kept
+    (void)pol;
     double s[M];
 #pragma unroll
-    for (int i = 0; i < M; ++i) s[i] = c.s.nm_s[(base + i) * R + rep];
-    double r_j = c.s.nm_r[(base + j) * R + rep];
+    for (int i = 0; i < M; ++i) s[i] = NLD_ONCE(c.s.nm_s + (base + i) * R + rep);
+    double r_j = NLD_ONCE(c.s.nm_r + (base + j) * R + rep);
     double r_other = (M == 2 && kind == 0) ? c.s.nm_r[(base + (1 - j)) * R + rep] : 0.0;
     double P[M];
     if (kind != 0) {
@@ -1196,8 +1212,8 @@ __device__ __forceinline__ void node_cols_body(const Ctx& c, double (*sh_f)[W][3
     // Node.update_links (node.py:146-162); a node that receives no sending flow stores nothing (rows are zero by
     // contract, see pns_node_flows), only the counters of its virtual links carry forward
     if (any_flow) {
-        c.n_outflow[(size_t)col * R + rep] = q_out;
-        c.n_inflow[(size_t)(col ^ 1) * R + rep] = q_in;
+        NST_KEEP(c.n_outflow + (size_t)col * R + rep, q_out);
+        NST_KEEP(c.n_inflow + (size_t)(col ^ 1) * R + rep, q_in);
     }
     if (dem_row >= 0 && j == 0) {
         // the virtual links have no link thread: slot 0's flows extend their counters (link.py:19-25)
@@ -1637,9 +1653,30 @@ __global__ void __launch_bounds__(kBlock) k_env_observe(const __grid_constant__ 
 constexpr int kRepBlock = 64;
 
 template <int PHASE, int MODE, bool ONECLASS, bool ENV>
+#ifndef PNS_REP_L2
+#define PNS_REP_L2 0
+#endif
+#if PNS_REP_L2
+#define RLD_KEEP(a) ldh((a), pol.keep)
+#define RLD_ONCE(a) ldh((a), pol.once)
+#define RST_KEEP(a, v) sth((a), (v), pol.keep)
+#define RST_ONCE(a, v) sth((a), (v), pol.once)
+#else
+#define RLD_KEEP(a) (*(a))
+#define RLD_ONCE(a) (*(a))
+#define RST_KEEP(a, v) (*(a) = (v))
+#define RST_ONCE(a, v) (*(a) = (v))
+#endif
 __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(const __grid_constant__ EnvCtx x) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
     const Ctx& c = x.c;
+    // L2 residency (PNS_REP_L2 = 1): a step moves about twice what L2 holds, so what the next launch reads back --
+    // the hand-over to the node pass, the row the update leaves for the next flow launch -- would be stored
+    // evict-last, and what is used once (lagged rows, the node pass's answer, series nobody reads inside a step)
+    // evict-first.  Measured: no difference (8192 replicas 110.0 vs 108.8 us per step, 4096: 61.4 vs 62.8) -- the
+    // kernels wait on dependent loads and arithmetic, not on DRAM bandwidth; left off.
+    const L2Pol pol = l2_policies();
+    (void)pol;
     __shared__ float sh_num[kRepBlock], sh_dens[kRepBlock];
     __shared__ double sh_noise[kRepBlock], sh_send[kRepBlock];
     const int R = c.n.replicas;
@@ -1674,15 +1711,44 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
     double gate = c.s.gate[e];
     double gate_rev = flw ? c.s.gate[er] : 0.0;
+    const bool windowed = c.u_tt_old != nullptr;
+    if (x.pf_pairs && pair + x.pf_pairs < n_pairs) {
+        // the loads below, for the CTA one resident wave later: its batch then finds the rows in L2.  One lane per
+        // 128-byte line asks (16 doubles / 32 floats).
+        const size_t a = e + x.pf_off;
+        const unsigned ln = threadIdx.x & 31u;
+        if ((ln & 15u) == 0) {
+            prefetch_l2(c.s.gate + a);
+            if (upd) {
+                prefetch_l2(c.n_cinp + a); prefetch_l2(c.n_coutp + a);
+                prefetch_l2(c.n_outflow + a); prefetch_l2(c.n_inflow + a);
+            }
+            if (flw) {
+                if (!upd) { prefetch_l2(c.f_cin + a); prefetch_l2(c.f_cou + a); }
+                prefetch_l2(c.f_sndp + a); prefetch_l2(c.f_rcvp + a);
+                if (ONECLASS) {
+                    if (c.c0_coulag) prefetch_l2(c.c0_coulag + a);
+                    if (c.c0_pre0) prefetch_l2(c.c0_pre0 + a);
+                    if (c.c0_pre1) prefetch_l2(c.c0_pre1 + a);
+                }
+            }
+        }
+        if (ln == 0) {
+            if (upd) {
+                prefetch_l2(c.u_num_prev + a); prefetch_l2(c.s.runsum + a);
+                if (windowed) prefetch_l2(c.u_tt_old + a);
+            }
+            if (flw && !upd) { prefetch_l2(c.f_num + a); prefetch_l2(c.f_dens + a); prefetch_l2(c.f_avg + a); }
+        }
+    }
     // ---- batch of independent loads --------------------------------------------------------
     double din = 0, dout = 0, cin_prev = 0, cou_prev = 0;
     float np_ = 0, rs = 0, tt_old = 0;
-    const bool windowed = c.u_tt_old != nullptr;
     if (upd) {
-        cin_prev = c.n_cinp[e]; cou_prev = c.n_coutp[e];
-        np_ = c.u_num_prev[e]; rs = c.s.runsum[e];
-        if (windowed) tt_old = c.u_tt_old[e];
-        dout = c.n_outflow[e]; din = c.n_inflow[e];
+        cin_prev = RLD_ONCE(c.n_cinp + e); cou_prev = RLD_ONCE(c.n_coutp + e);
+        np_ = RLD_ONCE(c.u_num_prev + e); rs = c.s.runsum[e];
+        if (windowed) tt_old = RLD_ONCE(c.u_tt_old + e);
+        dout = RLD_ONCE(c.n_outflow + e); din = RLD_ONCE(c.n_inflow + e);
     }
     double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
     LinkNow me;
@@ -1692,13 +1758,13 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     double pre_v0 = 0.0, pre_v1 = 0.0;
     if (flw) {
         if (!upd) {
-            cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e];
-            me.num = c.f_num[e]; me.dens = c.f_dens[e]; me.avg_tt = c.f_avg[e];
-            num_rev = c.f_num[er];
+            cin_tau = RLD_KEEP(c.f_cin + e); cou_tau = RLD_KEEP(c.f_cou + e);       // the update reads them again
+            me.num = RLD_KEEP(c.f_num + e); me.dens = RLD_ONCE(c.f_dens + e); me.avg_tt = RLD_ONCE(c.f_avg + e);
+            num_rev = RLD_KEEP(c.f_num + er);
         }
-        snd_prev = c.f_sndp[e]; rcv_prev = c.f_rcvp[e];
+        snd_prev = RLD_ONCE(c.f_sndp + e); rcv_prev = RLD_ONCE(c.f_rcvp + e);
         if (ONECLASS) {
-            if (c.c0_coulag) cou_lag = c.c0_coulag[e];
+            if (c.c0_coulag) cou_lag = RLD_ONCE(c.c0_coulag + e);
         } else {
             const int lag_i = tau + 1 - swtau;
             if (lag_i >= 0) cou_lag = H64(c, PNS_F64_CUM_OUTFLOW, lag_i)[e];
@@ -1716,8 +1782,8 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
                 pre_row1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1);
             }
         }
-        if (pre_row0) pre_v0 = pre_row0[e];
-        if (pre_row1) pre_v1 = pre_row1[e];
+        if (pre_row0) pre_v0 = RLD_ONCE(pre_row0 + e);
+        if (pre_row1) pre_v1 = RLD_ONCE(pre_row1 + e);
     }
     // ---- actions of this environment step (rl/builders.py:264-352; setters link.py:121-126, 462-478) --------
     // Each thread derives the new width of its own link and of its mate's from the old widths, so neither waits
@@ -1743,7 +1809,7 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     if (upd) {
         cin_tau = cin_prev + din;                                           // link.py:19-25
         cou_tau = cou_prev + dout;
-        if (valid) { c.n_cin[e] = cin_tau; c.n_cout[e] = cou_tau; }
+        if (valid) { RST_KEEP(c.n_cin + e, cin_tau); RST_KEEP(c.n_cout + e, cou_tau); }
         me.num = (float)((double)np_ + (din - dout));                      // link.py:134-135
         me.dens = div_by_area(me.num, ar);                                  // link.py:136
         const bool noisy = p.sigma > 0.0;
@@ -1779,12 +1845,13 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
             me.avg_tt = p.tt0;
         }
         if (valid) {
-            c.u_num[e] = me.num; c.u_dens[e] = me.dens; c.u_speed[e] = v; c.u_tt[e] = tt;
-            c.u_flow[e] = v * me.dens;                                      // functions.py:97-101
-            if (windowed) c.u_avg[e] = me.avg_tt;
+            RST_KEEP(c.u_num + e, me.num); RST_KEEP(c.u_dens + e, me.dens);
+            RST_ONCE(c.u_speed + e, v); RST_ONCE(c.u_tt + e, tt);
+            RST_ONCE(c.u_flow + e, v * me.dens);                            // functions.py:97-101
+            if (windowed) RST_KEEP(c.u_avg + e, me.avg_tt);
             c.s.runsum[e] = sum;
-            c.u_bgw[e] = gate;                                              // link.py:188, 451-452
-            if (is_sep(p)) c.u_sepw[e] = gate;
+            RST_ONCE(c.u_bgw + e, gate);                                    // link.py:188, 451-452
+            if (is_sep(p)) RST_ONCE(c.u_sepw + e, gate);
         }
         if (ENV && x.obs && valid) {
             // ObservationBuilder (rl/builders.py:68-177): the entries this directed link contributes
@@ -1850,10 +1917,10 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     if (valid) {
         // cal_receiving_flow_with_reverse (link.py:407-416; separators ignore the reverse flow, :509-512)
         const double rcv = pymax(is_sep(p) ? r : r - s_rev, 0.0);
-        c.f_snd[e] = s.flow;
-        c.f_rcv[e] = rcv;
-        c.s.nm_s[(size_t)slots.x * R + rep] = s.flow;
-        c.s.nm_r[(size_t)slots.y * R + rep] = rcv;
+        RST_ONCE(c.f_snd + e, s.flow);
+        RST_ONCE(c.f_rcv + e, rcv);
+        RST_KEEP(c.s.nm_s + (size_t)slots.x * R + rep, s.flow);
+        RST_KEEP(c.s.nm_r + (size_t)slots.y * R + rep, rcv);
         if (ENV && gate_changed) {
             c.s.gate[e] = gate;
             if (np64_now) c.s.sep_np64[e] = 1;   // np.clip returns numpy float64: the lane area becomes a float64
@@ -2288,9 +2355,19 @@ void launch_lane_mode(size_t n_links, cudaStream_t s, const Ctx& c) {
 #ifndef PNS_HOST_EMULATION
 // batched replicas on the GPU: one thread per (directed link, replica), optionally with the environment riding along
 template <int PHASE, bool ENV>
-void launch_rep_mode(const pns_net* net, cudaStream_t s, const EnvCtx& x) {
-    const dim3 nb((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)(net->n_links / 2) + (unsigned)x.c.route_blocks);
+void launch_rep_mode(const pns_net* net, cudaStream_t s, const EnvCtx& x0) {
+    const dim3 nb((unsigned)(((size_t)net->replicas + 31) / 32), (unsigned)(net->n_links / 2) + (unsigned)x0.c.route_blocks);
     const bool one = net->n_classes == 1;
+    EnvCtx x = x0;
+    {   // prefetch distance: the corridors half a resident wave of CTAs covers (148 SMs x PNS_REP_MIN_BLOCKS / 2), plus
+        // one (measured at 8192 replicas: off 113.0, quarter.. wave 108.3 / 109.5 / 112.6 us per environment step)
+        static const int wave = getenv("PNS_REP_PF_WAVE") ? atoi(getenv("PNS_REP_PF_WAVE")) : 148 * PNS_REP_MIN_BLOCKS / 2;
+        const unsigned ahead = wave > 0 ? (unsigned)((wave + nb.x - 1) / nb.x) + 1u : 0u;
+        if (ahead && ahead < (unsigned)(net->n_links / 2)) {
+            x.pf_pairs = ahead;
+            x.pf_off = (size_t)ahead * 2u * (size_t)net->replicas;
+        }
+    }
     if (x.c.mode == PNS_RNG_PHILOX) {
         if (one) PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_PHILOX, true, ENV>), nb, kRepBlock, s, x);
         else PNS_LAUNCH_CHAIN((k_link_rep<PHASE, PNS_RNG_PHILOX, false, ENV>), nb, kRepBlock, s, x);
