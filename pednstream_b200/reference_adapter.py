@@ -8,6 +8,10 @@ reference's *own* `src.LTM.network.Network` object and replaces the body of `net
     for t in range(1, net.simulation_steps):
         b200.step(t)            # == net.network_loading(t); every per-link array of `net` is filled in
 
+With `assign_flows_type: optimal` the device solves each node's linear program itself (csrc/pns_lp.cuh): the flows
+are optimal solutions of the same programs, but where an optimum is not unique, or a flow is an integer up to
+rounding, the vertex -- and so the trajectory -- is not the one scipy's solver would have produced.
+
 The reference object stays the source of truth for its consumers (output handler, visualiser, RL builders):
 after every step the rows the step produced are written into the reference's own numpy arrays
 (`link.inflow[t]`, ..., `link.sending_flow[t-1]`), and host mutations made on the reference objects between

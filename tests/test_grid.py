@@ -6,16 +6,20 @@ from pednstream_b200 import Network
 from pednstream_b200.grid import DEFAULT_LINK, build_grid_plan, default_origins, grid_adjacency
 
 
-@pytest.mark.parametrize("size,origins", [(3, [0, 8]), (5, None), (6, [0, 5, 14, 35]), (2, [0])])
-def test_grid_plan_equals_generic_plan(size, origins):
+@pytest.mark.parametrize("size,origins,node_model", [(3, [0, 8], "classic"), (5, None, "classic"),
+                                                     (6, [0, 5, 14, 35], "classic"), (2, [0], "classic"),
+                                                     (5, [0, 12, 24], "optimal")])
+def test_grid_plan_equals_generic_plan(size, origins, node_model):
     S = 80
     origins = default_origins(size, stride=3) if origins is None else origins
     params = {"unit_time": 10, "simulation_steps": S, "default_link": dict(DEFAULT_LINK),
+              "assign_flows_type": node_model,
               "demand": {f"origin_{o}": {"peak_lambda": 50, "base_lambda": 30} for o in origins}}
     np.random.seed(0)
     net = Network(grid_adjacency(size), params, origin_nodes=list(origins), verbose=False)
     want = net.plan
-    got, gate, tf, demand = build_grid_plan(size, S, origins=origins, demand_seed=0)
+    got, gate, tf, demand = build_grid_plan(size, S, origins=origins, demand_seed=0, node_model=node_model)
+    assert (((np.asarray(got["nd_meta"])[:, 1] >> 8) & 0xff) == 2).any() == (node_model == "optimal")
     assert list(net.nodes.keys()) == got["node_order"].tolist()
     for k, v in want.items():
         if isinstance(v, np.ndarray):
