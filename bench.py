@@ -19,6 +19,9 @@ Further blocks of the JSON line (rank 0):
                       (8192/N per GPU), random gate actions, with its own roofline and end-to-end figures
   small_configs       BASELINE configs 1-3 (long_corridor, nine_intersections, melbourne@2000): GPU wall time per
                       step in numpy-compatible and philox draw modes
+  optimal_node_model  assign_flows_type 'optimal' (one linear program per node, replica and step): the batched
+                      environment at 1024 replicas with the device simplex, beside scipy.optimize.linprog (the
+                      reference's solver) on the host for a sample of recorded programs
   cpu_baseline        the reference's own code (baseline/_ref, kind "reference"; the oracle port when the
                       reference is not installed) on one host core, bounded sample
 
@@ -421,6 +424,49 @@ def bench_env45(torch, dist, world, rank, dev, replicas, steps, warmup, peak, co
     return out
 
 
+# ================================================================================= 'optimal' node model
+def bench_optimal(torch, dev, steps=20):
+    """45_intersections x 1024 replicas with assign_flows_type 'optimal' (reference node.py:249-271): step time with
+    the warp-level simplex (k_node_lp), and the reference's solver call on the host for recorded programs."""
+    import numpy as np
+    from pednstream_b200.rl import BatchedPedNetEnv
+    R = 1024
+    out = {}
+    for model in ("classic", "optimal"):
+        env = BatchedPedNetEnv("45_intersections", replicas=R, obs_mode="option3", seed=1000, device=dev,
+                               params={"assign_flows_type": model})
+        acts = torch.rand((60 + steps, R, env.n_act), device=dev, dtype=torch.float32) * 4.0
+        env.rollout(acts[:60])                                  # into the loaded state: most nodes carry flow
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.rollout(acts[60:])
+        e1.record()
+        torch.cuda.synchronize()
+        env.engine.check_errors()
+        out[model] = {"us_per_env_step": 1e3 * e0.elapsed_time(e1) / steps, "lp_nodes": int(env.engine.net.n_lp_nodes)}
+        del env
+        torch.cuda.empty_cache()
+    n_prog = out["optimal"]["lp_nodes"] * R
+    extra_us = out["optimal"]["us_per_env_step"] - out["classic"]["us_per_env_step"]
+    out["programs_per_step"] = n_prog
+    out["ns_per_program"] = 1e3 * extra_us / n_prog
+    try:        # the reference's solver on the host (test infrastructure; the one place bench.py may execute oracle/)
+        from oracle.ltm_oracle import scipy_lp
+        gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "lp_programs.npz"))
+        n, t0 = 0, time.perf_counter()
+        for m in (3, 4, 5):
+            for k in range(40):
+                scipy_lp(m, gold[f"s_{m}"][k], gold[f"r_{m}"][k], gold[f"phi_{m}"][k])
+                n += 1
+        out["host_linprog_us_per_program"] = 1e6 * (time.perf_counter() - t0) / n
+        out["host_note"] = ("scipy.optimize.linprog as the reference calls it (node.py:262) on 120 programs recorded "
+                            "from the reference's runs, one host core")
+    except Exception as exc:                    # noqa: BLE001
+        out["host_note"] = f"host solver not timed: {exc!r}"[:200]
+    return out
+
+
 # ================================================================================= small configs (1-3)
 def bench_small_configs(torch, dev):
     """BASELINE configs 1-3 on the GPU through the facade: wall time per network_loading(t) in the numpy-compatible
@@ -672,6 +718,9 @@ def run_ours(args):
     small = None
     if rank == 0 and world == 1 and not args.no_small:
         small = bench_small_configs(torch, dev)
+    optimal = None
+    if rank == 0 and world == 1 and not args.no_small:
+        optimal = bench_optimal(torch, dev)
 
     if rank == 0:
         value = world * L * K / (ms * 1e-3)
@@ -724,6 +773,8 @@ def run_ours(args):
             line["batched_env"] = env_stats
         if small is not None:
             line["small_configs"] = small
+        if optimal is not None:
+            line["optimal_node_model"] = optimal
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

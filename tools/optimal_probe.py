@@ -21,6 +21,7 @@ def timed(eng, t0, n):
     return e0.elapsed_time(e1) / n
 
 
+torch.manual_seed(0)
 out = {}
 only_env = len(sys.argv) > 1 and sys.argv[1] == "env"          # `env`: the batched part only (ncu captures)
 for model in ("classic", "optimal"):
