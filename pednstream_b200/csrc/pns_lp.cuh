@@ -26,6 +26,7 @@
 namespace pns {
 
 constexpr int kLpMaxSlots = 8;             // = PNS_MAX_DEGREE
+constexpr int kLpColsPerPass = 3;          // tableau columns a lane updates together in a pivot (m <= 5: all of them)
 constexpr int kLpBlandAfter = 400;
 constexpr int kLpMaxPivots = 20000;
 constexpr double kLpCostTol = 1e-9;        // a reduced cost below -tol enters
@@ -142,15 +143,31 @@ __device__ inline int lp_node_solve(int m, const double* s, const double* r, con
         for (int i = lane; i <= rows; i += LANES) pcol[i] = T[(size_t)i * ld + zj];
         PNS_LP_SYNC();
         const double piv = pcol[ri];
-        for (int j = lane; j < cols; j += LANES) {
-            const double pr = T[(size_t)ri * ld + j] / piv;
-            if (pr != 0.0) {
-                for (int i = 0; i <= rows; ++i) {
-                    const double f = pcol[i];
-                    if (f != 0.0 && i != ri) T[(size_t)i * ld + j] -= f * pr;
+        // row operations, lanes own columns lane, lane + LANES, ...: the scaled pivot row of a lane's columns stays
+        // in registers, rows go by in the outer loop (one broadcast read of the pivot column per row; rows with a
+        // zero there are skipped by the whole warp), the lane's columns in the unrolled inner one
+        for (int j0 = lane; j0 < cols; j0 += LANES * kLpColsPerPass) {
+            double pr[kLpColsPerPass];
+#pragma unroll
+            for (int k = 0; k < kLpColsPerPass; ++k) {
+                const int j = j0 + k * LANES;
+                pr[k] = j < cols ? T[(size_t)ri * ld + j] / piv : 0.0;
+            }
+            for (int i = 0; i <= rows; ++i) {
+                const double f = pcol[i];
+                if (f == 0.0 || i == ri) continue;
+                double* __restrict__ row = T + (size_t)i * ld;
+#pragma unroll
+                for (int k = 0; k < kLpColsPerPass; ++k) {
+                    const int j = j0 + k * LANES;
+                    if (j < cols && pr[k] != 0.0) row[j] -= f * pr[k];
                 }
             }
-            T[(size_t)ri * ld + j] = pr;
+#pragma unroll
+            for (int k = 0; k < kLpColsPerPass; ++k) {
+                const int j = j0 + k * LANES;
+                if (j < cols) T[(size_t)ri * ld + j] = pr[k];
+            }
         }
         if (lane == 0) basis[ri] = zj;
         PNS_LP_SYNC();
