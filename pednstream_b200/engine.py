@@ -202,11 +202,11 @@ class Engine:
             _ptr(host_demand), _ptr(self._dev_metric), _ptr(host_metric), self._stream()), "pns_step_streamed")
         self._route_all(False)
 
-    def _native_env_step(self, actions, obs, reward, cum_reward, t):
+    def _native_env_step(self, actions, obs, reward, cum_reward, t, stream=None):
         _native.check(self.lib, self.lib.pns_env_step(
             C.byref(self.net), C.byref(self.state), C.byref(self.io), C.byref(self._env_struct),
             _ptr(actions) if actions is not None else C.c_void_p(0), int(t), _native.RNG_PHILOX, _ptr(obs), _ptr(reward),
-            _ptr(cum_reward), self._stream()), "pns_env_step")
+            _ptr(cum_reward), self._stream() if stream is None else stream), "pns_env_step")
         self._route_all(False)
 
     def _native_env_rollout(self, actions, obs, reward, cum_reward, t0, n_steps, host=None):

@@ -15,6 +15,8 @@ The first replica of every group is, in episode 0 with randomize="host", exactly
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from .batched_env import BatchedPedNetEnv
@@ -57,6 +59,8 @@ class GroupedPedNetEnv:
             self._done = [torch.cuda.Event() for _ in self.envs]
         self.obs = torch.zeros((self.R, self.n_obs), dtype=torch.float32, device=self.device)
         self.reward = torch.zeros((self.R,), dtype=torch.float32, device=self.device)
+        self._obs_views = {sl.start: self.obs[sl] for sl in self.slices}
+        self._reward_views = {sl.start: self.reward[sl] for sl in self.slices}
         self._gather_obs()
 
     @property
@@ -95,19 +99,28 @@ class GroupedPedNetEnv:
         return self.obs
 
     def step(self, actions: torch.Tensor):
-        """actions: float32 [R, n_act] on the device -> (obs [R, n_obs], reward [R], done, info)."""
-        if actions.shape != (self.R, self.n_act):
-            raise ValueError(f"actions must be [{self.R}, {self.n_act}]")
-        done = False
-        streams = self._fork()
-        for env, sl, st in zip(self.envs, self.slices, streams):
-            if st is None:
-                _, _, done, _ = env.step(actions[sl], obs_out=self.obs[sl], reward_out=self.reward[sl])
-            else:
-                with torch.cuda.stream(st):
-                    _, _, done, _ = env.step(actions[sl], obs_out=self.obs[sl], reward_out=self.reward[sl])
-        self._join()
-        return self.obs, self.reward, done, {}
+        """actions: float32 [R, n_act] on the device -> (obs [R, n_obs], reward [R], done, info).
+        One native call per group (pns_env_step on the group's stream), without the per-environment Python layers:
+        with eight groups those cost more than the kernels."""
+        if tuple(actions.shape) != (self.R, self.n_act) or actions.dtype != torch.float32:
+            raise ValueError(f"actions must be float32 [{self.R}, {self.n_act}]")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        t = self.envs[0].sim_step
+        if t > self.simulation_steps:
+            raise RuntimeError("episode finished: call reset()")
+        with self.envs[0].engine._guard():
+            streams = self._fork()
+            for env, sl, st in zip(self.envs, self.slices, streams):
+                eng = env.engine
+                eng._begin_steps(t, 1)
+                eng._native_env_step(actions[sl] if self.n_act else None, self._obs_views[sl.start],
+                                     self._reward_views[sl.start], env.cumulative_reward, t,
+                                     stream=None if st is None else C.c_void_p(st.cuda_stream))
+                eng.t_done = t
+                env.sim_step = t + 1
+            self._join()
+        return self.obs, self.reward, t >= self.simulation_steps, {"step": t}
 
     def kpis(self, t_last: int = None) -> torch.Tensor:
         return torch.cat([env.kpis(t_last) for env in self.envs], dim=0)
