@@ -796,6 +796,25 @@ __device__ __forceinline__ void route_thread(const Ctx& c, int t, int row_index,
     if (c.mode == PNS_RNG_REQUEST) return;
     routed_row_fractions(c, routed, m, i, row, t, rep, c.s.tf_routed + (size_t)(meta.w + i * (m - 1)) * R + rep);
 }
+#ifndef PNS_HOST_EMULATION
+// Single replica: one *warp* per row.  A row thread is a chain of a few thousand dependent fp64 instructions (the
+// logit of each of its (od, upstream) groups, then the OD mixing): 26 us for nine_intersections, more than the
+// link and node kernels together.  The groups are independent, so the lanes take one each; lane 0 then mixes.
+__device__ __forceinline__ void route_warp(const Ctx& c, int t, int row_index, unsigned lane) {
+    PNS_PDL_TRIGGER();
+    const int row = c.route_all ? row_index : __ldg(c.n.rt_dyn_rows + row_index);
+    const int routed = __ldg(c.n.rt_row_routed + row);
+    const int ga = __ldg(c.n.rt_row_grp_ptr + row), gb = __ldg(c.n.rt_row_grp_ptr + row + 1);
+    const int i = row - __ldg(c.n.rt_routed_row0 + routed);
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(c.n.nd_meta) + __ldg(c.n.rt_routed_nodes + routed));
+    const int m = meta.y & 0xff;
+    PNS_PDL_WAIT();
+    for (int x = ga + (int)lane; x < gb; x += 32) group_probs(c, __ldg(c.n.rt_row_grp + x), 0, t);
+    __syncwarp();                              // orders the lanes' stores of the probabilities before lane 0's loads
+    if (lane == 0 && c.mode != PNS_RNG_REQUEST)
+        routed_row_fractions(c, routed, m, i, row, t, 0, c.s.tf_routed + (size_t)(meta.w + i * (m - 1)));
+}
+#endif
 __global__ void __launch_bounds__(kBlock) k_route_fractions(const __grid_constant__ Ctx c) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned R = (unsigned)c.n.replicas;
@@ -1293,9 +1312,9 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     // sampler walks come first so that they overlap the rest of the grid
     unsigned bx = blockIdx.x, n_link_ctas = gridDim.x;
     if (flw && c.route_blocks > 0) {                     // route choice rides along (see Ctx::route_blocks)
-        if (bx < (unsigned)c.route_blocks) {
-            const unsigned row = bx * (unsigned)PNS_LANE_BLOCK + threadIdx.x;
-            if (row < (unsigned)route_rows(c)) route_thread(c, c.route_t, (int)row, 0);
+        if (bx < (unsigned)c.route_blocks) {             // one warp per row
+            const unsigned row = bx * (unsigned)(PNS_LANE_BLOCK / 32) + (threadIdx.x >> 5);
+            if (row < (unsigned)route_rows(c)) route_warp(c, c.route_t, (int)row, threadIdx.x & 31u);
             return;
         }
         bx -= (unsigned)c.route_blocks;
@@ -1684,6 +1703,8 @@ __global__ void __launch_bounds__(kRepBlock, PNS_REP_MIN_BLOCKS) k_link_rep(cons
     const int rep_raw = (int)(blockIdx.x * 32u + (threadIdx.x & 31u));
     const unsigned n_pairs = (unsigned)c.n.n_links >> 1;
     if (flw && blockIdx.y >= n_pairs) {                     // route choice rides along: two rows per CTA
+        // (one row per CTA with its groups split between the two warps was tried: 35.9 vs 34.3 us per step at 1024
+        // replicas, 115 vs 108 us at 8192 -- with 32 replicas per warp the rows are not the longest threads)
         const unsigned row = 2u * (blockIdx.y - n_pairs) + dir;
         if (row < (unsigned)route_rows(c) && rep_raw < R) route_thread(c, c.route_t, (int)row, rep_raw);
         return;
@@ -2421,7 +2442,8 @@ void launch_pair(const pns_net* net, size_t n, cudaStream_t s, const Ctx& c, con
     if (net->replicas == 1 && !getenv("PNS_PAIR_THREADS")) {      // single replica: one thread per directed link
         Ctx cl = c;
         if (with_route && (c.phase & PH_FLOWS)) {
-            cl.route_blocks = ((c.route_all ? net->n_rows : net->n_dyn_rows) + PNS_LANE_BLOCK - 1) / PNS_LANE_BLOCK;
+            constexpr int rows_per_cta = PNS_LANE_BLOCK / 32;               // route choice: one warp per row
+            cl.route_blocks = ((c.route_all ? net->n_rows : net->n_dyn_rows) + rows_per_cta - 1) / rows_per_cta;
             cl.route_t = c.t_flows;
             cl.route_recompute = (c.phase & PH_UPDATE) ? 1 : 0;
         }
