@@ -17,7 +17,11 @@ eng = Engine(plan, replicas=1, rng="philox", seed=0, device="cuda:0")
 eng.initialise(gate, None, tf, demand, None)
 eng.run(1, T0)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 eng.run(T0 + 1, N)
+e1.record()
 torch.cuda.synchronize()
+print("us per step", 1e3 * e0.elapsed_time(e1) / N)
 eng.check_errors()
 print("pedestrians on links", float(eng.history("num_pedestrians")[T0 + N].sum()))
