@@ -1059,6 +1059,13 @@ __device__ __forceinline__ void node_lp_body(const Ctx& c, int node, int rep, in
     const int info = pns::lp_node_solve<LANES>(m, sv, rv, phi, phi_stride, c.n.lp_w, lane, scratch + kLpHeader, &x,
                                                &objective);
     if ((info & (pns::LP_UNBOUNDED | pns::LP_PIVOT_LIMIT)) && lane == 0) atomicOr(c.s.err + rep, PNS_ERR_LP_FAILED);
+#ifdef PNS_HOST_EMULATION
+    if ((info & (pns::LP_UNBOUNDED | pns::LP_PIVOT_LIMIT)) && getenv("PNS_LP_DEBUG")) {    // test build: show the program
+        fprintf(stderr, "LP failed: info %x node %d rep %d t %d m %d\n", info, node, rep, c.t, m);
+        for (int i = 0; i < m; ++i) fprintf(stderr, " s %.17g r %.17g\n", sv[i], rv[i]);
+        for (int e = 0; e < m * (m - 1); ++e) fprintf(stderr, " phi %.17g\n", phi[(size_t)e * phi_stride]);
+    }
+#endif
     if (c.io.lp_x)
         for (int e = lane; e < m * (m - 1); e += LANES) c.io.lp_x[(size_t)(tf_ptr + e) * R + rep] = x[e];
     double q0_out = 0.0, q0_in = 0.0;

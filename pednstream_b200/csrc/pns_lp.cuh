@@ -29,8 +29,11 @@ constexpr int kLpMaxSlots = 8;             // = PNS_MAX_DEGREE
 constexpr int kLpColsPerPass = 3;          // tableau columns a lane updates together in a pivot (m <= 5: all of them)
 constexpr int kLpBlandAfter = 400;
 constexpr int kLpMaxPivots = 20000;
-constexpr double kLpCostTol = 1e-9;        // a reduced cost below -tol enters
-constexpr double kLpPivotTol = 1e-9;       // smallest tableau entry the ratio test pivots on
+constexpr double kLpCostTol = 1e-9;        // a reduced cost below -tol (x the column's scale, if that is below 1) enters
+constexpr double kLpPivotTol = 1e-9;       // the ratio test pivots on entries above tol x the largest of the column
+constexpr double kLpSmallEntry = 1e-9;     // HiGHS (the solver behind linprog) drops matrix entries below its
+                                           // small_matrix_value = 1e-9: the logit produces such fractions
+constexpr double kLpZero = 1e-13;          // tableau entries below this are rounding residue of exact zeros
 
 enum { LP_NOT_UNIQUE = 1 << 28, LP_UNBOUNDED = 1 << 29, LP_PIVOT_LIMIT = 1 << 30 };   // info bits above the pivot count
 
@@ -55,6 +58,21 @@ __host__ __device__ inline size_t lp_scratch_bytes(int m) {
 #else
 #define PNS_LP_SYNC() __syncwarp()
 #endif
+
+// max over the cooperating lanes
+template <int LANES>
+__device__ __forceinline__ double lp_max(double v) {
+#ifndef PNS_HOST_EMULATION
+    if (LANES > 1) {
+#pragma unroll
+        for (int d = LANES / 2; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = o > v ? o : v;
+        }
+    }
+#endif
+    return v;
+}
 
 // argmin over the cooperating lanes of (key, tie); lanes without a candidate pass idx < 0
 template <int LANES>
@@ -90,7 +108,8 @@ __device__ inline int lp_node_solve(int m, const double* s, const double* r, con
     PNS_LP_SYNC();
     for (int e = lane; e < E; e += LANES) {
         const int i = e / (m - 1), jj = e - i * (m - 1), j = jj < i ? jj : jj + 1;
-        const double f = phi[(size_t)e * phi_stride];
+        double f = phi[(size_t)e * phi_stride];
+        if (f < kLpSmallEntry && f > -kLpSmallEntry) f = 0.0;         // as the reference's solver does (see kLpSmallEntry)
         T[(size_t)i * ld + e] = 1.0;                                   // node.py:86-89
         T[(size_t)(m + j) * ld + e] = 1.0;                             // node.py:92-97
         double* q = T + (size_t)(2 * m + e) * ld;                      // node.py:127-135
@@ -126,15 +145,56 @@ __device__ inline int lp_node_solve(int m, const double* s, const double* r, con
             }
         }
         lp_argmin<LANES>(zk, zt, zj);
-        if (zj < 0) break;                                             // optimal
-        double rk = 0.0; int rt = 0, ri = -1;
+        if (zj < 0) {
+            // Nothing enters on the absolute test.  Turning fractions from the logit reach down to 1e-9 and below, and
+            // a variable whose column has only entries of that size moves the solution by O(1) per 1e9 of its units:
+            // its reduced cost is tiny although the step it allows is huge.  Such columns are judged relative to
+            // their own scale (largest entry, between kLpZero and 1).
+            for (int j = lane; j < rhs; j += LANES) {
+                const double z = T[(size_t)obj * ld + j];
+                if (z < 0.0) {
+                    double cmax = 0.0;
+                    for (int i = 0; i < rows; ++i) { const double a = fabs(T[(size_t)i * ld + j]); cmax = a > cmax ? a : cmax; }
+                    if (cmax > kLpZero && cmax < 1.0 && z < -kLpCostTol * cmax) {
+                        const double key = bland ? 0.0 : z / cmax;
+                        if (zj < 0 || key < zk) { zk = key; zt = j; zj = j; }
+                    }
+                }
+            }
+            lp_argmin<LANES>(zk, zt, zj);
+            if (zj < 0) break;                                         // optimal
+        }
+        double cmax = 0.0;
+        for (int i = lane; i < rows; i += LANES) { const double a = T[(size_t)i * ld + zj]; cmax = a > cmax ? a : cmax; }
+        cmax = lp_max<LANES>(cmax);
+        const double amin = cmax * kLpPivotTol > kLpZero ? cmax * kLpPivotTol : kLpZero;
+        // minimum ratio; among the rows that attain it (the program is degenerate by construction: many share
+        // ratio 0) the largest pivot element, for stability -- a 1e-9 pivot next to entries of 1 turned the
+        // tableau into 1e8s -- and, once Bland's rule is on, the lowest basic variable
+        double qmin = 1e300;
         for (int i = lane; i < rows; i += LANES) {
             const double a = T[(size_t)i * ld + zj];
-            if (a > kLpPivotTol) {
+            if (a > amin) {
                 const double b = T[(size_t)i * ld + rhs];
                 const double q = (b > 0.0 ? b : 0.0) / a;
-                const int bi = basis[i];
-                if (ri < 0 || q < rk || (q == rk && bi < rt)) { rk = q; rt = bi; ri = i; }
+                qmin = q < qmin ? q : qmin;
+            }
+        }
+        qmin = -lp_max<LANES>(-qmin);
+        double rk = 0.0; int rt = 0, ri = -1;
+        if (qmin < 1e300) {
+            const double qtie = qmin + 1e-13 * qmin + 1e-13;
+            for (int i = lane; i < rows; i += LANES) {
+                const double a = T[(size_t)i * ld + zj];
+                if (a > amin) {
+                    const double b = T[(size_t)i * ld + rhs];
+                    const double q = (b > 0.0 ? b : 0.0) / a;
+                    if (q <= qtie) {
+                        const double key = bland ? 0.0 : -a;
+                        const int bi = basis[i];
+                        if (ri < 0 || key < rk || (key == rk && bi < rt)) { rk = key; rt = bi; ri = i; }
+                    }
+                }
             }
         }
         lp_argmin<LANES>(rk, rt, ri);
@@ -190,6 +250,22 @@ __device__ inline int lp_node_solve(int m, const double* s, const double* r, con
     for (int i = lane; i < rows; i += LANES) {
         const int b = basis[i];
         if (b < E) { const double v = T[(size_t)i * ld + rhs]; x[b] = v > 0.0 ? v : 0.0; }
+    }
+    PNS_LP_SYNC();
+    // Fractions of 1e-7 and below make the tableau ill-conditioned (entries of 1e7 next to 1e-7); what is left of
+    // that in x is a 1e-7 overshoot of a sending or receiving flow in about one program in a hundred of that
+    // kind.  Scale the offending row / column back onto its bound (programs without such fractions are untouched:
+    // their sums meet the bounds exactly).
+    for (int i = lane; i < m; i += LANES) {
+        double sum = 0.0;
+        for (int k = 0; k < m - 1; ++k) sum += x[i * (m - 1) + k];
+        if (sum > s[i]) { const double f = s[i] / sum; for (int k = 0; k < m - 1; ++k) x[i * (m - 1) + k] *= f; }
+    }
+    PNS_LP_SYNC();
+    for (int j = lane; j < m; j += LANES) {
+        double sum = 0.0;
+        for (int i = 0; i < m; ++i) if (i != j) sum += x[i * (m - 1) + (j < i ? j : j - 1)];
+        if (sum > r[j]) { const double f = r[j] / sum; for (int i = 0; i < m; ++i) if (i != j) x[i * (m - 1) + (j < i ? j : j - 1)] *= f; }
     }
     PNS_LP_SYNC();
     *x_out = x;

@@ -51,6 +51,52 @@ def synthetic_programs(m, n, seed):
     return s, r, phi.reshape(n, m * (m - 1))
 
 
+def logit_programs(m, n, seed):
+    """Fractions as the route-choice logit produces them: softmax over utilities spread by up to 40, i.e. entries
+    down to 1e-18 next to entries of 1 (45_intersections with closed gates reaches 5e-10), closed gates (r = 0),
+    fractional receiving flows.  Such programs are ill-conditioned; HiGHS itself drops matrix entries below 1e-9
+    and stops at 1e-7, so the objective bar for this family is 1e-7."""
+    rng = np.random.RandomState(seed)
+    s = np.floor(rng.uniform(0, 60, (n, m)))
+    r = rng.uniform(0, 45, (n, m))
+    r[rng.uniform(size=(n, m)) < 0.2] = 0.0
+    s[rng.uniform(size=(n, m)) < 0.2] = 0
+    r[rng.uniform(size=(n, m)) < 0.1] = 1e6
+    u = rng.uniform(0, 1, (n, m, m - 1)) * rng.choice([1, 5, 20, 40], (n, m, 1))
+    phi = np.exp(-u)
+    phi /= phi.sum(axis=2, keepdims=True)
+    return s, r, phi.reshape(n, m * (m - 1))
+
+
+# a program of 45_intersections (node 24, random gate actions, step 16) on which the first version of the solver
+# stopped short: fractions of 5e-10 were below its absolute pivot tolerance
+TINY_FRACTIONS = dict(
+    s=[9.0, 9.0, 8.0, 9.0], r=[38.0, 16.0, 36.0, 34.0],
+    phi=[0.9946614260658514, 5.2423841856577401e-10, 0.0053385734099102222, 7.1941433940200466e-09,
+         7.1941433940200466e-09, 0.99999998561171322, 5.2423841856577401e-10, 0.9946614260658514,
+         0.0053385734099102222, 7.1941397348046033e-09, 0.99999998561172054, 7.1941397348046033e-09])
+
+
+def check_logit_programs(lib, device=None, per_shape=120):
+    out = {}
+    for m in (3, 4, 5):
+        s, r, phi = logit_programs(m, per_shape, seed=21 + m)
+        if m == 4:
+            s[0], r[0], phi[0] = TINY_FRACTIONS["s"], TINY_FRACTIONS["r"], TINY_FRACTIONS["phi"]
+        x, obj, info = solve_batch(lib, m, s, r, phi, device)
+        assert (info >> 29 == 0).all(), f"simplex failed, m={m}"
+        _, A_ub, _ = lp_matrices(m, phi[0])
+        for k in range(per_shape):
+            sol = scipy_lp(m, s[k], r[k], phi[k], W)
+            assert sol is not None
+            rhs = np.concatenate((s[k], r[k]))
+            assert (x[k] >= 0).all() and (rhs - A_ub[:, :m * (m - 1)] @ x[k] >= -1e-12 * np.maximum(1.0, rhs)).all()
+            got = lp_objective(m, phi[k], x[k])
+            assert abs(got - sol[1]) <= 1e-7 * max(1.0, abs(sol[1])), (m, k, got, sol[1])
+        out[m] = x
+    return out
+
+
 def solve_batch(lib, m, s, r, phi, device=None):
     n, E = len(s), m * (m - 1)
     if device is None:
@@ -144,6 +190,23 @@ def test_emulated_lp_solver_on_congested_programs(emu_lib):
     check_synthetic_programs(emu_lib)
 
 
+def test_emulated_lp_solver_on_logit_fractions(emu_lib):
+    check_logit_programs(emu_lib)
+
+
+def test_emulated_optimal_environment_with_gate_actions(emu_lib):
+    """Random gate actions close gates and push the logit to fractions of 1e-9: every program must still end at
+    an optimum (error bit PNS_ERR_LP_FAILED stays clear)."""
+    from pednstream_b200.rl import BatchedPedNetEnv
+    env = BatchedPedNetEnv("45_intersections", replicas=48, obs_mode="option3", seed=1000,
+                           params={"assign_flows_type": "optimal"}, _lib=emu_lib, _emulation=True)
+    gen = torch.Generator().manual_seed(0)
+    for _ in range(30):
+        env.step(torch.rand((48, env.n_act), generator=gen) * 4.0)
+    env.engine.check_errors()
+    assert float(env.engine.history("cumulative_inflow")[30].sum()) > 0
+
+
 def replay_against_oracle(case, steps, lib=None, emulation=False):
     """Device run keeping every program's x; then the oracle with those x, each verified against linprog."""
     dev_net = make_network(case)
@@ -211,6 +274,20 @@ def test_cuda_lp_solver_matches_linprog_and_the_host_build(emu_lib):
     want = check_synthetic_programs(emu_lib)
     for m in got:                                 # one source, no contraction: warp and sequential build agree bitwise
         assert np.array_equal(got[m], want[m]), m
+    got = check_logit_programs(lib, dev)
+    want = check_logit_programs(emu_lib, per_shape=120)
+    for m in got:
+        assert np.array_equal(got[m], want[m]), m
+
+
+@pytest.mark.gpu
+def test_cuda_optimal_environment_with_gate_actions():
+    from pednstream_b200.rl import BatchedPedNetEnv
+    env = BatchedPedNetEnv("45_intersections", replicas=1024, obs_mode="option3", seed=1000, device="cuda:0",
+                           params={"assign_flows_type": "optimal"})
+    torch.manual_seed(0)
+    env.rollout(torch.rand((80, 1024, env.n_act), device="cuda") * 4.0)
+    env.engine.check_errors()
 
 
 @pytest.mark.gpu
