@@ -90,9 +90,10 @@ constexpr int kBlock = 128;
 #define PNS_LANE_BLOCK 64      // threads per CTA of k_link_lane (measured: 64 < 128 < 256 < 512 in step time)
 #endif
 #ifndef PNS_PF_AHEAD_CTAS
-#define PNS_PF_AHEAD_CTAS (113664 / PNS_LANE_BLOCK)  // k_link_lane: each CTA pulls the rows of the CTA this far ahead
-                                                     // into L2: three quarters of a resident wave of 148 SMs x 1024
-                                                     // threads (measured 1/4 .. 1 wave: 43.0 42.3 41.4 41.0 41.6 us; 0 = off)
+#define PNS_PF_AHEAD_CTAS (99456 / PNS_LANE_BLOCK)   // k_link_lane: each CTA pulls the rows of the CTA this far ahead
+                                                     // into L2: three quarters of a resident wave of 148 SMs x 896
+                                                     // threads (round 1, at 1024 threads per SM, 1/4 .. 1 wave: 43.0 42.3
+                                                     // 41.4 41.0 41.6 us; now 1/2, 3/4, 1 wave: 39.1 38.4 38.7; 0 = off)
 #endif
 #ifndef PNS_SKIP_ZERO_HANDOVER
 #define PNS_SKIP_ZERO_HANDOVER 1
@@ -104,7 +105,9 @@ constexpr int kBlock = 128;
 #define PNS_PF_TAPS 1          // k_link_lane: early fetch of the diffusion taps of occupied links
 #endif
 #ifndef PNS_LANE_MIN_BLOCKS
-#define PNS_LANE_MIN_BLOCKS (1024 / PNS_LANE_BLOCK)
+#define PNS_LANE_MIN_BLOCKS (896 / PNS_LANE_BLOCK)   // 14 CTAs of 64 threads: 72 registers, no spills.  16 (64 registers) spilled
+                                                     // 56 bytes around the calls of the round-2 samplers and cost 8 % early in
+                                                     // the run, 5 % late (41.8 / 50.7 -> 38.5 / 48.2 us per step); 12: 40.4 / 50.4
 #endif
 #ifndef PNS_NODE_BLOCK
 #define PNS_NODE_BLOCK 128     // threads per CTA of k_node_flows

@@ -175,7 +175,9 @@ struct DrawKey {
 // dividing (a division is an 80-130 cycle dependent chain per step; a table load is off the critical path).
 // kPmfMode09[n] = pmf of Binomial(n, 1 - 0.9) at its mode, n <= PNS_MODE_TABLE_N: the blockers draw
 // (link.py:382) always has p = 0.9, so its mode-centred search starts from a table load.
+#ifndef PNS_INV_TABLE
 #define PNS_INV_TABLE 2048
+#endif
 #define PNS_MODE_TABLE_N 4096
 #define PNS_MODE_MEAN_TABULATED 12.0   // mean from which the search starts at the mode (mode pmf tabulated)
 #define PNS_MODE_MEAN_GENERIC 48.0     // ... for any other probability (mode pmf evaluated per draw)
