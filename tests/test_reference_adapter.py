@@ -66,6 +66,33 @@ def test_adapter_on_reference_network_emulated(dataset, steps, emu_lib):
     _compare(want, got, steps)
 
 
+def test_adapter_with_optimal_node_model_emulated(emu_lib):
+    """assign_flows_type 'optimal' on the reference's own object: the device solves the node programs itself, so
+    the trajectory is not linprog's (tests/test_optimal_node_model.py states what is equal); here: it runs, the
+    reference object's arrays are filled, pedestrians are conserved and every node passes on what it receives."""
+    from pednstream_b200.reference_adapter import B200Step
+    np.random.seed(0)
+    net, _ = rh.create_network("nine_intersections", params={"assign_flows_type": "optimal"})
+    assert net.assign_flows_type == "optimal"
+    b200 = B200Step(net, _lib=emu_lib, _emulation=True).install()
+    assert b200.facade.engine.net.n_lp_nodes > 0
+    steps = 120
+    for t in range(1, steps + 1):
+        net.network_loading(t)
+    b200.facade.engine.check_errors()
+    total = 0.0
+    for link in net.links.values():
+        stock = np.asarray(link.cumulative_inflow)[: steps + 1] - np.asarray(link.cumulative_outflow)[: steps + 1]
+        assert np.allclose(stock, np.asarray(link.num_pedestrians)[: steps + 1], atol=1e-3)
+        assert (np.asarray(link.inflow)[: steps + 1] >= 0).all() and (np.asarray(link.outflow)[: steps + 1] >= 0).all()
+        total += float(np.asarray(link.cumulative_inflow)[steps])
+    assert total > 0
+    for node in net.nodes.values():
+        taken = sum(np.asarray(l.outflow)[: steps + 1] for l in node.incoming_links)
+        given = sum(np.asarray(l.inflow)[: steps + 1] for l in node.outgoing_links)
+        assert np.array_equal(taken, given), node.node_id
+
+
 @pytest.mark.gpu
 def test_adapter_on_reference_network_cuda():
     want = _reference_run("nine_intersections", 200, _edits)
