@@ -1314,6 +1314,16 @@ __global__ void __launch_bounds__(32 * W) k_node_cols(const __grid_constant__ Ct
 // sending flow) with warp shuffles.  Same arithmetic as link_pair_body, half the critical path
 // per thread and no cross-direction state to keep in registers.  (The host-emulation test build
 // runs the pair-per-thread kernel above instead; the GPU parity tests cover this one.)
+#ifndef PNS_LANE_BULK
+#define PNS_LANE_BULK 0   // k_link_lane: stage the first batch of rows in shared memory with cp.async.bulk (experiment)
+#endif
+#if PNS_LANE_BULK
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#endif
 template <int PHASE, int MODE, bool ONECLASS>
 __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_lane(const __grid_constant__ Ctx c) {
     constexpr bool upd = (PHASE & PH_UPDATE) != 0, flw = (PHASE & PH_FLOWS) != 0;
@@ -1347,13 +1357,54 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
                                          : __ldg(reinterpret_cast<const int2*>(c.n.lk_slots) + l);   // {sending slot, receiving slot}
     const int fftau = p.fftau, swtau = p.swtau;
     PNS_PDL_WAIT();             // everything above is static; below reads what the previous kernel wrote
-    const double gate = ld_keep<2>(c.s.gate + e, pol);
+#if PNS_LANE_BULK
+    // Experiment: the first batch of rows of a full block of the fused launch of a
+    // single-class network comes in through the bulk-copy engine -- one thread issues up to thirteen 512 / 256 byte
+    // copies into shared memory, the block waits on one mbarrier -- instead of thirteen loads per thread.
+    constexpr bool kBulk = upd && flw && ONECLASS;
+    __shared__ alignas(128) double bk64[kBulk ? 10 : 1][PNS_LANE_BLOCK];
+    __shared__ alignas(128) float bk32[kBulk ? 3 : 1][PNS_LANE_BLOCK];
+    __shared__ alignas(8) uint64_t bk_bar;
+    const bool bulk = kBulk && (size_t)(blk + 1) * PNS_LANE_BLOCK <= (size_t)c.n.n_links;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bk_bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t e0 = (size_t)blk * PNS_LANE_BLOCK;
+            const bool win = c.u_tt_old != nullptr;
+            const uint32_t b64 = PNS_LANE_BLOCK * 8u, b32 = PNS_LANE_BLOCK * 4u;
+            const uint32_t total = b64 * (7u + (c.c0_coulag ? 1u : 0u) + (c.c0_pre0 ? 1u : 0u) + (c.c0_pre1 ? 1u : 0u)) +
+                                   b32 * (2u + (win ? 1u : 0u));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bk_bar)), "r"(total) : "memory");
+            bulk_g2s(bk64[0], c.s.gate + e0, b64, &bk_bar);
+            bulk_g2s(bk64[1], c.n_cinp + e0, b64, &bk_bar);
+            bulk_g2s(bk64[2], c.n_coutp + e0, b64, &bk_bar);
+            bulk_g2s(bk64[3], c.n_outflow + e0, b64, &bk_bar);
+            bulk_g2s(bk64[4], c.n_inflow + e0, b64, &bk_bar);
+            bulk_g2s(bk64[5], c.f_sndp + e0, b64, &bk_bar);
+            bulk_g2s(bk64[6], c.f_rcvp + e0, b64, &bk_bar);
+            if (c.c0_coulag) bulk_g2s(bk64[7], c.c0_coulag + e0, b64, &bk_bar);
+            if (c.c0_pre0) bulk_g2s(bk64[8], c.c0_pre0 + e0, b64, &bk_bar);
+            if (c.c0_pre1) bulk_g2s(bk64[9], c.c0_pre1 + e0, b64, &bk_bar);
+            bulk_g2s(bk32[0], c.u_num_prev + e0, b32, &bk_bar);
+            bulk_g2s(bk32[1], c.s.runsum + e0, b32, &bk_bar);
+            if (win) bulk_g2s(bk32[2], c.u_tt_old + e0, b32, &bk_bar);
+        }
+    }
+#else
+    constexpr bool bulk = false;
+#endif
+    double gate_ld = 0.0;
+    if (!bulk) gate_ld = ld_keep<2>(c.s.gate + e, pol);
     // ---- batch of independent loads --------------------------------------------------------
     double din = 0, dout = 0;
     float np_ = 0, rs = 0, tt_old = 0;
     const bool windowed = c.u_tt_old != nullptr;
     double cin_prev = 0, cou_prev = 0;
-    if (upd) {
+    if (upd && !bulk) {
         // Node.update_links for this link (node.py:146-162): the node pass wrote inflow[t] / outflow[t]
         cin_prev = ld_once<3>(c.n_cinp + e, pol); cou_prev = ld_once<3>(c.n_coutp + e, pol);
         np_ = ld_once<3>(c.u_num_prev + e, pol); rs = ld_keep<2>(c.s.runsum + e, pol);
@@ -1363,7 +1414,7 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
     double cin_tau = 0, cou_tau = 0, snd_prev = 0, rcv_prev = 0, cou_lag = 0;
     LinkNow me;
     me.num = 0; me.dens = 0; me.avg_tt = 0;
-    if (flw) {
+    if (flw && !bulk) {
         if (!upd) { cin_tau = c.f_cin[e]; cou_tau = c.f_cou[e]; }
         snd_prev = ld_once<3>(c.f_sndp + e, pol); rcv_prev = ld_once<3>(c.f_rcvp + e, pol);
         if (ONECLASS) {
@@ -1391,8 +1442,10 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
                 pre_row1 = H64(c, PNS_F64_CUM_INFLOW, pre_i1);
             }
         }
-        if (pre_row0) pre_v0 = ld_once<3>(pre_row0 + e, pol);
-        if (pre_row1) pre_v1 = ld_keep<3>(pre_row1 + e, pol);   // next step's pre_v0
+        if (!bulk) {
+            if (pre_row0) pre_v0 = ld_once<3>(pre_row0 + e, pol);
+            if (pre_row1) pre_v1 = ld_keep<3>(pre_row1 + e, pol);   // next step's pre_v0
+        }
     }
     // ---- software prefetch for later CTAs ----------------------------------------------------
     // A thread spends most of its memory time waiting for the batch above to come back from DRAM.
@@ -1425,6 +1478,24 @@ __global__ void __launch_bounds__(PNS_LANE_BLOCK, PNS_LANE_MIN_BLOCKS) k_link_la
             }
         }
     }
+#if PNS_LANE_BULK
+    if (bulk) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bk_bar)) : "memory");
+        const unsigned k = threadIdx.x;
+        gate_ld = bk64[0][k];
+        cin_prev = bk64[1][k]; cou_prev = bk64[2][k]; dout = bk64[3][k]; din = bk64[4][k];
+        snd_prev = bk64[5][k]; rcv_prev = bk64[6][k];
+        if (c.c0_coulag) cou_lag = bk64[7][k];
+        if (c.c0_pre0) pre_v0 = bk64[8][k];
+        if (c.c0_pre1) pre_v1 = bk64[9][k];
+        np_ = bk32[0][k]; rs = bk32[1][k];
+        if (windowed) tt_old = bk32[2][k];
+    }
+#endif
+    const double gate = gate_ld;
     const double gate_rev = __shfl_xor_sync(FULL, gate, 1);
     const Area ar = link_area(c, p, e, gate);
     const uint32_t k0 = (uint32_t)c.io.seed, k1 = (uint32_t)(c.io.seed >> 32);
