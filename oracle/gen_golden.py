@@ -199,6 +199,9 @@ ENV_CASES = {
                                         seed=21, steps=250),
     "env_45_intersections_opt4": dict(dataset="45_intersections", obs_mode="option4", normalize_obs=False,
                                       seed=4, steps=150),
+    # action_gap = 3: three simulation steps per decision, rewards summed over them (rl/pz_pednet_env.py:224-253)
+    "env_45_intersections_gap3": dict(dataset="45_intersections", obs_mode="option3", normalize_obs=False,
+                                      seed=6, steps=90, action_gap=3),
 }
 
 
@@ -219,7 +222,7 @@ def scripted_actions(env, steps, seed=7):
 def generate_env(name):
     case = ENV_CASES[name]
     env = rh.make_reference_env(case["dataset"], obs_mode=case["obs_mode"], normalize_obs=case["normalize_obs"],
-                                seed=case["seed"])
+                                seed=case["seed"], **({"action_gap": case["action_gap"]} if "action_gap" in case else {}))
     obs0, _ = env.reset()
     steps = case["steps"]
     actions = scripted_actions(env, steps)

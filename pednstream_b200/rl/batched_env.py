@@ -2,7 +2,7 @@
 
 The per-replica semantics are those of the reference's `PedNetParallelEnv`
 (rl/pz_pednet_env.py:143-254): actions are absolute widths (rate-limited, clipped,
-rl/builders.py:264-352), one `network_loading` per env step (`action_gap` = 1), observations in
+rl/builders.py:264-352), `action_gap` `network_loading` steps per env step (default 1), observations in
 the reference's link-major layout (rl/builders.py:68-177), the first agent's reward
 (pz_pednet_env.py:548-581), termination after S env steps.  Everything per step -- action
 application, the LTM step with on-device Philox draws, observation and reward -- is a CUDA kernel
@@ -52,13 +52,17 @@ def _gater_divisors(obs_mode, k):
 class BatchedPedNetEnv:
     def __init__(self, dataset: str, replicas: int, obs_mode: str = "option3", normalize_obs: bool = False,
                  seed: int = 0, replica_base: int = 0, device=None, data_dir="data", randomize: bool = False,
-                 params: dict = None, od_nodes_seed: int = None, _lib=None, _emulation: bool = False):
+                 params: dict = None, od_nodes_seed: int = None, action_gap: int = 1, _lib=None,
+                 _emulation: bool = False):
         """params: overrides of the scenario's parameter block (e.g. {"assign_flows_type": "optimal"}), applied
         before the template network is built.  od_nodes_seed: perturb the scenario's origin / destination nodes as
         the reference's generate_random_od_nodes(seed) does (env_loader.py:261-361) -- all replicas of this
         environment share that topology; `GroupedPedNetEnv` runs several such groups side by side."""
         if obs_mode not in OBS_LAYOUT:
             raise ValueError(f"obs_mode must be one of {list(OBS_LAYOUT)}, got: {obs_mode}")
+        if int(action_gap) < 1:
+            raise ValueError("action_gap must be >= 1")
+        self.action_gap = int(action_gap)      # simulation steps per decision (rl/pz_pednet_env.py:110-111, 224-253)
         self.dataset, self.R, self.obs_mode, self.seed = dataset, int(replicas), obs_mode, int(seed)
         self.replica_base = int(replica_base)
         state = np.random.get_state()                 # building the template must not disturb the caller's stream
@@ -445,6 +449,8 @@ class BatchedPedNetEnv:
             if actions.shape != (self.R, self.n_act) or actions.dtype != torch.float32:
                 raise ValueError(f"actions must be float32 [{self.R}, {self.n_act}]")
             actions = actions.contiguous()
+        if self.action_gap > 1:
+            return self._step_with_gap(actions, obs, reward)
         with eng._guard():      # actions, the LTM step, observations + reward: one native call behind one custom op
             eng._begin_steps(self.sim_step, 1)
             has_actions = actions is not None and self.n_act > 0
@@ -456,11 +462,45 @@ class BatchedPedNetEnv:
         self.sim_step += 1
         return obs, reward, done, {"step": self.sim_step - 1}
 
+    def _step_with_gap(self, actions, obs, reward):
+        """action_gap > 1 (rl/pz_pednet_env.py:224-253): the actions are applied once, then `action_gap` simulation
+        steps run; the observation is the last step's, the reward the float32 sum of the steps' rewards in step
+        order, and the running total grows by that sum once.  Sub-steps are ordinary native environment steps
+        without actions, their rewards are added up by torch."""
+        eng = self.engine
+        if self.sim_step + self.action_gap - 1 > self.simulation_steps:
+            raise RuntimeError("the decision's simulation steps run past the end of the episode")
+        if not hasattr(self, "_gap_reward"):
+            self._gap_reward = torch.zeros_like(self.reward)
+            self._gap_total = torch.zeros_like(self.reward)     # receives the native running total (not used)
+        done = False
+        with eng._guard():
+            eng._begin_steps(self.sim_step, self.action_gap)
+            for k in range(self.action_gap):
+                has_actions = k == 0 and actions is not None and self.n_act > 0
+                ops.env_step(eng.hist64, eng.hist32, eng.runsum, eng.tf_routed, eng.probs, eng.err, eng.gate,
+                             actions if has_actions else self._no_actions, obs, reward if k == 0 else self._gap_reward,
+                             self._gap_total, eng.handle, int(self.sim_step), has_actions)
+                if k:
+                    reward.add_(self._gap_reward)
+                eng.t_done = self.sim_step
+                done = self.sim_step >= self.simulation_steps
+                self.sim_step += 1
+            self.cumulative_reward.add_(reward)
+        return obs, reward, done, {"step": self.sim_step - 1}
+
     def rollout(self, actions: torch.Tensor, obs_out: torch.Tensor = None, reward_out: torch.Tensor = None):
         """K environment steps with given actions ([K, R, n_act] float32 on the device) in one native call
         (`torch.ops.pednstream.env_rollout` -> pns_env_rollout): returns (obs [K, R, n_obs], reward [K, R], done)."""
         eng = self.engine
         K = int(actions.shape[0])
+        if self.action_gap > 1:                # decisions with several simulation steps: a loop over `step`
+            obs = obs_out if obs_out is not None else torch.empty((K, self.R, self.obs.shape[1]), dtype=torch.float32, device=self.device)
+            rew = reward_out if reward_out is not None else torch.empty((K, self.R), dtype=torch.float32, device=self.device)
+            done = False
+            for k in range(K):
+                _, _, done, _ = self.step(actions[k], obs[k], rew[k])
+            return obs, rew, done
         if self.sim_step + K - 1 > self.simulation_steps:
             raise RuntimeError("rollout runs past the end of the episode")
         if tuple(actions.shape[1:]) != (self.R, self.n_act) or actions.dtype != torch.float32:
@@ -487,6 +527,9 @@ class BatchedPedNetEnv:
         k+1 go up and results of step k come down while the other step computes).  Returns after everything is
         enqueued; synchronise the device (or the current stream) before reading the host tensors."""
         K = int(host_actions.shape[0])
+        if self.action_gap > 1:
+            raise NotImplementedError("rollout_host runs decisions of one simulation step (action_gap = 1); "
+                                      "use step() / rollout() with action_gap > 1")
         if not (host_actions.is_pinned() and host_obs.is_pinned() and host_reward.is_pinned()):
             raise ValueError("rollout_host needs pinned host tensors")
         if host_obs.shape[0] < K or host_reward.shape[0] < K:

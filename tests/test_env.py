@@ -14,13 +14,16 @@ ENV_CASES = {"env_nine_intersections": ("nine_intersections", "option3", False),
              "env_nine_intersections_opt2n": ("nine_intersections", "option2", True),
              "env_butterfly_opt5": ("butterfly_scA", "option5", False),
              "env_nine_intersections_opt4": ("nine_intersections", "option4", False),
-             "env_45_intersections_opt4": ("45_intersections", "option4", False)}
+             "env_45_intersections_opt4": ("45_intersections", "option4", False),
+             "env_45_intersections_gap3": ("45_intersections", "option3", False, 3)}
 
 
 def run_env_case(name, **engine_kw):
-    dataset, obs_mode, norm = ENV_CASES[name]
+    dataset, obs_mode, norm, *gap = ENV_CASES[name]
+    gap = gap[0] if gap else 1
     gold = load_golden(name)
-    env = PedNetParallelEnv(dataset, obs_mode=obs_mode, normalize_obs=norm, seed=int(gold["seed"]), **engine_kw)
+    env = PedNetParallelEnv(dataset, obs_mode=obs_mode, normalize_obs=norm, seed=int(gold["seed"]), action_gap=gap,
+                            **engine_kw)
     agents = list(env.possible_agents)
     assert agents == gold["agents"].tolist()
     widths = gold["action_widths"].tolist()
@@ -40,9 +43,9 @@ def run_env_case(name, **engine_kw):
         r = np.array([float(rew.get(a, 0.0)) for a in agents])
         assert np.array_equal(r, gold["rewards"][k]), f"reward differs at env step {k + 1}: {r} vs {gold['rewards'][k]}"
         assert bool(term[agents[0]]) == bool(gold["done"][k]) and not any(trunc.values())
-        assert info[agents[0]]["step"] == k + 1
+        assert info[agents[0]]["step"] == gap * (k + 1)
     fields = {f: env.network._store.field(f) for f in F64_FIELDS[:7] + F32_FIELDS}
-    assert_matches_golden(gold, fields, steps, int(gold["n_links"]))
+    assert_matches_golden(gold, fields, gap * steps, int(gold["n_links"]))
     return env
 
 
@@ -288,6 +291,54 @@ def test_grouped_env_od_node_perturbation_emulated(emu_lib):
 @pytest.mark.gpu
 def test_grouped_env_od_node_perturbation_cuda():
     _grouped_vs_randomize_network("45_intersections", 150, 40, 5, device="cuda:0")
+
+
+def _batched_gap_vs_facade(gap, decisions, R, picks, lib=None, emulation=False, device=None):
+    """BatchedPedNetEnv(action_gap=gap): replica r against the single-network environment with the same gap (which
+    is pinned to the reference's own env by the env_45_intersections_gap3 fixture)."""
+    kw = dict(_lib=lib, _emulation=emulation) if emulation else dict(device=device)
+    benv = BatchedPedNetEnv("45_intersections", replicas=R, obs_mode="option3", seed=5, action_gap=gap, **kw)
+    dev = benv.device
+    acts = np.random.RandomState(2).uniform(0.0, 4.0, size=(decisions, R, benv.n_act)).astype(np.float32)
+    demand = benv.engine.demand.cpu().numpy().reshape(benv.simulation_steps + 1, -1, R)
+    obs_b, rew_b = [], []
+    half = decisions // 2
+    for k in range(half):                                   # first half through step(), second through rollout()
+        o, r, _, info = benv.step(torch.from_numpy(acts[k]).to(dev))
+        assert info["step"] == gap * (k + 1)
+        obs_b.append(o.cpu().numpy().copy()); rew_b.append(r.cpu().numpy().copy())
+    o, r, _ = benv.rollout(torch.from_numpy(acts[half:]).to(dev))
+    obs_b += list(o.cpu().numpy()); rew_b += list(r.cpu().numpy())
+    benv.engine.check_errors()
+    assert benv.sim_step == gap * decisions + 1
+    cum = benv.cumulative_reward.cpu().numpy()
+    for rep in picks:
+        fkw = dict(_lib=lib, _emulation=True) if emulation else dict(device=device)
+        env = PedNetParallelEnv("45_intersections", obs_mode="option3", seed=5, rng="philox", action_gap=gap, **fkw)
+        for row, node in enumerate(env.network.plan["demand_nodes"]):
+            node.demand = demand[:, row, rep].copy()
+        eng = env.network.engine
+        eng.io.seed = benv.engine.io.seed
+        eng.io.replica_base = rep
+        agents = env.possible_agents
+        for k in range(decisions):
+            obs, rew, *_ = env.step({a: acts[k, rep, benv.action_slices[a]] for a in agents})
+            assert np.array_equal(np.concatenate([obs[a] for a in agents]), obs_b[k][rep]), (rep, k)
+            assert np.float32(rew.get(agents[0], 0.0)) == rew_b[k][rep], (rep, k)
+        assert np.float32(env._cumulative_rewards[agents[0]]) == cum[rep]
+        for f in F64_FIELDS[:7] + F32_FIELDS:
+            want = env.network._store.field(f)
+            got = benv.engine.history(f)[:, :, rep].cpu().numpy()
+            assert np.array_equal(want[: gap * decisions + 1], got[: gap * decisions + 1]), (f, rep)
+
+
+def test_batched_env_action_gap_emulated(emu_lib):
+    _batched_gap_vs_facade(3, 20, 3, (0, 2), lib=emu_lib, emulation=True)
+
+
+@pytest.mark.gpu
+def test_batched_env_action_gap_cuda():
+    _batched_gap_vs_facade(3, 60, 40, (0, 21, 39), device="cuda:0")
 
 
 def test_batched_env_matches_facade_emulated(emu_lib):
