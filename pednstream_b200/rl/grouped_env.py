@@ -25,10 +25,11 @@ from .batched_env import BatchedPedNetEnv
 class GroupedPedNetEnv:
     def __init__(self, dataset: str, replicas: int, groups: int, obs_mode: str = "option3",
                  normalize_obs: bool = False, seed: int = 0, replica_base: int = 0, device=None, data_dir="data",
-                 randomize=True, perturb_first_group: bool = True, _lib=None, _emulation: bool = False):
+                 randomize=True, perturb_first_group: bool = True, action_gap: int = 1, _lib=None,
+                 _emulation: bool = False):
         if not 1 <= groups <= replicas:
             raise ValueError("1 <= groups <= replicas")
-        self.R, self.G = int(replicas), int(groups)
+        self.R, self.G, self.action_gap = int(replicas), int(groups), int(action_gap)
         sizes = [self.R // self.G + (1 if g < self.R % self.G else 0) for g in range(self.G)]
         self.envs, self.slices = [], []
         offset = 0
@@ -39,6 +40,7 @@ class GroupedPedNetEnv:
             env = BatchedPedNetEnv(dataset, n, obs_mode=obs_mode, normalize_obs=normalize_obs, seed=seed,
                                    replica_base=base, device=device, data_dir=data_dir, randomize=randomize,
                                    od_nodes_seed=od_seed if (g > 0 or perturb_first_group) else None,
+                                   action_gap=action_gap,
                                    _lib=_lib, _emulation=_emulation)
             self.envs.append(env)
             self.slices.append(slice(offset, offset + n))
@@ -109,6 +111,18 @@ class GroupedPedNetEnv:
         t = self.envs[0].sim_step
         if t > self.simulation_steps:
             raise RuntimeError("episode finished: call reset()")
+        if self.action_gap > 1:                 # several simulation steps per decision: the groups' own step()
+            done = False
+            with self.envs[0].engine._guard():
+                streams = self._fork()
+                for env, sl, st in zip(self.envs, self.slices, streams):
+                    if st is None:
+                        _, _, done, _ = env.step(actions[sl], self._obs_views[sl.start], self._reward_views[sl.start])
+                    else:
+                        with torch.cuda.stream(st):
+                            _, _, done, _ = env.step(actions[sl], self._obs_views[sl.start], self._reward_views[sl.start])
+                self._join()
+            return self.obs, self.reward, done, {"step": self.envs[0].sim_step - 1}
         with self.envs[0].engine._guard():
             streams = self._fork()
             for env, sl, st in zip(self.envs, self.slices, streams):
@@ -121,6 +135,18 @@ class GroupedPedNetEnv:
                 env.sim_step = t + 1
             self._join()
         return self.obs, self.reward, t >= self.simulation_steps, {"step": t}
+
+    def rollout(self, actions: torch.Tensor):
+        """K decisions with given actions [K, R, n_act]: (obs [K, R, n_obs], reward [K, R], done)."""
+        K = int(actions.shape[0])
+        obs = torch.empty((K, self.R, self.n_obs), dtype=torch.float32, device=self.device)
+        rew = torch.empty((K, self.R), dtype=torch.float32, device=self.device)
+        done = False
+        for k in range(K):
+            o, r, done, _ = self.step(actions[k])
+            obs[k].copy_(o)
+            rew[k].copy_(r)
+        return obs, rew, done
 
     def kpis(self, t_last: int = None) -> torch.Tensor:
         return torch.cat([env.kpis(t_last) for env in self.envs], dim=0)

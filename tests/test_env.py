@@ -288,6 +288,27 @@ def test_grouped_env_od_node_perturbation_emulated(emu_lib):
     _grouped_vs_randomize_network("45_intersections", 50, 5, 3, lib=emu_lib, emulation=True)
 
 
+def test_grouped_env_action_gap_and_rollout_emulated(emu_lib):
+    """Groups with action_gap 2: a rollout equals the same decisions through step(), and the groups' replicas equal
+    a stand-alone batched environment of that group (same seeds, same OD nodes)."""
+    from pednstream_b200.rl import GroupedPedNetEnv
+    kw = dict(_lib=emu_lib, _emulation=True)
+    a = GroupedPedNetEnv("45_intersections", replicas=4, groups=2, seed=5, randomize="host", action_gap=2, **kw)
+    b = GroupedPedNetEnv("45_intersections", replicas=4, groups=2, seed=5, randomize="host", action_gap=2, **kw)
+    acts = torch.from_numpy(np.random.RandomState(1).uniform(0, 4, (8, 4, a.n_act)).astype(np.float32))
+    obs, rew, _ = a.rollout(acts)
+    for k in range(8):
+        o, r, _, info = b.step(acts[k])
+        assert info["step"] == 2 * (k + 1)
+        assert torch.equal(o, obs[k]) and torch.equal(r, rew[k])
+    g1 = a.envs[1]
+    solo = BatchedPedNetEnv("45_intersections", replicas=g1.R, obs_mode="option3", seed=5, replica_base=g1.replica_base,
+                            randomize="host", od_nodes_seed=g1.od_nodes_seed, action_gap=2, **kw)
+    for k in range(8):
+        o, r, _, _ = solo.step(acts[k][a.slices[1]])
+        assert torch.equal(o, obs[k][a.slices[1]]) and torch.equal(r, rew[k][a.slices[1]])
+
+
 @pytest.mark.gpu
 def test_grouped_env_od_node_perturbation_cuda():
     _grouped_vs_randomize_network("45_intersections", 150, 40, 5, device="cuda:0")
